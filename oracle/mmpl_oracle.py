@@ -1,0 +1,376 @@
+"""CPU oracle for the multimodal-PL hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, in plain fp32/fp64 PyTorch + numpy on the CPU, the algorithm of the reference's dense hot
+path so that the CUDA kernels can be checked against it.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the product package never does.
+
+Parity pin: the reference (TThuraya/multimodal-PL) ships no tests and no golden vectors.
+The oracle is therefore pinned against *outputs of the reference itself*: ``oracle/make_golden.py`` imports the
+unmodified reference modules from ``/root/reference`` in the authoring container and writes small fixtures to
+``tests/golden/``; ``tests/test_oracle_golden.py`` replays them against this file on every CPU test run.
+
+All arithmetic below the Python level is PyTorch ATen (torch 2.11.0+cu128, oneDNN 3.10 on CPU) exactly as in
+the reference; this file only re-expresses *which* ATen ops are applied in *which* order, citing the reference.
+Citations are ``path:line`` relative to the reference repository root.
+"""
+from __future__ import annotations
+
+import csv
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------------------------------------------
+# Weight standardisation + convolution                                                    unet3D.py:16-27
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def ws_weight(w: torch.Tensor) -> torch.Tensor:
+    """Per-out-channel standardised weight (unet3D.py:22-26): nested means over dims 1..4, unbiased variance of
+    the centred weight, eps 1e-12 under the square root."""
+    m = w.mean(dim=1, keepdim=True).mean(dim=2, keepdim=True).mean(dim=3, keepdim=True).mean(dim=4, keepdim=True)
+    c = w - m
+    std = torch.sqrt(torch.var(c.view(c.size(0), -1), dim=1) + 1e-12).view(-1, 1, 1, 1, 1)
+    return c / std
+
+
+def ws_conv3d(x: torch.Tensor, w: torch.Tensor, stride: int, padding: int) -> torch.Tensor:
+    """Conv3d.forward (unet3D.py:21-27): F.conv3d with the standardised weight, no bias, dilation 1, groups 1."""
+    return F.conv3d(x, ws_weight(w), None, stride, padding, 1, 1)
+
+
+def gn_relu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int = 16) -> torch.Tensor:
+    """nn.GroupNorm(16, C) (eps 1e-5, affine) followed by ReLU (unet3D.py:44,47,49,59-60,64-65)."""
+    return F.relu(F.group_norm(x, groups, gamma, beta, 1e-5))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Topology of unet3D_baseline                                                            unet3D.py:585-718
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def backbone_spec(base: int = 32) -> List[Tuple[str, int, int, int]]:
+    """(prefix, inplanes, planes, stride) for every NoBottleneck in forward order, layers=[1,2,2,2,2]
+    (unet3D.py:596-626, _make_layer :641-661).  ``base`` = 32 reproduces the reference; 64 is the wide stress
+    config (BASELINE.json configs[4]) built from the same recipe with doubled widths."""
+    b = base
+    enc = [
+        ("layer0.0.", b, b, 1),
+        ("layer1.0.", b, 2 * b, 2), ("layer1.1.", 2 * b, 2 * b, 1),
+        ("layer2.0.", 2 * b, 4 * b, 2), ("layer2.1.", 4 * b, 4 * b, 1),
+        ("layer3.0.", 4 * b, 8 * b, 2), ("layer3.1.", 8 * b, 8 * b, 1),
+        ("layer4.0.", 8 * b, 8 * b, 2), ("layer4.1.", 8 * b, 8 * b, 1),
+    ]
+    dec = [
+        ("x8_resb.0.", 8 * b, 4 * b, 1),
+        ("x4_resb.0.", 4 * b, 2 * b, 1),
+        ("x2_resb.0.", 2 * b, b, 1),
+        ("x1_resb.0.", b, b, 1),
+    ]
+    return enc + dec
+
+
+def state_dict_shapes(base: int = 32, num_classes: int = 16) -> Dict[str, Tuple[int, ...]]:
+    """Key -> shape for the 107 tensors of unet3D_baseline (probed from the reference)."""
+    shapes: Dict[str, Tuple[int, ...]] = {"conv1.weight": (base, 1, 3, 3, 3)}
+    for p, cin, cout, stride in backbone_spec(base):
+        shapes[p + "gn1.weight"] = (cin,)
+        shapes[p + "gn1.bias"] = (cin,)
+        shapes[p + "conv1.weight"] = (cout, cin, 3, 3, 3)
+        shapes[p + "gn2.weight"] = (cout,)
+        shapes[p + "gn2.bias"] = (cout,)
+        shapes[p + "conv2.weight"] = (cout, cout, 3, 3, 3)
+        if stride != 1 or cin != cout:
+            shapes[p + "downsample.0.weight"] = (cin,)
+            shapes[p + "downsample.0.bias"] = (cin,)
+            shapes[p + "downsample.2.weight"] = (cout, cin, 1, 1, 1)
+    shapes["fusionConv.0.weight"] = (8 * base,)
+    shapes["fusionConv.0.bias"] = (8 * base,)
+    shapes["fusionConv.2.weight"] = (8 * base, 8 * base, 1, 1, 1)
+    shapes["precls_conv.0.weight"] = (base,)
+    shapes["precls_conv.0.bias"] = (base,)
+    shapes["precls_conv.2.weight"] = (num_classes, base, 1, 1, 1)
+    shapes["precls_conv.2.bias"] = (num_classes,)
+    return shapes
+
+
+def synth_state_dict(base: int = 32, num_classes: int = 16, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Deterministic random weights keyed by tensor name (independent of module construction order, so the same
+    values can be loaded into the reference model, this oracle and the CUDA path)."""
+    sd: Dict[str, torch.Tensor] = {}
+    for i, (k, shp) in enumerate(sorted(state_dict_shapes(base, num_classes).items())):
+        g = torch.Generator().manual_seed(seed * 100003 + i)
+        if k.endswith("gn1.weight") or k.endswith("gn2.weight") or k.endswith(".0.weight"):
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif k.endswith("bias") and len(shp) == 1 and not k.startswith("precls_conv.2"):
+            t = 0.1 * torch.randn(shp, generator=g)
+        elif k.startswith("precls_conv.2"):
+            bound = 1.0 / math.sqrt(base)
+            t = (torch.rand(shp, generator=g) * 2 - 1) * bound
+        else:
+            fan_in = int(np.prod(shp[1:]))
+            t = torch.randn(shp, generator=g) / math.sqrt(fan_in)
+        sd[k] = t.float()
+    return sd
+
+
+def no_bottleneck(x: torch.Tensor, sd: Dict[str, torch.Tensor], p: str, stride: int) -> torch.Tensor:
+    """NoBottleneck.forward (unet3D.py:56-73): pre-activation residual block; the residual branch is
+    downsample(x) = WSconv1x1(relu(GN(x))) computed from the block input when present (:68-69, :643-649)."""
+    out = gn_relu(x, sd[p + "gn1.weight"], sd[p + "gn1.bias"])
+    out = ws_conv3d(out, sd[p + "conv1.weight"], stride, 1)
+    out = gn_relu(out, sd[p + "gn2.weight"], sd[p + "gn2.bias"])
+    out = ws_conv3d(out, sd[p + "conv2.weight"], 1, 1)
+    if (p + "downsample.2.weight") in sd:
+        res = gn_relu(x, sd[p + "downsample.0.weight"], sd[p + "downsample.0.bias"])
+        res = ws_conv3d(res, sd[p + "downsample.2.weight"], stride, 0)
+    else:
+        res = x
+    return out + res
+
+
+def upsample2x_add(x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
+    """nn.Upsample(scale_factor=2, mode='trilinear') (align_corners=False) then ``x + skip``
+    (unet3D.py:608, :686-687)."""
+    return F.interpolate(x, scale_factor=2, mode="trilinear") + skip
+
+
+def unet3d_forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, base: int = 32) -> torch.Tensor:
+    """unet3D_baseline.forward (unet3D.py:663-718), returning the logits [B, num_classes, D, H, W]."""
+    spec = {p: (cin, cout, s) for p, cin, cout, s in backbone_spec(base)}
+
+    def blk(x, p):
+        return no_bottleneck(x, sd, p, spec[p][2])
+
+    x = ws_conv3d(image, sd["conv1.weight"], 1, 1)                                    # :666
+    x = blk(x, "layer0.0.")
+    skip0 = x                                                                         # :667-668
+    x = blk(blk(x, "layer1.0."), "layer1.1.")
+    skip1 = x                                                                         # :670-671
+    x = blk(blk(x, "layer2.0."), "layer2.1.")
+    skip2 = x
+    x = blk(blk(x, "layer3.0."), "layer3.1.")
+    skip3 = x
+    x = blk(blk(x, "layer4.0."), "layer4.1.")                                         # :679
+    x = ws_conv3d(gn_relu(x, sd["fusionConv.0.weight"], sd["fusionConv.0.bias"]), sd["fusionConv.2.weight"], 1, 0)
+    x = blk(upsample2x_add(x, skip3), "x8_resb.0.")                                   # :686-688
+    x = blk(upsample2x_add(x, skip2), "x4_resb.0.")
+    x = blk(upsample2x_add(x, skip1), "x2_resb.0.")
+    x = blk(upsample2x_add(x, skip0), "x1_resb.0.")                                   # :707-709
+    x = gn_relu(x, sd["precls_conv.0.weight"], sd["precls_conv.0.bias"])
+    return F.conv3d(x, sd["precls_conv.2.weight"], sd["precls_conv.2.bias"])         # :629-633, :713
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Partial-label loss                                                                      loss_partial.py:10-99
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def dice_term(score: torch.Tensor, target01: torch.Tensor) -> torch.Tensor:
+    """DiceLoss._dice_loss with an all-ones mask (loss_partial.py:24-36): pooled over batch and voxels,
+    squared-score denominator, smooth 1e-5 top and bottom."""
+    smooth = 1e-5
+    inter = torch.sum(score * target01)
+    y = torch.sum(target01 * target01)
+    z = torch.sum(score * score)
+    return 1 - (2 * inter + smooth) / (z + y + smooth)
+
+
+def partial_label_loss(logits: torch.Tensor, target: torch.Tensor, class_weight: Sequence[float],
+                       uce: bool = True) -> torch.Tensor:
+    """EDiceLoss_partial.forward(inputs, target, mask=[w,...], soft_max=True, uce) (loss_partial.py:71-99).
+
+    ``target`` is [B, D, H, W] float class ids; ``class_weight`` is ``mask[0]`` (the reference uses the first
+    sample's vector for the whole batch, :87/:92).  dice = sum_c w_c * dice_c / C (:49-57); ce = sum_c w_c *
+    BCELoss(p_c, [target == c]) with PyTorch's log clamp at -100 (:90-92)."""
+    C = logits.shape[1]
+    p = torch.softmax(logits, dim=1)
+    dice = 0.0
+    for c in range(C):                                   # DiceLoss.forward loop, loss_partial.py:49-56
+        t = (target == c).float()
+        dice = dice + dice_term(p[:, c], t) * float(class_weight[c])
+    dice = dice / C
+    if not uce:
+        return dice
+    ce = 0.0
+    for c in range(C):                                   # loss_partial.py:91-92
+        t = (target == c).float()
+        ce = ce + F.binary_cross_entropy(p[:, c].float(), t) * float(class_weight[c])
+    return dice + ce
+
+
+def partial_label_loss_sums(logits: np.ndarray, target: np.ndarray) -> Dict[str, np.ndarray]:
+    """float64 numpy restatement of the four per-class sums the fused kernel produces:
+    I = sum p t, Z = sum p^2, Y = sum t, E = sum BCE terms (log clamped at -100)."""
+    z = logits.astype(np.float64)
+    z = z - z.max(axis=1, keepdims=True)
+    e = np.exp(z)
+    p = e / e.sum(axis=1, keepdims=True)
+    C = logits.shape[1]
+    out = {k: np.zeros(C) for k in "IZYE"}
+    for c in range(C):
+        t = (target == c).astype(np.float64)
+        pc = p[:, c]
+        out["I"][c] = (pc * t).sum()
+        out["Z"][c] = (pc * pc).sum()
+        out["Y"][c] = t.sum()
+        with np.errstate(divide="ignore"):
+            lp = np.maximum(np.log(pc), -100.0)
+            l1p = np.maximum(np.log1p(-pc), -100.0)
+        out["E"][c] = -(t * lp + (1 - t) * l1p).sum()
+    return out
+
+
+def remap_unsupervised(labels: torch.Tensor, sup16: Sequence[float]) -> torch.Tensor:
+    """cmask construction (train_amos_atlas_final.py:252-255): voxels whose organ id is not supervised for this
+    volume are relabelled background.  ``sup16[l]`` is the supervision bit of class l (index 0 = background)."""
+    out = labels.clone()
+    for l in range(1, len(sup16)):
+        if not sup16[l]:
+            out[out == l] = 0
+    return out
+
+
+def read_supervise_mask(path: str, w_bg: float = 1.0) -> Dict[str, List[float]]:
+    """supervise_mask.csv adapter: skip the ``name,mask`` header, strip ``.nii.gz``, and prepend
+    the background slot the train loop expects (train_amos_atlas_final.py:177-183, :215-219)."""
+    table: Dict[str, List[float]] = {}
+    with open(path, "r") as f:
+        for name, mask in csv.reader(f):
+            if name == "name":
+                continue
+            bits = [float(v) for v in mask.strip("[] ").split(",")]
+            table[name.replace(".nii.gz", "")] = [float(w_bg)] + bits
+    return table
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Sliding-window inference + Dice                                                         evaluate_amos.py:92-279
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def gaussian_importance(tile: Sequence[int], sigma_scale: float = 1.0 / 8) -> np.ndarray:
+    """_get_gaussian (evaluate_amos.py:184-197): scipy gaussian_filter of a centred delta (sigma = tile/8,
+    mode constant), divided by its max, cast to fp32, zeros replaced by the smallest non-zero value."""
+    from scipy.ndimage import gaussian_filter
+
+    tmp = np.zeros(tile)
+    tmp[tuple(i // 2 for i in tile)] = 1
+    g = gaussian_filter(tmp, [i * sigma_scale for i in tile], 0, mode="constant", cval=0)
+    g = (g / np.max(g) * 1).astype(np.float32)
+    g[g == 0] = np.min(g[g != 0])
+    return g
+
+
+def tile_starts(size: int, tile: int, stride: int) -> List[int]:
+    """Window starts along one axis (evaluate_amos.py:218-239): ceil((S-t)/stride)+1 windows, each clamped so it
+    ends inside the volume (the last ones slide back to the border)."""
+    n = int(math.ceil((size - tile) / stride) + 1)
+    out = []
+    for i in range(n):
+        a = int(i * stride)
+        b = min(a + tile, size)
+        out.append(max(int(b - tile), 0))
+    return out
+
+
+def tile_grid(image_size: Sequence[int], tile: Sequence[int]) -> List[Tuple[int, int, int]]:
+    """All (d1, y1, x1) window origins in the reference's dep->row->col order (evaluate_amos.py:215-239).
+    Note the H/W stride is derived from tile[1] only (:217)."""
+    overlap = 1 / 4
+    stride_hw = int(math.ceil(tile[1] * (1 - overlap)))
+    stride_d = int(math.ceil(tile[0] * (1 - overlap)))
+    ds = tile_starts(image_size[0], tile[0], stride_d)
+    ys = tile_starts(image_size[1], tile[1], stride_hw)
+    xs = tile_starts(image_size[2], tile[2], stride_hw)
+    return [(d, y, x) for d in ds for y in ys for x in xs]
+
+
+def predict_sliding(net, image: np.ndarray, tile: Sequence[int], classes: int) -> torch.Tensor:
+    """predict_sliding without TTA (evaluate_amos.py:211-279): Gaussian-weighted logit accumulation in float64,
+    normalised by the accumulated weights.  ``net(img)`` maps a [B,1,d,h,w] fp32 tensor to logits."""
+    g = torch.from_numpy(gaussian_importance(tile))
+    B, _, D, H, W = image.shape
+    full = torch.zeros((B, classes, D, H, W), dtype=torch.float64)
+    count = torch.zeros((B, classes, D, H, W), dtype=torch.float64)
+    for d1, y1, x1 in tile_grid((D, H, W), tile):
+        d2, y2, x2 = d1 + tile[0], y1 + tile[1], x1 + tile[2]
+        img = torch.from_numpy(image[:, :, d1:d2, y1:y2, x1:x2])
+        pred = net(img).float().cpu()
+        pred = pred * g
+        count[:, :, d1:d2, y1:y2, x1:x2] += g
+        full[:, :, d1:d2, y1:y2, x1:x2] += pred
+    return full / count
+
+
+def get_dice(preds: torch.Tensor, labels: torch.Tensor, num_class: int = 13):
+    """get_dice without atlas (evaluate_amos.py:128-141) on dice/senc/spec_score (:92-126): argmax of the softmax,
+    then per class l=1..num_class 2|P&T| / (|P|+|T|+1), |P&T|/(|T|+1), |P&T|/(|P|+1), each averaged over batch."""
+    pr = F.softmax(preds, dim=1)
+    am = torch.argmax(pr, dim=1)
+    lab = labels.reshape(labels.shape[0], -1)
+    dices, senc, spec = [], [], []
+    for l in range(1, num_class + 1):
+        p = (am == l).reshape(am.shape[0], -1).double()
+        t = (lab == l).double()
+        num = (p * t).sum(1)
+        dices.append((2 * num / (p.sum(1) + t.sum(1) + 1)).mean())
+        senc.append((num / (t.sum(1) + 1)).mean())
+        spec.append((num / (p.sum(1) + 1)).mean())
+    return dices, senc, spec, am
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Optimiser                                                          train_amos_atlas_final.py:132-135, utils.py:53-60
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def sgd_step(p: torch.Tensor, g: torch.Tensor, buf: Optional[torch.Tensor], lr: float, momentum: float = 0.9,
+             weight_decay: float = 1e-4) -> Tuple[torch.Tensor, torch.Tensor]:
+    """torch.optim.SGD(momentum=0.9, weight_decay=1e-4, dampening=0, nesterov=False): d = g + wd*p;
+    buf = d on the first step else momentum*buf + d; p -= lr*buf."""
+    d = g + weight_decay * p
+    buf = d.clone() if buf is None else momentum * buf + d
+    return p - lr * buf, buf
+
+
+def lr_poly(base_lr: float, it: int, max_iter: int, power: float = 0.9) -> float:
+    """utils.py:53-54."""
+    return base_lr * ((1 - float(it) / max_iter) ** power)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Synthetic inputs
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def synth_patch(shape: Sequence[int], seed: int, modality: str = "ct") -> torch.Tensor:
+    """CT: clip(N(0, .5), -1, 1) (mimics the +-325 HU window, MOTSDataset.py:171-183); MRI: z-scored N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(tuple(shape), generator=g)
+    return (0.5 * x).clamp_(-1, 1) if modality == "ct" else x
+
+
+def synth_labels(shape: Sequence[int], seed: int, num_classes: int = 16, n_seeds: int = 48) -> torch.Tensor:
+    """Piecewise-constant blobs: nearest-seed Voronoi over [B, D, H, W], about half of the seeds background, every
+    class present when n_seeds >= 2*num_classes.  Returned as float class ids [B,1,D,H,W] like the reference's
+    label tensors (train_amos_atlas_final.py:214)."""
+    B, D, H, W = shape
+    rng = np.random.RandomState(seed)
+    out = np.zeros((B, D, H, W), dtype=np.float32)
+    zz, yy, xx = np.meshgrid(np.arange(D), np.arange(H), np.arange(W), indexing="ij")
+    for b in range(B):
+        pts = rng.rand(n_seeds, 3) * np.array([D, H, W])
+        cls = np.where(np.arange(n_seeds) % 2 == 0, 0, (np.arange(n_seeds) // 2) % (num_classes - 1) + 1)
+        best = np.full((D, H, W), np.inf)
+        lab = np.zeros((D, H, W), dtype=np.float32)
+        for (pz, py, px), c in zip(pts, cls):
+            d2 = ((zz - pz) * 3.0) ** 2 + (yy - py) ** 2 + (xx - px) ** 2
+            m = d2 < best
+            best[m] = d2[m]
+            lab[m] = c
+        out[b] = lab
+    return torch.from_numpy(out).unsqueeze(1)
