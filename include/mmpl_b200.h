@@ -1,0 +1,138 @@
+/* mmpl_b200.h -- C ABI of libmmpl_b200.so: the B200 (sm_100a) kernels behind the multimodal-PL dense hot path.
+ *
+ * Every entry point enqueues work on the caller's CUDA stream and returns immediately (no host synchronisation,
+ * no device allocation).  All pointers are DEVICE pointers unless stated otherwise; the caller owns every buffer.
+ * Return value: 0 = ok, negative = MMPL_E_*; the message is available from mmpl_last_error() (thread-local).
+ * There is no CPU fallback: a device that is not compute capability 10.x yields MMPL_E_ARCH.
+ *
+ * Layout conventions
+ *   activations : NDHWC ("channels last"), element type selected by `dtype` (MMPL_F32 | MMPL_BF16)
+ *   image       : [N,1,D,H,W] fp32 (identical to NDHWC for one channel)
+ *   logits      : [N,C,D,H,W] fp32, the layout the reference modules return (unet3D.py:713)
+ *   weights     : master copy fp32 in the reference layout [Cout,Cin,kd,kh,kw] (unet3D.py:18); kernels consume
+ *                 the standardised, tap-major packing produced by mmpl_ws_weight_fwd:
+ *                   fprop packing  [tap][Cout][Cin]   (tap = (kd*k+kh)*k+kw)
+ *                   dgrad packing  [tap'][Cin][Cout]  (tap' = flipped tap, so dgrad is a plain correlation)
+ *   GN stats    : double [N][G][2] raw sums (sum x, sum x^2) per sample and group; consumers derive mean/rstd.
+ *
+ * Each function cites the reference code it replaces (path:line in TThuraya/multimodal-PL).
+ */
+#ifndef MMPL_B200_H_
+#define MMPL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mmpl_stream_t; /* cudaStream_t */
+
+enum { MMPL_F32 = 0, MMPL_BF16 = 1 };
+enum { MMPL_ALGO_DIRECT = 0, MMPL_ALGO_TCGEN05 = 1 };
+enum {
+  MMPL_OK = 0,
+  MMPL_E_SHAPE = -1,
+  MMPL_E_DTYPE = -2,
+  MMPL_E_ALIGN = -3,
+  MMPL_E_ARCH = -4,
+  MMPL_E_CUDA = -5,
+  MMPL_E_UNSUPPORTED = -6
+};
+
+int mmpl_version(void);
+const char* mmpl_last_error(void);
+/* 0 if the current device is sm_100-class, else MMPL_E_ARCH. */
+int mmpl_check_device(void);
+/* Number of kernel launches issued by this library in this process (for bench.py's gpu_launches). */
+uint64_t mmpl_launch_count(void);
+
+/* ---- weight standardisation: Conv3d.forward, unet3D.py:22-26 -------------------------------------------------
+ * w [Cout][Cin][taps] fp32.  Outputs: w_hat fp32 (same layout), inv_std [Cout] fp32, and the two tap-major
+ * packings in `dtype` (either may be NULL).  standardise=0 copies/packs w unchanged (plain nn.Conv3d). */
+int mmpl_ws_weight_fwd(const float* w, int cout, int cin, int taps, int standardise, float* w_hat, float* inv_std,
+                       void* packed_fprop, void* packed_dgrad, int dtype, mmpl_stream_t stream);
+/* Backward of the standardisation: g_hat = dL/dw_hat given tap-major [tap][Cout][Cin] fp32 (as wgrad writes it);
+ * dw (reference layout, fp32) = (g - mean(g) - w_hat * sum(g*w_hat)/(n-1)) * inv_std.  standardise=0: un-pack. */
+int mmpl_ws_weight_bwd(const float* g_hat_tapmajor, const float* w_hat, const float* inv_std, int cout, int cin,
+                       int taps, int standardise, float* dw, mmpl_stream_t stream);
+
+/* ---- convolution: F.conv3d in Conv3d.forward, unet3D.py:27; k in {1,3}, pad = k/2, stride in {1,2} -----------
+ * fprop : y[N,Do,Ho,Wo,Cout] = conv(x[N,D,H,W,Cin], w_fprop) (+ residual if non-NULL, same shape/dtype as y)
+ * dgrad : dx[N,D,H,W,Cin]    = conv^T(dy[N,Do,Ho,Wo,Cout], w_dgrad) (+ addend if non-NULL)
+ * wgrad : dw_tapmajor[tap][Cout][Cin] fp32 = sum_voxels dy * x_shifted   (overwritten, not accumulated)
+ * algo MMPL_ALGO_TCGEN05 requires bf16, stride 1, k=3, Cin,Cout in {32,64,128,256} (fprop/dgrad) and returns
+ * MMPL_E_UNSUPPORTED otherwise; MMPL_ALGO_DIRECT (CUDA cores, fp32 accumulate) handles every case. */
+int mmpl_conv3d_fprop(const void* x, const void* w_fprop, const void* residual, void* y, int n, int d, int h, int w,
+                      int cin, int cout, int ksize, int stride, int dtype, int algo, mmpl_stream_t stream);
+int mmpl_conv3d_dgrad(const void* dy, const void* w_dgrad, const void* addend, void* dx, int n, int d, int h, int w,
+                      int cin, int cout, int ksize, int stride, int dtype, int algo, mmpl_stream_t stream);
+int mmpl_conv3d_wgrad(const void* x, const void* dy, float* dw_tapmajor, int n, int d, int h, int w, int cin,
+                      int cout, int ksize, int stride, int dtype, int algo, void* workspace, size_t workspace_bytes,
+                      mmpl_stream_t stream);
+size_t mmpl_conv3d_wgrad_workspace(int n, int d, int h, int w, int cin, int cout, int ksize, int stride, int algo);
+
+/* ---- stem (Cin = 1) and classifier (1x1x1 with bias, NCDHW fp32 logits): unet3D.py:594, :629-633 -------------- */
+int mmpl_stem_conv_fwd(const float* image, const float* w_hat /*[Cout][27]*/, void* y, int n, int d, int h, int w,
+                       int cout, int dtype, mmpl_stream_t stream);
+int mmpl_stem_conv_wgrad(const float* image, const void* dy, float* dw_hat /*[Cout][27]*/, int n, int d, int h,
+                         int w, int cout, int dtype, mmpl_stream_t stream);
+int mmpl_cls_fwd(const void* a, const float* wc /*[C][Cin]*/, const float* bias, float* logits, int n, int64_t spatial,
+                 int cin, int classes, int dtype, mmpl_stream_t stream);
+int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits, void* da, float* dwc, float* dbias, int n,
+                 int64_t spatial, int cin, int classes, int dtype, mmpl_stream_t stream);
+
+/* ---- GroupNorm(16)+ReLU: NoBottleneck.forward, unet3D.py:59-60,64-65 and downsample.0/1, :645-646 -------------
+ * stats: double [N][G][2], must be zero before mmpl_gn_stats accumulates into it. */
+int mmpl_gn_stats(const void* x, double* stats, int n, int64_t spatial, int c, int groups, int dtype,
+                  mmpl_stream_t stream);
+/* y = relu(gn(x; gamma,beta)); if gamma2 != NULL also y2 = relu(gn(x; gamma2,beta2)) from the same read of x
+ * (gn1 and downsample.0 share their input, unet3D.py:59 and :69). */
+int mmpl_gn_relu_fwd(const void* x, const double* stats, const float* gamma, const float* beta, void* y,
+                     const float* gamma2, const float* beta2, void* y2, int n, int64_t spatial, int c, int groups,
+                     float eps, int dtype, mmpl_stream_t stream);
+/* dx = d/dx of the one or two GN+ReLU heads (+ addend if non-NULL); dgamma/dbeta per head (fp32 [C]).
+ * workspace: double [N][C][4], zeroed by the call. */
+int mmpl_gn_relu_bwd(const void* x, const double* stats, const float* gamma, const float* beta, const void* dy,
+                     const float* gamma2, const float* beta2, const void* dy2, const void* addend, void* dx,
+                     float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, double* workspace, int n,
+                     int64_t spatial, int c, int groups, float eps, int dtype, mmpl_stream_t stream);
+
+/* ---- trilinear x2 upsample (align_corners=False) + skip add: unet3D.py:608, :686-687 -------------------------- */
+int mmpl_upsample2x_add_fwd(const void* x_lo, const void* skip, void* y, int n, int d, int h, int w, int c,
+                            int dtype, mmpl_stream_t stream);
+int mmpl_upsample2x_bwd(const void* dy, void* dx_lo, int n, int d, int h, int w, int c, int dtype,
+                        mmpl_stream_t stream);
+
+/* ---- partial-label loss: EDiceLoss_partial.forward + DiceLoss.forward, loss_partial.py:38-57, :71-99 ----------
+ * logits [N,C,S] fp32, target [N,S] fp32 class ids, class_weight [C] fp32 (= mask[0]); lut (may be NULL) is the
+ * 16-entry cmask remap of train_amos_atlas_final.py:252-255 applied to the target on the fly.
+ * sums: double [4][C] = I, Z, Y, E (zeroed by the call); loss: one fp32.  classes <= 32. */
+int mmpl_partial_loss_fwd(const float* logits, const float* target, const float* class_weight, const float* lut,
+                          double* sums, float* loss, int n, int64_t spatial, int classes, int uce,
+                          mmpl_stream_t stream);
+int mmpl_partial_loss_bwd(const float* logits, const float* target, const float* class_weight, const float* lut,
+                          const double* sums, const float* grad_out /*device scalar*/, float* dlogits, int n,
+                          int64_t spatial, int classes, int uce, mmpl_stream_t stream);
+
+/* ---- SGD with momentum: torch.optim.SGD at train_amos_atlas_final.py:132-135,378 ------------------------------
+ * d = grad*grad_scale + wd*p; buf = first ? d : mom*buf + d; p -= lr*buf.  lr is read from a device scalar so a
+ * captured CUDA graph can be replayed while the poly schedule (utils.py:53-60) changes it. */
+int mmpl_sgd_step(float* p, const float* grad, float* buf, int64_t count, const float* lr_dev, float momentum,
+                  float weight_decay, float grad_scale, int first_step, mmpl_stream_t stream);
+
+/* ---- sliding-window blend + argmax/Dice: predict_sliding evaluate_amos.py:261-279, get_dice :128-141 ----------
+ * acc [C][D][H][W] and wsum [D][H][W] in `acc_dtype` bytes per element (4 = fp32, 8 = fp64 like the reference). */
+int mmpl_sw_blend(void* acc, void* wsum, const float* tile_logits /*[C][td][th][tw]*/, const float* gauss, int c,
+                  int d, int h, int w, int td, int th, int tw, int d0, int h0, int w0, int acc_bytes,
+                  mmpl_stream_t stream);
+/* out_logits (may be NULL) [C][D][H][W] fp32 = acc/wsum; argmax uint8 [D][H][W]; counts int64 [3][C] = |P&T|,|P|,|T|
+ * (zeroed by the call) against label fp32 [D][H][W] (may be NULL). */
+int mmpl_sw_finalize(const void* acc, const void* wsum, const float* label, float* out_logits, uint8_t* argmax,
+                     long long* counts, int c, int64_t voxels, int acc_bytes, mmpl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMPL_B200_H_ */

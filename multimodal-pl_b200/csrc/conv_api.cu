@@ -1,0 +1,67 @@
+// C-ABI dispatch for the convolution entry points (see include/mmpl_b200.h).
+#include "common.cuh"
+
+namespace mmpl {
+int conv_direct_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int conv_direct_dgrad(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int conv_direct_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int conv_tc_3x3x3_s1(const void*, const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int conv_tc_wgrad_3x3x3_s1(const void*, const void*, float*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+size_t conv_tc_wgrad_workspace(int, int, int, int, int, int);
+
+static int check_common(int n, int d, int h, int w, int cin, int cout, int k, int stride) {
+  MMPL_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0, MMPL_E_SHAPE, "conv3d: empty tensor [%d,%d,%d,%d]", n, d, h, w);
+  MMPL_REQUIRE(k == 1 || k == 3, MMPL_E_SHAPE, "conv3d: kernel size %d (1 or 3)", k);
+  MMPL_REQUIRE(stride == 1 || stride == 2, MMPL_E_SHAPE, "conv3d: stride %d (1 or 2)", stride);
+  MMPL_REQUIRE(cin % 32 == 0 && cout % 32 == 0, MMPL_E_SHAPE, "conv3d: cin=%d cout=%d must be multiples of 32", cin, cout);
+  return MMPL_OK;
+}
+}  // namespace mmpl
+
+using namespace mmpl;
+
+extern "C" int mmpl_conv3d_fprop(const void* x, const void* w_fprop, const void* residual, void* y, int n, int d, int h,
+                                 int w, int cin, int cout, int ksize, int stride, int dtype, int algo,
+                                 mmpl_stream_t stream) {
+  if (int e = check_common(n, d, h, w, cin, cout, ksize, stride)) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (algo == MMPL_ALGO_TCGEN05) {
+    MMPL_REQUIRE(dtype == MMPL_BF16 && ksize == 3 && stride == 1, MMPL_E_UNSUPPORTED,
+                 "conv3d_fprop: tcgen05 path needs bf16, k=3, stride=1 (got dtype=%d k=%d stride=%d)", dtype, ksize, stride);
+    return conv_tc_3x3x3_s1(x, w_fprop, residual, y, n, d, h, w, cin, cout, s);
+  }
+  return conv_direct_fprop(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, stride, dtype, s);
+}
+
+extern "C" int mmpl_conv3d_dgrad(const void* dy, const void* w_dgrad, const void* addend, void* dx, int n, int d, int h,
+                                 int w, int cin, int cout, int ksize, int stride, int dtype, int algo,
+                                 mmpl_stream_t stream) {
+  if (int e = check_common(n, d, h, w, cin, cout, ksize, stride)) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (algo == MMPL_ALGO_TCGEN05) {
+    MMPL_REQUIRE(dtype == MMPL_BF16 && ksize == 3 && stride == 1, MMPL_E_UNSUPPORTED,
+                 "conv3d_dgrad: tcgen05 path needs bf16, k=3, stride=1 (got dtype=%d k=%d stride=%d)", dtype, ksize, stride);
+    // stride-1 dgrad is a correlation of dy with the flipped/transposed packing: channels swap roles
+    return conv_tc_3x3x3_s1(dy, w_dgrad, addend, dx, n, d, h, w, cout, cin, s);
+  }
+  return conv_direct_dgrad(dy, w_dgrad, addend, dx, n, d, h, w, cin, cout, ksize, stride, dtype, s);
+}
+
+extern "C" size_t mmpl_conv3d_wgrad_workspace(int n, int d, int h, int w, int cin, int cout, int ksize, int stride,
+                                              int algo) {
+  if (algo == MMPL_ALGO_TCGEN05 && ksize == 3 && stride == 1) return conv_tc_wgrad_workspace(n, d, h, w, cin, cout);
+  return 0;
+}
+
+extern "C" int mmpl_conv3d_wgrad(const void* x, const void* dy, float* dw_tapmajor, int n, int d, int h, int w, int cin,
+                                 int cout, int ksize, int stride, int dtype, int algo, void* workspace,
+                                 size_t workspace_bytes, mmpl_stream_t stream) {
+  if (int e = check_common(n, d, h, w, cin, cout, ksize, stride)) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (algo == MMPL_ALGO_TCGEN05) {
+    MMPL_REQUIRE(dtype == MMPL_BF16 && ksize == 3 && stride == 1, MMPL_E_UNSUPPORTED,
+                 "conv3d_wgrad: tcgen05 path needs bf16, k=3, stride=1 (got dtype=%d k=%d stride=%d)", dtype, ksize, stride);
+    return conv_tc_wgrad_3x3x3_s1(x, dy, dw_tapmajor, n, d, h, w, cin, cout, workspace, workspace_bytes, s);
+  }
+  return conv_direct_wgrad(x, dy, dw_tapmajor, n, d, h, w, cin, cout, ksize, stride, dtype, s);
+}

@@ -1,0 +1,422 @@
+// GroupNorm(16)+ReLU forward/backward on NDHWC activations (reference: NoBottleneck.forward, unet3D.py:59-60,64-65;
+// downsample.0/1, unet3D.py:645-646).  All kernels are HBM-bound streaming kernels: 16-byte vector loads along the
+// channel dimension, fp32 math, fp64 cross-thread accumulation of the statistics.
+//
+// Thread mapping shared by all kernels: a block of 256 threads covers 256/VPV voxels per iteration, where
+// VPV = C / (channels per 16-byte vector); thread t owns vector column t % VPV for the whole kernel, so per-channel
+// parameters and partial sums live in registers.
+#include "common.cuh"
+
+namespace mmpl {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxC = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ stats,
+                                                            int64_t spatial, int C, int groups, int64_t vox_per_block) {
+  constexpr int VN = Vec<T>::N;
+  const int vpv = C / VN;
+  const int cv = threadIdx.x % vpv, vl = threadIdx.x / vpv, vstep = kThreads / vpv;
+  const int n = blockIdx.y;
+  const int64_t v0 = static_cast<int64_t>(blockIdx.x) * vox_per_block;
+  const int64_t v1 = min(v0 + vox_per_block, spatial);
+  const T* base = x + (static_cast<int64_t>(n) * spatial) * C + cv * VN;
+  __shared__ double sg[32][2];
+  if (threadIdx.x < 64) (&sg[0][0])[threadIdx.x] = 0.0;
+  __syncthreads();
+  double ds[VN], dq[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) ds[i] = dq[i] = 0.0;
+  int64_t v = v0 + vl;
+  while (v < v1) {
+    float s[VN], q[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) s[i] = q[i] = 0.f;
+    for (int it = 0; it < 32 && v < v1; ++it, v += vstep) {
+      Vec<T> a;
+      a.load(base + v * C);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        s[i] += a.v[i];
+        q[i] = fmaf(a.v[i], a.v[i], q[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VN; ++i) ds[i] += s[i], dq[i] += q[i];
+  }
+  const int cpg = C / groups;
+  // reduce the VN channels of this thread into per-group partials, then across lanes that share the column
+  const int gpt = cpg >= VN ? 1 : VN / cpg;  // groups per thread
+  const int cpp = VN / gpt;                  // channels per partial
+  for (int j = 0; j < gpt; ++j) {
+    double a = 0, b = 0;
+    for (int i = 0; i < cpp; ++i) a += ds[j * cpp + i], b += dq[j * cpp + i];
+    for (int o = 16; o >= vpv && o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const bool leader = vpv >= 32 ? true : ((threadIdx.x & 31) < vpv);
+    if (leader) {
+      const int g = (cv * VN + j * cpp) / cpg;
+      atomicAdd(&sg[g][0], a);
+      atomicAdd(&sg[g][1], b);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < groups * 2) {
+    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+    atomicAdd(&stats[(static_cast<int64_t>(n) * groups + g) * 2 + k], sg[g][k]);
+  }
+}
+
+__device__ __forceinline__ void mean_rstd(const double* st, double m, float eps, float& mean, float& rstd) {
+  const double mu = st[0] / m;
+  double var = st[1] / m - mu * mu;
+  if (var < 0) var = 0;
+  mean = static_cast<float>(mu);
+  rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// The ReLU gate of the backward must reproduce the forward's rounding exactly (same fused multiply-add on the same
+// folded scale/shift), otherwise elements whose pre-activation is within rounding of zero get a gate that disagrees
+// with the stored output.
+__device__ __forceinline__ bool relu_gate(float x, float mean, float rstd, float gamma, float beta) {
+  const float sc = rstd * gamma;
+  const float sh = beta - mean * sc;
+  return fmaf(x, sc, sh) > 0.f;
+}
+
+template <typename T, bool DUAL>
+__global__ void __launch_bounds__(kThreads)
+gn_relu_fwd_kernel(const T* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, T* __restrict__ y, const float* __restrict__ gamma2,
+                   const float* __restrict__ beta2, T* __restrict__ y2, int64_t spatial, int C, int groups, float eps,
+                   int64_t vox_per_block) {
+  constexpr int VN = Vec<T>::N;
+  const int vpv = C / VN;
+  const int cv = threadIdx.x % vpv, vl = threadIdx.x / vpv, vstep = kThreads / vpv;
+  const int n = blockIdx.y;
+  const int cpg = C / groups;
+  const double m = static_cast<double>(cpg) * static_cast<double>(spatial);
+  float sc[VN], sh[VN], sc2[VN], sh2[VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    const int c = cv * VN + i;
+    float mean, rstd;
+    mean_rstd(stats + (static_cast<int64_t>(n) * groups + c / cpg) * 2, m, eps, mean, rstd);
+    sc[i] = rstd * gamma[c];
+    sh[i] = beta[c] - mean * sc[i];
+    if (DUAL) {
+      sc2[i] = rstd * gamma2[c];
+      sh2[i] = beta2[c] - mean * sc2[i];
+    }
+  }
+  const int64_t v0 = static_cast<int64_t>(blockIdx.x) * vox_per_block;
+  const int64_t v1 = min(v0 + vox_per_block, spatial);
+  const int64_t off = (static_cast<int64_t>(n) * spatial) * C + cv * VN;
+  for (int64_t v = v0 + vl; v < v1; v += vstep) {
+    Vec<T> a, o;
+    a.load(x + off + v * C);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) o.v[i] = fmaxf(fmaf(a.v[i], sc[i], sh[i]), 0.f);
+    o.store(y + off + v * C);
+    if (DUAL) {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) o.v[i] = fmaxf(fmaf(a.v[i], sc2[i], sh2[i]), 0.f);
+      o.store(y2 + off + v * C);
+    }
+  }
+}
+
+// Pass 1 of the backward: per (n, c) sums of g = dy*[y>0] and g*xhat for each head -> ws[N][C][4] (fp64).
+template <typename T, bool DUAL>
+__global__ void __launch_bounds__(kThreads)
+gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, const T* __restrict__ dy, const float* __restrict__ gamma2,
+                          const float* __restrict__ beta2, const T* __restrict__ dy2, double* __restrict__ ws,
+                          int64_t spatial, int C, int groups, float eps, int64_t vox_per_block) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int NH = DUAL ? 2 : 1;
+  const int vpv = C / VN;
+  const int cv = threadIdx.x % vpv, vl = threadIdx.x / vpv, vstep = kThreads / vpv;
+  const int n = blockIdx.y;
+  const int cpg = C / groups;
+  const double m = static_cast<double>(cpg) * static_cast<double>(spatial);
+  float mu[VN], rs[VN], ga[NH][VN], be[NH][VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    const int c = cv * VN + i;
+    mean_rstd(stats + (static_cast<int64_t>(n) * groups + c / cpg) * 2, m, eps, mu[i], rs[i]);
+    ga[0][i] = gamma[c], be[0][i] = beta[c];
+    if (DUAL) ga[1][i] = gamma2[c], be[1][i] = beta2[c];
+  }
+  const int64_t v0 = static_cast<int64_t>(blockIdx.x) * vox_per_block;
+  const int64_t v1 = min(v0 + vox_per_block, spatial);
+  const int64_t off = (static_cast<int64_t>(n) * spatial) * C + cv * VN;
+  double d1[NH][VN], d2[NH][VN];
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+    for (int i = 0; i < VN; ++i) d1[hh][i] = d2[hh][i] = 0.0;
+  int64_t v = v0 + vl;
+  while (v < v1) {
+    float s1[NH][VN], s2[NH][VN];
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+      for (int i = 0; i < VN; ++i) s1[hh][i] = s2[hh][i] = 0.f;
+    for (int it = 0; it < 32 && v < v1; ++it, v += vstep) {
+      Vec<T> a, g;
+      a.load(x + off + v * C);
+      g.load(dy + off + v * C);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        const float xh = (a.v[i] - mu[i]) * rs[i];
+        const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[0][i], be[0][i]) ? g.v[i] : 0.f;
+        s1[0][i] += gg;
+        s2[0][i] = fmaf(gg, xh, s2[0][i]);
+      }
+      if (DUAL) {
+        g.load(dy2 + off + v * C);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          const float xh = (a.v[i] - mu[i]) * rs[i];
+          const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[NH - 1][i], be[NH - 1][i]) ? g.v[i] : 0.f;
+          s1[NH - 1][i] += gg;
+          s2[NH - 1][i] = fmaf(gg, xh, s2[NH - 1][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+      for (int i = 0; i < VN; ++i) d1[hh][i] += s1[hh][i], d2[hh][i] += s2[hh][i];
+  }
+  __shared__ double sc[kMaxC][4];
+  for (int i = threadIdx.x; i < C * 4; i += kThreads) (&sc[0][0])[i] = 0.0;
+  __syncthreads();
+  const bool leader = vpv >= 32 ? true : ((threadIdx.x & 31) < vpv);
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+      double a = d1[hh][i], b = d2[hh][i];
+      for (int o = 16; o >= vpv && o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (leader) {
+        atomicAdd(&sc[cv * VN + i][hh * 2 + 0], a);
+        atomicAdd(&sc[cv * VN + i][hh * 2 + 1], b);
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2 * NH; i += kThreads) {
+    const int c = i / (2 * NH), k = i % (2 * NH);
+    atomicAdd(&ws[(static_cast<int64_t>(n) * C + c) * 4 + k], sc[c][k]);
+  }
+}
+
+// Pass 2: dx = sum_heads rstd*(gamma*g - m1 - xhat*m2) (+ addend); block (0,0) also emits dgamma/dbeta.
+template <typename T, bool DUAL, bool ADD>
+__global__ void __launch_bounds__(kThreads)
+gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, const T* __restrict__ dy, const float* __restrict__ gamma2,
+                         const float* __restrict__ beta2, const T* __restrict__ dy2, const T* __restrict__ addend,
+                         T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         float* __restrict__ dgamma2, float* __restrict__ dbeta2, const double* __restrict__ ws,
+                         int N, int64_t spatial, int C, int groups, float eps, int64_t vox_per_block) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int NH = DUAL ? 2 : 1;
+  const int vpv = C / VN;
+  const int cv = threadIdx.x % vpv, vl = threadIdx.x / vpv, vstep = kThreads / vpv;
+  const int n = blockIdx.y;
+  const int cpg = C / groups;
+  const double m = static_cast<double>(cpg) * static_cast<double>(spatial);
+  __shared__ float gm[32][4];  // per group: m1,m2 per head (already divided by m)
+  if (threadIdx.x < groups * NH) {
+    const int g = threadIdx.x / NH, hh = threadIdx.x % NH;
+    const float* gam = hh == 0 ? gamma : gamma2;
+    double a = 0, b = 0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const double* w = ws + (static_cast<int64_t>(n) * C + c) * 4 + hh * 2;
+      a += static_cast<double>(gam[c]) * w[0];
+      b += static_cast<double>(gam[c]) * w[1];
+    }
+    gm[g][hh * 2 + 0] = static_cast<float>(a / m);
+    gm[g][hh * 2 + 1] = static_cast<float>(b / m);
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int i = threadIdx.x; i < C * NH; i += kThreads) {
+      const int c = i / NH, hh = i % NH;
+      double a = 0, b = 0;
+      for (int nn = 0; nn < N; ++nn) {
+        const double* w = ws + (static_cast<int64_t>(nn) * C + c) * 4 + hh * 2;
+        a += w[0];
+        b += w[1];
+      }
+      (hh == 0 ? dbeta : dbeta2)[c] = static_cast<float>(a);
+      (hh == 0 ? dgamma : dgamma2)[c] = static_cast<float>(b);
+    }
+  }
+  __syncthreads();
+  float mu[VN], rs[VN], ga[NH][VN], be[NH][VN], m1[NH][VN], m2[NH][VN];
+#pragma unroll
+  for (int i = 0; i < VN; ++i) {
+    const int c = cv * VN + i, g = c / cpg;
+    mean_rstd(stats + (static_cast<int64_t>(n) * groups + g) * 2, m, eps, mu[i], rs[i]);
+    ga[0][i] = gamma[c], be[0][i] = beta[c], m1[0][i] = gm[g][0], m2[0][i] = gm[g][1];
+    if (DUAL) ga[NH - 1][i] = gamma2[c], be[NH - 1][i] = beta2[c], m1[NH - 1][i] = gm[g][2], m2[NH - 1][i] = gm[g][3];
+  }
+  const int64_t v0 = static_cast<int64_t>(blockIdx.x) * vox_per_block;
+  const int64_t v1 = min(v0 + vox_per_block, spatial);
+  const int64_t off = (static_cast<int64_t>(n) * spatial) * C + cv * VN;
+  for (int64_t v = v0 + vl; v < v1; v += vstep) {
+    Vec<T> a, g, o;
+    a.load(x + off + v * C);
+    g.load(dy + off + v * C);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+      const float xh = (a.v[i] - mu[i]) * rs[i];
+      const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[0][i], be[0][i]) ? g.v[i] : 0.f;
+      o.v[i] = rs[i] * (ga[0][i] * gg - m1[0][i] - xh * m2[0][i]);
+    }
+    if (DUAL) {
+      g.load(dy2 + off + v * C);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        const float xh = (a.v[i] - mu[i]) * rs[i];
+        const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[NH - 1][i], be[NH - 1][i]) ? g.v[i] : 0.f;
+        o.v[i] += rs[i] * (ga[NH - 1][i] * gg - m1[NH - 1][i] - xh * m2[NH - 1][i]);
+      }
+    }
+    if (ADD) {
+      g.load(addend + off + v * C);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) o.v[i] += g.v[i];
+    }
+    o.store(dx + off + v * C);
+  }
+}
+
+int check_shape(int c, int groups, int dtype) {
+  const int vn = dtype == MMPL_BF16 ? 8 : 4;
+  MMPL_REQUIRE(groups > 0 && groups <= 32 && c % groups == 0, MMPL_E_SHAPE, "GroupNorm: C=%d groups=%d", c, groups);
+  MMPL_REQUIRE(c % vn == 0 && c <= kMaxC && kThreads % (c / vn) == 0, MMPL_E_SHAPE,
+               "GroupNorm: C=%d must be a power-of-two multiple of %d and <= %d", c, vn, kMaxC);
+  const int cpg = c / groups;
+  MMPL_REQUIRE(cpg >= vn ? cpg % vn == 0 : vn % cpg == 0, MMPL_E_SHAPE, "GroupNorm: C/groups=%d vs vector %d", cpg, vn);
+  return MMPL_OK;
+}
+
+// Blocks per sample: enough to give every SM several blocks, at least 64 voxel-rows per block.
+void plan(int n, int64_t spatial, int c, int dtype, int& blocks_x, int64_t& vox_per_block) {
+  const int vn = dtype == MMPL_BF16 ? 8 : 4;
+  const int vstep = kThreads / (c / vn);
+  int64_t want = static_cast<int64_t>(num_sms()) * 8 / (n > 0 ? n : 1);
+  if (want < 1) want = 1;
+  int64_t vpb = (spatial + want - 1) / want;
+  const int64_t min_vpb = static_cast<int64_t>(vstep) * 16;
+  if (vpb < min_vpb) vpb = min_vpb;
+  vpb = (vpb + vstep - 1) / vstep * vstep;
+  vox_per_block = vpb;
+  blocks_x = ceil_div(spatial, vpb);
+}
+
+template <typename T>
+int launch_gn_bwd(const void* x, const double* stats, const float* gamma, const float* beta, const void* dy,
+                  const float* gamma2, const float* beta2, const void* dy2, const void* addend, void* dx,
+                  float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, double* workspace, int n,
+                  int64_t spatial, int c, int groups, float eps, int bx, int64_t vpb, cudaStream_t s) {
+  const bool dual = gamma2 != nullptr;
+  const bool add = addend != nullptr;
+  const T* xx = static_cast<const T*>(x);
+  const T* g1 = static_cast<const T*>(dy);
+  const T* g2 = static_cast<const T*>(dy2);
+  const T* ad = static_cast<const T*>(addend);
+  T* out = static_cast<T*>(dx);
+  const dim3 grid(bx, n);
+  if (dual)
+    gn_relu_bwd_reduce_kernel<T, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
+                                                                workspace, spatial, c, groups, eps, vpb);
+  else
+    gn_relu_bwd_reduce_kernel<T, false><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, nullptr, nullptr,
+                                                                 nullptr, workspace, spatial, c, groups, eps, vpb);
+  MMPL_CHECK_LAUNCH("gn_relu_bwd_reduce");
+  if (dual && add)
+    gn_relu_bwd_apply_kernel<T, true, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, eps, vpb);
+  else if (dual)
+    gn_relu_bwd_apply_kernel<T, true, false><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, eps, vpb);
+  else if (add)
+    gn_relu_bwd_apply_kernel<T, false, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, eps, vpb);
+  else
+    gn_relu_bwd_apply_kernel<T, false, false><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, eps, vpb);
+  return MMPL_OK;
+}
+
+}  // namespace
+}  // namespace mmpl
+
+using namespace mmpl;
+
+extern "C" int mmpl_gn_stats(const void* x, double* stats, int n, int64_t spatial, int c, int groups, int dtype,
+                             mmpl_stream_t stream) {
+  if (int e = check_shape(c, groups, dtype)) return e;
+  int bx;
+  int64_t vpb;
+  plan(n, spatial, c, dtype, bx, vpb);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MMPL_DISPATCH_DTYPE(dtype, T, (gn_stats_kernel<T><<<dim3(bx, n), kThreads, 0, s>>>(
+                                    static_cast<const T*>(x), stats, spatial, c, groups, vpb)));
+  MMPL_CHECK_LAUNCH("gn_stats");
+  return MMPL_OK;
+}
+
+extern "C" int mmpl_gn_relu_fwd(const void* x, const double* stats, const float* gamma, const float* beta, void* y,
+                                const float* gamma2, const float* beta2, void* y2, int n, int64_t spatial, int c,
+                                int groups, float eps, int dtype, mmpl_stream_t stream) {
+  if (int e = check_shape(c, groups, dtype)) return e;
+  int bx;
+  int64_t vpb;
+  plan(n, spatial, c, dtype, bx, vpb);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool dual = gamma2 != nullptr;
+  MMPL_DISPATCH_DTYPE(dtype, T, {
+    if (dual)
+      gn_relu_fwd_kernel<T, true><<<dim3(bx, n), kThreads, 0, s>>>(static_cast<const T*>(x), stats, gamma, beta,
+                                                                  static_cast<T*>(y), gamma2, beta2,
+                                                                  static_cast<T*>(y2), spatial, c, groups, eps, vpb);
+    else
+      gn_relu_fwd_kernel<T, false><<<dim3(bx, n), kThreads, 0, s>>>(static_cast<const T*>(x), stats, gamma, beta,
+                                                                   static_cast<T*>(y), nullptr, nullptr, nullptr,
+                                                                   spatial, c, groups, eps, vpb);
+  });
+  MMPL_CHECK_LAUNCH("gn_relu_fwd");
+  return MMPL_OK;
+}
+
+extern "C" int mmpl_gn_relu_bwd(const void* x, const double* stats, const float* gamma, const float* beta,
+                                const void* dy, const float* gamma2, const float* beta2, const void* dy2,
+                                const void* addend, void* dx, float* dgamma, float* dbeta, float* dgamma2,
+                                float* dbeta2, double* workspace, int n, int64_t spatial, int c, int groups, float eps,
+                                int dtype, mmpl_stream_t stream) {
+  if (int e = check_shape(c, groups, dtype)) return e;
+  int bx;
+  int64_t vpb;
+  plan(n, spatial, c, dtype, bx, vpb);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MMPL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 4 * n * c, s));
+  int rc = MMPL_OK;
+  MMPL_DISPATCH_DTYPE(dtype, T, rc = (launch_gn_bwd<T>(x, stats, gamma, beta, dy, gamma2, beta2, dy2, addend, dx, dgamma,
+                                                     dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, eps, bx,
+                                                     vpb, s)));
+  if (rc) return rc;
+  MMPL_CHECK_LAUNCH("gn_relu_bwd_apply");
+  return MMPL_OK;
+}

@@ -1,0 +1,344 @@
+// The two convolutions at the ends of the network that are bandwidth-bound, not tensor-core work:
+//  * stem   : conv3x3x3(1 -> base) on the fp32 image (unet3D.py:594, :666); K = 27, output-write bound.
+//  * cls    : nn.Conv3d(base, classes, 1) with bias (unet3D.py:632, :713); reads NDHWC activations, writes the
+//             NCDHW fp32 logits the reference returns, so no layout transpose is ever materialised.
+#include "common.cuh"
+
+namespace mmpl {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ stem forward
+template <typename T, int COUT>
+__global__ void __launch_bounds__(128)
+stem_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w_hat, T* __restrict__ y, int N, int D, int H,
+                int W) {
+  __shared__ float sw[27][COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i % 27][i / 27] = w_hat[i];  // w_hat is [COUT][27]
+  __syncthreads();
+  const int64_t total = static_cast<int64_t>(N) * D * H * W;
+  for (int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v < total;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(v % W);
+    int64_t r = v / W;
+    const int yy = static_cast<int>(r % H);
+    r /= H;
+    const int z = static_cast<int>(r % D);
+    const int n = static_cast<int>(r / D);
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    const float* base = img + static_cast<int64_t>(n) * D * H * W;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const int zz = z + kd - 1;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int y2 = yy + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int x2 = x + kw - 1;
+          float xv = 0.f;
+          if (zz >= 0 && zz < D && y2 >= 0 && y2 < H && x2 >= 0 && x2 < W)
+            xv = base[(static_cast<int64_t>(zz) * H + y2) * W + x2];
+          const int t = (kd * 3 + kh) * 3 + kw;
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) acc[c] = fmaf(xv, sw[t][c], acc[c]);
+        }
+      }
+    }
+    constexpr int VN = Vec<T>::N;
+    T* out = y + v * COUT;
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += VN) {
+      Vec<T> o;
+#pragma unroll
+      for (int k = 0; k < VN; ++k) o.v[k] = acc[c0 + k];
+      o.store(out + c0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stem wgrad
+// block = (256/COUT) voxel lanes x COUT channels; each thread keeps 27 accumulators for its channel.
+template <typename T, int COUT>
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const float* __restrict__ img, const T* __restrict__ dy, float* __restrict__ dw_tapmajor, int N, int D,
+                  int H, int W) {
+  constexpr int LANES = 256 / COUT;
+  const int co = threadIdx.x % COUT, vl = threadIdx.x / COUT;
+  float acc[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+  const int64_t total = static_cast<int64_t>(N) * D * H * W;
+  for (int64_t v = blockIdx.x * static_cast<int64_t>(LANES) + vl; v < total;
+       v += static_cast<int64_t>(gridDim.x) * LANES) {
+    const int x = static_cast<int>(v % W);
+    int64_t r = v / W;
+    const int yy = static_cast<int>(r % H);
+    r /= H;
+    const int z = static_cast<int>(r % D);
+    const int n = static_cast<int>(r / D);
+    const float g = to_f32<T>(dy[v * COUT + co]);
+    const float* base = img + static_cast<int64_t>(n) * D * H * W;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const int zz = z + kd - 1;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int y2 = yy + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int x2 = x + kw - 1;
+          float xv = 0.f;
+          if (zz >= 0 && zz < D && y2 >= 0 && y2 < H && x2 >= 0 && x2 < W)
+            xv = base[(static_cast<int64_t>(zz) * H + y2) * W + x2];
+          acc[(kd * 3 + kh) * 3 + kw] = fmaf(xv, g, acc[(kd * 3 + kh) * 3 + kw]);
+        }
+      }
+    }
+  }
+  __shared__ float red[LANES][27][COUT + 1];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) red[vl][t][co] = acc[t];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * COUT; i += 256) {
+    const int t = i / COUT, c = i % COUT;
+    float s = 0.f;
+    for (int l = 0; l < LANES; ++l) s += red[l][t][c];
+    atomicAdd(&dw_tapmajor[t * COUT + c], s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ classifier fwd
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256)
+cls_fwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const float* __restrict__ bias,
+               float* __restrict__ logits, int N, int64_t S, int classes) {
+  __shared__ float sw[16][CIN];
+  __shared__ float sb[16];
+  for (int i = threadIdx.x; i < 16 * CIN; i += blockDim.x) sw[i / CIN][i % CIN] = (i / CIN) < classes ? wc[i] : 0.f;
+  if (threadIdx.x < 16) sb[threadIdx.x] = threadIdx.x < classes ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  constexpr int VN = Vec<T>::N;
+  const int64_t total = static_cast<int64_t>(N) * S;
+  // one voxel per thread (no grid-stride loop: keeps the 16xCIN weights in shared memory instead of registers)
+  const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (v >= total) return;
+  const int64_t n = v / S, s = v - n * S;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = sb[c];
+#pragma unroll
+  for (int k0 = 0; k0 < CIN; k0 += VN) {
+    Vec<T> x;
+    x.load(a + v * CIN + k0);
+#pragma unroll
+    for (int k = 0; k < VN; ++k)
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = fmaf(x.v[k], sw[c][k0 + k], acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c)
+    if (c < classes) logits[(n * classes + c) * S + s] = acc[c];
+}
+
+// ------------------------------------------------------------------------------------------------ classifier bwd
+// One pass over dlogits and a: da[v][k] = sum_c dl[c][v] W[c][k];  dW[c][k] = sum_v dl[c][v] a[v][k];  db[c] = sum_v dl.
+// Tile of TV voxels staged in shared memory; dW accumulators are register-tiled 4(c) x 4(k) per thread.
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256)
+cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const float* __restrict__ dl, T* __restrict__ da,
+               float* __restrict__ dwc, float* __restrict__ dbias, int N, int64_t S, int classes) {
+  constexpr int TV = 128;
+  constexpr int KB = CIN / 4;           // k-blocks of 4
+  constexpr int SLOTS = 4 * KB;         // (c-block, k-block) pairs
+  constexpr int REP = SLOTS / 32;       // pairs per lane (1 for CIN=32, 2 for CIN=64)
+  __shared__ float sw[16][CIN];
+  __shared__ __align__(16) float s_dl[TV][16];
+  __shared__ __align__(16) float s_a[TV][CIN];
+  for (int i = threadIdx.x; i < 16 * CIN; i += 256) sw[i / CIN][i % CIN] = (i / CIN) < classes ? wc[i] : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float accw[REP][4][4];
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < REP; ++r)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) accw[r][i][j] = 0.f;
+  constexpr int VN = Vec<T>::N;
+  const int64_t total = static_cast<int64_t>(N) * S;
+  const int64_t ntiles = (total + TV - 1) / TV;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t v0 = tile * TV;
+    __syncthreads();
+    // stage dl (coalesced per class plane) and a (vector loads)
+    for (int i = threadIdx.x; i < 16 * TV; i += 256) {
+      const int c = i / TV, j = i % TV;
+      const int64_t v = v0 + j;
+      float val = 0.f;
+      if (c < classes && v < total) {
+        const int64_t n = v / S, s = v - n * S;
+        val = dl[(n * classes + c) * S + s];
+      }
+      s_dl[j][c] = val;
+    }
+    for (int i = threadIdx.x; i < TV * (CIN / VN); i += 256) {
+      const int j = i / (CIN / VN), k0 = (i % (CIN / VN)) * VN;
+      const int64_t v = v0 + j;
+      Vec<T> x;
+      if (v < total) {
+        x.load(a + v * CIN + k0);
+      } else {
+#pragma unroll
+        for (int k = 0; k < VN; ++k) x.v[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < VN; ++k) s_a[j][k0 + k] = x.v[k];
+    }
+    __syncthreads();
+    // phase 1: da for voxel j = threadIdx.x % TV, half of the channels per thread (256 threads / 128 voxels)
+    {
+      const int j = threadIdx.x % TV, half = threadIdx.x / TV;
+      const int64_t v = v0 + j;
+      if (v < total) {
+        float g[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) g[c] = s_dl[j][c];
+#pragma unroll
+        for (int k0 = half * (CIN / 2); k0 < (half + 1) * (CIN / 2); k0 += VN) {
+          Vec<T> o;
+#pragma unroll
+          for (int k = 0; k < VN; ++k) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) s = fmaf(g[c], sw[c][k0 + k], s);
+            o.v[k] = s;
+          }
+          o.store(da + v * CIN + k0);
+        }
+      }
+    }
+    // phase 2: dW / dbias; warp w covers voxels w, w+8, ... of the tile
+#pragma unroll
+    for (int r = 0; r < REP; ++r) {
+      const int slot = lane + 32 * r, cb = slot / KB, kb = slot % KB;
+      for (int j = warp; j < TV; j += 8) {
+        const float4 g = *reinterpret_cast<const float4*>(&s_dl[j][cb * 4]);
+        const float4 x = *reinterpret_cast<const float4*>(&s_a[j][kb * 4]);
+        const float gg[4] = {g.x, g.y, g.z, g.w}, xx[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) accw[r][i][k] = fmaf(gg[i], xx[k], accw[r][i][k]);
+        if (r == 0 && kb == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) accb[i] += gg[i];
+        }
+      }
+    }
+  }
+  // cross-warp reduction through shared memory (reuse the staging tiles), then one atomic per (c,k) per block
+  __syncthreads();
+  float* red = &s_a[0][0];    // 8 warps x 16 classes x CIN floats == TV*CIN
+  float* redb = &s_dl[0][0];  // 8 warps x 16 classes
+  for (int r = 0; r < REP; ++r) {
+    const int slot = lane + 32 * r, cb = slot / KB, kb = slot % KB;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) red[(warp * 16 + cb * 4 + i) * CIN + kb * 4 + k] = accw[r][i][k];
+    if (r == 0 && kb == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) redb[warp * 16 + cb * 4 + i] = accb[i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * CIN; i += 256) {
+    const int c = i / CIN, k = i % CIN;
+    if (c >= classes) continue;
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[(w * 16 + c) * CIN + k];
+    atomicAdd(&dwc[c * CIN + k], s);
+  }
+  if (threadIdx.x < classes) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += redb[w * 16 + threadIdx.x];
+    atomicAdd(&dbias[threadIdx.x], s);
+  }
+}
+
+}  // namespace
+}  // namespace mmpl
+
+using namespace mmpl;
+
+extern "C" int mmpl_stem_conv_fwd(const float* image, const float* w_hat, void* y, int n, int d, int h, int w, int cout,
+                                  int dtype, mmpl_stream_t stream) {
+  MMPL_REQUIRE(cout == 32 || cout == 64, MMPL_E_SHAPE, "stem: cout=%d (32 or 64)", cout);
+  const int64_t total = static_cast<int64_t>(n) * d * h * w;
+  const int blocks = static_cast<int>(std::min<int64_t>((total + 127) / 128, static_cast<int64_t>(num_sms()) * 16));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MMPL_DISPATCH_DTYPE(dtype, T, {
+    if (cout == 32)
+      stem_fwd_kernel<T, 32><<<blocks, 128, 0, s>>>(image, w_hat, static_cast<T*>(y), n, d, h, w);
+    else
+      stem_fwd_kernel<T, 64><<<blocks, 128, 0, s>>>(image, w_hat, static_cast<T*>(y), n, d, h, w);
+  });
+  MMPL_CHECK_LAUNCH("stem_conv_fwd");
+  return MMPL_OK;
+}
+
+extern "C" int mmpl_stem_conv_wgrad(const float* image, const void* dy, float* dw_tapmajor, int n, int d, int h, int w,
+                                    int cout, int dtype, mmpl_stream_t stream) {
+  MMPL_REQUIRE(cout == 32 || cout == 64, MMPL_E_SHAPE, "stem: cout=%d (32 or 64)", cout);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MMPL_CUDA(cudaMemsetAsync(dw_tapmajor, 0, sizeof(float) * 27 * cout, s));
+  const int blocks = num_sms() * 4;
+  MMPL_DISPATCH_DTYPE(dtype, T, {
+    if (cout == 32)
+      stem_wgrad_kernel<T, 32><<<blocks, 256, 0, s>>>(image, static_cast<const T*>(dy), dw_tapmajor, n, d, h, w);
+    else
+      stem_wgrad_kernel<T, 64><<<blocks, 256, 0, s>>>(image, static_cast<const T*>(dy), dw_tapmajor, n, d, h, w);
+  });
+  MMPL_CHECK_LAUNCH("stem_conv_wgrad");
+  return MMPL_OK;
+}
+
+extern "C" int mmpl_cls_fwd(const void* a, const float* wc, const float* bias, float* logits, int n, int64_t spatial,
+                            int cin, int classes, int dtype, mmpl_stream_t stream) {
+  MMPL_REQUIRE((cin == 32 || cin == 64) && classes >= 1 && classes <= 16, MMPL_E_SHAPE,
+               "cls: cin=%d classes=%d (cin 32|64, classes<=16)", cin, classes);
+  const int64_t total = static_cast<int64_t>(n) * spatial;
+  const int blocks = static_cast<int>((total + 255) / 256);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MMPL_DISPATCH_DTYPE(dtype, T, {
+    if (cin == 32)
+      cls_fwd_kernel<T, 32><<<blocks, 256, 0, s>>>(static_cast<const T*>(a), wc, bias, logits, n, spatial, classes);
+    else
+      cls_fwd_kernel<T, 64><<<blocks, 256, 0, s>>>(static_cast<const T*>(a), wc, bias, logits, n, spatial, classes);
+  });
+  MMPL_CHECK_LAUNCH("cls_fwd");
+  return MMPL_OK;
+}
+
+extern "C" int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits, void* da, float* dwc, float* dbias,
+                            int n, int64_t spatial, int cin, int classes, int dtype, mmpl_stream_t stream) {
+  MMPL_REQUIRE((cin == 32 || cin == 64) && classes >= 1 && classes <= 16, MMPL_E_SHAPE,
+               "cls: cin=%d classes=%d (cin 32|64, classes<=16)", cin, classes);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MMPL_CUDA(cudaMemsetAsync(dwc, 0, sizeof(float) * classes * cin, s));
+  MMPL_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * classes, s));
+  const int64_t ntiles = (static_cast<int64_t>(n) * spatial + 127) / 128;
+  const int blocks = static_cast<int>(std::min<int64_t>(ntiles, static_cast<int64_t>(num_sms()) * 4));
+  MMPL_DISPATCH_DTYPE(dtype, T, {
+    if (cin == 32)
+      cls_bwd_kernel<T, 32><<<blocks, 256, 0, s>>>(static_cast<const T*>(a), wc, dlogits, static_cast<T*>(da), dwc, dbias,
+                                                 n, spatial, classes);
+    else
+      cls_bwd_kernel<T, 64><<<blocks, 256, 0, s>>>(static_cast<const T*>(a), wc, dlogits, static_cast<T*>(da), dwc, dbias,
+                                                 n, spatial, classes);
+  });
+  MMPL_CHECK_LAUNCH("cls_bwd");
+  return MMPL_OK;
+}

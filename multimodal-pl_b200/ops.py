@@ -1,0 +1,393 @@
+"""Autograd glue between PyTorch tensors and the C-ABI kernels.
+
+Activations travel as logical NCDHW tensors in ``torch.channels_last_3d`` memory format, i.e. physically NDHWC --
+the layout the kernels want -- so the reference's module interfaces (NCDHW in, NCDHW out) are kept without any
+transpose kernels.  Gradients use the same convention.  Every function enqueues on torch's current stream.
+"""
+import os
+
+import torch
+
+from . import _lib
+from ._lib import p as _p
+
+_CL = torch.channels_last_3d
+
+_cfg = {"dtype": torch.bfloat16, "conv_algo": os.environ.get("MMPL_CONV_ALGO", "auto")}
+
+
+def set_compute_dtype(dt: torch.dtype):
+    """torch.bfloat16 (tcgen05 path, default) or torch.float32 (exact CUDA-core path for argmax/Dice parity)."""
+    _lib.dtype_code(dt)
+    _cfg["dtype"] = dt
+
+
+def get_compute_dtype() -> torch.dtype:
+    return _cfg["dtype"]
+
+
+def set_conv_algo(algo: str):
+    """'auto' (tcgen05 where supported), 'direct' (CUDA cores everywhere) or 'tcgen05' (fail if unsupported)."""
+    assert algo in ("auto", "direct", "tcgen05")
+    _cfg["conv_algo"] = algo
+
+
+def to_cl(x: torch.Tensor, dtype=None) -> torch.Tensor:
+    """Logical NCDHW tensor -> compute dtype with physically dense NDHWC storage (no copy if already so)."""
+    dtype = dtype or _cfg["dtype"]
+    if x.dtype != dtype:
+        x = x.to(dtype)
+    v = x.permute(0, 2, 3, 4, 1)
+    if not v.is_contiguous():
+        x = v.contiguous().permute(0, 4, 1, 2, 3)
+    return x
+
+
+def empty_cl(n, c, d, h, w, dtype, device) -> torch.Tensor:
+    return torch.empty((n, d, h, w, c), dtype=dtype, device=device).permute(0, 4, 1, 2, 3)
+
+
+def _tc_supported(dtype, k, stride, cin, cout) -> bool:
+    if dtype != torch.bfloat16 or k != 3 or stride != 1:
+        return False
+    ok_in = cin == 32 or cin % 64 == 0
+    ok_out = cout in (32, 64, 128, 256) or (cout > 256 and cout % 256 == 0)
+    if cin == 32 and cout not in (32, 64):
+        return False
+    return ok_in and ok_out
+
+
+def _algo(dtype, k, stride, cin, cout) -> int:
+    mode = _cfg["conv_algo"]
+    if mode == "direct":
+        return _lib.ALGO_DIRECT
+    if _tc_supported(dtype, k, stride, cin, cout):
+        return _lib.ALGO_TCGEN05
+    if mode == "tcgen05":
+        raise RuntimeError(f"tcgen05 conv path does not cover dtype={dtype} k={k} stride={stride} {cin}->{cout}")
+    return _lib.ALGO_DIRECT
+
+
+def _out_dim(i, k, s):
+    return (i + 2 * (k // 2) - k) // s + 1
+
+
+# --------------------------------------------------------------------------------------------------------------
+class WSConv3dFn(torch.autograd.Function):
+    """Weight-standardised (or plain) k^3 convolution, optional fused residual add.  unet3D.py:16-27."""
+
+    @staticmethod
+    def forward(ctx, x, weight, residual, stride, standardise):
+        _lib.require_device()
+        L = _lib.lib()
+        dt = _cfg["dtype"]
+        x = to_cl(x, dt)
+        cout, cin, k = weight.shape[0], weight.shape[1], weight.shape[2]
+        taps = k * k * k
+        n, _, d, h, w = x.shape
+        assert x.shape[1] == cin, f"conv: input has {x.shape[1]} channels, weight expects {cin}"
+        w32 = weight.detach().float().contiguous()
+        dev = x.device
+        w_hat = torch.empty_like(w32)
+        inv_std = torch.empty(cout, dtype=torch.float32, device=dev)
+        pf = torch.empty(taps * cout * cin, dtype=dt, device=dev)
+        pd = torch.empty(taps * cout * cin, dtype=dt, device=dev)
+        code = _lib.dtype_code(dt)
+        st = _lib.stream_ptr()
+        _lib.check(L.mmpl_ws_weight_fwd(_p(w32), cout, cin, taps, int(standardise), _p(w_hat), _p(inv_std), _p(pf),
+                                        _p(pd), code, st), "ws_weight_fwd")
+        do, ho, wo = _out_dim(d, k, stride), _out_dim(h, k, stride), _out_dim(w, k, stride)
+        y = empty_cl(n, cout, do, ho, wo, dt, dev)
+        res = None
+        if residual is not None:
+            res = to_cl(residual, dt)
+            assert res.shape == y.shape
+        algo = _algo(dt, k, stride, cin, cout)
+        _lib.check(L.mmpl_conv3d_fprop(_p(x), _p(pf), _p(res), _p(y), n, d, h, w, cin, cout, k, stride, code, algo, st),
+                   "conv3d_fprop")
+        ctx.save_for_backward(x, w_hat, inv_std, pd)
+        ctx.meta = (n, d, h, w, cin, cout, k, stride, int(standardise), residual is not None, weight.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x, w_hat, inv_std, pd = ctx.saved_tensors
+        n, d, h, w, cin, cout, k, stride, standardise, has_res, wdtype = ctx.meta
+        dt = x.dtype
+        code = _lib.dtype_code(dt)
+        st = _lib.stream_ptr()
+        dy = to_cl(dy, dt)
+        dev = x.device
+        dx = dw = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_cl(n, cin, d, h, w, dt, dev)
+            algo = _algo(dt, k, stride, cout, cin)
+            _lib.check(L.mmpl_conv3d_dgrad(_p(dy), _p(pd), None, _p(dx), n, d, h, w, cin, cout, k, stride, code, algo,
+                                           st), "conv3d_dgrad")
+        if ctx.needs_input_grad[1]:
+            taps = k * k * k
+            g_hat = torch.empty(taps * cout * cin, dtype=torch.float32, device=dev)
+            algo = _lib.ALGO_DIRECT
+            if _cfg["conv_algo"] != "direct" and _tc_wgrad_supported(dt, k, stride, cin, cout):
+                algo = _lib.ALGO_TCGEN05
+            wsb = int(L.mmpl_conv3d_wgrad_workspace(n, d, h, w, cin, cout, k, stride, algo))
+            ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev) if wsb else None
+            _lib.check(L.mmpl_conv3d_wgrad(_p(x), _p(dy), _p(g_hat), n, d, h, w, cin, cout, k, stride, code, algo,
+                                           _p(ws), wsb, st), "conv3d_wgrad")
+            dw = torch.empty_like(w_hat)
+            _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, cin, taps, standardise, _p(dw), st),
+                       "ws_weight_bwd")
+            dw = dw.to(wdtype)
+        if has_res and ctx.needs_input_grad[2]:
+            dres = dy
+        return dx, dw, dres, None, None
+
+
+_TC_WGRAD = {"enabled": os.environ.get("MMPL_TC_WGRAD", "1") != "0"}
+
+
+def _tc_wgrad_supported(dtype, k, stride, cin, cout) -> bool:
+    if not (_TC_WGRAD["enabled"] and dtype == torch.bfloat16 and k == 3 and stride == 1):
+        return False
+    if cin == 32:
+        return cout == 32
+    return cin % 64 == 0 and (cout == 32 or cout % 64 == 0)
+
+
+def ws_conv3d(x, weight, stride=1, standardise=True, residual=None):
+    return WSConv3dFn.apply(x, weight, residual, int(stride), bool(standardise))
+
+
+# --------------------------------------------------------------------------------------------------------------
+class StemConvFn(torch.autograd.Function):
+    """conv3x3x3(1 -> base) on the fp32 image (unet3D.py:594, :666)."""
+
+    @staticmethod
+    def forward(ctx, image, weight, standardise):
+        _lib.require_device()
+        L = _lib.lib()
+        dt = _cfg["dtype"]
+        img = image.detach().float().contiguous()
+        n, c, d, h, w = img.shape
+        assert c == 1 and tuple(weight.shape[1:]) == (1, 3, 3, 3)
+        cout = weight.shape[0]
+        w32 = weight.detach().float().contiguous()
+        dev = img.device
+        w_hat = torch.empty_like(w32)
+        inv_std = torch.empty(cout, dtype=torch.float32, device=dev)
+        st = _lib.stream_ptr()
+        _lib.check(L.mmpl_ws_weight_fwd(_p(w32), cout, 1, 27, int(standardise), _p(w_hat), _p(inv_std), None, None,
+                                        _lib.F32, st), "ws_weight_fwd")
+        y = empty_cl(n, cout, d, h, w, dt, dev)
+        _lib.check(L.mmpl_stem_conv_fwd(_p(img), _p(w_hat), _p(y), n, d, h, w, cout, _lib.dtype_code(dt), st),
+                   "stem_conv_fwd")
+        ctx.save_for_backward(img, w_hat, inv_std)
+        ctx.meta = (n, d, h, w, cout, int(standardise), weight.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        img, w_hat, inv_std = ctx.saved_tensors
+        n, d, h, w, cout, standardise, wdtype = ctx.meta
+        dy = to_cl(dy)
+        st = _lib.stream_ptr()
+        g_hat = torch.empty(27 * cout, dtype=torch.float32, device=img.device)
+        _lib.check(L.mmpl_stem_conv_wgrad(_p(img), _p(dy), _p(g_hat), n, d, h, w, cout, _lib.dtype_code(dy.dtype), st),
+                   "stem_conv_wgrad")
+        dw = torch.empty_like(w_hat)
+        _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, 1, 27, standardise, _p(dw), st),
+                   "ws_weight_bwd")
+        return None, dw.to(wdtype), None
+
+
+def stem_conv(image, weight, standardise=True):
+    return StemConvFn.apply(image, weight, bool(standardise))
+
+
+# --------------------------------------------------------------------------------------------------------------
+class GNReLUFn(torch.autograd.Function):
+    """GroupNorm(groups, C) + ReLU, optionally two affine heads on the same input (gn1 and downsample.0 share the
+    block input, unet3D.py:59-60 and :69 / :645-646)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps):
+        _lib.require_device()
+        L = _lib.lib()
+        dt = _cfg["dtype"]
+        x = to_cl(x, dt)
+        n, c, d, h, w = x.shape
+        spatial = d * h * w
+        dev = x.device
+        stats = torch.zeros(n * groups * 2, dtype=torch.float64, device=dev)
+        code = _lib.dtype_code(dt)
+        st = _lib.stream_ptr()
+        g1, b1 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        dual = gamma2 is not None
+        g2 = gamma2.detach().float().contiguous() if dual else None
+        b2 = beta2.detach().float().contiguous() if dual else None
+        _lib.check(L.mmpl_gn_stats(_p(x), _p(stats), n, spatial, c, groups, code, st), "gn_stats")
+        y = empty_cl(n, c, d, h, w, dt, dev)
+        y2 = empty_cl(n, c, d, h, w, dt, dev) if dual else None
+        _lib.check(L.mmpl_gn_relu_fwd(_p(x), _p(stats), _p(g1), _p(b1), _p(y), _p(g2), _p(b2), _p(y2), n, spatial, c,
+                                      groups, eps, code, st), "gn_relu_fwd")
+        ctx.save_for_backward(x, stats, g1, b1, g2, b2)
+        ctx.meta = (n, c, spatial, groups, eps, dual, gamma.dtype)
+        if dual:
+            return y, y2
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, dy2=None):
+        L = _lib.lib()
+        x, stats, g1, b1, g2, b2 = ctx.saved_tensors
+        n, c, spatial, groups, eps, dual, pdtype = ctx.meta
+        dt = x.dtype
+        dev = x.device
+        code = _lib.dtype_code(dt)
+        st = _lib.stream_ptr()
+        if dy is None:
+            dy = torch.zeros_like(x)
+        dy = to_cl(dy, dt)
+        if dual:
+            if dy2 is None:
+                dy2 = torch.zeros_like(x)
+            dy2 = to_cl(dy2, dt)
+        dx = torch.empty_like(x)
+        dg1 = torch.empty(c, dtype=torch.float32, device=dev)
+        db1 = torch.empty(c, dtype=torch.float32, device=dev)
+        dg2 = torch.empty(c, dtype=torch.float32, device=dev) if dual else None
+        db2 = torch.empty(c, dtype=torch.float32, device=dev) if dual else None
+        ws = torch.empty(n * c * 4, dtype=torch.float64, device=dev)
+        _lib.check(L.mmpl_gn_relu_bwd(_p(x), _p(stats), _p(g1), _p(b1), _p(dy), _p(g2), _p(b2), _p(dy2) if dual else None,
+                                      None, _p(dx), _p(dg1), _p(db1), _p(dg2), _p(db2), _p(ws), n, spatial, c, groups,
+                                      eps, code, st), "gn_relu_bwd")
+        if dual:
+            return dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype), None, None
+        return dx, dg1.to(pdtype), db1.to(pdtype), None, None, None, None
+
+
+def gn_relu(x, gamma, beta, groups=16, eps=1e-5):
+    return GNReLUFn.apply(x, gamma, beta, None, None, int(groups), float(eps))
+
+
+def gn_relu_dual(x, gamma, beta, gamma2, beta2, groups=16, eps=1e-5):
+    return GNReLUFn.apply(x, gamma, beta, gamma2, beta2, int(groups), float(eps))
+
+
+# --------------------------------------------------------------------------------------------------------------
+class Upsample2xAddFn(torch.autograd.Function):
+    """nn.Upsample(scale_factor=2, mode='trilinear') followed by ``+ skip`` (unet3D.py:608, :686-687)."""
+
+    @staticmethod
+    def forward(ctx, x_lo, skip):
+        _lib.require_device()
+        L = _lib.lib()
+        dt = _cfg["dtype"]
+        x_lo, skip = to_cl(x_lo, dt), to_cl(skip, dt)
+        n, c, d, h, w = x_lo.shape
+        assert tuple(skip.shape) == (n, c, 2 * d, 2 * h, 2 * w), f"skip {tuple(skip.shape)} vs 2x of {tuple(x_lo.shape)}"
+        y = empty_cl(n, c, 2 * d, 2 * h, 2 * w, dt, x_lo.device)
+        _lib.check(L.mmpl_upsample2x_add_fwd(_p(x_lo), _p(skip), _p(y), n, d, h, w, c, _lib.dtype_code(dt),
+                                             _lib.stream_ptr()), "upsample2x_add_fwd")
+        ctx.meta = (n, c, d, h, w, dt)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        n, c, d, h, w, dt = ctx.meta
+        dy = to_cl(dy, dt)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_cl(n, c, d, h, w, dt, dy.device)
+            _lib.check(L.mmpl_upsample2x_bwd(_p(dy), _p(dx), n, d, h, w, c, _lib.dtype_code(dt), _lib.stream_ptr()),
+                       "upsample2x_bwd")
+        return dx, (dy if ctx.needs_input_grad[1] else None)
+
+
+def upsample2x_add(x_lo, skip):
+    return Upsample2xAddFn.apply(x_lo, skip)
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClassifierFn(torch.autograd.Function):
+    """nn.Conv3d(base, classes, 1) with bias -> fp32 NCDHW logits (unet3D.py:632, :713)."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias):
+        _lib.require_device()
+        L = _lib.lib()
+        dt = _cfg["dtype"]
+        a = to_cl(a, dt)
+        n, cin, d, h, w = a.shape
+        classes = weight.shape[0]
+        spatial = d * h * w
+        wc = weight.detach().float().reshape(classes, cin).contiguous()
+        b = bias.detach().float().contiguous()
+        logits = torch.empty((n, classes, d, h, w), dtype=torch.float32, device=a.device)
+        _lib.check(L.mmpl_cls_fwd(_p(a), _p(wc), _p(b), _p(logits), n, spatial, cin, classes, _lib.dtype_code(dt),
+                                  _lib.stream_ptr()), "cls_fwd")
+        ctx.save_for_backward(a, wc)
+        ctx.meta = (n, cin, d, h, w, classes, weight.dtype, tuple(weight.shape))
+        return logits
+
+    @staticmethod
+    def backward(ctx, dl):
+        L = _lib.lib()
+        a, wc = ctx.saved_tensors
+        n, cin, d, h, w, classes, wdtype, wshape = ctx.meta
+        dl = dl.float().contiguous()
+        da = torch.empty_like(a)
+        dwc = torch.empty(classes * cin, dtype=torch.float32, device=a.device)
+        db = torch.empty(classes, dtype=torch.float32, device=a.device)
+        _lib.check(L.mmpl_cls_bwd(_p(a), _p(wc), _p(dl), _p(da), _p(dwc), _p(db), n, d * h * w, cin, classes,
+                                  _lib.dtype_code(a.dtype), _lib.stream_ptr()), "cls_bwd")
+        return da, dwc.reshape(wshape).to(wdtype), db.to(wdtype)
+
+
+def classifier(a, weight, bias):
+    return ClassifierFn.apply(a, weight, bias)
+
+
+# --------------------------------------------------------------------------------------------------------------
+class PartialLossFn(torch.autograd.Function):
+    """EDiceLoss_partial.forward with soft_max=True (loss_partial.py:71-99): one fused forward pass, one fused
+    backward pass, no host synchronisation."""
+
+    @staticmethod
+    def forward(ctx, logits, target, class_weight, lut, uce):
+        _lib.require_device()
+        L = _lib.lib()
+        z = logits.detach().float().contiguous()
+        n, c = z.shape[0], z.shape[1]
+        spatial = z[0, 0].numel()
+        t = target.detach().float().contiguous()
+        assert t.numel() == n * spatial, f"target {tuple(target.shape)} does not match logits {tuple(logits.shape)}"
+        dev = z.device
+        cw = class_weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+        assert cw.numel() == c
+        lt = None if lut is None else lut.detach().to(device=dev, dtype=torch.float32).contiguous()
+        sums = torch.empty(4 * c, dtype=torch.float64, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        _lib.check(L.mmpl_partial_loss_fwd(_p(z), _p(t), _p(cw), _p(lt), _p(sums), _p(loss), n, spatial, c, int(uce),
+                                           _lib.stream_ptr()), "partial_loss_fwd")
+        ctx.save_for_backward(z, t, cw, lt, sums)
+        ctx.meta = (n, spatial, c, int(uce), logits.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        L = _lib.lib()
+        z, t, cw, lt, sums = ctx.saved_tensors
+        n, spatial, c, uce, ldtype = ctx.meta
+        g = gout.detach().float().contiguous()
+        dz = torch.empty_like(z)
+        _lib.check(L.mmpl_partial_loss_bwd(_p(z), _p(t), _p(cw), _p(lt), _p(sums), _p(g), _p(dz), n, spatial, c, uce,
+                                           _lib.stream_ptr()), "partial_loss_bwd")
+        return dz.to(ldtype), None, None, None, None
+
+
+def partial_label_loss(logits, target, class_weight, lut=None, uce=True):
+    return PartialLossFn.apply(logits, target, class_weight, lut, bool(uce))

@@ -1,0 +1,202 @@
+"""Drop-in for the reference's ``unet3D.py`` backbone, running on the B200 kernels of libmmpl_b200.so.
+
+Same class names, constructor signatures, ``state_dict`` keys/shapes and call signatures as the reference
+(TThuraya/multimodal-PL ``unet3D.py``): ``Conv3d`` (:16-27), ``conv3x3x3`` (:30-35), ``NoBottleneck`` (:40-73),
+``unet3D_baseline`` (:584-718).  Checkpoints of the reference load unchanged.
+
+Differences that are deliberate:
+  * tensors between layers are logical NCDHW but stored channels-last (NDHWC) in the compute dtype
+    (``ops.set_compute_dtype``: bf16 -> tcgen05 kernels, fp32 -> exact CUDA-core kernels);
+  * GroupNorm+ReLU, the residual add, weight standardisation and up-sample+skip are fused kernels;
+  * ``base`` (init width, 32 in the reference) is a keyword so the wide stress config (BASELINE configs[4]) can be
+    built from the same recipe.
+There is no CPU path: calling a module without a CUDA device raises.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+in_place = True
+affine_par = True
+
+
+def _triple(v):
+    if isinstance(v, (tuple, list)):
+        assert len(v) == 3 and v[0] == v[1] == v[2], f"anisotropic value {v} is not supported"
+        return int(v[0])
+    return int(v)
+
+
+class Conv3d(nn.Conv3d):
+    """Weight-standardised convolution (reference unet3D.py:16-27).  Supports what the backbone uses: kernel 1 or 3,
+    padding k//2, stride 1 or 2, dilation 1, groups 1, no bias."""
+
+    _standardise = True
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=(1, 1, 1), padding=(0, 0, 0), dilation=(1, 1, 1),
+                 groups=1, bias=False):
+        super(Conv3d, self).__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias)
+        k, s, p, d = _triple(self.kernel_size), _triple(self.stride), _triple(self.padding), _triple(self.dilation)
+        if k not in (1, 3) or s not in (1, 2) or p != k // 2 or d != 1 or groups != 1 or self.bias is not None:
+            raise NotImplementedError(
+                f"B200 conv path covers k in {{1,3}}, stride in {{1,2}}, padding k//2, dilation 1, groups 1, bias=False; "
+                f"got k={k} stride={s} padding={p} dilation={d} groups={groups} bias={self.bias is not None}")
+        self._k, self._s = k, s
+
+    def forward(self, x, residual=None):
+        if self.in_channels == 1:
+            assert residual is None
+            return ops.stem_conv(x, self.weight, self._standardise)
+        return ops.ws_conv3d(x, self.weight, self._s, self._standardise, residual)
+
+
+class PlainConv3d(Conv3d):
+    """nn.Conv3d without weight standardisation (what conv3x3x3(weight_std=False) returns, unet3D.py:35)."""
+
+    _standardise = False
+
+
+def conv3x3x3(in_planes, out_planes, kernel_size=(3, 3, 3), stride=(1, 1, 1), padding=1, dilation=1, bias=False,
+              weight_std=False):
+    "3x3x3 convolution with padding"
+    cls = Conv3d if weight_std else PlainConv3d
+    return cls(in_planes, out_planes, kernel_size=kernel_size, stride=stride, padding=padding, dilation=dilation,
+               bias=bias)
+
+
+class GNReLUConv(nn.Sequential):
+    """Sequential(GroupNorm, ReLU, conv) as used for ``downsample`` (:643-649) and ``fusionConv`` (:602-606); the
+    children keep the reference's indices (0 = GroupNorm, 2 = conv) so state_dict keys are unchanged."""
+
+    def forward(self, x, residual=None):
+        gn, conv = self[0], self[2]
+        a = ops.gn_relu(x, gn.weight, gn.bias, gn.num_groups, gn.eps)
+        return conv(a, residual) if residual is not None else conv(a)
+
+
+class GNReLUClassifier(nn.Sequential):
+    """precls_conv = Sequential(GroupNorm(16, base), ReLU, nn.Conv3d(base, classes, 1)) (:629-633): plain 1x1x1
+    convolution WITH bias and without weight standardisation, emitting fp32 NCDHW logits."""
+
+    def forward(self, x):
+        gn, conv = self[0], self[2]
+        a = ops.gn_relu(x, gn.weight, gn.bias, gn.num_groups, gn.eps)
+        return ops.classifier(a, conv.weight, conv.bias)
+
+
+class NoBottleneck(nn.Module):
+    """Pre-activation residual block (reference unet3D.py:40-73):
+    out = conv2(relu(gn2(conv1(relu(gn1(x)))))) + (downsample(x) if downsample is not None else x)."""
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, fist_dilation=1, multi_grid=1,
+                 weight_std=False, group=16):
+        super(NoBottleneck, self).__init__()
+        self.weight_std = weight_std
+        self.gn1 = nn.GroupNorm(group, inplanes)
+        self.conv1 = conv3x3x3(inplanes, planes, kernel_size=(3, 3, 3), stride=stride, padding=(1, 1, 1),
+                               dilation=dilation * multi_grid, bias=False, weight_std=self.weight_std)
+        self.relu = nn.ReLU(inplace=in_place)
+        self.gn2 = nn.GroupNorm(group, planes)
+        self.conv2 = conv3x3x3(planes, planes, kernel_size=(3, 3, 3), stride=1, padding=(1, 1, 1),
+                               dilation=dilation * multi_grid, bias=False, weight_std=self.weight_std)
+        self.downsample = downsample
+        self.dilation = dilation
+        self.stride = stride
+
+    def forward(self, x):
+        ds = self.downsample
+        fused_ds = isinstance(ds, GNReLUConv) and ds[0].num_groups == self.gn1.num_groups and ds[0].eps == self.gn1.eps
+        if fused_ds:
+            # gn1 and downsample.0 normalise the same tensor: one statistics pass, one read, two affine heads
+            a1, ads = ops.gn_relu_dual(x, self.gn1.weight, self.gn1.bias, ds[0].weight, ds[0].bias,
+                                       self.gn1.num_groups, self.gn1.eps)
+            residual = ds[2](ads)
+        else:
+            a1 = ops.gn_relu(x, self.gn1.weight, self.gn1.bias, self.gn1.num_groups, self.gn1.eps)
+            residual = ds(x) if ds is not None else x
+        out = self.conv1(a1)
+        a2 = ops.gn_relu(out, self.gn2.weight, self.gn2.bias, self.gn2.num_groups, self.gn2.eps)
+        return self.conv2(a2, residual)          # residual add fused into conv2's epilogue
+
+
+class _Upsample2xAdd(nn.Upsample):
+    """nn.Upsample(scale_factor=2, mode='trilinear'); ``forward(x, skip)`` fuses the additive skip (:686-687)."""
+
+    def forward(self, x, skip=None):
+        if skip is None:
+            skip = torch.zeros((x.shape[0], x.shape[1], 2 * x.shape[2], 2 * x.shape[3], 2 * x.shape[4]),
+                               dtype=x.dtype, device=x.device)
+        return ops.upsample2x_add(x, skip)
+
+
+class unet3D_baseline(nn.Module):
+    """Reference unet3D.py:584-718.  forward(input, mask=None) -> (logits, [], []) in train mode, logits in eval."""
+
+    def __init__(self, layers, num_classes=12, weight_std=False, ema=False, use_cm=[True, True, True], deep_up=False,
+                 base=32):
+        self.inplanes = 128
+        self.weight_std = weight_std
+        self.num_classes = num_classes
+        self.use_cm = use_cm
+        self.alpha = 0.01
+        self.deep_up = deep_up
+        super(unet3D_baseline, self).__init__()
+        b = base
+        self.conv1 = conv3x3x3(1, b, stride=[1, 1, 1], weight_std=self.weight_std)
+        self.layer0 = self._make_layer(NoBottleneck, b, b, layers[0], stride=(1, 1, 1))
+        self.layer1 = self._make_layer(NoBottleneck, b, 2 * b, layers[1], stride=(2, 2, 2))
+        self.layer2 = self._make_layer(NoBottleneck, 2 * b, 4 * b, layers[2], stride=(2, 2, 2))
+        self.layer3 = self._make_layer(NoBottleneck, 4 * b, 8 * b, layers[3], stride=(2, 2, 2))
+        self.layer4 = self._make_layer(NoBottleneck, 8 * b, 8 * b, layers[4], stride=(2, 2, 2))
+        self.fusionConv = GNReLUConv(
+            nn.GroupNorm(16, 8 * b),
+            nn.ReLU(inplace=in_place),
+            conv3x3x3(8 * b, 8 * b, kernel_size=(1, 1, 1), padding=(0, 0, 0), weight_std=self.weight_std))
+        self.upsamplex2 = _Upsample2xAdd(scale_factor=2, mode='trilinear')
+        self.x8_resb = self._make_layer(NoBottleneck, 8 * b, 4 * b, 1, stride=(1, 1, 1))
+        self.x4_resb = self._make_layer(NoBottleneck, 4 * b, 2 * b, 1, stride=(1, 1, 1))
+        self.x2_resb = self._make_layer(NoBottleneck, 2 * b, b, 1, stride=(1, 1, 1))
+        self.x1_resb = self._make_layer(NoBottleneck, b, b, 1, stride=(1, 1, 1))
+        self.precls_conv = GNReLUClassifier(
+            nn.GroupNorm(16, b),
+            nn.ReLU(inplace=in_place),
+            nn.Conv3d(b, num_classes, kernel_size=1))
+        if ema:
+            for param in self.parameters():
+                param.detach_()
+
+    def _make_layer(self, block, inplanes, planes, blocks, stride=(1, 1, 1), dilation=1, multi_grid=1):
+        downsample = None
+        if stride[0] != 1 or stride[1] != 1 or stride[2] != 1 or inplanes != planes:
+            downsample = GNReLUConv(
+                nn.GroupNorm(16, inplanes),
+                nn.ReLU(inplace=in_place),
+                conv3x3x3(inplanes, planes, kernel_size=(1, 1, 1), stride=stride, padding=0,
+                          weight_std=self.weight_std))
+        layers = [block(inplanes, planes, stride, dilation=dilation, downsample=downsample, multi_grid=1,
+                        weight_std=self.weight_std)]
+        for _ in range(1, blocks):
+            layers.append(block(planes, planes, dilation=dilation, multi_grid=1, weight_std=self.weight_std))
+        return nn.Sequential(*layers)
+
+    def forward(self, input, mask=None):
+        x = self.conv1(input)
+        x = self.layer0(x)
+        skip0 = x
+        x = self.layer1(x)
+        skip1 = x
+        x = self.layer2(x)
+        skip2 = x
+        x = self.layer3(x)
+        skip3 = x
+        x = self.layer4(x)
+        x = self.fusionConv(x)
+        x = self.x8_resb(self.upsamplex2(x, skip3))
+        x = self.x4_resb(self.upsamplex2(x, skip2))
+        x = self.x2_resb(self.upsamplex2(x, skip1))
+        x = self.x1_resb(self.upsamplex2(x, skip0))
+        logits = self.precls_conv(x)
+        if self.training:
+            return logits, [], []
+        return logits

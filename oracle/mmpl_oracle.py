@@ -138,28 +138,36 @@ def upsample2x_add(x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
     return F.interpolate(x, scale_factor=2, mode="trilinear") + skip
 
 
-def unet3d_forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, base: int = 32) -> torch.Tensor:
-    """unet3D_baseline.forward (unet3D.py:663-718), returning the logits [B, num_classes, D, H, W]."""
+def unet3d_forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, base: int = 32, feats: Optional[dict] = None
+                   ) -> torch.Tensor:
+    """unet3D_baseline.forward (unet3D.py:663-718), returning the logits [B, num_classes, D, H, W].  When ``feats``
+    is a dict, the stage outputs are stored in it (debugging aid for gradient localisation)."""
     spec = {p: (cin, cout, s) for p, cin, cout, s in backbone_spec(base)}
 
     def blk(x, p):
         return no_bottleneck(x, sd, p, spec[p][2])
 
-    x = ws_conv3d(image, sd["conv1.weight"], 1, 1)                                    # :666
-    x = blk(x, "layer0.0.")
+    def keep(name, t):
+        if feats is not None:
+            feats[name] = t
+        return t
+
+    x = keep("stem", ws_conv3d(image, sd["conv1.weight"], 1, 1))                      # :666
+    x = keep("layer0", blk(x, "layer0.0."))
     skip0 = x                                                                         # :667-668
-    x = blk(blk(x, "layer1.0."), "layer1.1.")
+    x = keep("layer1", blk(blk(x, "layer1.0."), "layer1.1."))
     skip1 = x                                                                         # :670-671
-    x = blk(blk(x, "layer2.0."), "layer2.1.")
+    x = keep("layer2", blk(blk(x, "layer2.0."), "layer2.1."))
     skip2 = x
-    x = blk(blk(x, "layer3.0."), "layer3.1.")
+    x = keep("layer3", blk(blk(x, "layer3.0."), "layer3.1."))
     skip3 = x
-    x = blk(blk(x, "layer4.0."), "layer4.1.")                                         # :679
-    x = ws_conv3d(gn_relu(x, sd["fusionConv.0.weight"], sd["fusionConv.0.bias"]), sd["fusionConv.2.weight"], 1, 0)
-    x = blk(upsample2x_add(x, skip3), "x8_resb.0.")                                   # :686-688
-    x = blk(upsample2x_add(x, skip2), "x4_resb.0.")
-    x = blk(upsample2x_add(x, skip1), "x2_resb.0.")
-    x = blk(upsample2x_add(x, skip0), "x1_resb.0.")                                   # :707-709
+    x = keep("layer4", blk(blk(x, "layer4.0."), "layer4.1."))                         # :679
+    x = keep("fusion", ws_conv3d(gn_relu(x, sd["fusionConv.0.weight"], sd["fusionConv.0.bias"]),
+                                 sd["fusionConv.2.weight"], 1, 0))
+    x = keep("x8", blk(keep("up8", upsample2x_add(x, skip3)), "x8_resb.0."))          # :686-688
+    x = keep("x4", blk(keep("up4", upsample2x_add(x, skip2)), "x4_resb.0."))
+    x = keep("x2", blk(keep("up2", upsample2x_add(x, skip1)), "x2_resb.0."))
+    x = keep("x1", blk(keep("up1", upsample2x_add(x, skip0)), "x1_resb.0."))          # :707-709
     x = gn_relu(x, sd["precls_conv.0.weight"], sd["precls_conv.0.bias"])
     return F.conv3d(x, sd["precls_conv.2.weight"], sd["precls_conv.2.bias"])         # :629-633, :713
 

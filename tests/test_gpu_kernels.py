@@ -1,0 +1,232 @@
+"""GPU parity tests, kernel by kernel: the CUDA path (through the C ABI) vs the CPU oracle on seeded inputs.
+
+Tolerances (stated per SURVEY.md 8c):  fp32 path  rel-L2 <= 1e-5 forward, <= 1e-4 gradients;
+bf16 path  rel-L2 <= 2e-2 forward, <= 5e-2 gradients (inputs are bf16-rounded on both sides where noted).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import mmpl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def mm():
+    import multimodal_pl_b200 as m
+    from multimodal_pl_b200 import _lib
+
+    _lib.require_device()
+    return m
+
+
+def _rand(shape, seed, scale=1.0):
+    return scale * torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.mark.parametrize("dtype,tol_f,tol_b", [(torch.float32, 1e-5, 1e-4), (torch.bfloat16, 2e-2, 5e-2)])
+@pytest.mark.parametrize("shape", [(2, 32, 4, 6, 10), (1, 64, 3, 5, 7), (2, 256, 2, 3, 3)])
+def test_gn_relu(mm, dtype, tol_f, tol_b, shape):
+    mm.set_compute_dtype(dtype)
+    ops = mm.ops
+    x = _rand(shape, 1) + 0.3
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    C = shape[1]
+    g1, b1, g2, b2 = 1 + 0.2 * _rand((C,), 2), 0.2 * _rand((C,), 3), 1 + 0.2 * _rand((C,), 4), 0.2 * _rand((C,), 5)
+    dy1, dy2 = _rand(shape, 6), _rand(shape, 7)
+    # oracle
+    xr = x.clone().requires_grad_(True)
+    pr = [t.clone().requires_grad_(True) for t in (g1, b1, g2, b2)]
+    y1r, y2r = O.gn_relu(xr, pr[0], pr[1]), O.gn_relu(xr, pr[2], pr[3])
+    (y1r * dy1).sum().backward(retain_graph=True)
+    gx1 = xr.grad.clone()
+    (y2r * dy2).sum().backward()
+    # device: single head
+    xd = x.cuda().requires_grad_(True)
+    pd = [t.cuda().requires_grad_(True) for t in (g1, b1, g2, b2)]
+    y1 = ops.gn_relu(xd, pd[0], pd[1])
+    assert rel(y1.float(), y1r) < tol_f
+    (y1.float() * dy1.cuda()).sum().backward()
+    assert rel(xd.grad.float(), gx1) < tol_b
+    assert rel(pd[0].grad, pr[0].grad) < tol_b and rel(pd[1].grad, pr[1].grad) < tol_b
+    # device: dual head
+    xd2 = x.cuda().requires_grad_(True)
+    pd2 = [t.cuda().requires_grad_(True) for t in (g1, b1, g2, b2)]
+    a, b = ops.gn_relu_dual(xd2, *pd2)
+    assert rel(a.float(), y1r) < tol_f and rel(b.float(), y2r) < tol_f
+    ((a.float() * dy1.cuda()).sum() + (b.float() * dy2.cuda()).sum()).backward()
+    assert rel(xd2.grad.float(), xr.grad) < tol_b
+    for i in range(4):
+        assert rel(pd2[i].grad, pr[i].grad) < tol_b, i
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("shape", [(2, 32, 3, 4, 5), (1, 64, 1, 2, 2), (1, 256, 2, 3, 1)])
+def test_upsample2x_add(mm, dtype, tol, shape):
+    mm.set_compute_dtype(dtype)
+    x = _rand(shape, 1)
+    n, c, d, h, w = shape
+    skip = _rand((n, c, 2 * d, 2 * h, 2 * w), 2)
+    dy = _rand(skip.shape, 3)
+    if dtype == torch.bfloat16:
+        x, skip, dy = x.bfloat16().float(), skip.bfloat16().float(), dy.bfloat16().float()
+    xr, sr = x.clone().requires_grad_(True), skip.clone().requires_grad_(True)
+    yr = O.upsample2x_add(xr, sr)
+    (yr * dy).sum().backward()
+    xd, sd = x.cuda().requires_grad_(True), skip.cuda().requires_grad_(True)
+    y = mm.ops.upsample2x_add(xd, sd)
+    assert tuple(y.shape) == tuple(yr.shape)
+    assert rel(y.float(), yr) < tol
+    y.backward(dy.cuda().to(y.dtype))
+    assert rel(xd.grad.float(), xr.grad) < tol and rel(sd.grad.float(), sr.grad) < tol
+
+
+CONV_CASES = [
+    # cin, cout, k, stride, spatial
+    (32, 32, 3, 1, (5, 9, 11)),
+    (32, 64, 3, 2, (6, 8, 10)),
+    (64, 64, 3, 1, (3, 17, 9)),
+    (32, 64, 1, 2, (4, 6, 6)),
+    (64, 32, 1, 1, (3, 5, 7)),
+    (256, 128, 3, 1, (2, 3, 4)),
+    (64, 128, 3, 2, (5, 7, 9)),      # odd sizes with stride 2
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,sp", CONV_CASES)
+@pytest.mark.parametrize("dtype,algo,tol_f,tol_b", [
+    (torch.float32, "direct", 1e-5, 1e-4),
+    (torch.bfloat16, "direct", 1e-2, 2e-2),
+    (torch.bfloat16, "auto", 1e-2, 2e-2),
+])
+def test_ws_conv3d(mm, cin, cout, k, stride, sp, dtype, algo, tol_f, tol_b):
+    mm.set_compute_dtype(dtype)
+    mm.set_conv_algo(algo)
+    try:
+        x = _rand((2, cin) + sp, 1)
+        w = _rand((cout, cin, k, k, k), 2)
+        if dtype == torch.bfloat16:
+            x = x.bfloat16().float()
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        yr = O.ws_conv3d(xr, wr, stride, k // 2)
+        res = _rand(tuple(yr.shape), 4)
+        dy = _rand(tuple(yr.shape), 3)
+        if dtype == torch.bfloat16:
+            res, dy = res.bfloat16().float(), dy.bfloat16().float()
+        ((yr + res) * dy).sum().backward()
+        xd, wd, rd = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), res.cuda().requires_grad_(True)
+        y = mm.ops.ws_conv3d(xd, wd, stride, True, rd)
+        assert tuple(y.shape) == tuple(yr.shape)
+        assert rel(y.float(), yr + res) < tol_f
+        y.backward(dy.cuda().to(y.dtype))
+        assert rel(xd.grad.float(), xr.grad) < tol_b
+        assert rel(wd.grad, wr.grad) < tol_b
+        assert rel(rd.grad.float(), dy) < 1e-6
+    finally:
+        mm.set_conv_algo("auto")
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_stem_and_classifier(mm, dtype, tol):
+    mm.set_compute_dtype(dtype)
+    img = O.synth_patch((2, 1, 5, 7, 9), 3)
+    w = _rand((32, 1, 3, 3, 3), 1)
+    wr = w.clone().requires_grad_(True)
+    yr = O.ws_conv3d(img, wr, 1, 1)
+    dy = _rand(tuple(yr.shape), 2)
+    if dtype == torch.bfloat16:
+        dy = dy.bfloat16().float()
+    (yr * dy).sum().backward()
+    wd = w.cuda().requires_grad_(True)
+    y = mm.ops.stem_conv(img.cuda(), wd, True)
+    assert rel(y.float(), yr) < tol
+    y.backward(dy.cuda().to(y.dtype))
+    assert rel(wd.grad, wr.grad) < max(tol, 1e-4)
+    # classifier
+    a = _rand((2, 32, 3, 5, 6), 5)
+    if dtype == torch.bfloat16:
+        a = a.bfloat16().float()
+    wc, bc = 0.2 * _rand((16, 32, 1, 1, 1), 6), 0.2 * _rand((16,), 7)
+    ar, wcr, bcr = a.clone().requires_grad_(True), wc.clone().requires_grad_(True), bc.clone().requires_grad_(True)
+    lr = F.conv3d(ar, wcr, bcr)
+    dl = _rand(tuple(lr.shape), 8)
+    (lr * dl).sum().backward()
+    ad, wcd, bcd = a.cuda().requires_grad_(True), wc.cuda().requires_grad_(True), bc.cuda().requires_grad_(True)
+    lg = mm.ops.classifier(ad, wcd, bcd)
+    assert lg.dtype == torch.float32 and lg.is_contiguous()
+    assert rel(lg, lr) < 1e-5
+    lg.backward(dl.cuda())
+    assert rel(ad.grad.float(), ar.grad) < tol
+    assert rel(wcd.grad, wcr.grad) < 1e-4 and rel(bcd.grad, bcr.grad) < 1e-4
+
+
+def test_partial_loss_golden(mm, golden_dir):
+    """Fused loss vs the reference's own outputs (fixtures written by oracle/make_golden.py)."""
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+
+    g = np.load(os.path.join(golden_dir, "partial_loss.npz"))
+    for name in ["ct_one_organ", "mri_bg_only", "all_ones", "all_zero", "c4_frac"]:
+        z0, t, w = torch.from_numpy(g[name + "_z"]), torch.from_numpy(g[name + "_t"]), torch.from_numpy(g[name + "_w"])
+        for uce in (True, False):
+            z = z0.cuda().requires_grad_(True)
+            L = EDiceLoss_partial(z.shape[1])(z, t.cuda(), mask=[w] * z.shape[0], soft_max=True, uce=uce)
+            tag = f"{name}_uce{int(uce)}"
+            ref = float(g[tag + "_loss"])
+            assert abs(L.item() - ref) <= 2e-6 * max(1.0, abs(ref)), tag
+            L.backward()
+            gr = torch.from_numpy(g[tag + "_grad"])
+            if gr.abs().max() > 0:
+                assert rel(z.grad, gr) < 1e-5, tag
+            else:
+                assert z.grad.abs().max().item() == 0.0
+    # log clamp at -100 (saturated probabilities)
+    z = torch.zeros((1, 4, 2, 2, 2))
+    z[:, 0] = 200.0
+    L = EDiceLoss_partial(4)(z.cuda(), torch.ones((1, 2, 2, 2)).cuda(), mask=None)
+    assert abs(L.item() - float(g["saturated_loss"])) < 1e-4 * float(g["saturated_loss"])
+
+
+def test_partial_loss_lut_and_mask0(mm):
+    """cmask remap folded in as a LUT == remapping the labels first; mask[0] drives the whole batch (F8)."""
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+
+    z = _rand((2, 16, 4, 6, 6), 1, 2.0).cuda()
+    lab = torch.randint(0, 16, (2, 4, 6, 6), generator=torch.Generator().manual_seed(2)).float()
+    w16 = [1.0, 0, 0, 0, 1.0] + [0.0] * 11
+    cm = O.remap_unsupervised(lab, w16)
+    lut = torch.tensor([float(l) if w16[l] or l == 0 else 0.0 for l in range(16)])
+    crit = EDiceLoss_partial(16)
+    a = crit(z, cm.cuda(), mask=[torch.tensor(w16)] * 2)
+    b = crit(z, lab.cuda(), mask=[torch.tensor(w16), torch.ones(16)], lut=lut)
+    assert abs(a.item() - b.item()) < 1e-7
+    ref = O.partial_label_loss(z.cpu(), cm, w16)
+    assert abs(a.item() - ref.item()) < 2e-6 * max(1.0, ref.item())
+
+
+def test_sgd_step(mm):
+    from multimodal_pl_b200 import _lib
+
+    L = _lib.lib()
+    n = 1000 + 3
+    p0, g = _rand((n,), 1), _rand((n,), 2)
+    p = p0.cuda().clone()
+    buf = torch.zeros(n, device="cuda")
+    lr = torch.tensor([0.01], device="cuda")
+    q, qb = p0.clone(), None
+    for step in range(3):
+        gs = g * (step + 1)
+        gd = gs.cuda()
+        _lib.check(L.mmpl_sgd_step(p.data_ptr(), gd.data_ptr(), buf.data_ptr(), n, lr.data_ptr(), 0.9, 1e-4, 1.0,
+                                   int(step == 0), _lib.stream_ptr()))
+        q, qb = O.sgd_step(q, gs, qb, 0.01)
+    assert torch.allclose(p.cpu(), q, atol=1e-6)
