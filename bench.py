@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the multimodal-PL hot path on B200: 3-D patches/s of the unet3D train step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg5]
+
+A "step" is one pass of the hot path over one batch of synthetic patches: unet3D_baseline forward, partial-label loss,
+backward, (N>1: NCCL gradient all-reduce), fused SGD step.  Default workload = BASELINE.json configs[1] ("cfg2"):
+bf16, batch 2 per GPU, 1x64x192x192 patches, 16 classes, random init.  Inputs are 2 x 2.36 M voxels per step and the
+activations touched per step (> 4 GB) exceed the 126 MB L2, so no explicit L2 flush is needed (stated in config).
+
+Rank 0 prints ONE JSON line (see README / the task contract): value = patches/s over all ranks with inputs resident
+in HBM; e2e = the same metric through the public API with pinned-host inputs copied H2D and the loss read back D2H
+every step; roofline = the dominant kernel (tcgen05 conv) against the measured bf16 peak; cpu_baseline = the CPU
+oracle timed on this box's host cores on a bounded sample.
+
+--impl reference times the reference's own CPU implementation of the path (the oracle port: the same ATen ops in the
+same order as the reference modules, see oracle/mmpl_oracle.py) on all host threads, on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (batch per GPU, patch D,H,W, base width, classes)
+    "cfg1": (1, (64, 128, 128), 32, 16),
+    "cfg2": (2, (64, 192, 192), 32, 16),
+    "cfg5": (4, (96, 224, 224), 64, 16),
+}
+# algorithmic conv FLOPs per patch, train step
+TRAIN_TFLOP_PER_PATCH = {"cfg1": 1.3662, "cfg2": 3.0740, "cfg5": 25.041}
+
+
+def conv_flops_tc(batch, dhw, base):
+    """Algorithmic FLOPs (2*M*N*K) of the stride-1 3x3x3 convolutions handled by the tcgen05 kernels in ONE train
+    step (fprop + dgrad + wgrad), i.e. the launches the roofline line is about."""
+    D, H, W = dhw
+    v = batch * D * H * W
+    b = base
+    # (cin, cout, level) of every stride-1 3^3 conv in forward order
+    convs = [(b, b, 0), (b, b, 0),                                   # layer0.0 conv1, conv2
+             (2 * b, 2 * b, 1), (2 * b, 2 * b, 1), (2 * b, 2 * b, 1),  # layer1.0.conv2, layer1.1.*
+             (4 * b, 4 * b, 2), (4 * b, 4 * b, 2), (4 * b, 4 * b, 2),
+             (8 * b, 8 * b, 3), (8 * b, 8 * b, 3), (8 * b, 8 * b, 3),
+             (8 * b, 8 * b, 4), (8 * b, 8 * b, 4), (8 * b, 8 * b, 4),
+             (8 * b, 4 * b, 3), (4 * b, 4 * b, 3),                   # x8_resb
+             (4 * b, 2 * b, 2), (2 * b, 2 * b, 2),                   # x4_resb
+             (2 * b, b, 1), (b, b, 1),                               # x2_resb
+             (b, b, 0), (b, b, 0)]                                   # x1_resb
+    total = 0
+    for cin, cout, lvl in convs:
+        total += 2 * (v // (8 ** lvl)) * cout * cin * 27
+    return 3 * total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_reference_step(patch_dhw, base, classes, threads):
+    """One fwd + partial-label loss + bwd of the CPU oracle on a [1,1,*patch_dhw] sample; returns seconds."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mmpl_oracle as O
+
+    torch.set_num_threads(threads)
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.synth_state_dict(base, classes, 0).items()}
+    x = O.synth_patch((1, 1) + tuple(patch_dhw), 1, "ct")
+    lab = torch.randint(0, classes, (1,) + tuple(patch_dhw)).float()
+    w = [1.0, 0, 0, 0, 1.0] + [0.0] * (classes - 5)
+    t0 = time.perf_counter()
+    logits = O.unet3d_forward(sd, x, base)
+    loss = O.partial_label_loss(logits, lab, w)
+    loss.backward()
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """Reference arm: the path's CPU implementation (oracle port, same ATen ops/order as the reference modules) on all
+    host threads.  Each step is a bounded sample: a 32x96x96 crop = 1/8 of a cfg2 patch (conv work is linear in
+    voxels), so patches/s = (1/8) / seconds."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch, dhw, base, classes = WORKLOADS[args.workload]
+    crop = tuple(max(16, s // 2) for s in dhw)
+    frac = (crop[0] * crop[1] * crop[2]) / (dhw[0] * dhw[1] * dhw[2])
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_reference_step(crop, base, classes, threads)
+    times = [cpu_reference_step(crop, base, classes, threads) for _ in range(args.steps)]
+    total = sum(times)
+    value = frac * args.steps / total
+    line = {
+        "impl": "reference", "metric": "3D patches/sec (train fwd+bwd)", "value": value, "unit": "patches/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "patch": list(dhw), "batch_per_gpu": batch, "base": base, "classes": classes},
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": threads, "kind": "port",
+                         "sample": f"one {crop[0]}x{crop[1]}x{crop[2]} crop (={frac:.4f} patch) fwd+loss+bwd per step, fp32, torch CPU"},
+        "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200 import _lib, ops
+    from multimodal_pl_b200.engine import DataParallelModel, FusedSGD
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+    from multimodal_pl_b200.supervise_mask import cmask_lut
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))   # synthetic-data generators only (no oracle compute here)
+    import mmpl_oracle as O
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    _lib.require_device()
+    mm.set_compute_dtype(torch.bfloat16)
+
+    batch, dhw, base, classes = WORKLOADS[args.workload]
+    torch.manual_seed(0)
+    model = unet3D_baseline([1, 2, 2, 2, 2], num_classes=classes, weight_std=True, base=base).to(dev)
+    model.train()
+    dp = DataParallelModel(model, world, average=False)
+    opt = FusedSGD(dp.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4, flat_grad=dp.flat_grad)
+    crit = EDiceLoss_partial(classes)
+
+    # synthetic batch: mixed CT / MRI samples, Voronoi labels, one supervised organ (CT) or background only (MRI)
+    shape = (batch, 1) + dhw
+    imgs, labs = [], []
+    for b in range(batch):
+        imgs.append(O.synth_patch((1, 1) + dhw, 100 + rank * 16 + b, "ct" if b % 2 == 0 else "mri"))
+        labs.append(O.synth_labels((1,) + tuple(s // 4 for s in dhw), 200 + rank * 16 + b, classes, 32))
+    image_h = torch.cat(imgs).pin_memory()
+    label_lo = torch.cat(labs)
+    label_h = torch.nn.functional.interpolate(label_lo, size=dhw, mode="nearest").contiguous().pin_memory()
+    w16 = [1.0, 0, 0, 0, 1.0] + [0.0] * (classes - 5)
+    wt = [torch.tensor(w16)] * batch
+    lut = cmask_lut(w16).to(dev)
+    image_d, label_d = image_h.to(dev), label_h.to(dev)
+
+    def step(img, lab):
+        opt.zero_grad()
+        logits, _, _ = dp(img, lab)
+        loss = crit(logits, lab.squeeze(1), mask=wt, soft_max=True, lut=lut)
+        loss.backward()
+        opt.step(grad_scale=1.0 / world)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        step(image_d, label_d)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------------------------
+    conv_prof = ops.enable_conv_profile(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(image_d, label_d)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    prof = ops.collect_conv_profile()
+    ops.enable_conv_profile(False)
+
+    # ---- timed region 2: end to end through the public API with host buffers -------------------------------------
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        img = image_h.to(dev, non_blocking=True)
+        lab = label_h.to(dev, non_blocking=True)
+        last = step(img, lab).item()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    patches = batch * world * args.steps
+    value = patches / (ms / 1e3)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    # timed inside a multi-second step loop under the power cap -> sustained bf16 peak; else the recipe's fallback
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md, sustained)"
+    tc_ms = prof["ms"]
+    tc_flops = conv_flops_tc(batch, dhw, base) * args.steps
+    achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "conv3_tc / wgrad_tc (tcgen05 3x3x3 s1 fprop+dgrad+wgrad)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": None, "peak_source": peak_src, "launches": prof["launches"],
+                "kernel_ms_per_step": tc_ms / args.steps, "share_of_step": tc_ms / ms,
+                "whole_step_conv_tflops": TRAIN_TFLOP_PER_PATCH[args.workload] * value}
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        crop = tuple(max(16, s // 2) for s in dhw)
+        frac = (crop[0] * crop[1] * crop[2]) / (dhw[0] * dhw[1] * dhw[2])
+        cpu_reference_step(crop, base, classes, threads)          # warm-up
+        n, tsum = 0, 0.0
+        while tsum < 12.0 and n < 8:
+            tsum += cpu_reference_step(crop, base, classes, threads)
+            n += 1
+        cpu = {"value": frac * n / tsum, "unit": "patches/s", "cores": threads, "kind": "port",
+               "sample": f"{n} x one {crop[0]}x{crop[1]}x{crop[2]} crop (={frac:.4f} patch) fwd+loss+bwd, fp32, torch CPU oracle"}
+    line = {
+        "metric": "3D patches/sec (train fwd+bwd)", "value": value, "unit": "patches/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "patch": list(dhw), "batch_per_gpu": batch, "base": base, "classes": classes,
+                   "parallelism": f"dp{world}", "l2": "inputs+activations per step >> 126 MB L2, no flush needed",
+                   "optimizer": "fused SGD momentum 0.9 wd 1e-4", "loss": "EDiceLoss_partial (fused)"},
+        "clocks": clocks,
+        "e2e": {"value": patches / (ms_e2e / 1e3), "unit": "patches/s",
+                "h2d_bytes_per_step": image_h.numel() * 4 + label_h.numel() * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

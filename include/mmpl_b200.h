@@ -127,7 +127,7 @@ int mmpl_sgd_step(float* p, const float* grad, float* buf, int64_t count, const 
 int mmpl_sw_blend(void* acc, void* wsum, const float* tile_logits /*[C][td][th][tw]*/, const float* gauss, int c,
                   int d, int h, int w, int td, int th, int tw, int d0, int h0, int w0, int acc_bytes,
                   mmpl_stream_t stream);
-/* out_logits (may be NULL) [C][D][H][W] fp32 = acc/wsum; argmax uint8 [D][H][W]; counts int64 [3][C] = |P&T|,|P|,|T|
+/* wsum may be NULL (acc already normalised).  out_logits (may be NULL) [C][D][H][W] fp32 = acc/wsum; argmax uint8 [D][H][W]; counts int64 [3][C] = |P&T|,|P|,|T|
  * (zeroed by the call) against label fp32 [D][H][W] (may be NULL). */
 int mmpl_sw_finalize(const void* acc, const void* wsum, const float* label, float* out_logits, uint8_t* argmax,
                      long long* counts, int c, int64_t voxels, int acc_bytes, mmpl_stream_t stream);

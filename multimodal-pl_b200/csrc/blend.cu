@@ -38,7 +38,7 @@ sw_finalize_kernel(const A* __restrict__ acc, const A* __restrict__ wsum, const 
   __syncthreads();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < vol;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const A ws = wsum[i];
+    const A ws = wsum ? wsum[i] : static_cast<A>(1);
     int best = 0;
     A bv = acc[i] / ws;
     if (out_logits) out_logits[i] = static_cast<float>(bv);

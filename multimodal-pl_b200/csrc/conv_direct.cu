@@ -16,6 +16,11 @@ constexpr int TK = 32;   // channels per k-chunk
 
 struct ConvDims {
   int N, Di, Hi, Wi, Do, Ho, Wo, Cin, Cout, k, pad, SO, SI;
+  // Output sub-grid (stride-2 dgrad is run as 8 parity classes, each with only the taps that can hit it):
+  // the kernel enumerates voxels (osd + 2*d', osh + 2*h', osw + 2*w') when ostep == 2; sub-grid extents Ds,Hs,Ws.
+  int ostep, osd, osh, osw, Ds, Hs, Ws;
+  int ntaps;
+  int taplist[27];
 };
 
 template <typename T>
@@ -43,31 +48,32 @@ conv_direct_kernel(const T* __restrict__ x, const T* __restrict__ wp, const T* _
   __shared__ int s_n[TM], s_d[TM], s_h[TM], s_w[TM];
   __shared__ int64_t s_off[TM];
   const int tid = threadIdx.x;
-  const int64_t M = static_cast<int64_t>(dm.N) * dm.Do * dm.Ho * dm.Wo;
+  const int64_t M = static_cast<int64_t>(dm.N) * dm.Ds * dm.Hs * dm.Ws;
   const int64_t m0 = static_cast<int64_t>(blockIdx.x) * TM;
   const int co0 = blockIdx.y * TN;
   if (tid < TM) {
     int64_t m = m0 + tid;
     if (m < M) {
-      s_w[tid] = static_cast<int>(m % dm.Wo);
-      m /= dm.Wo;
-      s_h[tid] = static_cast<int>(m % dm.Ho);
-      m /= dm.Ho;
-      s_d[tid] = static_cast<int>(m % dm.Do);
-      s_n[tid] = static_cast<int>(m / dm.Do);
+      s_w[tid] = dm.osw + dm.ostep * static_cast<int>(m % dm.Ws);
+      m /= dm.Ws;
+      s_h[tid] = dm.osh + dm.ostep * static_cast<int>(m % dm.Hs);
+      m /= dm.Hs;
+      s_d[tid] = dm.osd + dm.ostep * static_cast<int>(m % dm.Ds);
+      s_n[tid] = static_cast<int>(m / dm.Ds);
     } else {
       s_n[tid] = -1;
     }
   }
+  __syncthreads();  // coordinates are read by every thread in the epilogue (and the tap loop may be empty)
   const int tm = tid / 16, tn = tid % 16;
   float acc[4][CN];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < CN; ++j) acc[i][j] = 0.f;
-  const int taps = dm.k * dm.k * dm.k;
   const int lv = tid / 4, lc = (tid % 4) * 8;  // loader mapping: voxel / weight row, 8 channels
-  for (int t = 0; t < taps; ++t) {
+  for (int ti = 0; ti < dm.ntaps; ++ti) {
+    const int t = dm.taplist[ti];
     const int kd = t / (dm.k * dm.k), kh = (t / dm.k) % dm.k, kw = t % dm.k;
     __syncthreads();
     if (tid < TM) {
@@ -119,9 +125,10 @@ conv_direct_kernel(const T* __restrict__ x, const T* __restrict__ wp, const T* _
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int64_t m = m0 + tm * 4 + i;
-    if (m >= M) continue;
-    const int64_t o = m * dm.Cout + co0 + tn * CN;
+    const int r = tm * 4 + i;
+    if (m0 + r >= M) continue;
+    const int64_t o = ((((static_cast<int64_t>(s_n[r]) * dm.Do + s_d[r]) * dm.Ho + s_h[r]) * dm.Wo + s_w[r])) * dm.Cout +
+                      co0 + tn * CN;
 #pragma unroll
     for (int j = 0; j < CN; ++j) {
       float v = acc[i][j];
@@ -191,7 +198,8 @@ conv_wgrad_direct_kernel(const T* __restrict__ x, const T* __restrict__ dy, floa
 
 template <typename T>
 int launch_direct(const void* x, const void* wp, const void* addend, void* y, const ConvDims& dm, cudaStream_t s) {
-  const int64_t M = static_cast<int64_t>(dm.N) * dm.Do * dm.Ho * dm.Wo;
+  const int64_t M = static_cast<int64_t>(dm.N) * dm.Ds * dm.Hs * dm.Ws;
+  if (M == 0) return MMPL_OK;
   const int mt = ceil_div(M, TM);
   if (dm.Cout % 64 == 0)
     conv_direct_kernel<T, 64><<<dim3(mt, dm.Cout / 64), 256, 0, s>>>(static_cast<const T*>(x), static_cast<const T*>(wp),
@@ -206,10 +214,18 @@ int launch_direct(const void* x, const void* wp, const void* addend, void* y, co
 
 int conv_out_dim(int in, int k, int stride) { return (in + 2 * (k / 2) - k) / stride + 1; }
 
+static void full_grid(ConvDims& dm) {
+  dm.ostep = 1, dm.osd = dm.osh = dm.osw = 0;
+  dm.Ds = dm.Do, dm.Hs = dm.Ho, dm.Ws = dm.Wo;
+  dm.ntaps = dm.k * dm.k * dm.k;
+  for (int t = 0; t < dm.ntaps; ++t) dm.taplist[t] = t;
+}
+
 int conv_direct_fprop(const void* x, const void* w, const void* residual, void* y, int n, int d, int h, int wd, int cin,
                       int cout, int k, int stride, int dtype, cudaStream_t s) {
   ConvDims dm{n, d, h, wd, conv_out_dim(d, k, stride), conv_out_dim(h, k, stride), conv_out_dim(wd, k, stride),
               cin, cout, k, k / 2, stride, 1};
+  full_grid(dm);
   MMPL_DISPATCH_DTYPE(dtype, T, launch_direct<T>(x, w, residual, y, dm, s));
   MMPL_CHECK_LAUNCH("conv_direct_fprop");
   return MMPL_OK;
@@ -220,8 +236,27 @@ int conv_direct_dgrad(const void* dy, const void* w, const void* addend, void* d
                       int cout, int k, int stride, int dtype, cudaStream_t s) {
   ConvDims dm{n, conv_out_dim(d, k, stride), conv_out_dim(h, k, stride), conv_out_dim(wd, k, stride), d, h, wd,
               cout, cin, k, k / 2, 1, stride};
-  MMPL_DISPATCH_DTYPE(dtype, T, launch_direct<T>(dy, w, addend, dx, dm, s));
-  MMPL_CHECK_LAUNCH("conv_direct_dgrad");
+  if (stride == 1) {
+    full_grid(dm);
+    MMPL_DISPATCH_DTYPE(dtype, T, launch_direct<T>(dy, w, addend, dx, dm, s));
+    MMPL_CHECK_LAUNCH("conv_direct_dgrad");
+    return MMPL_OK;
+  }
+  // stride 2: one launch per parity class of dx; a tap t' reaches parity p only if (p + t' - pad) is even per axis
+  const int pad = k / 2;
+  for (int pc = 0; pc < 8; ++pc) {
+    const int pd = pc >> 2, ph = (pc >> 1) & 1, pw = pc & 1;
+    dm.ostep = 2, dm.osd = pd, dm.osh = ph, dm.osw = pw;
+    dm.Ds = (d - pd + 1) / 2, dm.Hs = (h - ph + 1) / 2, dm.Ws = (wd - pw + 1) / 2;
+    dm.ntaps = 0;
+    for (int t = 0; t < k * k * k; ++t) {
+      const int kd = t / (k * k), kh = (t / k) % k, kw = t % k;
+      if (((pd + kd - pad) & 1) == 0 && ((ph + kh - pad) & 1) == 0 && ((pw + kw - pad) & 1) == 0) dm.taplist[dm.ntaps++] = t;
+    }
+    // parity classes no tap can reach (k = 1: everything but the even class) are plain zeros (+ addend)
+    MMPL_DISPATCH_DTYPE(dtype, T, launch_direct<T>(dy, w, addend, dx, dm, s));
+    MMPL_CHECK_LAUNCH("conv_direct_dgrad");
+  }
   return MMPL_OK;
 }
 

@@ -1,0 +1,237 @@
+"""Drop-in for the reference's ``engine.py`` with the data-parallel hooks actually implemented.
+
+The reference ``Engine`` (engine.py:10-77) is a stub: ``data_parallel`` returns the model unchanged (:30-32),
+``all_reduce_tensor`` is ``torch.mean`` (:57-58), samplers are ``None`` (:44).  The authors' log shows the code was
+run as 3-process DDP (run_files/amos_ours_77.txt:4-6).  Here the same method names are backed by one process per GPU
+(``torchrun`` env: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*), NCCL over NVLink for the gradient all-reduce
+(gloo on CPU-only hosts, used by the tests), and a fused SGD step on a flat parameter buffer.
+
+Training is embarrassingly parallel over samples (GroupNorm has no cross-sample statistics) with ONE exchange step:
+the gradient all-reduce.  Gradients live in one flat fp32 buffer cut into buckets in reverse registration order;
+each bucket is all-reduced asynchronously as soon as its last gradient has been produced, so the collective overlaps
+the rest of the backward pass.
+"""
+import argparse
+import os
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class DataParallelModel(torch.nn.Module):
+    """Wraps a module for bucketed, overlapped gradient averaging.  ``.module`` is the wrapped model (the train loop
+    uses ``model.module.renew_token``, train_amos_atlas_final.py:391)."""
+
+    def __init__(self, module: torch.nn.Module, world_size: int, bucket_mb: float = 16.0, average: bool = True):
+        super().__init__()
+        self.module = module
+        self.world_size = world_size
+        self.average = average
+        params = [p for p in module.parameters() if p.requires_grad]
+        self._params = params
+        if world_size > 1:
+            for p in module.parameters():
+                dist.broadcast(p.data, src=0)
+            for b in module.buffers():
+                dist.broadcast(b.data, src=0)
+        total = sum(p.numel() for p in params)
+        dev = params[0].device if params else torch.device("cpu")
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        # gradients are produced roughly in reverse registration order: bucket 0 holds the LAST parameters
+        self._buckets: List[dict] = []
+        limit = int(bucket_mb * 1024 * 1024 / 4)
+        off = total
+        cur = {"hi": total, "lo": total, "pending": 0, "count": 0}
+        for p in reversed(params):
+            off -= p.numel()
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            p._mmpl_bucket = len(self._buckets)
+            cur["lo"] = off
+            cur["count"] += 1
+            if cur["hi"] - cur["lo"] >= limit:
+                self._buckets.append(cur)
+                cur = {"hi": off, "lo": off, "pending": 0, "count": 0}
+        if cur["count"]:
+            self._buckets.append(cur)
+        self._handles = []
+        self._callback_queued = False
+        if world_size > 1:
+            for p in params:
+                p.register_post_accumulate_grad_hook(self._on_grad)
+        self._reset()
+
+    def _reset(self):
+        for b in self._buckets:
+            b["pending"] = b["count"]
+        self._handles = []
+        self._callback_queued = False
+
+    def _on_grad(self, p):
+        if not self._callback_queued:
+            torch.autograd.Variable._execution_engine.queue_callback(self._finish)
+            self._callback_queued = True
+        b = self._buckets[p._mmpl_bucket]
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            view = self.flat_grad[b["lo"]:b["hi"]]
+            self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True))
+
+    def _finish(self):
+        for h in self._handles:
+            h.wait()
+        # buckets whose parameters received no gradient this step still have to take part in the collective
+        for b in self._buckets:
+            if b["pending"] > 0:
+                dist.all_reduce(self.flat_grad[b["lo"]:b["hi"]], op=dist.ReduceOp.SUM)
+        if self.average:
+            self.flat_grad.mul_(1.0 / self.world_size)
+        self._reset()
+
+    def zero_grad(self, set_to_none: bool = False):
+        # gradients are views of the flat buffer: keep them, just clear
+        self.flat_grad.zero_()
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+
+class FusedSGD(torch.optim.Optimizer):
+    """torch.optim.SGD(lr, momentum, weight_decay) semantics (train_amos_atlas_final.py:132-135) as ONE kernel launch
+    over flat parameter / gradient / momentum buffers (mmpl_sgd_step).  ``param_groups[0]['lr']`` stays writable for
+    the reference's poly schedule (utils.py:56-60).  Parameters are re-pointed into the flat buffer (values kept)."""
+
+    def __init__(self, params, lr=1e-2, momentum=0.9, weight_decay=1e-4, flat_grad: Optional[torch.Tensor] = None):
+        params = [p for p in params if p.requires_grad]
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        own_grad = flat_grad is None
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev) if own_grad else flat_grad
+        assert self.flat_grad.numel() == total
+        off = 0
+        for p in params:
+            n = p.numel()
+            self.flat_param[off:off + n].copy_(p.data.reshape(-1).float())
+            p.data = self.flat_param[off:off + n].view_as(p)
+            if own_grad:
+                p.grad = self.flat_grad[off:off + n].view_as(p)
+            else:
+                assert p.grad is not None and p.grad.data_ptr() == self.flat_grad[off:off + n].data_ptr(), \
+                    "flat_grad must be laid out in parameter order (use DataParallelModel.flat_grad)"
+            off += n
+        self.momentum_buf = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._lr_host = None
+        self._steps = 0
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.flat_grad.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        g = self.param_groups[0]
+        if self._lr_host != g["lr"]:
+            self._lr_dev.fill_(float(g["lr"]))
+            self._lr_host = g["lr"]
+        _lib.require_device()
+        _lib.check(_lib.lib().mmpl_sgd_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(),
+                                            self.momentum_buf.data_ptr(), self.flat_param.numel(),
+                                            self._lr_dev.data_ptr(), float(g["momentum"]), float(g["weight_decay"]),
+                                            float(grad_scale), int(self._steps == 0), _lib.stream_ptr()), "sgd_step")
+        self._steps += 1
+
+
+def extant_file(x):
+    if not os.path.exists(x):
+        raise argparse.ArgumentTypeError("{0} does not exist".format(x))
+    return x
+
+
+class Engine(object):
+    """Same surface as the reference Engine (engine.py:10-77): context manager, ``.args``, ``.distributed``,
+    ``.local_rank``, ``.world_size``, ``.devices``, ``data_parallel``, ``get_train_loader``, ``get_test_loader``,
+    ``all_reduce_tensor``."""
+
+    def __init__(self, custom_parser=None):
+        self.devices = None
+        if custom_parser is None:
+            self.parser = argparse.ArgumentParser()
+        else:
+            assert isinstance(custom_parser, argparse.ArgumentParser)
+            self.parser = custom_parser
+        self.inject_default_parser()
+        self.args = self.parser.parse_args()
+        self.continue_state_object = self.args.continue_fpath
+        self.world_size = _env_int("WORLD_SIZE", 1)
+        self.local_rank = _env_int("LOCAL_RANK", 0)
+        self.rank = _env_int("RANK", 0)
+        self.distributed = self.world_size > 1
+        self.devices = [self.local_rank]
+        if torch.cuda.is_available():
+            torch.cuda.set_device(self.local_rank)
+        if self.distributed and not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29500")
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            kw = {"device_id": torch.device("cuda", self.local_rank)} if backend == "nccl" else {}
+            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world_size, **kw)
+
+    def data_parallel(self, model):
+        return DataParallelModel(model, self.world_size)
+
+    def _loader(self, dataset, batch_size, shuffle, collate_fn=None):
+        sampler = None
+        if self.distributed:
+            sampler = torch.utils.data.distributed.DistributedSampler(dataset, num_replicas=self.world_size,
+                                                                      rank=self.rank, shuffle=shuffle)
+        loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size,
+                                             num_workers=getattr(self.args, "num_workers", 0), drop_last=False,
+                                             shuffle=(shuffle and sampler is None), pin_memory=torch.cuda.is_available(),
+                                             sampler=sampler, collate_fn=collate_fn)
+        return loader, sampler
+
+    def get_train_loader(self, train_dataset, collate_fn=None):
+        return self._loader(train_dataset, getattr(self.args, "batch_size", 1), True, collate_fn)
+
+    def get_test_loader(self, test_dataset):
+        return self._loader(test_dataset, 1, False)
+
+    def all_reduce_tensor(self, tensor, norm=True):
+        """Mean over ranks of the (scalar) tensor; single process: ``torch.mean`` like the reference stub (:57-58)."""
+        if not self.distributed:
+            return torch.mean(tensor)
+        t = tensor.detach().clone().float()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if norm:
+            t = t / self.world_size
+        return torch.mean(t)
+
+    def inject_default_parser(self):
+        p = self.parser
+        p.add_argument('-d', '--devices', default='', help='set data parallel training')
+        p.add_argument('-c', '--continue', type=extant_file, metavar="FILE", dest="continue_fpath",
+                       help='continue from one certain checkpoint')
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, type, value, tb):
+        if dist.is_initialized():
+            try:
+                dist.barrier()
+            except Exception:
+                pass
+        if type is not None:
+            print("A exception occurred during Engine initialization, give up running process")
+            return False

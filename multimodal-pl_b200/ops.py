@@ -32,6 +32,41 @@ def set_conv_algo(algo: str):
     _cfg["conv_algo"] = algo
 
 
+_PROF = {"on": False, "events": []}
+
+
+def enable_conv_profile(on: bool):
+    """bench.py: bracket every tcgen05 conv launch (fprop / dgrad / wgrad) with CUDA events on the launching stream."""
+    _PROF["on"] = bool(on)
+    _PROF["events"] = []
+    return _PROF
+
+
+def collect_conv_profile():
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in _PROF["events"])
+    return {"ms": ms, "launches": len(_PROF["events"])}
+
+
+class _timed:
+    """Context manager recording an event pair around a tcgen05 launch when profiling is on."""
+
+    def __init__(self, algo):
+        self.on = _PROF["on"] and algo == _lib.ALGO_TCGEN05
+
+    def __enter__(self):
+        if self.on:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.b.record()
+            _PROF["events"].append((self.a, self.b))
+        return False
+
+
 def to_cl(x: torch.Tensor, dtype=None) -> torch.Tensor:
     """Logical NCDHW tensor -> compute dtype with physically dense NDHWC storage (no copy if already so)."""
     dtype = dtype or _cfg["dtype"]
@@ -103,8 +138,9 @@ class WSConv3dFn(torch.autograd.Function):
             res = to_cl(residual, dt)
             assert res.shape == y.shape
         algo = _algo(dt, k, stride, cin, cout)
-        _lib.check(L.mmpl_conv3d_fprop(_p(x), _p(pf), _p(res), _p(y), n, d, h, w, cin, cout, k, stride, code, algo, st),
-                   "conv3d_fprop")
+        with _timed(algo):
+            _lib.check(L.mmpl_conv3d_fprop(_p(x), _p(pf), _p(res), _p(y), n, d, h, w, cin, cout, k, stride, code, algo,
+                                           st), "conv3d_fprop")
         ctx.save_for_backward(x, w_hat, inv_std, pd)
         ctx.meta = (n, d, h, w, cin, cout, k, stride, int(standardise), residual is not None, weight.dtype)
         return y
@@ -123,8 +159,9 @@ class WSConv3dFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = empty_cl(n, cin, d, h, w, dt, dev)
             algo = _algo(dt, k, stride, cout, cin)
-            _lib.check(L.mmpl_conv3d_dgrad(_p(dy), _p(pd), None, _p(dx), n, d, h, w, cin, cout, k, stride, code, algo,
-                                           st), "conv3d_dgrad")
+            with _timed(algo):
+                _lib.check(L.mmpl_conv3d_dgrad(_p(dy), _p(pd), None, _p(dx), n, d, h, w, cin, cout, k, stride, code,
+                                               algo, st), "conv3d_dgrad")
         if ctx.needs_input_grad[1]:
             taps = k * k * k
             g_hat = torch.empty(taps * cout * cin, dtype=torch.float32, device=dev)
@@ -133,8 +170,9 @@ class WSConv3dFn(torch.autograd.Function):
                 algo = _lib.ALGO_TCGEN05
             wsb = int(L.mmpl_conv3d_wgrad_workspace(n, d, h, w, cin, cout, k, stride, algo))
             ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev) if wsb else None
-            _lib.check(L.mmpl_conv3d_wgrad(_p(x), _p(dy), _p(g_hat), n, d, h, w, cin, cout, k, stride, code, algo,
-                                           _p(ws), wsb, st), "conv3d_wgrad")
+            with _timed(algo):
+                _lib.check(L.mmpl_conv3d_wgrad(_p(x), _p(dy), _p(g_hat), n, d, h, w, cin, cout, k, stride, code, algo,
+                                               _p(ws), wsb, st), "conv3d_wgrad")
             dw = torch.empty_like(w_hat)
             _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, cin, taps, standardise, _p(dw), st),
                        "ws_weight_bwd")

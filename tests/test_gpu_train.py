@@ -1,0 +1,83 @@
+"""Train-step level checks on the device: fused SGD == torch.optim.SGD on the model, loss decreases over a few steps
+of the bf16 tcgen05 path, and (when >= 2 GPUs are visible) the NCCL data-parallel step equals the single-process
+step on the concatenated batch."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import mmpl_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fused_sgd_matches_torch_sgd_on_model():
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.engine import DataParallelModel, FusedSGD
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    mm.set_compute_dtype(torch.float32)
+    mm.set_conv_algo("direct")
+    try:
+        sd = O.synth_state_dict(32, 16, 0)
+        x = O.synth_patch((1, 1, 16, 16, 32), 5, "ct").cuda()
+        lab = O.synth_labels((1, 16, 16, 32), 6, 16, 32).cuda()
+        w = [torch.ones(16)]
+        crit = EDiceLoss_partial(16)
+        a = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True).cuda()
+        b = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True).cuda()
+        a.load_state_dict(sd)
+        b.load_state_dict(sd)
+        opt_a = torch.optim.SGD(a.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+        dp = DataParallelModel(b, 1)
+        opt_b = FusedSGD(dp.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, flat_grad=dp.flat_grad)
+        for _ in range(3):
+            opt_a.zero_grad()
+            crit(a(x)[0], lab.squeeze(1), mask=w).backward()
+            opt_a.step()
+            opt_b.zero_grad()
+            crit(dp(x)[0], lab.squeeze(1), mask=w).backward()
+            opt_b.step()
+        for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6), k
+    finally:
+        mm.set_conv_algo("auto")
+        mm.set_compute_dtype(torch.bfloat16)
+
+
+def test_bf16_training_reduces_loss():
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.engine import DataParallelModel, FusedSGD
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    mm.set_compute_dtype(torch.bfloat16)
+    torch.manual_seed(0)
+    model = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True).cuda()
+    dp = DataParallelModel(model, 1)
+    opt = FusedSGD(dp.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, flat_grad=dp.flat_grad)
+    x = O.synth_patch((2, 1, 16, 32, 32), 5, "ct").cuda()
+    lab = O.synth_labels((2, 16, 32, 32), 6, 16, 32).cuda()
+    crit = EDiceLoss_partial(16)
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss = crit(dp(x, lab)[0], lab.squeeze(1), mask=[torch.ones(16)] * 2)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < 0.8 * losses[0], losses
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_nccl_data_parallel_equals_single_process():
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611",
+                          os.path.join(ROOT, "tests", "dp_worker.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "DP_OK" in out.stdout

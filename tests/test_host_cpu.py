@@ -1,0 +1,167 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol declared in include/mmpl_b200.h, the
+drop-in modules keep the reference's state_dict / signatures, host-side logic (tile grid, mask table, tile sharding,
+gradient bucketing over a 2-process gloo group) behaves like the oracle.  No compute kernels are called."""
+import inspect
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import mmpl_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from multimodal_pl_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "mmpl_b200.h")).read()
+    declared = set(re.findall(r"\b(mmpl_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 24
+    l = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(l, name), f"{name} declared in include/mmpl_b200.h but not exported"
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    assert l.mmpl_version() >= 100
+    assert _lib.launch_count() == 0            # nothing may have launched on a CPU-only host
+
+
+def test_product_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    net = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 1, 16, 32, 32))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "multimodal-pl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "mmpl_oracle" not in src and "import oracle" not in src, f
+
+
+def test_state_dict_contract_and_signatures():
+    from multimodal_pl_b200 import unet3D
+    from multimodal_pl_b200.loss_functions import loss_partial, losses
+
+    net = unet3D.unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True)
+    sd, shapes = net.state_dict(), O.state_dict_shapes(32, 16)
+    assert len(sd) == 107 and set(sd) == set(shapes)
+    assert all(tuple(sd[k].shape) == shapes[k] for k in shapes)
+    assert sum(p.numel() for p in net.parameters()) == 17286512
+    net.load_state_dict(O.synth_state_dict(32, 16, 0))          # reference-shaped checkpoints load unchanged
+    sig = inspect.signature
+    assert list(sig(unet3D.unet3D_baseline.__init__).parameters)[1:7] == \
+        ["layers", "num_classes", "weight_std", "ema", "use_cm", "deep_up"]
+    assert list(sig(unet3D.unet3D_baseline.forward).parameters) == ["self", "input", "mask"]
+    assert list(sig(unet3D.NoBottleneck.__init__).parameters)[1:] == \
+        ["inplanes", "planes", "stride", "dilation", "downsample", "fist_dilation", "multi_grid", "weight_std", "group"]
+    assert list(sig(unet3D.Conv3d.__init__).parameters)[1:] == \
+        ["in_channels", "out_channels", "kernel_size", "stride", "padding", "dilation", "groups", "bias"]
+    assert list(sig(loss_partial.EDiceLoss_partial.forward).parameters)[:6] == \
+        ["self", "inputs", "target", "mask", "soft_max", "uce"]
+    assert list(sig(losses.get_loss).parameters)[:5] == ["output", "cm", "deep_out", "target", "mask"]
+    with pytest.raises(NotImplementedError):
+        unet3D.Conv3d(32, 32, kernel_size=(5, 5, 5), padding=(2, 2, 2))
+
+
+def test_tile_grid_matches_oracle():
+    from multimodal_pl_b200.evaluate import _get_gaussian, tile_origins
+
+    for vol, tile in [((300, 512, 512), (64, 192, 192)), ((19, 37, 41), (8, 16, 16)), ((64, 192, 192), (64, 192, 192)),
+                      ((70, 200, 193), (64, 192, 192))]:
+        assert tile_origins((1, 1) + vol, tile) == O.tile_grid(vol, tile)
+    assert len(tile_origins((1, 1, 300, 512, 512), (64, 192, 192))) == 96
+    assert np.array_equal(_get_gaussian((8, 16, 16)), O.gaussian_importance((8, 16, 16)))
+    # round-robin sharding over 8 ranks covers every tile exactly once, 12 each
+    tiles = list(range(96))
+    owned = [[t for t in tiles if t % 8 == r] for r in range(8)]
+    assert sorted(sum(owned, [])) == tiles and all(len(o) == 12 for o in owned)
+
+
+def test_supervise_mask_adapter(tmp_path):
+    from multimodal_pl_b200.supervise_mask import cmask_lut, read_supervise_mask, remap_unsupervised
+
+    p = tmp_path / "m.csv"
+    p.write_text('name,mask\namos_0001.nii.gz,"[0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]"\n'
+                 'amos_0507.nii.gz,"[0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]"\n')
+    t = read_supervise_mask(str(p))
+    assert t == O.read_supervise_mask(str(p))
+    lab = torch.randint(0, 16, (2, 1, 3, 4, 5)).float()
+    for key in t:
+        assert torch.equal(remap_unsupervised(lab, t[key]), O.remap_unsupervised(lab, t[key]))
+        assert cmask_lut(t[key])[0] == 0 and len(cmask_lut(t[key])) == 16
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _dp_worker(rank, world, port, out):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from multimodal_pl_b200.engine import DataParallelModel
+
+    torch.manual_seed(100 + rank)                       # different init per rank: the wrapper must broadcast rank 0's
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    dp = DataParallelModel(model, world, bucket_mb=0.0002)        # tiny buckets -> several collectives
+    assert len(dp._buckets) >= 2
+    g = torch.Generator().manual_seed(7)
+    xs, ys = torch.randn(world, 5, 8, generator=g), torch.randn(world, 5, 4, generator=g)
+    for step in range(2):
+        dp.zero_grad()
+        ((dp(xs[rank]) - ys[rank]) ** 2).mean().backward()
+    torch.save({"flat": dp.flat_grad.clone(), "w0": model[0].weight.detach().clone()}, os.path.join(out, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_allreduce_gloo(tmp_path):
+    """2-process gloo: bucketed, overlapped all-reduce == gradient of the mean loss over the concatenated batch."""
+    world, port = 2, _free_port()
+    mp.spawn(_dp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"r{i}.pt")) for i in range(world)]
+    assert torch.equal(r[0]["w0"], r[1]["w0"])                          # parameters were broadcast
+    assert torch.allclose(r[0]["flat"], r[1]["flat"], atol=1e-7)        # same averaged gradient everywhere
+    torch.manual_seed(100)
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    g = torch.Generator().manual_seed(7)
+    xs, ys = torch.randn(world, 5, 8, generator=g), torch.randn(world, 5, 4, generator=g)
+    loss = sum(((ref(xs[i]) - ys[i]) ** 2).mean() for i in range(world)) / world
+    loss.backward()
+    flat_ref = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    assert torch.allclose(r[0]["flat"], flat_ref, atol=1e-6)
+
+
+def test_engine_surface():
+    import argparse
+    import sys
+
+    from multimodal_pl_b200.engine import Engine
+
+    argv, sys.argv = sys.argv, ["prog"]
+    try:
+        with Engine(custom_parser=argparse.ArgumentParser()) as e:
+            assert e.world_size == 1 and e.local_rank == 0 and not e.distributed
+            assert abs(e.all_reduce_tensor(torch.tensor([1.0, 3.0])).item() - 2.0) < 1e-7
+            for name in ("data_parallel", "get_train_loader", "get_test_loader", "all_reduce_tensor"):
+                assert callable(getattr(e, name))
+    finally:
+        sys.argv = argv
