@@ -262,9 +262,9 @@ def run_ours(args):
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md, sustained)"
     tc_ms = prof["ms"]
-    tc_flops = conv_flops_tc(batch, dhw, base) * args.steps
+    tc_flops = prof["flops"]          # algorithmic 2*M*N*K of every tcgen05 conv launch inside the timed region
     achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv3_tc / wgrad_tc (tcgen05 3x3x3 s1 fprop+dgrad+wgrad)",
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel / wgrad_tc_kernel (all tcgen05 conv launches: fprop+dgrad+wgrad)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "traffic": None, "peak_source": peak_src, "launches": prof["launches"],
                 "kernel_ms_per_step": tc_ms / args.steps, "share_of_step": tc_ms / ms,

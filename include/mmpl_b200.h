@@ -30,7 +30,7 @@ extern "C" {
 typedef void* mmpl_stream_t; /* cudaStream_t */
 
 enum { MMPL_F32 = 0, MMPL_BF16 = 1 };
-enum { MMPL_ALGO_DIRECT = 0, MMPL_ALGO_TCGEN05 = 1 };
+enum { MMPL_ALGO_DIRECT = 0, MMPL_ALGO_TCGEN05 = 1, MMPL_ALGO_TCGEN05_PSPLIT = 2 };
 enum {
   MMPL_OK = 0,
   MMPL_E_SHAPE = -1,
@@ -62,8 +62,12 @@ int mmpl_ws_weight_bwd(const float* g_hat_tapmajor, const float* w_hat, const fl
  * fprop : y[N,Do,Ho,Wo,Cout] = conv(x[N,D,H,W,Cin], w_fprop) (+ residual if non-NULL, same shape/dtype as y)
  * dgrad : dx[N,D,H,W,Cin]    = conv^T(dy[N,Do,Ho,Wo,Cout], w_dgrad) (+ addend if non-NULL)
  * wgrad : dw_tapmajor[tap][Cout][Cin] fp32 = sum_voxels dy * x_shifted   (overwritten, not accumulated)
- * algo MMPL_ALGO_TCGEN05 requires bf16, stride 1, k=3, Cin,Cout in {32,64,128,256} (fprop/dgrad) and returns
- * MMPL_E_UNSUPPORTED otherwise; MMPL_ALGO_DIRECT (CUDA cores, fp32 accumulate) handles every case. */
+ * algo MMPL_ALGO_TCGEN05 requires bf16 and channel counts of 32 or multiples of 64 (MMPL_E_UNSUPPORTED otherwise);
+ * for stride-2 3x3x3 fprop/wgrad the activation argument is the parity-split copy written by mmpl_parity_split and
+ * the algo is MMPL_ALGO_TCGEN05_PSPLIT.  MMPL_ALGO_DIRECT (CUDA cores, fp32 accumulate) handles every case. */
+/* P[(p*N + n)][d'][h'][w'][c] = X[n][2d'+pd][2h'+ph][2w'+pw][c], p = pd*4+ph*2+pw, extents ceil(D/2) etc., zeros
+ * where the source index is out of range.  bf16 only. */
+int mmpl_parity_split(const void* x, void* p_out, int n, int d, int h, int w, int c, int dtype, mmpl_stream_t stream);
 int mmpl_conv3d_fprop(const void* x, const void* w_fprop, const void* residual, void* y, int n, int d, int h, int w,
                       int cin, int cout, int ksize, int stride, int dtype, int algo, mmpl_stream_t stream);
 int mmpl_conv3d_dgrad(const void* dy, const void* w_dgrad, const void* addend, void* dx, int n, int d, int h, int w,

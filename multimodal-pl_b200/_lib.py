@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmmpl_b200.so")
 
 F32, BF16 = 0, 1
-ALGO_DIRECT, ALGO_TCGEN05 = 0, 1
+ALGO_DIRECT, ALGO_TCGEN05, ALGO_TCGEN05_PSPLIT = 0, 1, 2
 
 _c_int, _c_i64, _c_f32, _ptr, _c_size = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 
@@ -25,6 +25,7 @@ _SIGNATURES = {
     "mmpl_launch_count": [],
     "mmpl_ws_weight_fwd": [_ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr],
     "mmpl_ws_weight_bwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
+    "mmpl_parity_split": [_ptr, _ptr] + [_c_int] * 6 + [_ptr],
     "mmpl_conv3d_fprop": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr],
     "mmpl_conv3d_dgrad": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr],
     "mmpl_conv3d_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr, _c_size, _ptr],

@@ -5,7 +5,10 @@ namespace mmpl {
 int conv_direct_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_direct_dgrad(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_direct_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int conv_tc_3x3x3_s1(const void*, const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int conv_tc_s1(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int conv_tc_s2_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int conv_tc_s2_dgrad(const void*, const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int parity_split(const void*, void*, int, int, int, int, int, cudaStream_t);
 int conv_tc_wgrad_3x3x3_s1(const void*, const void*, float*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 size_t conv_tc_wgrad_workspace(int, int, int, int, int, int);
 
@@ -20,15 +23,24 @@ static int check_common(int n, int d, int h, int w, int cin, int cout, int k, in
 
 using namespace mmpl;
 
+extern "C" int mmpl_parity_split(const void* x, void* p_out, int n, int d, int h, int w, int c, int dtype,
+                                 mmpl_stream_t stream) {
+  MMPL_REQUIRE(dtype == MMPL_BF16, MMPL_E_DTYPE, "parity_split: bf16 only");
+  MMPL_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0, MMPL_E_SHAPE, "parity_split: empty tensor");
+  return parity_split(x, p_out, n, d, h, w, c, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mmpl_conv3d_fprop(const void* x, const void* w_fprop, const void* residual, void* y, int n, int d, int h,
                                  int w, int cin, int cout, int ksize, int stride, int dtype, int algo,
                                  mmpl_stream_t stream) {
   if (int e = check_common(n, d, h, w, cin, cout, ksize, stride)) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (algo == MMPL_ALGO_TCGEN05) {
-    MMPL_REQUIRE(dtype == MMPL_BF16 && ksize == 3 && stride == 1, MMPL_E_UNSUPPORTED,
-                 "conv3d_fprop: tcgen05 path needs bf16, k=3, stride=1 (got dtype=%d k=%d stride=%d)", dtype, ksize, stride);
-    return conv_tc_3x3x3_s1(x, w_fprop, residual, y, n, d, h, w, cin, cout, s);
+  if (algo == MMPL_ALGO_TCGEN05 || algo == MMPL_ALGO_TCGEN05_PSPLIT) {
+    MMPL_REQUIRE(dtype == MMPL_BF16, MMPL_E_UNSUPPORTED, "conv3d_fprop: tcgen05 path needs bf16 (got dtype=%d)", dtype);
+    if (stride == 1) return conv_tc_s1(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, s);
+    MMPL_REQUIRE((ksize == 3) == (algo == MMPL_ALGO_TCGEN05_PSPLIT), MMPL_E_UNSUPPORTED,
+                 "conv3d_fprop: stride-2 3x3x3 takes the parity-split input (MMPL_ALGO_TCGEN05_PSPLIT), 1x1x1 takes x");
+    return conv_tc_s2_fprop(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, s);
   }
   return conv_direct_fprop(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, stride, dtype, s);
 }
@@ -39,10 +51,13 @@ extern "C" int mmpl_conv3d_dgrad(const void* dy, const void* w_dgrad, const void
   if (int e = check_common(n, d, h, w, cin, cout, ksize, stride)) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (algo == MMPL_ALGO_TCGEN05) {
-    MMPL_REQUIRE(dtype == MMPL_BF16 && ksize == 3 && stride == 1, MMPL_E_UNSUPPORTED,
-                 "conv3d_dgrad: tcgen05 path needs bf16, k=3, stride=1 (got dtype=%d k=%d stride=%d)", dtype, ksize, stride);
+    MMPL_REQUIRE(dtype == MMPL_BF16, MMPL_E_UNSUPPORTED, "conv3d_dgrad: tcgen05 path needs bf16 (got dtype=%d)", dtype);
     // stride-1 dgrad is a correlation of dy with the flipped/transposed packing: channels swap roles
-    return conv_tc_3x3x3_s1(dy, w_dgrad, addend, dx, n, d, h, w, cout, cin, s);
+    if (stride == 1) return conv_tc_s1(dy, w_dgrad, addend, dx, n, d, h, w, cout, cin, ksize, s);
+    MMPL_REQUIRE(addend == nullptr, MMPL_E_UNSUPPORTED, "conv3d_dgrad: stride-2 tcgen05 path has no addend input");
+    if (ksize == 1)  // only the even parity class receives gradient; the rest of dx is zero
+      MMPL_CUDA(cudaMemsetAsync(dx, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(n) * d * h * w * cin, s));
+    return conv_tc_s2_dgrad(dy, w_dgrad, dx, n, d, h, w, cin, cout, ksize, s);
   }
   return conv_direct_dgrad(dy, w_dgrad, addend, dx, n, d, h, w, cin, cout, ksize, stride, dtype, s);
 }

@@ -1,21 +1,26 @@
-// tcgen05 / TMEM / TMA implicit-GEMM 3x3x3 stride-1 convolution for sm_100a (bf16 in, fp32 accumulate in TMEM).
-// Reference op: F.conv3d in Conv3d.forward (unet3D.py:27) for the 23 stride-1 3x3x3 sites of the backbone, and -- with
-// the flipped/transposed dgrad packing -- their autograd data gradient.
+// tcgen05 / TMEM / TMA implicit-GEMM convolutions for sm_100a (bf16 in, fp32 accumulate in TMEM).
+// Reference op: F.conv3d in Conv3d.forward (unet3D.py:27) -- all 35 weight-standardised convolutions of the backbone
+// (3x3x3 and 1x1x1, stride 1 and 2) and their autograd data gradients.
 //
 // Design (B200-first, not an im2col translation):
-//  * The activation tensor is NDHWC bf16.  One work item is a TD x 16 x 8 block of output voxels (x one tile of NT
-//    output channels).  For each 64-(or 32-)channel chunk of Cin, ONE 5-D TMA box load brings the halo block
-//    (TD+2) x 18 x 10 voxels x KC channels into shared memory (hardware zero-fill implements the padding).
-//  * The 27 filter taps are NOT materialised: each tap is the same shared-memory block viewed through a UMMA
-//    K-major descriptor whose start address is shifted by ((kd*18 + kh)*10 + kw) rows and whose 8-row-group stride
-//    (SBO) is the 10-voxel line pitch.  Hardware swizzling is a pure function of the shared-memory address
-//    (verified on B200 by tools/probe_umma.cu, profiles/r01_probe_umma.log), so any row shift is legal.
-//    L2->SMEM traffic is therefore ~2.1x the activation instead of the 27x of a tap-by-tap im2col.
+//  * Activations are NDHWC bf16.  One work item is a TD x 16 x 8 block of output voxels x one tile of NT output
+//    channels.  For each 64-(or 32-)channel chunk of the reduction channels ONE 5-D TMA box load brings the halo block
+//    PD x PH x PW voxels x KC channels into shared memory (hardware zero-fill implements the padding).
+//  * Filter taps are NOT materialised: each tap is the same shared-memory block viewed through a UMMA K-major
+//    descriptor whose start address is shifted by ((sd*PH + sh)*PW + sw) rows and whose 8-row-group stride (SBO) is the
+//    PW-voxel line pitch.  Hardware swizzling is a pure function of the shared-memory address (verified on B200 by
+//    tools/probe_umma.cu, profiles/r01_probe_umma.log), so any row shift is legal.  L2->SMEM traffic is ~2x the
+//    activation instead of the 27x of a tap-by-tap im2col.
 //  * M = 128 rows = 16 h-lines x 8 w-voxels of one d-plane; TD planes share every weight tile (TD accumulators in
-//    TMEM), N = NT output channels, K = 16 per tcgen05.mma.  Accumulators are double-buffered in TMEM so the
-//    epilogue of item i overlaps the MMAs of item i+1.
-//  * Warp roles: 0 = activation TMA producer, 1 = weight TMA producer, 2 = MMA issuer (one elected thread) and TMEM
-//    allocator, 3..6 = epilogue (tcgen05.ld -> +residual -> bf16 -> 16-byte global stores).
+//    TMEM), N = NT, K = 16 per tcgen05.mma.  Accumulators are double-buffered in TMEM so the epilogue of item i
+//    overlaps the MMAs of item i+1.
+//  * Stride 2 never uses strided gathers in the MMA path:
+//      fprop  reads a parity-split copy P[8*N][D/2][H/2][W/2][C] of the input (P_p[i] = X[2i+p], written by
+//             mmpl_parity_split); tap k of parity p is P_p shifted by (k != 0) -> 8 chunks x (1..8 taps) per item;
+//      dgrad  runs per parity class of dX: a 1..8-tap stride-1 correlation over dY whose epilogue stores to 2i+p.
+//  * Warp roles: 0 = activation TMA producer, 1 = weight TMA producer, 2 = MMA issuer (warp-uniform loop, one elected
+//    lane issues) and TMEM allocator, 3..6 = epilogue (tcgen05.ld -> +residual -> bf16 -> 16-byte global stores).
+//  * WRES: for 32->32 layers all 27 weight tiles (55 KB) stay resident in shared memory for the life of the CTA.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -24,43 +29,73 @@ namespace {
 
 using namespace ptx;
 
-constexpr int TC_TH = 16, TC_TW = 8, TC_PH = TC_TH + 2, TC_PW = TC_TW + 2;
+constexpr int TC_TH = 16, TC_TW = 8;
 constexpr int TC_THREADS = 224;
 
-template <int KC, int NT, int TD>
+enum : int {
+  MODE_S1K3 = 0,   // 3x3x3 stride 1 (fprop, or dgrad with the flipped/transposed packing)
+  MODE_S1K1 = 1,   // 1x1x1 stride 1
+  MODE_S2F = 2,    // 3x3x3 stride 2 fprop from the parity-split input
+  MODE_S2D = 3,    // 3x3x3 stride 2 dgrad (one parity class of dX per item, strided store)
+  MODE_S2K1F = 4,  // 1x1x1 stride 2 fprop (element-strided TMA straight from NDHWC)
+  MODE_S2K1D = 5   // 1x1x1 stride 2 dgrad (only the even parity class is non-zero; dX is pre-zeroed)
+};
+
+template <int MODE>
+struct Geo {
+  static constexpr int KS = (MODE == MODE_S1K3 || MODE == MODE_S2F || MODE == MODE_S2D) ? 3 : 1;
+  static constexpr int EXTRA = MODE == MODE_S1K3 ? 2 : (MODE == MODE_S2F || MODE == MODE_S2D) ? 1 : 0;  // halo voxels
+  static constexpr int LO = (MODE == MODE_S1K3 || MODE == MODE_S2F) ? -1 : 0;   // block origin relative to the tile
+  static constexpr int PH = TC_TH + EXTRA, PW = TC_TW + EXTRA;
+  static constexpr bool STRIDED_OUT = (MODE == MODE_S2D || MODE == MODE_S2K1D);
+  static constexpr bool PARITY_CHUNKS = (MODE == MODE_S2F);
+};
+
+template <int KC, int NT, int TD, int MODE, bool WRES>
 struct TcCfg {
+  using G = Geo<MODE>;
   static constexpr int RB = KC * 2;
   static constexpr uint32_t SWZ = RB == 128 ? SWZ_128B : SWZ_64B;
-  static constexpr int PD = TD + 2;
-  static constexpr int A_BYTES = PD * TC_PH * TC_PW * RB;
+  static constexpr int PD = TD + G::EXTRA;
+  static constexpr int A_BYTES = PD * G::PH * G::PW * RB;
   static constexpr int A_STAGE = (A_BYTES + 1023) / 1024 * 1024;
   static constexpr int NA = 2;
   static constexpr int B_BYTES = NT * RB;
   static constexpr int SMEM_LIMIT = 227 * 1024 - 2048;
   static constexpr int NB_FIT = (SMEM_LIMIT - NA * A_STAGE) / B_BYTES;
-  static constexpr int NB = NB_FIT > 8 ? 8 : NB_FIT;
+  static constexpr int NB = WRES ? 27 : (NB_FIT > 8 ? 8 : NB_FIT);
   static constexpr int ACC_COLS = TD * NT;
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(B_BYTES % 1024 == 0, "weight stage must keep 1024-byte alignment");
   static_assert(NB >= 2, "need at least two weight stages");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  static_assert(!WRES || (MODE == MODE_S1K3), "resident weights only for the 3x3x3 stride-1 mode");
 };
 
 struct TcParams {
   __nv_bfloat16* y;
   const __nv_bfloat16* residual;
-  int N, D, H, W;
-  int nch;         // Cin / KC
-  int cout_total;  // full output-channel count (row stride of y)
-  int DT, HT, WT, NTILES;
+  int N;            // batch
+  int D, H, W;      // extents of the OUTPUT tensor y (full dims, also for the strided modes)
+  int Ds, Hs, Ws;   // extents of the tile grid domain (== D,H,W except strided-output modes: the parity sub-grid)
+  int nch;          // reduction channels / KC
+  int cout_total;   // row stride of y in elements
+  int DT, HT, WT, NTILES, NPAR;
   int total_items;
 };
 
-template <int KC, int NT, int TD>
+// Tap enumeration shared by the weight producer and the MMA issuer.
+// For the parity modes an axis of parity 1 sees taps {0,2}, parity 0 sees tap {1}.
+__device__ __forceinline__ int axis_ntaps(int par) { return par ? 2 : 1; }
+__device__ __forceinline__ int axis_tap(int par, int i) { return par ? 2 * i : 1; }
+
+template <int KC, int NT, int TD, int MODE, bool WRES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  using Cfg = TcCfg<KC, NT, TD>;
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  using Cfg = TcCfg<KC, NT, TD, MODE, WRES>;
+  using G = Geo<MODE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_stage = smem;
@@ -92,7 +127,8 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto item_coords = [&](int item, int& nt, int& n, int& d0, int& h0, int& w0) {
+  // item -> (nt, parity class, n, tile origin in the tile-grid domain)
+  auto item_coords = [&](int item, int& nt, int& pc, int& n, int& d0, int& h0, int& w0) {
     w0 = (item % p.WT) * TC_TW;
     item /= p.WT;
     h0 = (item % p.HT) * TC_TH;
@@ -100,79 +136,137 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     d0 = (item % p.DT) * TD;
     item /= p.DT;
     n = item % p.N;
-    nt = item / p.N;
+    item /= p.N;
+    pc = item % p.NPAR;
+    nt = item / p.NPAR;
   };
+  // number of (A-chunk) loads per item and taps per chunk
+  const int chunks_per_item = G::PARITY_CHUNKS ? p.nch * 8 : p.nch;
 
   if (warp == 0) {
-    // ===================================================== activation producer: one halo block per (item, chunk)
+    // ===================================================== activation producer
     if (lane == 0) {
       uint32_t it = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        int nt, n, d0, h0, w0;
-        item_coords(item, nt, n, d0, h0, w0);
-        for (int ch = 0; ch < p.nch; ++ch, ++it) {
+        int nt, pc, n, d0, h0, w0;
+        item_coords(item, nt, pc, n, d0, h0, w0);
+        for (int c = 0; c < chunks_per_item; ++c, ++it) {
+          const int ch = G::PARITY_CHUNKS ? (c >> 3) : c;
           const uint32_t s = it % Cfg::NA, ph = (it / Cfg::NA) & 1;
           mbar_wait(&a_empty[s], ph ^ 1);
           mbar_expect_tx(&a_full[s], Cfg::A_BYTES);
-          tma_load_5d(a_stage + s * Cfg::A_STAGE, &tmA, &a_full[s], ch * KC, w0 - 1, h0 - 1, d0 - 1, n);
+          int cw = w0 + G::LO, chh = h0 + G::LO, cd = d0 + G::LO, cn = n;
+          if (MODE == MODE_S2F) cn = (c & 7) * p.N + n;          // parity plane of the split tensor
+          if (MODE == MODE_S2K1F) cw = 2 * w0, chh = 2 * h0, cd = 2 * d0;
+          tma_load_5d(a_stage + s * Cfg::A_STAGE, &tmA, &a_full[s], ch * KC, cw, chh, cd, cn);
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== weight producer: one [NT x KC] tile per (item, chunk, tap)
+    // ===================================================== weight producer
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        int nt, n, d0, h0, w0;
-        item_coords(item, nt, n, d0, h0, w0);
-        for (int ch = 0; ch < p.nch; ++ch) {
-          for (int tap = 0; tap < 27; ++tap, ++it) {
-            const uint32_t s = it % Cfg::NB, ph = (it / Cfg::NB) & 1;
-            mbar_wait(&b_empty[s], ph ^ 1);
-            mbar_expect_tx(&b_full[s], Cfg::B_BYTES);
-            tma_load_3d(b_stage + s * Cfg::B_BYTES, &tmB, &b_full[s], ch * KC, nt * NT, tap);
+      if (WRES) {
+        // all 27 tiles once; every stage has its own barrier, completed exactly once
+        for (int tap = 0; tap < 27; ++tap) {
+          mbar_expect_tx(&b_full[tap], Cfg::B_BYTES);
+          tma_load_3d(b_stage + tap * Cfg::B_BYTES, &tmB, &b_full[tap], 0, 0, tap);
+        }
+      } else {
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+          int nt, pc, n, d0, h0, w0;
+          item_coords(item, nt, pc, n, d0, h0, w0);
+          for (int c = 0; c < chunks_per_item; ++c) {
+            const int ch = G::PARITY_CHUNKS ? (c >> 3) : c;
+            const int par = G::PARITY_CHUNKS ? (c & 7) : pc;
+            const int nd = G::KS == 1 ? 1 : (MODE == MODE_S1K3 ? 3 : axis_ntaps(par >> 2));
+            const int nh = G::KS == 1 ? 1 : (MODE == MODE_S1K3 ? 3 : axis_ntaps((par >> 1) & 1));
+            const int nw = G::KS == 1 ? 1 : (MODE == MODE_S1K3 ? 3 : axis_ntaps(par & 1));
+            for (int id = 0; id < nd; ++id)
+              for (int ih = 0; ih < nh; ++ih)
+                for (int iw = 0; iw < nw; ++iw, ++it) {
+                  int tap = 0;
+                  if (MODE == MODE_S1K3) tap = (id * 3 + ih) * 3 + iw;
+                  if (MODE == MODE_S2F || MODE == MODE_S2D)
+                    tap = (axis_tap(par >> 2, id) * 3 + axis_tap((par >> 1) & 1, ih)) * 3 + axis_tap(par & 1, iw);
+                  const uint32_t s = it % Cfg::NB, ph = (it / Cfg::NB) & 1;
+                  mbar_wait(&b_empty[s], ph ^ 1);
+                  mbar_expect_tx(&b_full[s], Cfg::B_BYTES);
+                  tma_load_3d(b_stage + s * Cfg::B_BYTES, &tmB, &b_full[s], ch * KC, nt * NT, tap);
+                }
           }
         }
       }
     }
   } else if (warp == 2) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
-      const uint32_t a_base = smem_u32(a_stage), b_base = smem_u32(b_stage);
-      uint32_t ita = 0, itb = 0, iti = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++iti) {
-        const uint32_t buf = iti & 1, bph = (iti >> 1) & 1;
-        mbar_wait(&acc_empty[buf], bph ^ 1);
+    // ===================================================== MMA issuer: warp-uniform control flow, one lane issues
+    const uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
+    const uint32_t a_base = smem_u32(a_stage), b_base = smem_u32(b_stage);
+    const uint64_t a_hi = make_smem_desc(0, 16, G::PW * Cfg::RB, Cfg::SWZ, 0);
+    const uint64_t b_hi = make_smem_desc(0, 16, 8 * Cfg::RB, Cfg::SWZ, 0);
+    uint32_t ita = 0, itb = 0, iti = 0;
+    if (WRES) {
+      for (int tap = 0; tap < 27; ++tap) mbar_wait(&b_full[tap], 0);
+    }
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++iti) {
+      int nt, pc, n, d0, h0, w0;
+      item_coords(item, nt, pc, n, d0, h0, w0);
+      const uint32_t buf = iti & 1, bph = (iti >> 1) & 1;
+      mbar_wait(&acc_empty[buf], bph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * Cfg::ACC_COLS;
+      uint32_t first = 1;
+      for (int c = 0; c < chunks_per_item; ++c, ++ita) {
+        const int par = G::PARITY_CHUNKS ? (c & 7) : pc;
+        const uint32_t sa = ita % Cfg::NA, pha = (ita / Cfg::NA) & 1;
+        mbar_wait(&a_full[sa], pha);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * Cfg::ACC_COLS;
-        for (int ch = 0; ch < p.nch; ++ch, ++ita) {
-          const uint32_t sa = ita % Cfg::NA, pha = (ita / Cfg::NA) & 1;
-          mbar_wait(&a_full[sa], pha);
-          tc_fence_after();
-          const uint32_t a_addr = a_base + sa * Cfg::A_STAGE;
-          for (int tap = 0; tap < 27; ++tap, ++itb) {
-            const uint32_t sb = itb % Cfg::NB, phb = (itb / Cfg::NB) & 1;
-            mbar_wait(&b_full[sb], phb);
-            tc_fence_after();
-            const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-            const uint32_t b_addr = b_base + sb * Cfg::B_BYTES;
-#pragma unroll
-            for (int pl = 0; pl < TD; ++pl) {
-              const uint32_t a_row = a_addr + (((pl + kd) * TC_PH + kh) * TC_PW + kw) * Cfg::RB;
-#pragma unroll
-              for (int ks = 0; ks < KC / 16; ++ks) {
-                const uint64_t ad = make_smem_desc(a_row + ks * 32, 16, TC_PW * Cfg::RB, Cfg::SWZ, 0);
-                const uint64_t bd = make_smem_desc(b_addr + ks * 32, 16, 8 * Cfg::RB, Cfg::SWZ, 0);
-                umma_f16(d_tmem + pl * NT, ad, bd, idesc, (ch | tap | ks) != 0 ? 1u : 0u);
+        const uint32_t a_addr = a_base + sa * Cfg::A_STAGE;
+        const int nd = G::KS == 1 ? 1 : (MODE == MODE_S1K3 ? 3 : axis_ntaps(par >> 2));
+        const int nh = G::KS == 1 ? 1 : (MODE == MODE_S1K3 ? 3 : axis_ntaps((par >> 1) & 1));
+        const int nw = G::KS == 1 ? 1 : (MODE == MODE_S1K3 ? 3 : axis_ntaps(par & 1));
+        for (int id = 0; id < nd; ++id)
+          for (int ih = 0; ih < nh; ++ih)
+            for (int iw = 0; iw < nw; ++iw, ++itb) {
+              // row shift of this tap inside the halo block
+              int sd = 0, sh = 0, sw = 0, tap = 0;
+              if (MODE == MODE_S1K3) sd = id, sh = ih, sw = iw, tap = (id * 3 + ih) * 3 + iw;
+              if (MODE == MODE_S2F) {   // tap k of parity p: P_p[o + (k != 0) - 1], block origin is o0 - 1
+                sd = axis_tap(par >> 2, id) != 0, sh = axis_tap((par >> 1) & 1, ih) != 0, sw = axis_tap(par & 1, iw) != 0;
               }
+              if (MODE == MODE_S2D) {   // tap t' of parity p: dY[i' + (t' == 2)], block origin is i0'
+                sd = axis_tap(par >> 2, id) == 2, sh = axis_tap((par >> 1) & 1, ih) == 2, sw = axis_tap(par & 1, iw) == 2;
+              }
+              uint32_t sb;
+              if (WRES) {
+                sb = tap;
+              } else {
+                sb = itb % Cfg::NB;
+                mbar_wait(&b_full[sb], (itb / Cfg::NB) & 1);
+                tc_fence_after();
+              }
+              const uint32_t b_addr = b_base + sb * Cfg::B_BYTES;
+              const uint32_t a_tap = a_addr + ((sd * G::PH + sh) * G::PW + sw) * Cfg::RB;
+              if (elect_one()) {
+#pragma unroll
+                for (int pl = 0; pl < TD; ++pl) {
+#pragma unroll
+                  for (int ks = 0; ks < KC / 16; ++ks) {
+                    const uint64_t ad = a_hi | static_cast<uint64_t>((a_tap + pl * (G::PH * G::PW * Cfg::RB) + ks * 32) >> 4);
+                    const uint64_t bd = b_hi | static_cast<uint64_t>((b_addr + ks * 32) >> 4);
+                    umma_f16(d_tmem + pl * NT, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+                  }
+                }
+                if (!WRES) umma_commit(&b_empty[sb]);
+              }
+              __syncwarp();
+              first = 0;
             }
-            umma_commit(&b_empty[sb]);
-          }
-          umma_commit(&a_empty[sa]);
-        }
-        umma_commit(&acc_full[buf]);
+        if (elect_one()) umma_commit(&a_empty[sa]);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else {
     // ===================================================== epilogue warps 3..6 (TMEM lane quarter = warp % 4)
@@ -181,16 +275,18 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int rh = row >> 3, rw = row & 7;
     uint32_t iti = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++iti) {
-      int nt, n, d0, h0, w0;
-      item_coords(item, nt, n, d0, h0, w0);
+      int nt, pc, n, d0, h0, w0;
+      item_coords(item, nt, pc, n, d0, h0, w0);
       const uint32_t buf = iti & 1, bph = (iti >> 1) & 1;
       mbar_wait(&acc_full[buf], bph);
       tc_fence_after();
-      const int hh = h0 + rh, ww = w0 + rw;
+      int hh = h0 + rh, ww = w0 + rw;
+      if (G::STRIDED_OUT) hh = 2 * hh + ((pc >> 1) & 1), ww = 2 * ww + (pc & 1);
       const bool in_hw = hh < p.H && ww < p.W;
 #pragma unroll
       for (int pl = 0; pl < TD; ++pl) {
-        const int dd = d0 + pl;
+        int dd = d0 + pl;
+        if (G::STRIDED_OUT) dd = 2 * dd + (pc >> 2);
         const bool valid = in_hw && dd < p.D;
         const int64_t off = ((((static_cast<int64_t>(n) * p.D + dd) * p.H + hh) * p.W + ww) * p.cout_total) + nt * NT;
 #pragma unroll
@@ -250,22 +346,24 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_act_map(CUtensorMap* m, const void* ptr, int N, int D, int H, int W, int C, int kc, int pd, int ph, int pw,
-                 int rb) {
+// 5-D map over an NDHWC bf16 tensor [N][D][H][W][C]; box counts are OUTPUT elements, estride the traversal stride.
+int make_act_map(CUtensorMap* m, const void* ptr, int64_t N, int D, int H, int W, int C, int kc, int pd, int ph, int pw,
+                 int estride) {
   EncodeTiledFn enc = get_encode();
   MMPL_REQUIRE(enc != nullptr, MMPL_E_CUDA, "cuTensorMapEncodeTiled unavailable");
+  const cuuint32_t e = static_cast<cuuint32_t>(estride);
   cuuint64_t gd[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
   cuuint64_t gs[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
-  cuuint32_t bx[5] = {(cuuint32_t)kc, (cuuint32_t)pw, (cuuint32_t)ph, (cuuint32_t)pd, 1};
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  cuuint32_t bx[5] = {(cuuint32_t)kc, (cuuint32_t)pw * e, (cuuint32_t)ph * e, (cuuint32_t)pd * e, 1};
+  cuuint32_t es[5] = {1, e, e, e, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MMPL_REQUIRE(r == CUDA_SUCCESS, MMPL_E_CUDA, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
   return MMPL_OK;
 }
 
-int make_weight_map(CUtensorMap* m, const void* ptr, int taps, int cout, int cin, int kc, int nt, int rb) {
+int make_weight_map(CUtensorMap* m, const void* ptr, int taps, int cout, int cin, int kc, int nt) {
   EncodeTiledFn enc = get_encode();
   MMPL_REQUIRE(enc != nullptr, MMPL_E_CUDA, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t gd[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps};
@@ -273,65 +371,158 @@ int make_weight_map(CUtensorMap* m, const void* ptr, int taps, int cout, int cin
   cuuint32_t bx[3] = {(cuuint32_t)kc, (cuuint32_t)nt, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MMPL_REQUIRE(r == CUDA_SUCCESS, MMPL_E_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   return MMPL_OK;
 }
 
-template <int KC, int NT, int TD>
-int launch_tc(const void* x, const void* wp, const void* residual, void* y, int N, int D, int H, int W, int cin,
-              int cout, cudaStream_t s) {
-  using Cfg = TcCfg<KC, NT, TD>;
+// Problem description for one launch.
+//   a        : TMA source (X, dY or the parity-split P), channels = kred (reduction channels)
+//   aN,aD..  : extents of the TMA source tensor
+//   y        : output [N][D][H][W][nout]
+struct TcProblem {
+  const void* a;
+  int64_t aN;
+  int aD, aH, aW;
+  const void* wp;
+  const void* residual;
+  void* y;
+  int N, D, H, W;
+  int kred, nout;
+};
+
+template <int KC, int NT, int TD, int MODE, bool WRES>
+int launch_tc(const TcProblem& q, cudaStream_t s) {
+  using Cfg = TcCfg<KC, NT, TD, MODE, WRES>;
+  using G = Geo<MODE>;
   CUtensorMap tmA, tmB;
-  if (int e = make_act_map(&tmA, x, N, D, H, W, cin, KC, Cfg::PD, TC_PH, TC_PW, Cfg::RB)) return e;
-  if (int e = make_weight_map(&tmB, wp, 27, cout, cin, KC, NT, Cfg::RB)) return e;
+  if (int e = make_act_map(&tmA, q.a, q.aN, q.aD, q.aH, q.aW, q.kred, KC, Cfg::PD, G::PH, G::PW, MODE == MODE_S2K1F ? 2 : 1)) return e;
+  if (int e = make_weight_map(&tmB, q.wp, G::KS * G::KS * G::KS, q.nout, q.kred, KC, NT)) return e;
   TcParams p;
-  p.y = static_cast<__nv_bfloat16*>(y);
-  p.residual = static_cast<const __nv_bfloat16*>(residual);
-  p.N = N, p.D = D, p.H = H, p.W = W;
-  p.nch = cin / KC;
-  p.cout_total = cout;
-  p.DT = ceil_div(D, TD), p.HT = ceil_div(H, TC_TH), p.WT = ceil_div(W, TC_TW), p.NTILES = cout / NT;
-  const int64_t items = static_cast<int64_t>(p.NTILES) * N * p.DT * p.HT * p.WT;
+  p.y = static_cast<__nv_bfloat16*>(q.y);
+  p.residual = static_cast<const __nv_bfloat16*>(q.residual);
+  p.N = q.N, p.D = q.D, p.H = q.H, p.W = q.W;
+  p.Ds = G::STRIDED_OUT ? (q.D + 1) / 2 : q.D;
+  p.Hs = G::STRIDED_OUT ? (q.H + 1) / 2 : q.H;
+  p.Ws = G::STRIDED_OUT ? (q.W + 1) / 2 : q.W;
+  p.nch = q.kred / KC;
+  p.cout_total = q.nout;
+  p.DT = ceil_div(p.Ds, TD), p.HT = ceil_div(p.Hs, TC_TH), p.WT = ceil_div(p.Ws, TC_TW), p.NTILES = q.nout / NT;
+  p.NPAR = MODE == MODE_S2D ? 8 : 1;
+  const int64_t items = static_cast<int64_t>(p.NTILES) * p.NPAR * q.N * p.DT * p.HT * p.WT;
   MMPL_REQUIRE(items < (1ll << 31), MMPL_E_SHAPE, "conv_tc: too many work items");
   p.total_items = static_cast<int>(items);
   static bool attr_set = false;
   if (!attr_set) {
-    MMPL_CUDA(cudaFuncSetAttribute(conv3_tc_kernel<KC, NT, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    MMPL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, NT, TD, MODE, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int grid = static_cast<int>(std::min<int64_t>(items, num_sms()));
-  conv3_tc_kernel<KC, NT, TD><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
-  MMPL_CHECK_LAUNCH("conv3_tc");
+  conv_tc_kernel<KC, NT, TD, MODE, WRES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  MMPL_CHECK_LAUNCH("conv_tc");
   return MMPL_OK;
+}
+
+template <int MODE>
+int dispatch_tc(const TcProblem& q, cudaStream_t s) {
+  const int kred = q.kred, nout = q.nout;
+  MMPL_REQUIRE(kred == 32 || kred % 64 == 0, MMPL_E_UNSUPPORTED, "conv_tc: reduction channels %d (32 or a multiple of 64)", kred);
+  int nt = nout;
+  if (nout > 256) {
+    MMPL_REQUIRE(nout % 256 == 0, MMPL_E_UNSUPPORTED, "conv_tc: output channels %d", nout);
+    nt = 256;
+  }
+  MMPL_REQUIRE(nt == 32 || nt == 64 || nt == 128 || nt == 256, MMPL_E_UNSUPPORTED, "conv_tc: output channels %d", nout);
+  if (kred == 32) {
+    if (nt == 32) {
+      if (MODE == MODE_S1K3) return launch_tc<32, 32, 4, MODE, MODE == MODE_S1K3>(q, s);
+      return launch_tc<32, 32, 4, MODE, false>(q, s);
+    }
+    if (nt == 64) return launch_tc<32, 64, 4, MODE, false>(q, s);
+    MMPL_FAIL(MMPL_E_UNSUPPORTED, "conv_tc: 32 reduction channels with %d output channels", nout);
+  }
+  if (nt == 32) return launch_tc<64, 32, 2, MODE, false>(q, s);
+  if (nt == 64) return launch_tc<64, 64, 2, MODE, false>(q, s);
+  if (nt == 128) return launch_tc<64, 128, 2, MODE, false>(q, s);
+  return launch_tc<64, 256, 1, MODE, false>(q, s);
+}
+
+// parity split: P[p*N + n][d'][h'][w'][c] = X[n][2d'+pd][2h'+ph][2w'+pw][c]  (zero where the source is out of range)
+__global__ void __launch_bounds__(256)
+parity_split_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ pout, int N, int D, int H, int W,
+                    int C, int Dp, int Hp, int Wp) {
+  const int vpv = C / 8;
+  const int64_t total = static_cast<int64_t>(8) * N * Dp * Hp * Wp * vpv;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % vpv);
+    int64_t r = idx / vpv;
+    const int w = static_cast<int>(r % Wp);
+    r /= Wp;
+    const int h = static_cast<int>(r % Hp);
+    r /= Hp;
+    const int d = static_cast<int>(r % Dp);
+    r /= Dp;
+    const int n = static_cast<int>(r % N);
+    const int pc = static_cast<int>(r / N);
+    const int sd = 2 * d + (pc >> 2), sh = 2 * h + ((pc >> 1) & 1), sw = 2 * w + (pc & 1);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (sd < D && sh < H && sw < W)
+      v = *reinterpret_cast<const uint4*>(x + ((((static_cast<int64_t>(n) * D + sd) * H + sh) * W + sw) * C) + cv * 8);
+    *reinterpret_cast<uint4*>(pout + idx * 8) = v;
+  }
 }
 
 }  // namespace
 
-// x [N,D,H,W,cin] bf16, wp [27][cout][cin] bf16 (either packing), y [N,D,H,W,cout] bf16 (+ residual).
-int conv_tc_3x3x3_s1(const void* x, const void* wp, const void* residual, void* y, int N, int D, int H, int W, int cin,
-                     int cout, cudaStream_t s) {
-  MMPL_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wp) | reinterpret_cast<uintptr_t>(y) |
-                reinterpret_cast<uintptr_t>(residual)) % 16 == 0,
+static int check_align(const void* a, const void* b, const void* c, const void* d) {
+  MMPL_REQUIRE((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                reinterpret_cast<uintptr_t>(d)) % 16 == 0,
                MMPL_E_ALIGN, "conv_tc: pointers must be 16-byte aligned");
-  const int kc = cin < 64 ? cin : 64;
-  MMPL_REQUIRE(cin == 32 || cin % 64 == 0, MMPL_E_UNSUPPORTED, "conv_tc: cin=%d (32 or a multiple of 64)", cin);
-  int nt = cout;
-  if (cout > 256) {
-    MMPL_REQUIRE(cout % 256 == 0, MMPL_E_UNSUPPORTED, "conv_tc: cout=%d", cout);
-    nt = 256;
+  return MMPL_OK;
+}
+
+// ---- stride 1 (k = 3 or 1): x [N,D,H,W,cin] -> y [N,D,H,W,cout]; also stride-1 dgrad with swapped channel roles
+int conv_tc_s1(const void* x, const void* wp, const void* residual, void* y, int N, int D, int H, int W, int cin,
+               int cout, int ksize, cudaStream_t s) {
+  if (int e = check_align(x, wp, y, residual)) return e;
+  TcProblem q{x, N, D, H, W, wp, residual, y, N, D, H, W, cin, cout};
+  return ksize == 3 ? dispatch_tc<MODE_S1K3>(q, s) : dispatch_tc<MODE_S1K1>(q, s);
+}
+
+// ---- stride 2 fprop.  k=3: `src` is the parity-split tensor P [8N][Dp][Hp][Wp][cin]; k=1: `src` is x itself.
+int conv_tc_s2_fprop(const void* src, const void* wp, const void* residual, void* y, int N, int D, int H, int W, int cin,
+                     int cout, int ksize, cudaStream_t s) {
+  if (int e = check_align(src, wp, y, residual)) return e;
+  const int Do = (D + 1) / 2, Ho = (H + 1) / 2, Wo = (W + 1) / 2;   // == (in + 2*pad - k)/2 + 1 for k in {1,3}
+  if (ksize == 3) {
+    TcProblem q{src, static_cast<int64_t>(8) * N, Do, Ho, Wo, wp, residual, y, N, Do, Ho, Wo, cin, cout};
+    return dispatch_tc<MODE_S2F>(q, s);
   }
-  MMPL_REQUIRE(nt == 32 || nt == 64 || nt == 128 || nt == 256, MMPL_E_UNSUPPORTED, "conv_tc: cout=%d", cout);
-  if (kc == 32) {
-    if (nt == 32) return launch_tc<32, 32, 4>(x, wp, residual, y, N, D, H, W, cin, cout, s);
-    if (nt == 64) return launch_tc<32, 64, 4>(x, wp, residual, y, N, D, H, W, cin, cout, s);
-    MMPL_FAIL(MMPL_E_UNSUPPORTED, "conv_tc: cin=32 with cout=%d", cout);
-  }
-  if (nt == 32) return launch_tc<64, 32, 2>(x, wp, residual, y, N, D, H, W, cin, cout, s);
-  if (nt == 64) return launch_tc<64, 64, 2>(x, wp, residual, y, N, D, H, W, cin, cout, s);
-  if (nt == 128) return launch_tc<64, 128, 2>(x, wp, residual, y, N, D, H, W, cin, cout, s);
-  return launch_tc<64, 256, 1>(x, wp, residual, y, N, D, H, W, cin, cout, s);
+  TcProblem q{src, N, D, H, W, wp, residual, y, N, Do, Ho, Wo, cin, cout};
+  return dispatch_tc<MODE_S2K1F>(q, s);
+}
+
+// ---- stride 2 dgrad: dy [N,Do,Ho,Wo,cout] -> dx [N,D,H,W,cin] (k=1: dx must be zero-filled by the caller)
+int conv_tc_s2_dgrad(const void* dy, const void* wp_dgrad, void* dx, int N, int D, int H, int W, int cin, int cout,
+                     int ksize, cudaStream_t s) {
+  if (int e = check_align(dy, wp_dgrad, dx, nullptr)) return e;
+  const int Do = (D + 1) / 2, Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  TcProblem q{dy, N, Do, Ho, Wo, wp_dgrad, nullptr, dx, N, D, H, W, cout, cin};
+  return ksize == 3 ? dispatch_tc<MODE_S2D>(q, s) : dispatch_tc<MODE_S2K1D>(q, s);
+}
+
+int parity_split(const void* x, void* pout, int N, int D, int H, int W, int C, cudaStream_t s) {
+  MMPL_REQUIRE(C % 8 == 0, MMPL_E_SHAPE, "parity_split: C=%d", C);
+  const int Dp = (D + 1) / 2, Hp = (H + 1) / 2, Wp = (W + 1) / 2;
+  const int64_t total = static_cast<int64_t>(8) * N * Dp * Hp * Wp * (C / 8);
+  const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(num_sms()) * 16));
+  parity_split_kernel<<<blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(pout), N, D,
+                                            H, W, C, Dp, Hp, Wp);
+  MMPL_CHECK_LAUNCH("parity_split");
+  return MMPL_OK;
 }
 
 }  // namespace mmpl

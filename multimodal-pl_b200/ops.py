@@ -44,15 +44,16 @@ def enable_conv_profile(on: bool):
 
 def collect_conv_profile():
     torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b in _PROF["events"])
-    return {"ms": ms, "launches": len(_PROF["events"])}
+    ms = sum(a.elapsed_time(b) for a, b, _ in _PROF["events"])
+    return {"ms": ms, "launches": len(_PROF["events"]), "flops": float(sum(f for _, _, f in _PROF["events"]))}
 
 
 class _timed:
     """Context manager recording an event pair around a tcgen05 launch when profiling is on."""
 
-    def __init__(self, algo):
-        self.on = _PROF["on"] and algo == _lib.ALGO_TCGEN05
+    def __init__(self, algo, flops=0):
+        self.on = _PROF["on"] and algo != _lib.ALGO_DIRECT
+        self.flops = flops
 
     def __enter__(self):
         if self.on:
@@ -63,7 +64,7 @@ class _timed:
     def __exit__(self, *exc):
         if self.on:
             self.b.record()
-            _PROF["events"].append((self.a, self.b))
+            _PROF["events"].append((self.a, self.b, self.flops))
         return False
 
 
@@ -82,24 +83,26 @@ def empty_cl(n, c, d, h, w, dtype, device) -> torch.Tensor:
     return torch.empty((n, d, h, w, c), dtype=dtype, device=device).permute(0, 4, 1, 2, 3)
 
 
-def _tc_supported(dtype, k, stride, cin, cout) -> bool:
-    if dtype != torch.bfloat16 or k != 3 or stride != 1:
+def _tc_supported(dtype, kred, nout) -> bool:
+    """tcgen05 conv kernels: bf16, reduction channels 32 or a multiple of 64, output channels 32/64/128/256 (or a
+    multiple of 256); 32 reduction channels only with 32 or 64 outputs."""
+    if dtype != torch.bfloat16:
         return False
-    ok_in = cin == 32 or cin % 64 == 0
-    ok_out = cout in (32, 64, 128, 256) or (cout > 256 and cout % 256 == 0)
-    if cin == 32 and cout not in (32, 64):
+    ok_in = kred == 32 or kred % 64 == 0
+    ok_out = nout in (32, 64, 128, 256) or (nout > 256 and nout % 256 == 0)
+    if kred == 32 and nout not in (32, 64):
         return False
     return ok_in and ok_out
 
 
-def _algo(dtype, k, stride, cin, cout) -> int:
+def _algo(dtype, kred, nout) -> int:
     mode = _cfg["conv_algo"]
     if mode == "direct":
         return _lib.ALGO_DIRECT
-    if _tc_supported(dtype, k, stride, cin, cout):
+    if _tc_supported(dtype, kred, nout):
         return _lib.ALGO_TCGEN05
     if mode == "tcgen05":
-        raise RuntimeError(f"tcgen05 conv path does not cover dtype={dtype} k={k} stride={stride} {cin}->{cout}")
+        raise RuntimeError(f"tcgen05 conv path does not cover dtype={dtype} {kred}->{nout}")
     return _lib.ALGO_DIRECT
 
 
@@ -137,12 +140,20 @@ class WSConv3dFn(torch.autograd.Function):
         if residual is not None:
             res = to_cl(residual, dt)
             assert res.shape == y.shape
-        algo = _algo(dt, k, stride, cin, cout)
-        with _timed(algo):
-            _lib.check(L.mmpl_conv3d_fprop(_p(x), _p(pf), _p(res), _p(y), n, d, h, w, cin, cout, k, stride, code, algo,
+        algo = _algo(dt, cin, cout)
+        src = x
+        if algo == _lib.ALGO_TCGEN05 and stride == 2 and k == 3:
+            # stride-2 3x3x3 on tensor cores reads a parity-split copy of the input (one extra streaming pass)
+            src = torch.empty((8 * n, do, ho, wo, cin), dtype=dt, device=dev)
+            _lib.check(L.mmpl_parity_split(_p(x), _p(src), n, d, h, w, cin, code, st), "parity_split")
+            algo = _lib.ALGO_TCGEN05_PSPLIT
+        flops = 2 * n * do * ho * wo * cout * cin * taps
+        with _timed(algo, flops):
+            _lib.check(L.mmpl_conv3d_fprop(_p(src), _p(pf), _p(res), _p(y), n, d, h, w, cin, cout, k, stride, code, algo,
                                            st), "conv3d_fprop")
         ctx.save_for_backward(x, w_hat, inv_std, pd)
         ctx.meta = (n, d, h, w, cin, cout, k, stride, int(standardise), residual is not None, weight.dtype)
+        ctx.flops = flops
         return y
 
     @staticmethod
@@ -158,8 +169,8 @@ class WSConv3dFn(torch.autograd.Function):
         dx = dw = dres = None
         if ctx.needs_input_grad[0]:
             dx = empty_cl(n, cin, d, h, w, dt, dev)
-            algo = _algo(dt, k, stride, cout, cin)
-            with _timed(algo):
+            algo = _algo(dt, cout, cin)
+            with _timed(algo, ctx.flops):
                 _lib.check(L.mmpl_conv3d_dgrad(_p(dy), _p(pd), None, _p(dx), n, d, h, w, cin, cout, k, stride, code,
                                                algo, st), "conv3d_dgrad")
         if ctx.needs_input_grad[1]:
@@ -170,7 +181,7 @@ class WSConv3dFn(torch.autograd.Function):
                 algo = _lib.ALGO_TCGEN05
             wsb = int(L.mmpl_conv3d_wgrad_workspace(n, d, h, w, cin, cout, k, stride, algo))
             ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev) if wsb else None
-            with _timed(algo):
+            with _timed(algo, ctx.flops):
                 _lib.check(L.mmpl_conv3d_wgrad(_p(x), _p(dy), _p(g_hat), n, d, h, w, cin, cout, k, stride, code, algo,
                                                _p(ws), wsb, st), "conv3d_wgrad")
             dw = torch.empty_like(w_hat)
