@@ -9,7 +9,7 @@ int conv_tc_s1(const void*, const void*, const void*, void*, int, int, int, int,
 int conv_tc_s2_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int conv_tc_s2_dgrad(const void*, const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int parity_split(const void*, void*, int, int, int, int, int, cudaStream_t);
-int conv_tc_wgrad_3x3x3_s1(const void*, const void*, float*, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+int conv_tc_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 size_t conv_tc_wgrad_workspace(int, int, int, int, int, int);
 
 static int check_common(int n, int d, int h, int w, int cin, int cout, int k, int stride) {
@@ -64,8 +64,8 @@ extern "C" int mmpl_conv3d_dgrad(const void* dy, const void* w_dgrad, const void
 
 extern "C" size_t mmpl_conv3d_wgrad_workspace(int n, int d, int h, int w, int cin, int cout, int ksize, int stride,
                                               int algo) {
-  if (algo == MMPL_ALGO_TCGEN05 && ksize == 3 && stride == 1) return conv_tc_wgrad_workspace(n, d, h, w, cin, cout);
-  return 0;
+  (void)n, (void)d, (void)h, (void)w, (void)cin, (void)cout, (void)ksize, (void)stride, (void)algo;
+  return 0;  // split-K partials live in TMEM; no global workspace is needed by any algorithm
 }
 
 extern "C" int mmpl_conv3d_wgrad(const void* x, const void* dy, float* dw_tapmajor, int n, int d, int h, int w, int cin,
@@ -73,10 +73,13 @@ extern "C" int mmpl_conv3d_wgrad(const void* x, const void* dy, float* dw_tapmaj
                                  size_t workspace_bytes, mmpl_stream_t stream) {
   if (int e = check_common(n, d, h, w, cin, cout, ksize, stride)) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (algo == MMPL_ALGO_TCGEN05) {
-    MMPL_REQUIRE(dtype == MMPL_BF16 && ksize == 3 && stride == 1, MMPL_E_UNSUPPORTED,
-                 "conv3d_wgrad: tcgen05 path needs bf16, k=3, stride=1 (got dtype=%d k=%d stride=%d)", dtype, ksize, stride);
-    return conv_tc_wgrad_3x3x3_s1(x, dy, dw_tapmajor, n, d, h, w, cin, cout, workspace, workspace_bytes, s);
+  if (algo == MMPL_ALGO_TCGEN05 || algo == MMPL_ALGO_TCGEN05_PSPLIT) {
+    MMPL_REQUIRE(dtype == MMPL_BF16, MMPL_E_UNSUPPORTED, "conv3d_wgrad: tcgen05 path needs bf16 (got dtype=%d)", dtype);
+    MMPL_REQUIRE((stride == 2 && ksize == 3) == (algo == MMPL_ALGO_TCGEN05_PSPLIT), MMPL_E_UNSUPPORTED,
+                 "conv3d_wgrad: stride-2 3x3x3 takes the parity-split input (MMPL_ALGO_TCGEN05_PSPLIT)");
+    MMPL_REQUIRE(!(stride == 2 && ksize == 3) || cout % 64 == 0, MMPL_E_UNSUPPORTED, "conv3d_wgrad: stride-2 cout=%d", cout);
+    (void)workspace, (void)workspace_bytes;
+    return conv_tc_wgrad(x, dy, dw_tapmajor, n, d, h, w, cin, cout, ksize, stride, s);
   }
   return conv_direct_wgrad(x, dy, dw_tapmajor, n, d, h, w, cin, cout, ksize, stride, dtype, s);
 }

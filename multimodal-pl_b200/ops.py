@@ -151,7 +151,10 @@ class WSConv3dFn(torch.autograd.Function):
         with _timed(algo, flops):
             _lib.check(L.mmpl_conv3d_fprop(_p(src), _p(pf), _p(res), _p(y), n, d, h, w, cin, cout, k, stride, code, algo,
                                            st), "conv3d_fprop")
-        ctx.save_for_backward(x, w_hat, inv_std, pd)
+        # stride-2 3x3x3 on tensor cores: the parity-split copy is what wgrad reads, so keep it instead of x
+        keep = src if (algo == _lib.ALGO_TCGEN05_PSPLIT and _tc_wgrad_supported(dt, k, stride, cin, cout)) else x
+        ctx.save_for_backward(keep, w_hat, inv_std, pd)
+        ctx.x_is_psplit = keep is not x
         ctx.meta = (n, d, h, w, cin, cout, k, stride, int(standardise), residual is not None, weight.dtype)
         ctx.flops = flops
         return y
@@ -161,7 +164,7 @@ class WSConv3dFn(torch.autograd.Function):
         L = _lib.lib()
         x, w_hat, inv_std, pd = ctx.saved_tensors
         n, d, h, w, cin, cout, k, stride, standardise, has_res, wdtype = ctx.meta
-        dt = x.dtype
+        dt = pd.dtype
         code = _lib.dtype_code(dt)
         st = _lib.stream_ptr()
         dy = to_cl(dy, dt)
@@ -177,7 +180,10 @@ class WSConv3dFn(torch.autograd.Function):
             taps = k * k * k
             g_hat = torch.empty(taps * cout * cin, dtype=torch.float32, device=dev)
             algo = _lib.ALGO_DIRECT
-            if _cfg["conv_algo"] != "direct" and _tc_wgrad_supported(dt, k, stride, cin, cout):
+            if ctx.x_is_psplit:
+                algo = _lib.ALGO_TCGEN05_PSPLIT
+            elif _cfg["conv_algo"] != "direct" and _tc_wgrad_supported(dt, k, stride, cin, cout) and not (
+                    stride == 2 and k == 3):
                 algo = _lib.ALGO_TCGEN05
             wsb = int(L.mmpl_conv3d_wgrad_workspace(n, d, h, w, cin, cout, k, stride, algo))
             ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev) if wsb else None
@@ -197,10 +203,12 @@ _TC_WGRAD = {"enabled": os.environ.get("MMPL_TC_WGRAD", "1") != "0"}
 
 
 def _tc_wgrad_supported(dtype, k, stride, cin, cout) -> bool:
-    if not (_TC_WGRAD["enabled"] and dtype == torch.bfloat16 and k == 3 and stride == 1):
+    if not (_TC_WGRAD["enabled"] and dtype == torch.bfloat16 and _cfg["conv_algo"] != "direct"):
+        return False
+    if stride == 2 and k == 3 and cout % 64 != 0:
         return False
     if cin == 32:
-        return cout == 32
+        return cout == 32 or cout % 64 == 0
     return cin % 64 == 0 and (cout == 32 or cout % 64 == 0)
 
 
