@@ -80,8 +80,10 @@ size_t mmpl_conv3d_wgrad_workspace(int n, int d, int h, int w, int cin, int cout
 /* ---- stem (Cin = 1) and classifier (1x1x1 with bias, NCDHW fp32 logits): unet3D.py:594, :629-633 -------------- */
 int mmpl_stem_conv_fwd(const float* image, const float* w_hat /*[Cout][27]*/, void* y, int n, int d, int h, int w,
                        int cout, int dtype, mmpl_stream_t stream);
-int mmpl_stem_conv_wgrad(const float* image, const void* dy, float* dw_hat /*[Cout][27]*/, int n, int d, int h,
-                         int w, int cout, int dtype, mmpl_stream_t stream);
+/* dw is tap-major [27][Cout] fp32; workspace (>= mmpl_stem_conv_wgrad_workspace bytes) holds a zero-padded image copy. */
+size_t mmpl_stem_conv_wgrad_workspace(int n, int d, int h, int w);
+int mmpl_stem_conv_wgrad(const float* image, const void* dy, float* dw_tapmajor /*[27][Cout]*/, int n, int d, int h,
+                         int w, int cout, int dtype, void* workspace, size_t workspace_bytes, mmpl_stream_t stream);
 int mmpl_cls_fwd(const void* a, const float* wc /*[C][Cin]*/, const float* bias, float* logits, int n, int64_t spatial,
                  int cin, int classes, int dtype, mmpl_stream_t stream);
 int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits, void* da, float* dwc, float* dbias, int n,

@@ -31,7 +31,8 @@ _SIGNATURES = {
     "mmpl_conv3d_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr, _c_size, _ptr],
     "mmpl_conv3d_wgrad_workspace": [_c_int] * 9,
     "mmpl_stem_conv_fwd": [_ptr, _ptr, _ptr] + [_c_int] * 6 + [_ptr],
-    "mmpl_stem_conv_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 6 + [_ptr],
+    "mmpl_stem_conv_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 6 + [_ptr, _c_size, _ptr],
+    "mmpl_stem_conv_wgrad_workspace": [_c_int] * 4,
     "mmpl_cls_fwd": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_cls_bwd": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_gn_stats": [_ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
@@ -46,7 +47,7 @@ _SIGNATURES = {
     "mmpl_sw_finalize": [_ptr] * 6 + [_c_int, _c_i64, _c_int, _ptr],
 }
 _RESTYPES = {"mmpl_last_error": ctypes.c_char_p, "mmpl_launch_count": ctypes.c_uint64,
-             "mmpl_conv3d_wgrad_workspace": ctypes.c_size_t}
+             "mmpl_conv3d_wgrad_workspace": ctypes.c_size_t, "mmpl_stem_conv_wgrad_workspace": ctypes.c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

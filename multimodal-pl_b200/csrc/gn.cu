@@ -26,25 +26,19 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const T* __restrict_
   __shared__ double sg[32][2];
   if (threadIdx.x < 64) (&sg[0][0])[threadIdx.x] = 0.0;
   __syncthreads();
-  double ds[VN], dq[VN];
+  // each thread sums <= a few hundred values per channel in fp32 (short runs), fp64 is used only across threads
+  float ds[VN], dq[VN];
 #pragma unroll
-  for (int i = 0; i < VN; ++i) ds[i] = dq[i] = 0.0;
-  int64_t v = v0 + vl;
-  while (v < v1) {
-    float s[VN], q[VN];
+  for (int i = 0; i < VN; ++i) ds[i] = dq[i] = 0.f;
+#pragma unroll 2
+  for (int64_t v = v0 + vl; v < v1; v += vstep) {
+    Vec<T> a;
+    a.load(base + v * C);
 #pragma unroll
-    for (int i = 0; i < VN; ++i) s[i] = q[i] = 0.f;
-    for (int it = 0; it < 32 && v < v1; ++it, v += vstep) {
-      Vec<T> a;
-      a.load(base + v * C);
-#pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        s[i] += a.v[i];
-        q[i] = fmaf(a.v[i], a.v[i], q[i]);
-      }
+    for (int i = 0; i < VN; ++i) {
+      ds[i] += a.v[i];
+      dq[i] = fmaf(a.v[i], a.v[i], dq[i]);
     }
-#pragma unroll
-    for (int i = 0; i < VN; ++i) ds[i] += s[i], dq[i] += q[i];
   }
   const int cpg = C / groups;
   // reduce the VN channels of this thread into per-group partials, then across lanes that share the column
@@ -52,7 +46,7 @@ __global__ void __launch_bounds__(kThreads) gn_stats_kernel(const T* __restrict_
   const int cpp = VN / gpt;                  // channels per partial
   for (int j = 0; j < gpt; ++j) {
     double a = 0, b = 0;
-    for (int i = 0; i < cpp; ++i) a += ds[j * cpp + i], b += dq[j * cpp + i];
+    for (int i = 0; i < cpp; ++i) a += static_cast<double>(ds[j * cpp + i]), b += static_cast<double>(dq[j * cpp + i]);
     for (int o = 16; o >= vpv && o > 0; o >>= 1) {
       a += __shfl_xor_sync(0xffffffffu, a, o);
       b += __shfl_xor_sync(0xffffffffu, b, o);
@@ -155,44 +149,33 @@ gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ st
   const int64_t v0 = static_cast<int64_t>(blockIdx.x) * vox_per_block;
   const int64_t v1 = min(v0 + vox_per_block, spatial);
   const int64_t off = (static_cast<int64_t>(n) * spatial) * C + cv * VN;
-  double d1[NH][VN], d2[NH][VN];
+  float d1[NH][VN], d2[NH][VN];   // fp32 over this thread's short voxel run; fp64 across threads below
 #pragma unroll
   for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
-    for (int i = 0; i < VN; ++i) d1[hh][i] = d2[hh][i] = 0.0;
-  int64_t v = v0 + vl;
-  while (v < v1) {
-    float s1[NH][VN], s2[NH][VN];
+    for (int i = 0; i < VN; ++i) d1[hh][i] = d2[hh][i] = 0.f;
+#pragma unroll 2
+  for (int64_t v = v0 + vl; v < v1; v += vstep) {
+    Vec<T> a, g;
+    a.load(x + off + v * C);
+    g.load(dy + off + v * C);
 #pragma unroll
-    for (int hh = 0; hh < NH; ++hh)
-#pragma unroll
-      for (int i = 0; i < VN; ++i) s1[hh][i] = s2[hh][i] = 0.f;
-    for (int it = 0; it < 32 && v < v1; ++it, v += vstep) {
-      Vec<T> a, g;
-      a.load(x + off + v * C);
-      g.load(dy + off + v * C);
+    for (int i = 0; i < VN; ++i) {
+      const float xh = (a.v[i] - mu[i]) * rs[i];
+      const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[0][i], be[0][i]) ? g.v[i] : 0.f;
+      d1[0][i] += gg;
+      d2[0][i] = fmaf(gg, xh, d2[0][i]);
+    }
+    if (DUAL) {
+      g.load(dy2 + off + v * C);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
         const float xh = (a.v[i] - mu[i]) * rs[i];
-        const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[0][i], be[0][i]) ? g.v[i] : 0.f;
-        s1[0][i] += gg;
-        s2[0][i] = fmaf(gg, xh, s2[0][i]);
-      }
-      if (DUAL) {
-        g.load(dy2 + off + v * C);
-#pragma unroll
-        for (int i = 0; i < VN; ++i) {
-          const float xh = (a.v[i] - mu[i]) * rs[i];
-          const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[NH - 1][i], be[NH - 1][i]) ? g.v[i] : 0.f;
-          s1[NH - 1][i] += gg;
-          s2[NH - 1][i] = fmaf(gg, xh, s2[NH - 1][i]);
-        }
+        const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[NH - 1][i], be[NH - 1][i]) ? g.v[i] : 0.f;
+        d1[NH - 1][i] += gg;
+        d2[NH - 1][i] = fmaf(gg, xh, d2[NH - 1][i]);
       }
     }
-#pragma unroll
-    for (int hh = 0; hh < NH; ++hh)
-#pragma unroll
-      for (int i = 0; i < VN; ++i) d1[hh][i] += s1[hh][i], d2[hh][i] += s2[hh][i];
   }
   __shared__ double sc[kMaxC][4];
   for (int i = threadIdx.x; i < C * 4; i += kThreads) (&sc[0][0])[i] = 0.0;
@@ -202,7 +185,7 @@ gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ st
   for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
-      double a = d1[hh][i], b = d2[hh][i];
+      double a = static_cast<double>(d1[hh][i]), b = static_cast<double>(d2[hh][i]);
       for (int o = 16; o >= vpv && o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
         b += __shfl_xor_sync(0xffffffffu, b, o);
@@ -273,6 +256,7 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
   const int64_t v0 = static_cast<int64_t>(blockIdx.x) * vox_per_block;
   const int64_t v1 = min(v0 + vox_per_block, spatial);
   const int64_t off = (static_cast<int64_t>(n) * spatial) * C + cv * VN;
+#pragma unroll 2
   for (int64_t v = v0 + vl; v < v1; v += vstep) {
     Vec<T> a, g, o;
     a.load(x + off + v * C);

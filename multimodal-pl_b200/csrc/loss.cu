@@ -43,8 +43,9 @@ __device__ __forceinline__ void softmax_regs(const float* __restrict__ logits, i
     p[c] = c < C ? expf(p[c] - mx) : 0.f;
     sum += p[c];
   }
+  const float inv = 1.0f / sum;
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c) p[c] = p[c] / sum;
+  for (int c = 0; c < MAXC; ++c) p[c] *= inv;
 }
 
 template <int MAXC>
@@ -55,8 +56,16 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
   __shared__ float s_lut[MAXC];
   __shared__ float s_part[kThreads / 32][4 * MAXC];
   __shared__ bool s_last;
+  __shared__ unsigned int s_ce_mask;   // classes whose BCE term is needed (weight != 0)
   if (threadIdx.x < MAXC) s_lut[threadIdx.x] = (lut && threadIdx.x < C) ? lut[threadIdx.x] : static_cast<float>(threadIdx.x);
+  if (threadIdx.x == 0) {
+    unsigned int m = 0;
+    for (int c = 0; c < C; ++c)
+      if (uce && cw[c] != 0.f) m |= 1u << c;
+    s_ce_mask = m;
+  }
   __syncthreads();
+  const unsigned int ce_mask = s_ce_mask;
   float aI[MAXC], aZ[MAXC], aY[MAXC], aE[MAXC];
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) aI[c] = aZ[c] = aY[c] = aE[c] = 0.f;
@@ -74,7 +83,7 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
         aI[c] += t ? p[c] : 0.f;
         aZ[c] = fmaf(p[c], p[c], aZ[c]);
         aY[c] += t ? 1.f : 0.f;
-        if (uce) {
+        if (ce_mask & (1u << c)) {
           // nn.BCELoss semantics: log() of the fp32 probability, clamped at -100
           const float l = t ? logf(p[c]) : logf(1.0f - p[c]);
           aE[c] -= fmaxf(l, -100.f);
@@ -154,7 +163,7 @@ partial_loss_bwd_kernel(const float* __restrict__ logits, const float* __restric
     for (int c = 0; c < MAXC; ++c) {
       const float t = (c == tc) ? 1.f : 0.f;
       float gc = t * s_a[c] + p[c] * s_b[c];
-      gc += s_e[c] * (p[c] - t) / fmaxf(p[c] * (1.0f - p[c]), 1e-12f);
+      if (s_e[c] != 0.f) gc += s_e[c] * (p[c] - t) / fmaxf(p[c] * (1.0f - p[c]), 1e-12f);   // warp-uniform branch
       g[c] = gc;
       dot = fmaf(gc, p[c], dot);
     }

@@ -12,7 +12,7 @@ template <typename T, int COUT>
 __global__ void __launch_bounds__(128)
 stem_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w_hat, T* __restrict__ y, int N, int D, int H,
                 int W) {
-  __shared__ float sw[27][COUT];
+  __shared__ __align__(16) float sw[27][COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i % 27][i / 27] = w_hat[i];  // w_hat is [COUT][27]
   __syncthreads();
   const int64_t total = static_cast<int64_t>(N) * D * H * W;
@@ -42,7 +42,13 @@ stem_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w_hat, 
             xv = base[(static_cast<int64_t>(zz) * H + y2) * W + x2];
           const int t = (kd * 3 + kh) * 3 + kw;
 #pragma unroll
-          for (int c = 0; c < COUT; ++c) acc[c] = fmaf(xv, sw[t][c], acc[c]);
+          for (int c = 0; c < COUT; c += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&sw[t][c]);   // warp-broadcast LDS.128
+            acc[c] = fmaf(xv, w4.x, acc[c]);
+            acc[c + 1] = fmaf(xv, w4.y, acc[c + 1]);
+            acc[c + 2] = fmaf(xv, w4.z, acc[c + 2]);
+            acc[c + 3] = fmaf(xv, w4.w, acc[c + 3]);
+          }
         }
       }
     }
@@ -59,53 +65,89 @@ stem_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w_hat, 
 }
 
 // ------------------------------------------------------------------------------------------------ stem wgrad
-// block = (256/COUT) voxel lanes x COUT channels; each thread keeps 27 accumulators for its channel.
+// dW[t][co] = sum_v x[v + t - 1] * dy[v][co].  The image is first copied into a zero-padded buffer so the 27 window
+// loads need no bounds checks; block = 16 voxel lanes x (COUT/2) channel pairs, each thread keeps 27 x 2 accumulators.
+__global__ void __launch_bounds__(256)
+pad_image_kernel(const float* __restrict__ img, float* __restrict__ pad, int N, int D, int H, int W) {
+  const int64_t total = static_cast<int64_t>(N) * (D + 2) * (H + 2) * (W + 2);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % (W + 2)) - 1;
+    int64_t r = i / (W + 2);
+    const int y = static_cast<int>(r % (H + 2)) - 1;
+    r /= (H + 2);
+    const int z = static_cast<int>(r % (D + 2)) - 1;
+    const int n = static_cast<int>(r / (D + 2));
+    float v = 0.f;
+    if (x >= 0 && x < W && y >= 0 && y < H && z >= 0 && z < D)
+      v = img[((static_cast<int64_t>(n) * D + z) * H + y) * W + x];
+    pad[i] = v;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void load2(const T* p, float& a, float& b);
+template <>
+__device__ __forceinline__ void load2<float>(const float* p, float& a, float& b) {
+  const float2 t = *reinterpret_cast<const float2*>(p);
+  a = t.x, b = t.y;
+}
+template <>
+__device__ __forceinline__ void load2<__nv_bfloat16>(const __nv_bfloat16* p, float& a, float& b) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  a = __uint_as_float(u << 16), b = __uint_as_float(u & 0xFFFF0000u);
+}
+
 template <typename T, int COUT>
 __global__ void __launch_bounds__(256)
-stem_wgrad_kernel(const float* __restrict__ img, const T* __restrict__ dy, float* __restrict__ dw_tapmajor, int N, int D,
+stem_wgrad_kernel(const float* __restrict__ pad, const T* __restrict__ dy, float* __restrict__ dw_tapmajor, int N, int D,
                   int H, int W) {
-  constexpr int LANES = 256 / COUT;
-  const int co = threadIdx.x % COUT, vl = threadIdx.x / COUT;
-  float acc[27];
+  constexpr int CP = COUT / 2;       // channel pairs
+  constexpr int LANES = 256 / CP;    // voxel lanes per block
+  const int cp = threadIdx.x % CP, vl = threadIdx.x / CP;
+  float acc[27][2];
 #pragma unroll
-  for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+  for (int t = 0; t < 27; ++t) acc[t][0] = acc[t][1] = 0.f;
   const int64_t total = static_cast<int64_t>(N) * D * H * W;
+  const int64_t prow = W + 2, pplane = static_cast<int64_t>(H + 2) * (W + 2);
   for (int64_t v = blockIdx.x * static_cast<int64_t>(LANES) + vl; v < total;
        v += static_cast<int64_t>(gridDim.x) * LANES) {
     const int x = static_cast<int>(v % W);
     int64_t r = v / W;
-    const int yy = static_cast<int>(r % H);
+    const int y = static_cast<int>(r % H);
     r /= H;
     const int z = static_cast<int>(r % D);
     const int n = static_cast<int>(r / D);
-    const float g = to_f32<T>(dy[v * COUT + co]);
-    const float* base = img + static_cast<int64_t>(n) * D * H * W;
+    float g0, g1;
+    load2<T>(dy + v * COUT + 2 * cp, g0, g1);
+    const float* win = pad + (static_cast<int64_t>(n) * (D + 2) + z) * pplane + y * prow + x;  // window origin
 #pragma unroll
-    for (int kd = 0; kd < 3; ++kd) {
-      const int zz = z + kd - 1;
+    for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        const int y2 = yy + kh - 1;
+        const float* row = win + kd * pplane + kh * prow;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const int x2 = x + kw - 1;
-          float xv = 0.f;
-          if (zz >= 0 && zz < D && y2 >= 0 && y2 < H && x2 >= 0 && x2 < W)
-            xv = base[(static_cast<int64_t>(zz) * H + y2) * W + x2];
-          acc[(kd * 3 + kh) * 3 + kw] = fmaf(xv, g, acc[(kd * 3 + kh) * 3 + kw]);
+          const float xv = row[kw];
+          acc[(kd * 3 + kh) * 3 + kw][0] = fmaf(xv, g0, acc[(kd * 3 + kh) * 3 + kw][0]);
+          acc[(kd * 3 + kh) * 3 + kw][1] = fmaf(xv, g1, acc[(kd * 3 + kh) * 3 + kw][1]);
         }
       }
-    }
   }
-  __shared__ float red[LANES][27][COUT + 1];
+  // reduce the voxel lanes through shared memory, nine taps at a time (keeps static shared memory under 48 KB)
+  __shared__ float red[LANES][9][COUT + 1];
 #pragma unroll
-  for (int t = 0; t < 27; ++t) red[vl][t][co] = acc[t];
-  __syncthreads();
-  for (int i = threadIdx.x; i < 27 * COUT; i += 256) {
-    const int t = i / COUT, c = i % COUT;
-    float s = 0.f;
-    for (int l = 0; l < LANES; ++l) s += red[l][t][c];
-    atomicAdd(&dw_tapmajor[t * COUT + c], s);
+  for (int t0 = 0; t0 < 27; t0 += 9) {
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 9; ++t) red[vl][t][2 * cp] = acc[t0 + t][0], red[vl][t][2 * cp + 1] = acc[t0 + t][1];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * COUT; i += 256) {
+      const int t = i / COUT, c = i % COUT;
+      float s = 0.f;
+      for (int l = 0; l < LANES; ++l) s += red[l][t][c];
+      atomicAdd(&dw_tapmajor[(t0 + t) * COUT + c], s);
+    }
   }
 }
 
@@ -114,9 +156,9 @@ template <typename T, int CIN>
 __global__ void __launch_bounds__(256)
 cls_fwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const float* __restrict__ bias,
                float* __restrict__ logits, int N, int64_t S, int classes) {
-  __shared__ float sw[16][CIN];
+  __shared__ __align__(16) float sw[CIN][16];   // transposed: [input channel][class]
   __shared__ float sb[16];
-  for (int i = threadIdx.x; i < 16 * CIN; i += blockDim.x) sw[i / CIN][i % CIN] = (i / CIN) < classes ? wc[i] : 0.f;
+  for (int i = threadIdx.x; i < 16 * CIN; i += blockDim.x) sw[i % CIN][i / CIN] = (i / CIN) < classes ? wc[i] : 0.f;
   if (threadIdx.x < 16) sb[threadIdx.x] = threadIdx.x < classes ? bias[threadIdx.x] : 0.f;
   __syncthreads();
   constexpr int VN = Vec<T>::N;
@@ -135,7 +177,13 @@ cls_fwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
 #pragma unroll
     for (int k = 0; k < VN; ++k)
 #pragma unroll
-      for (int c = 0; c < 16; ++c) acc[c] = fmaf(x.v[k], sw[c][k0 + k], acc[c]);
+      for (int c = 0; c < 16; c += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&sw[k0 + k][c]);
+        acc[c] = fmaf(x.v[k], w4.x, acc[c]);
+        acc[c + 1] = fmaf(x.v[k], w4.y, acc[c + 1]);
+        acc[c + 2] = fmaf(x.v[k], w4.z, acc[c + 2]);
+        acc[c + 3] = fmaf(x.v[k], w4.w, acc[c + 3]);
+      }
   }
 #pragma unroll
   for (int c = 0; c < 16; ++c)
@@ -153,8 +201,9 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
   constexpr int KB = CIN / 4;           // k-blocks of 4
   constexpr int SLOTS = 4 * KB;         // (c-block, k-block) pairs
   constexpr int REP = SLOTS / 32;       // pairs per lane (1 for CIN=32, 2 for CIN=64)
-  __shared__ float sw[16][CIN];
-  __shared__ __align__(16) float s_dl[TV][16];
+  constexpr int DLP = TV + 1;            // odd pitch: conflict-free both for the staging stores and the phase-2 reads
+  __shared__ __align__(16) float sw[16][CIN];
+  __shared__ float s_dl[16 * DLP];
   __shared__ __align__(16) float s_a[TV][CIN];
   for (int i = threadIdx.x; i < 16 * CIN; i += 256) sw[i / CIN][i % CIN] = (i / CIN) < classes ? wc[i] : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,7 +230,7 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
         const int64_t n = v / S, s = v - n * S;
         val = dl[(n * classes + c) * S + s];
       }
-      s_dl[j][c] = val;
+      s_dl[c * DLP + j] = val;
     }
     for (int i = threadIdx.x; i < TV * (CIN / VN); i += 256) {
       const int j = i / (CIN / VN), k0 = (i % (CIN / VN)) * VN;
@@ -204,17 +253,22 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
       if (v < total) {
         float g[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) g[c] = s_dl[j][c];
+        for (int c = 0; c < 16; ++c) g[c] = s_dl[c * DLP + j];
 #pragma unroll
         for (int k0 = half * (CIN / 2); k0 < (half + 1) * (CIN / 2); k0 += VN) {
           Vec<T> o;
 #pragma unroll
-          for (int k = 0; k < VN; ++k) {
-            float s = 0.f;
+          for (int k = 0; k < VN; ++k) o.v[k] = 0.f;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) s = fmaf(g[c], sw[c][k0 + k], s);
-            o.v[k] = s;
-          }
+          for (int c = 0; c < 16; ++c)
+#pragma unroll
+            for (int k = 0; k < VN; k += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(&sw[c][k0 + k]);
+              o.v[k] = fmaf(g[c], w4.x, o.v[k]);
+              o.v[k + 1] = fmaf(g[c], w4.y, o.v[k + 1]);
+              o.v[k + 2] = fmaf(g[c], w4.z, o.v[k + 2]);
+              o.v[k + 3] = fmaf(g[c], w4.w, o.v[k + 3]);
+            }
           o.store(da + v * CIN + k0);
         }
       }
@@ -224,9 +278,10 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
     for (int r = 0; r < REP; ++r) {
       const int slot = lane + 32 * r, cb = slot / KB, kb = slot % KB;
       for (int j = warp; j < TV; j += 8) {
-        const float4 g = *reinterpret_cast<const float4*>(&s_dl[j][cb * 4]);
         const float4 x = *reinterpret_cast<const float4*>(&s_a[j][kb * 4]);
-        const float gg[4] = {g.x, g.y, g.z, g.w}, xx[4] = {x.x, x.y, x.z, x.w};
+        const float gg[4] = {s_dl[(cb * 4 + 0) * DLP + j], s_dl[(cb * 4 + 1) * DLP + j], s_dl[(cb * 4 + 2) * DLP + j],
+                             s_dl[(cb * 4 + 3) * DLP + j]};
+        const float xx[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -241,7 +296,7 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
   // cross-warp reduction through shared memory (reuse the staging tiles), then one atomic per (c,k) per block
   __syncthreads();
   float* red = &s_a[0][0];    // 8 warps x 16 classes x CIN floats == TV*CIN
-  float* redb = &s_dl[0][0];  // 8 warps x 16 classes
+  float* redb = &s_dl[0];     // 8 warps x 16 classes
   for (int r = 0; r < REP; ++r) {
     const int slot = lane + 32 * r, cb = slot / KB, kb = slot % KB;
 #pragma unroll
@@ -289,17 +344,29 @@ extern "C" int mmpl_stem_conv_fwd(const float* image, const float* w_hat, void* 
   return MMPL_OK;
 }
 
+extern "C" size_t mmpl_stem_conv_wgrad_workspace(int n, int d, int h, int w) {
+  return sizeof(float) * static_cast<size_t>(n) * (d + 2) * (h + 2) * (w + 2);
+}
+
 extern "C" int mmpl_stem_conv_wgrad(const float* image, const void* dy, float* dw_tapmajor, int n, int d, int h, int w,
-                                    int cout, int dtype, mmpl_stream_t stream) {
+                                    int cout, int dtype, void* workspace, size_t workspace_bytes,
+                                    mmpl_stream_t stream) {
   MMPL_REQUIRE(cout == 32 || cout == 64, MMPL_E_SHAPE, "stem: cout=%d (32 or 64)", cout);
+  MMPL_REQUIRE(workspace != nullptr && workspace_bytes >= mmpl_stem_conv_wgrad_workspace(n, d, h, w), MMPL_E_SHAPE,
+               "stem_conv_wgrad: workspace of %zu bytes required", mmpl_stem_conv_wgrad_workspace(n, d, h, w));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* pad = static_cast<float*>(workspace);
+  const int64_t ptotal = static_cast<int64_t>(n) * (d + 2) * (h + 2) * (w + 2);
+  pad_image_kernel<<<static_cast<int>(std::min<int64_t>((ptotal + 255) / 256, static_cast<int64_t>(num_sms()) * 8)), 256, 0, s>>>(
+      image, pad, n, d, h, w);
+  MMPL_CHECK_LAUNCH("pad_image");
   MMPL_CUDA(cudaMemsetAsync(dw_tapmajor, 0, sizeof(float) * 27 * cout, s));
-  const int blocks = num_sms() * 4;
+  const int blocks = num_sms() * 2;
   MMPL_DISPATCH_DTYPE(dtype, T, {
     if (cout == 32)
-      stem_wgrad_kernel<T, 32><<<blocks, 256, 0, s>>>(image, static_cast<const T*>(dy), dw_tapmajor, n, d, h, w);
+      stem_wgrad_kernel<T, 32><<<blocks, 256, 0, s>>>(pad, static_cast<const T*>(dy), dw_tapmajor, n, d, h, w);
     else
-      stem_wgrad_kernel<T, 64><<<blocks, 256, 0, s>>>(image, static_cast<const T*>(dy), dw_tapmajor, n, d, h, w);
+      stem_wgrad_kernel<T, 64><<<blocks, 256, 0, s>>>(pad, static_cast<const T*>(dy), dw_tapmajor, n, d, h, w);
   });
   MMPL_CHECK_LAUNCH("stem_conv_wgrad");
   return MMPL_OK;

@@ -13,14 +13,28 @@ from torch import nn
 from .. import ops
 
 
+_weight_cache = {}
+
+
 def _class_weight(mask, n_classes, device):
-    """``mask[0]`` of the reference (loss_partial.py:87,92): the first sample's class-weight vector."""
+    """``mask[0]`` of the reference (loss_partial.py:87,92): the first sample's class-weight vector, as a device
+    tensor.  Host vectors are uploaded once per distinct value (a pageable H2D copy per step would serialise the host
+    with the GPU stream)."""
     if mask is None:
-        return torch.ones(n_classes, dtype=torch.float32, device=device)
+        key = ("ones", n_classes, str(device))
+        if key not in _weight_cache:
+            _weight_cache[key] = torch.ones(n_classes, dtype=torch.float32, device=device)
+        return _weight_cache[key]
     w = mask[0]
-    if not torch.is_tensor(w):
-        w = torch.tensor(list(w), dtype=torch.float32)
-    return w.to(device=device, dtype=torch.float32)
+    if torch.is_tensor(w) and w.device == torch.device(device) and w.dtype == torch.float32:
+        return w
+    vals = tuple(float(v) for v in (w.tolist() if torch.is_tensor(w) else w))
+    key = (vals, str(device))
+    if key not in _weight_cache:
+        if len(_weight_cache) > 4096:
+            _weight_cache.clear()
+        _weight_cache[key] = torch.tensor(vals, dtype=torch.float32, device=device)
+    return _weight_cache[key]
 
 
 class DiceLoss(nn.Module):

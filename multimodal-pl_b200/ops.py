@@ -251,8 +251,10 @@ class StemConvFn(torch.autograd.Function):
         dy = to_cl(dy)
         st = _lib.stream_ptr()
         g_hat = torch.empty(27 * cout, dtype=torch.float32, device=img.device)
-        _lib.check(L.mmpl_stem_conv_wgrad(_p(img), _p(dy), _p(g_hat), n, d, h, w, cout, _lib.dtype_code(dy.dtype), st),
-                   "stem_conv_wgrad")
+        wsb = int(L.mmpl_stem_conv_wgrad_workspace(n, d, h, w))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=img.device)
+        _lib.check(L.mmpl_stem_conv_wgrad(_p(img), _p(dy), _p(g_hat), n, d, h, w, cout, _lib.dtype_code(dy.dtype),
+                                          _p(ws), wsb, st), "stem_conv_wgrad")
         dw = torch.empty_like(w_hat)
         _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, 1, 27, standardise, _p(dw), st),
                    "ws_weight_bwd")
