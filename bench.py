@@ -151,7 +151,7 @@ def run_ours(args):
 
     import multimodal_pl_b200 as mm
     from multimodal_pl_b200 import _lib, ops
-    from multimodal_pl_b200.engine import DataParallelModel, FusedSGD
+    from multimodal_pl_b200.engine import DataParallelModel, FusedSGD, GraphedTrainStep
     from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
     from multimodal_pl_b200.supervise_mask import cmask_lut
     from multimodal_pl_b200.unet3D import unet3D_baseline
@@ -192,10 +192,13 @@ def run_ours(args):
     lut = cmask_lut(w16).to(dev)
     image_d, label_d = image_h.to(dev), label_h.to(dev)
 
-    def step(img, lab):
+    def loss_fn(logits, lab):
+        return crit(logits, lab.squeeze(1), mask=wt, soft_max=True, lut=lut)
+
+    def eager_step(img, lab):
         opt.zero_grad()
         logits, _, _ = dp(img, lab)
-        loss = crit(logits, lab.squeeze(1), mask=wt, soft_max=True, lut=lut)
+        loss = loss_fn(logits, lab)
         loss.backward()
         opt.step(grad_scale=1.0 / world)
         return loss
@@ -205,12 +208,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 1)):
+    use_graph = not args.eager
+    if use_graph:
+        # the public API for a launch-overhead-free step: capture once, replay per batch (engine.GraphedTrainStep)
+        step = GraphedTrainStep(dp, loss_fn, opt, image_d, label_d, warmup=max(args.warmup, 3))
+    else:
+        step = eager_step
+    for _ in range(max(args.warmup, 3)):
         step(image_d, label_d)
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------------------------
-    conv_prof = ops.enable_conv_profile(True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -225,8 +233,6 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    prof = ops.collect_conv_profile()
-    ops.enable_conv_profile(False)
 
     # ---- timed region 2: end to end through the public API with host buffers -------------------------------------
     barrier()
@@ -234,17 +240,35 @@ def run_ours(args):
     f0.record()
     last = 0.0
     for _ in range(args.steps):
-        img = image_h.to(dev, non_blocking=True)
-        lab = label_h.to(dev, non_blocking=True)
-        last = step(img, lab).item()
+        if use_graph:
+            last = step(image_h, label_h).item()        # pinned host -> static device buffers -> replay -> loss D2H
+        else:
+            img = image_h.to(dev, non_blocking=True)
+            lab = label_h.to(dev, non_blocking=True)
+            last = step(img, lab).item()
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
+    # ---- roofline region: the same step run eagerly with every tcgen05 conv launch bracketed by CUDA events on the
+    # launching stream (a graph replay cannot be bracketed per kernel); identical kernels, shapes and data
+    dp.sync_in_backward = True
+    ops.enable_conv_profile(True)
+    launches_eager0 = _lib.launch_count()
+    for _ in range(3):
+        # let the host run ahead of the device (about 30 ms of spin on the stream) so the bracketed launches execute
+        # back to back and an event pair measures the kernel, not the Python launch latency in front of it
+        torch.cuda._sleep(int(0.030 * 1.9e9))
+        eager_step(image_d, label_d)
+    launches_per_step = (_lib.launch_count() - launches_eager0) // 3
+    prof = ops.collect_conv_profile()
+    prof_steps = 3
+    ops.enable_conv_profile(False)
+    if use_graph:
+        launches = launches_per_step * args.steps      # kernels executed by the replayed graphs in the timed region
+    barrier()
+
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -261,13 +285,22 @@ def run_ours(args):
     # timed inside a multi-second step loop under the power cap -> sustained bf16 peak; else the recipe's fallback
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md, sustained)"
-    tc_ms = prof["ms"]
-    tc_flops = prof["flops"]          # algorithmic 2*M*N*K of every tcgen05 conv launch inside the timed region
-    achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel / wgrad_tc_kernel (all tcgen05 conv launches: fprop+dgrad+wgrad)",
+    # dominant kernel = the tcgen05 conv instantiation with the largest total time in the timed region
+    # (cfg2: conv_tc_kernel<32,32,4> on the full-resolution 32->32 3x3x3 layers, fprop + dgrad launches)
+    dom = prof["dominant"]
+    dom_ms, dom_flops, dom_n = dom["ms"], dom["flops"], max(dom["launches"], 1)
+    ms_prof_step = ms / args.steps
+    achieved = dom_flops / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else 0.0
+    tc_ms, tc_flops = prof["ms"], prof["flops"]
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv) " + str(dom["key"]),
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": None, "peak_source": peak_src, "launches": prof["launches"],
-                "kernel_ms_per_step": tc_ms / args.steps, "share_of_step": tc_ms / ms,
+                "traffic": None, "peak_source": peak_src, "launches": dom["launches"],
+                "flops_per_launch": dom_flops / dom_n, "avg_launch_ms": dom_ms / dom_n,
+                "share_of_step": (dom_ms / prof_steps) / ms_prof_step,
+                "measured": f"{prof_steps} eager steps right after the timed region (host queued ahead of the device), one CUDA-event pair per launch",
+                "all_tcgen05_convs": {"achieved": tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0,
+                                      "launches": prof["launches"], "ms_per_step": tc_ms / prof_steps,
+                                      "share_of_step": (tc_ms / prof_steps) / ms_prof_step},
                 "whole_step_conv_tflops": TRAIN_TFLOP_PER_PATCH[args.workload] * value}
     cpu = None
     if not args.no_cpu_baseline:
@@ -287,7 +320,8 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "patch": list(dhw), "batch_per_gpu": batch, "base": base, "classes": classes,
                    "parallelism": f"dp{world}", "l2": "inputs+activations per step >> 126 MB L2, no flush needed",
-                   "optimizer": "fused SGD momentum 0.9 wd 1e-4", "loss": "EDiceLoss_partial (fused)"},
+                   "optimizer": "fused SGD momentum 0.9 wd 1e-4", "loss": "EDiceLoss_partial (fused)",
+                   "launch": "cuda graph replay (engine.GraphedTrainStep)" if use_graph else "eager"},
         "clocks": clocks,
         "e2e": {"value": patches / (ms_e2e / 1e3), "unit": "patches/s",
                 "h2d_bytes_per_step": image_h.numel() * 4 + label_h.numel() * 4, "d2h_bytes_per_step": 4,
@@ -309,6 +343,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="drive every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -21,6 +21,8 @@
 //  * Warp roles: 0 = activation TMA producer, 1 = weight TMA producer, 2 = MMA issuer (warp-uniform loop, one elected
 //    lane issues) and TMEM allocator, 3..6 = epilogue (tcgen05.ld -> +residual -> bf16 -> 16-byte global stores).
 //  * WRES: for 32->32 layers all 27 weight tiles (55 KB) stay resident in shared memory for the life of the CTA.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -51,7 +53,7 @@ struct Geo {
   static constexpr bool PARITY_CHUNKS = (MODE == MODE_S2F);
 };
 
-template <int KC, int NT, int TD, int MODE, bool WRES>
+template <int KC, int NT, int TD, int MODE, bool WRES, int NA_>
 struct TcCfg {
   using G = Geo<MODE>;
   static constexpr int RB = KC * 2;
@@ -59,7 +61,7 @@ struct TcCfg {
   static constexpr int PD = TD + G::EXTRA;
   static constexpr int A_BYTES = PD * G::PH * G::PW * RB;
   static constexpr int A_STAGE = (A_BYTES + 1023) / 1024 * 1024;
-  static constexpr int NA = 2;
+  static constexpr int NA = NA_;
   static constexpr int B_BYTES = NT * RB;
   static constexpr int SMEM_LIMIT = 227 * 1024 - 2048;
   static constexpr int NB_FIT = (SMEM_LIMIT - NA * A_STAGE) / B_BYTES;
@@ -91,10 +93,10 @@ struct TcParams {
 __device__ __forceinline__ int axis_ntaps(int par) { return par ? 2 : 1; }
 __device__ __forceinline__ int axis_tap(int par, int i) { return par ? 2 * i : 1; }
 
-template <int KC, int NT, int TD, int MODE, bool WRES>
+template <int KC, int NT, int TD, int MODE, bool WRES, int NA_>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  using Cfg = TcCfg<KC, NT, TD, MODE, WRES>;
+  using Cfg = TcCfg<KC, NT, TD, MODE, WRES, NA_>;
   using G = Geo<MODE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -202,8 +204,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================== MMA issuer: warp-uniform control flow, one lane issues
     const uint32_t idesc = make_idesc_bf16(128, NT, 0, 0);
     const uint32_t a_base = smem_u32(a_stage), b_base = smem_u32(b_stage);
-    const uint64_t a_hi = make_smem_desc(0, 16, G::PW * Cfg::RB, Cfg::SWZ, 0);
-    const uint64_t b_hi = make_smem_desc(0, 16, 8 * Cfg::RB, Cfg::SWZ, 0);
+    const uint64_t a_fix = make_smem_desc(0, 16, G::PW * Cfg::RB, Cfg::SWZ, 0);
+    const uint64_t b_fix = make_smem_desc(0, 16, 8 * Cfg::RB, Cfg::SWZ, 0);
+    const uint32_t a_hi = static_cast<uint32_t>(a_fix >> 32), a_lo_fix = static_cast<uint32_t>(a_fix);
+    const uint32_t b_hi = static_cast<uint32_t>(b_fix >> 32), b_lo_fix = static_cast<uint32_t>(b_fix);
     uint32_t ita = 0, itb = 0, iti = 0;
     if (WRES) {
       for (int tap = 0; tap < 27; ++tap) mbar_wait(&b_full[tap], 0);
@@ -245,16 +249,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&b_full[sb], (itb / Cfg::NB) & 1);
                 tc_fence_after();
               }
-              const uint32_t b_addr = b_base + sb * Cfg::B_BYTES;
-              const uint32_t a_tap = a_addr + ((sd * G::PH + sh) * G::PW + sw) * Cfg::RB;
+              // start-address fields (>>4) of this tap; every MMA below adds a compile-time constant
+              const uint32_t b_lo = b_lo_fix | ((b_base + sb * Cfg::B_BYTES) >> 4);
+              const uint32_t a_lo = a_lo_fix | ((a_addr + ((sd * G::PH + sh) * G::PW + sw) * Cfg::RB) >> 4);
               if (elect_one()) {
 #pragma unroll
                 for (int pl = 0; pl < TD; ++pl) {
 #pragma unroll
                   for (int ks = 0; ks < KC / 16; ++ks) {
-                    const uint64_t ad = a_hi | static_cast<uint64_t>((a_tap + pl * (G::PH * G::PW * Cfg::RB) + ks * 32) >> 4);
-                    const uint64_t bd = b_hi | static_cast<uint64_t>((b_addr + ks * 32) >> 4);
-                    umma_f16(d_tmem + pl * NT, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+                    umma_f16_lohi(d_tmem + pl * NT, a_lo + ((pl * (G::PH * G::PW * Cfg::RB) + ks * 32) >> 4), a_hi,
+                                  b_lo + ((ks * 32) >> 4), b_hi, idesc, (first && ks == 0) ? 0u : 1u);
                   }
                 }
                 if (!WRES) umma_commit(&b_empty[sb]);
@@ -392,9 +396,9 @@ struct TcProblem {
   int kred, nout;
 };
 
-template <int KC, int NT, int TD, int MODE, bool WRES>
+template <int KC, int NT, int TD, int MODE, bool WRES, int NA_ = 2>
 int launch_tc(const TcProblem& q, cudaStream_t s) {
-  using Cfg = TcCfg<KC, NT, TD, MODE, WRES>;
+  using Cfg = TcCfg<KC, NT, TD, MODE, WRES, NA_>;
   using G = Geo<MODE>;
   CUtensorMap tmA, tmB;
   if (int e = make_act_map(&tmA, q.a, q.aN, q.aD, q.aH, q.aW, q.kred, KC, Cfg::PD, G::PH, G::PW, MODE == MODE_S2K1F ? 2 : 1)) return e;
@@ -415,12 +419,12 @@ int launch_tc(const TcProblem& q, cudaStream_t s) {
   p.total_items = static_cast<int>(items);
   static bool attr_set = false;
   if (!attr_set) {
-    MMPL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, NT, TD, MODE, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MMPL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, NT, TD, MODE, WRES, NA_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int grid = static_cast<int>(std::min<int64_t>(items, num_sms()));
-  conv_tc_kernel<KC, NT, TD, MODE, WRES><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  conv_tc_kernel<KC, NT, TD, MODE, WRES, NA_><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
   MMPL_CHECK_LAUNCH("conv_tc");
   return MMPL_OK;
 }
@@ -442,6 +446,16 @@ int dispatch_tc(const TcProblem& q, cudaStream_t s) {
     }
     if (nt == 64) return launch_tc<32, 64, 4, MODE, false>(q, s);
     MMPL_FAIL(MMPL_E_UNSUPPORTED, "conv_tc: 32 reduction channels with %d output channels", nout);
+  }
+  // Default for the streamed-weight 64-channel configs: ONE activation stage, more planes per item and a deeper weight
+  // ring (the weight tiles, one TMA round trip per tap, are the latency-critical stream).  MMPL_TC_DEEPB=0 selects
+  // the double-buffered-activation variant instead.
+  static const bool deep_b = [] { const char* e = getenv("MMPL_TC_DEEPB"); return !(e && e[0] == '0'); }();
+  if (deep_b && MODE == MODE_S1K3) {
+    if (nt == 32) return launch_tc<64, 32, 4, MODE, false, 1>(q, s);
+    if (nt == 64) return launch_tc<64, 64, 4, MODE, false, 1>(q, s);
+    if (nt == 128) return launch_tc<64, 128, 2, MODE, false, 1>(q, s);
+    return launch_tc<64, 256, 1, MODE, false, 1>(q, s);
   }
   if (nt == 32) return launch_tc<64, 32, 2, MODE, false>(q, s);
   if (nt == 64) return launch_tc<64, 64, 2, MODE, false>(q, s);

@@ -132,8 +132,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // MMA issuer: warp-uniform loop, one elected lane issues
     const uint32_t idesc = make_idesc_bf16(128, NCO, 1, 1);
     const uint32_t xb0 = smem_u32(x_stage), yb0 = smem_u32(y_stage);
-    const uint64_t a_hi = make_smem_desc(0, Cfg::RBX, Cfg::PW * Cfg::RBX, Cfg::SWX, 0);
-    const uint64_t b_hi = make_smem_desc(0, 64 * Cfg::RBY, WG_TW * Cfg::RBY, Cfg::SWY, 0);
+    const uint64_t a_fix = make_smem_desc(0, Cfg::RBX, Cfg::PW * Cfg::RBX, Cfg::SWX, 0);
+    const uint64_t b_fix = make_smem_desc(0, 64 * Cfg::RBY, WG_TW * Cfg::RBY, Cfg::SWY, 0);
+    const uint32_t a_hi = static_cast<uint32_t>(a_fix >> 32), a_lo_fix = static_cast<uint32_t>(a_fix);
+    const uint32_t b_hi = static_cast<uint32_t>(b_fix >> 32), b_lo_fix = static_cast<uint32_t>(b_fix);
     uint32_t it = 0;
     for (int b = split; b < p.total_blocks; b += p.ksplit, ++it) {
       const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1;
@@ -144,14 +146,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int g = 0; g < ng; ++g) {
           const uint32_t acc = tmem_base + g * NCO;
           const uint32_t xg = xs + p.groups[var][g].xblk * Cfg::XBLK_STRIDE + p.groups[var][g].row_shift * Cfg::RBX;
-#pragma unroll 1
+          const uint32_t a_lo = a_lo_fix | (xg >> 4), b_lo = b_lo_fix | (ys >> 4);
+#pragma unroll
           for (int pl = 0; pl < TD; ++pl) {
 #pragma unroll
             for (int hl = 0; hl < WG_TH; hl += 2) {
-              const uint32_t xa = xg + ((pl * Cfg::PH + hl) * Cfg::PW) * Cfg::RBX;
-              const uint32_t ya = ys + ((pl * WG_TH + hl) * WG_TW) * Cfg::RBY;
-              umma_f16(acc, a_hi | static_cast<uint64_t>(xa >> 4), b_hi | static_cast<uint64_t>(ya >> 4), idesc,
-                       (it | pl | hl) != 0 ? 1u : 0u);
+              umma_f16_lohi(acc, a_lo + ((((pl * Cfg::PH + hl) * Cfg::PW) * Cfg::RBX) >> 4), a_hi,
+                            b_lo + ((((pl * WG_TH + hl) * WG_TW) * Cfg::RBY) >> 4), b_hi, idesc,
+                            (it | pl | hl) != 0 ? 1u : 0u);
             }
           }
         }

@@ -65,6 +65,7 @@ class DataParallelModel(torch.nn.Module):
             self._buckets.append(cur)
         self._handles = []
         self._callback_queued = False
+        self.sync_in_backward = True      # False: the caller reduces flat_grad itself (CUDA-graph replay path)
         if world_size > 1:
             for p in params:
                 p.register_post_accumulate_grad_hook(self._on_grad)
@@ -76,7 +77,16 @@ class DataParallelModel(torch.nn.Module):
         self._handles = []
         self._callback_queued = False
 
+    def all_reduce_flat(self):
+        """One blocking all-reduce of the whole flat gradient buffer (used after a CUDA-graph replay)."""
+        if self.world_size > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+            if self.average:
+                self.flat_grad.mul_(1.0 / self.world_size)
+
     def _on_grad(self, p):
+        if not self.sync_in_backward:
+            return
         if not self._callback_queued:
             torch.autograd.Variable._execution_engine.queue_callback(self._finish)
             self._callback_queued = True
@@ -138,18 +148,82 @@ class FusedSGD(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = False):
         self.flat_grad.zero_()
 
-    @torch.no_grad()
-    def step(self, closure=None, grad_scale: float = 1.0):
+    def _sync_lr(self):
+        """Mirror param_groups[0]['lr'] into the device scalar the kernel reads (outside any graph capture)."""
         g = self.param_groups[0]
         if self._lr_host != g["lr"]:
             self._lr_dev.fill_(float(g["lr"]))
             self._lr_host = g["lr"]
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        g = self.param_groups[0]
+        if not torch.cuda.is_current_stream_capturing():
+            self._sync_lr()
         _lib.require_device()
         _lib.check(_lib.lib().mmpl_sgd_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(),
                                             self.momentum_buf.data_ptr(), self.flat_param.numel(),
                                             self._lr_dev.data_ptr(), float(g["momentum"]), float(g["weight_decay"]),
                                             float(grad_scale), int(self._steps == 0), _lib.stream_ptr()), "sgd_step")
         self._steps += 1
+
+
+class GraphedTrainStep:
+    """One train step (zero_grad -> forward -> loss -> backward [-> fused SGD]) captured ONCE into a CUDA graph and
+    replayed per batch: ~500 kernel launches per step cost one graph launch on the host, so the GPU never waits for
+    Python.  The reference drives every op from the Python loop (train_amos_atlas_final.py:258-378).
+
+    ``loss_fn(logits, labels) -> scalar``.  With world_size > 1 the graph ends after backward; the flat gradient is
+    all-reduced with one NCCL call after the replay and the SGD step follows (3 launches outside the graph).
+    The constructor runs ``warmup`` real optimisation steps on the example batch (CUDA-graph capture needs warmed-up
+    allocators and lazily initialised kernels); inputs are copied into static buffers before each replay."""
+
+    def __init__(self, dp_model: "DataParallelModel", loss_fn, optimizer: "FusedSGD", image, label, warmup: int = 3):
+        self.dp, self.loss_fn, self.opt = dp_model, loss_fn, optimizer
+        self.world = dp_model.world_size
+        self.static_image = image.clone()
+        self.static_label = label.clone()
+        prev = dp_model.sync_in_backward
+        dp_model.sync_in_backward = False
+        self.opt._sync_lr()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                self._body(in_graph=False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        try:   # gradients are views of a flat buffer created on the default stream: the mismatch is intentional
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._body(in_graph=True)
+        self._prev_sync = prev
+
+    def _body(self, in_graph: bool):
+        self.opt.zero_grad()
+        logits = self.dp(self.static_image, self.static_label)
+        logits = logits[0] if isinstance(logits, (tuple, list)) else logits
+        loss = self.loss_fn(logits, self.static_label)
+        loss.backward()
+        if self.world == 1:
+            self.opt.step()
+        elif not in_graph:
+            self.dp.all_reduce_flat()
+            self.opt.step(grad_scale=1.0 if self.dp.average else 1.0 / self.world)
+        return loss
+
+    def __call__(self, image, label):
+        self.static_image.copy_(image, non_blocking=True)
+        self.static_label.copy_(label, non_blocking=True)
+        self.opt._sync_lr()
+        self.graph.replay()
+        if self.world > 1:
+            self.dp.all_reduce_flat()
+            self.opt.step(grad_scale=1.0 if self.dp.average else 1.0 / self.world)
+        return self.static_loss
 
 
 def extant_file(x):

@@ -43,17 +43,31 @@ def enable_conv_profile(on: bool):
 
 
 def collect_conv_profile():
+    """Totals over every tcgen05 conv launch, plus the same per kernel key (op, Cin, Cout, k, stride, voxels); the
+    key with the largest total time is the dominant kernel of the step."""
     torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b, _ in _PROF["events"])
-    return {"ms": ms, "launches": len(_PROF["events"]), "flops": float(sum(f for _, _, f in _PROF["events"]))}
+    per = {}
+    tot_ms, tot_fl = 0.0, 0.0
+    for a, b, f, key in _PROF["events"]:
+        t = a.elapsed_time(b)
+        tot_ms += t
+        tot_fl += f
+        e = per.setdefault(key, [0.0, 0.0, 0])
+        e[0] += t
+        e[1] += f
+        e[2] += 1
+    dom = max(per.items(), key=lambda kv: kv[1][0]) if per else (None, [0.0, 0.0, 0])
+    return {"ms": tot_ms, "launches": len(_PROF["events"]), "flops": float(tot_fl),
+            "dominant": {"key": dom[0], "ms": dom[1][0], "flops": float(dom[1][1]), "launches": dom[1][2]}}
 
 
 class _timed:
     """Context manager recording an event pair around a tcgen05 launch when profiling is on."""
 
-    def __init__(self, algo, flops=0):
+    def __init__(self, algo, flops=0, key=None):
         self.on = _PROF["on"] and algo != _lib.ALGO_DIRECT
         self.flops = flops
+        self.key = key
 
     def __enter__(self):
         if self.on:
@@ -64,7 +78,7 @@ class _timed:
     def __exit__(self, *exc):
         if self.on:
             self.b.record()
-            _PROF["events"].append((self.a, self.b, self.flops))
+            _PROF["events"].append((self.a, self.b, self.flops, self.key))
         return False
 
 
@@ -148,7 +162,9 @@ class WSConv3dFn(torch.autograd.Function):
             _lib.check(L.mmpl_parity_split(_p(x), _p(src), n, d, h, w, cin, code, st), "parity_split")
             algo = _lib.ALGO_TCGEN05_PSPLIT
         flops = 2 * n * do * ho * wo * cout * cin * taps
-        with _timed(algo, flops):
+        # fprop and stride-1 dgrad of a Cin==Cout layer are the same kernel instantiation on the same problem size
+        ctx_key = ("conv_tc", min(cin, cout), max(cin, cout), k, stride, n * d * h * w)
+        with _timed(algo, flops, ctx_key):
             _lib.check(L.mmpl_conv3d_fprop(_p(src), _p(pf), _p(res), _p(y), n, d, h, w, cin, cout, k, stride, code, algo,
                                            st), "conv3d_fprop")
         # stride-2 3x3x3 on tensor cores: the parity-split copy is what wgrad reads, so keep it instead of x
@@ -157,6 +173,7 @@ class WSConv3dFn(torch.autograd.Function):
         ctx.x_is_psplit = keep is not x
         ctx.meta = (n, d, h, w, cin, cout, k, stride, int(standardise), residual is not None, weight.dtype)
         ctx.flops = flops
+        ctx.key = ctx_key
         return y
 
     @staticmethod
@@ -173,7 +190,7 @@ class WSConv3dFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = empty_cl(n, cin, d, h, w, dt, dev)
             algo = _algo(dt, cout, cin)
-            with _timed(algo, ctx.flops):
+            with _timed(algo, ctx.flops, ctx.key):
                 _lib.check(L.mmpl_conv3d_dgrad(_p(dy), _p(pd), None, _p(dx), n, d, h, w, cin, cout, k, stride, code,
                                                algo, st), "conv3d_dgrad")
         if ctx.needs_input_grad[1]:
@@ -187,7 +204,7 @@ class WSConv3dFn(torch.autograd.Function):
                 algo = _lib.ALGO_TCGEN05
             wsb = int(L.mmpl_conv3d_wgrad_workspace(n, d, h, w, cin, cout, k, stride, algo))
             ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev) if wsb else None
-            with _timed(algo, ctx.flops):
+            with _timed(algo, ctx.flops, ("wgrad_tc",) + ctx.key[1:]):
                 _lib.check(L.mmpl_conv3d_wgrad(_p(x), _p(dy), _p(g_hat), n, d, h, w, cin, cout, k, stride, code, algo,
                                                _p(ws), wsb, st), "conv3d_wgrad")
             dw = torch.empty_like(w_hat)
