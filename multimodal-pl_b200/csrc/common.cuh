@@ -83,6 +83,35 @@ struct Vec<__nv_bfloat16> {
   }
 };
 
+// VecH<T> moves 8 bytes: 4 bf16 or 2 fp32 channels (half the per-thread state of Vec<T>: used where per-channel
+// constants would otherwise push the register count past the occupancy a streaming kernel needs).
+template <typename T>
+struct VecH;
+template <>
+struct VecH<float> {
+  static constexpr int N = 2;
+  float v[2];
+  __device__ __forceinline__ void load(const float* p) {
+    float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x, v[1] = t.y;
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+template <>
+struct VecH<__nv_bfloat16> {
+  static constexpr int N = 4;
+  float v[4];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(t.x << 16), v[1] = __uint_as_float(t.x & 0xFFFF0000u);
+    v[2] = __uint_as_float(t.y << 16), v[3] = __uint_as_float(t.y & 0xFFFF0000u);
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  }
+};
+
 template <typename T>
 __device__ __forceinline__ float to_f32(T x);
 template <>

@@ -131,7 +131,8 @@ gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ st
                           const float* __restrict__ beta, const T* __restrict__ dy, const float* __restrict__ gamma2,
                           const float* __restrict__ beta2, const T* __restrict__ dy2, double* __restrict__ ws,
                           int64_t spatial, int C, int groups, float eps, int64_t vox_per_block) {
-  constexpr int VN = Vec<T>::N;
+  using V = VecH<T>;   // 8-byte vectors: half the per-thread channel state -> higher occupancy
+  constexpr int VN = V::N;
   constexpr int NH = DUAL ? 2 : 1;
   const int vpv = C / VN;
   const int cv = threadIdx.x % vpv, vl = threadIdx.x / vpv, vstep = kThreads / vpv;
@@ -156,7 +157,7 @@ gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ st
     for (int i = 0; i < VN; ++i) d1[hh][i] = d2[hh][i] = 0.f;
 #pragma unroll 2
   for (int64_t v = v0 + vl; v < v1; v += vstep) {
-    Vec<T> a, g;
+    V a, g;
     a.load(x + off + v * C);
     g.load(dy + off + v * C);
 #pragma unroll
@@ -211,7 +212,8 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
                          T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                          float* __restrict__ dgamma2, float* __restrict__ dbeta2, const double* __restrict__ ws,
                          int N, int64_t spatial, int C, int groups, float eps, int64_t vox_per_block) {
-  constexpr int VN = Vec<T>::N;
+  using V = VecH<T>;
+  constexpr int VN = V::N;
   constexpr int NH = DUAL ? 2 : 1;
   const int vpv = C / VN;
   const int cv = threadIdx.x % vpv, vl = threadIdx.x / vpv, vstep = kThreads / vpv;
@@ -258,7 +260,7 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
   const int64_t off = (static_cast<int64_t>(n) * spatial) * C + cv * VN;
 #pragma unroll 2
   for (int64_t v = v0 + vl; v < v1; v += vstep) {
-    Vec<T> a, g, o;
+    V a, g, o;
     a.load(x + off + v * C);
     g.load(dy + off + v * C);
 #pragma unroll
@@ -285,8 +287,8 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
   }
 }
 
-int check_shape(int c, int groups, int dtype) {
-  const int vn = dtype == MMPL_BF16 ? 8 : 4;
+int check_shape(int c, int groups, int dtype, bool half = false) {
+  const int vn = (dtype == MMPL_BF16 ? 8 : 4) / (half ? 2 : 1);
   MMPL_REQUIRE(groups > 0 && groups <= 32 && c % groups == 0, MMPL_E_SHAPE, "GroupNorm: C=%d groups=%d", c, groups);
   MMPL_REQUIRE(c % vn == 0 && c <= kMaxC && kThreads % (c / vn) == 0, MMPL_E_SHAPE,
                "GroupNorm: C=%d must be a power-of-two multiple of %d and <= %d", c, vn, kMaxC);
@@ -296,8 +298,8 @@ int check_shape(int c, int groups, int dtype) {
 }
 
 // Blocks per sample: enough to give every SM several blocks, at least 64 voxel-rows per block.
-void plan(int n, int64_t spatial, int c, int dtype, int& blocks_x, int64_t& vox_per_block) {
-  const int vn = dtype == MMPL_BF16 ? 8 : 4;
+void plan(int n, int64_t spatial, int c, int dtype, int& blocks_x, int64_t& vox_per_block, bool half = false) {
+  const int vn = (dtype == MMPL_BF16 ? 8 : 4) / (half ? 2 : 1);
   const int vstep = kThreads / (c / vn);
   int64_t want = static_cast<int64_t>(num_sms()) * 8 / (n > 0 ? n : 1);
   if (want < 1) want = 1;
@@ -390,10 +392,10 @@ extern "C" int mmpl_gn_relu_bwd(const void* x, const double* stats, const float*
                                 const void* addend, void* dx, float* dgamma, float* dbeta, float* dgamma2,
                                 float* dbeta2, double* workspace, int n, int64_t spatial, int c, int groups, float eps,
                                 int dtype, mmpl_stream_t stream) {
-  if (int e = check_shape(c, groups, dtype)) return e;
+  if (int e = check_shape(c, groups, dtype, true)) return e;
   int bx;
   int64_t vpb;
-  plan(n, spatial, c, dtype, bx, vpb);
+  plan(n, spatial, c, dtype, bx, vpb, true);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   MMPL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 4 * n * c, s));
   int rc = MMPL_OK;
