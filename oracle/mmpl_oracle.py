@@ -210,6 +210,39 @@ def partial_label_loss(logits: torch.Tensor, target: torch.Tensor, class_weight:
     return dice + ce
 
 
+def dice_loss_class(probs: torch.Tensor, target: torch.Tensor, weight: Optional[Sequence[float]] = None,
+                    gate: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """DiceLoss.forward(inputs=probabilities, target, weight, softmax=False, mask=gate) (loss_partial.py:38-57):
+    per-class ``_dice_loss`` over the voxels where ``gate[:, c]`` is true, weighted sum divided by the class count."""
+    C = probs.shape[1]
+    loss = 0.0
+    for c in range(C):
+        t = (target == c).float()
+        sc = probs[:, c]
+        if gate is not None:
+            m = gate[:, c].bool()
+            sc, t = sc[m], t[m]
+        loss = loss + dice_term(sc, t) * (1.0 if weight is None else float(weight[c]))
+    return loss / C
+
+
+def binary_gated_dice(x: torch.Tensor, target: torch.Tensor, gate: Optional[torch.Tensor] = None, uce: bool = True,
+                      sigmoid: bool = True) -> torch.Tensor:
+    """EDiceLoss_full2.forward (loss_partial.py:150-170): Dice between sigmoid(x) (or x) and a soft target over the
+    gated voxels, plus BCE-with-logits when ``uce``."""
+    p = torch.sigmoid(x) if sigmoid else x
+    if gate is None:
+        gate = torch.ones_like(target).unsqueeze(0)
+    t = target.float()
+    m = gate.bool()
+    sc = p[m]
+    tt = t[gate.squeeze(1).bool()] if gate.dim() == t.dim() + 1 else t[m]
+    dice = dice_term(sc, tt)
+    if uce:
+        return dice + F.binary_cross_entropy_with_logits(x.float().squeeze(0), t)
+    return dice
+
+
 def partial_label_loss_sums(logits: np.ndarray, target: np.ndarray) -> Dict[str, np.ndarray]:
     """float64 numpy restatement of the four per-class sums the fused kernel produces:
     I = sum p t, Z = sum p^2, Y = sum t, E = sum BCE terms (log clamped at -100)."""

@@ -1,0 +1,132 @@
+"""More §8 rows on the device: the wide (base 64) backbone of BASELINE configs[4], the full configs[0] extent
+(1x64x128x128) against the CPU oracle, the remaining loss classes, and the poly LR + fused SGD interplay."""
+import numpy as np
+import pytest
+import torch
+
+import mmpl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _model(base, dtype, algo, seed=0):
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    mm.set_compute_dtype(dtype)
+    mm.set_conv_algo(algo)
+    sd = O.synth_state_dict(base, 16, seed)
+    m = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True, base=base).cuda()
+    m.load_state_dict(sd)
+    return m, sd
+
+
+def _reset():
+    import multimodal_pl_b200 as mm
+
+    mm.set_conv_algo("auto")
+    mm.set_compute_dtype(torch.bfloat16)
+
+
+@pytest.mark.parametrize("dtype,algo,tol", [(torch.float32, "direct", 1e-5), (torch.bfloat16, "auto", 2e-2)])
+def test_wide_backbone_base64(dtype, algo, tol):
+    """configs[4] recipe (widths 64..512) at a small extent: logits / loss vs the oracle built from the same recipe."""
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+
+    try:
+        model, sd = _model(64, dtype, algo)
+        model.train()
+        x = O.synth_patch((1, 1, 16, 32, 32), 7, "mri")
+        lab = O.synth_labels((1, 16, 32, 32), 8, 16, 32)
+        w = [1.0] + [0.0] * 7 + [1.0] + [0.0] * 7
+        ref = O.unet3d_forward(sd, x, base=64)
+        ref_loss = O.partial_label_loss(ref, lab.squeeze(1), w).item()
+        logits = model(x.cuda())[0]
+        assert rel(logits, ref) < tol
+        L = EDiceLoss_partial(16)(logits, lab.squeeze(1).cuda(), mask=[torch.tensor(w)])
+        assert abs(L.item() - ref_loss) < max(tol, 1e-5) * max(1.0, ref_loss)
+        L.backward()
+        assert all(torch.isfinite(p.grad).all() for p in model.parameters())
+    finally:
+        _reset()
+
+
+@pytest.mark.parametrize("dtype,algo,tol", [(torch.float32, "direct", 2e-5), (torch.bfloat16, "auto", 2e-2)])
+def test_cfg1_full_extent_vs_oracle(dtype, algo, tol):
+    """BASELINE configs[0]: batch 1, 1x64x128x128, 16 classes -- forward + loss at the full extent."""
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+
+    try:
+        model, sd = _model(32, dtype, algo)
+        model.eval()
+        x = O.synth_patch((1, 1, 64, 128, 128), 21, "ct")
+        lab = torch.nn.functional.interpolate(O.synth_labels((1, 16, 32, 32), 22, 16, 32), size=(64, 128, 128),
+                                              mode="nearest")
+        w = [1.0, 0, 0, 0, 1.0] + [0.0] * 11
+        with torch.no_grad():
+            ref = O.unet3d_forward(sd, x)
+            ref_loss = O.partial_label_loss(ref, lab.squeeze(1), w).item()
+            logits = model(x.cuda())
+            L = EDiceLoss_partial(16)(logits, lab.squeeze(1).cuda(), mask=[torch.tensor(w)]).item()
+        assert rel(logits, ref) < tol
+        assert abs(L - ref_loss) < max(tol, 1e-5) * max(1.0, ref_loss)
+        if dtype == torch.float32:
+            top2 = ref.topk(2, dim=1).values
+            near_tie = (top2[:, 0] - top2[:, 1]) < 1e-4
+            assert ((logits.cpu().argmax(1) != ref.argmax(1)) & ~near_tie).sum().item() == 0
+    finally:
+        _reset()
+
+
+def test_dice_and_gated_losses_match_oracle():
+    from multimodal_pl_b200.loss_functions.loss_partial import DiceLoss, EDiceLoss_full2, EDiceLoss_partial
+
+    g = torch.Generator().manual_seed(4)
+    z = torch.randn((2, 5, 4, 6, 6), generator=g)
+    p = torch.softmax(z, 1)
+    tgt = torch.randint(0, 5, (2, 4, 6, 6), generator=g).float()
+    w = [0.5, 1.0, 0.0, 2.0, 1.0]
+    gate = (torch.rand((2, 5, 4, 6, 6), generator=g) > 0.3)
+    d = DiceLoss(5)
+    assert abs(d(p.cuda(), tgt.cuda(), weight=w, softmax=False).item() - O.dice_loss_class(p, tgt, w).item()) < 1e-6
+    assert abs(d(p.cuda(), tgt.cuda(), weight=w, softmax=False, mask=gate.cuda()).item() -
+               O.dice_loss_class(p, tgt, w, gate).item()) < 1e-6
+    # sigmoid variant of EDiceLoss_partial (soft_max=False)
+    ps = torch.sigmoid(z)
+    ref = O.dice_loss_class(ps, tgt, w)
+    for c in range(5):
+        ref = ref + torch.nn.functional.binary_cross_entropy(ps[:, c], (tgt == c).float()) * w[c]
+    got = EDiceLoss_partial(5)(z.cuda(), tgt.cuda(), mask=[torch.tensor(w)] * 2, soft_max=False)
+    assert abs(got.item() - ref.item()) < 1e-5
+    # binary gated Dice (EDiceLoss_full2), the form get_loss uses: inputs [1,1,D,H,W], target [1,D,H,W], mask [1,1,D,H,W]
+    x = torch.randn((1, 1, 4, 6, 6), generator=g)
+    t = torch.rand((1, 4, 6, 6), generator=g)
+    m = (torch.rand((1, 1, 4, 6, 6), generator=g) > 0.4).float()
+    f2 = EDiceLoss_full2(2)
+    for uce, sig in [(False, True), (False, False), (True, True)]:
+        xin = x if sig else torch.sigmoid(x)
+        a = f2(xin.cuda(), t.cuda(), uce=uce, mask=m.cuda(), sigmoid=sig).item()
+        b = O.binary_gated_dice(xin, t, m, uce=uce, sigmoid=sig).item()
+        assert abs(a - b) < 1e-6, (uce, sig)
+
+
+def test_poly_lr_drives_fused_sgd():
+    from multimodal_pl_b200.engine import FusedSGD
+    from multimodal_pl_b200.utils import adjust_learning_rate, lr_poly
+
+    p = torch.nn.Parameter(torch.ones(1000, device="cuda"))
+    opt = FusedSGD([p], lr=0.1, momentum=0.0, weight_decay=0.0)
+    ref = torch.ones(1000)
+    for epoch in range(3):
+        lr = adjust_learning_rate(opt, epoch, 0.1, 10, 0.9)
+        assert abs(lr - O.lr_poly(0.1, epoch, 10)) < 1e-12 and abs(lr - lr_poly(0.1, epoch, 10, 0.9)) < 1e-12
+        opt.zero_grad()
+        (p * 2.0).sum().backward()
+        opt.step()
+        ref = ref - lr * 2.0
+    assert torch.allclose(p.detach().cpu(), ref, atol=1e-6)
