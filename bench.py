@@ -287,6 +287,12 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md, sustained)"
     # dominant kernel = the tcgen05 conv instantiation with the largest total time in the timed region
     # (cfg2: conv_tc_kernel<32,32,4> on the full-resolution 32->32 3x3x3 layers, fprop + dgrad launches)
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_dominant.json")) as f:
+            traffic = json.load(f).get("traffic_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     dom = prof["dominant"]
     dom_ms, dom_flops, dom_n = dom["ms"], dom["flops"], max(dom["launches"], 1)
     ms_prof_step = ms / args.steps
@@ -294,7 +300,9 @@ def run_ours(args):
     tc_ms, tc_flops = prof["ms"], prof["flops"]
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv) " + str(dom["key"]),
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": None, "peak_source": peak_src, "launches": dom["launches"],
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_ncu_dominant.json)",
+                "algorithmic_bytes_per_launch": 2 * batch * dhw[0] * dhw[1] * dhw[2] * base * 2,
+                "peak_source": peak_src, "launches": dom["launches"],
                 "flops_per_launch": dom_flops / dom_n, "avg_launch_ms": dom_ms / dom_n,
                 "share_of_step": (dom_ms / prof_steps) / ms_prof_step,
                 "measured": f"{prof_steps} eager steps right after the timed region (host queued ahead of the device), one CUDA-event pair per launch",
