@@ -169,9 +169,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       if (WRES) {
         // all 27 tiles once; every stage has its own barrier, completed exactly once
+        // slot order (kh, kw, 2-kd): for a fixed (kh,kw) the three kd tiles are consecutive rows of ONE [3*NT x KC]
+        // B matrix, so a single MMA with N = 3*NT feeds the accumulators of three output planes (see the MMA issuer)
         for (int tap = 0; tap < 27; ++tap) {
-          mbar_expect_tx(&b_full[tap], Cfg::B_BYTES);
-          tma_load_3d(b_stage + tap * Cfg::B_BYTES, &tmB, &b_full[tap], 0, 0, tap);
+          const int kd = tap / 9, khw = tap % 9, slot = khw * 3 + (2 - kd);
+          mbar_expect_tx(&b_full[slot], Cfg::B_BYTES);
+          tma_load_3d(b_stage + slot * Cfg::B_BYTES, &tmB, &b_full[slot], 0, 0, tap);
         }
       } else {
         uint32_t it = 0;
@@ -219,6 +222,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&acc_empty[buf], bph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * Cfg::ACC_COLS;
+      if (WRES) {
+        // ---- plane-major issue (resident weights, one reduction chunk): for input plane s and tap (kh,kw) the SAME A view
+        // multiplies W[kd] for every output plane p = s - kd, so one MMA with N = NT * (#valid kd) accumulates into
+        // the adjacent TMEM accumulators of planes p_lo..p_hi.  Halves the MMA count and the A-operand reads.
+        const uint32_t sa = ita % Cfg::NA, pha = (ita / Cfg::NA) & 1;
+        mbar_wait(&a_full[sa], pha);
+        tc_fence_after();
+        const uint32_t a_addr = a_base + sa * Cfg::A_STAGE;
+        if (elect_one()) {
+#pragma unroll
+          for (int sp = 0; sp < TD + 2; ++sp) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int kd_hi = sp < 2 ? sp : 2;                       // p_lo = sp - kd_hi
+            const int kd_lo = sp - (TD - 1) > 0 ? sp - (TD - 1) : 0;  // p_hi = sp - kd_lo
+            const int nblk = kd_hi - kd_lo + 1;
+            const bool fresh = sp < TD;                              // plane p_hi == sp gets its first contribution here
+            const uint32_t d_lo = d_tmem + (sp - kd_hi) * NT;
+#pragma unroll
+            for (int khw = 0; khw < 9; ++khw) {
+              const int kh = khw / 3, kw = khw % 3;
+              const uint32_t a_lo = a_lo_fix | ((a_addr + (((sp * G::PH) + kh) * G::PW + kw) * Cfg::RB) >> 4);
+              const uint32_t b_lo = b_lo_fix | ((b_base + (khw * 3 + (2 - kd_hi)) * Cfg::B_BYTES) >> 4);
+#pragma unroll
+              for (int ks = 0; ks < KC / 16; ++ks) {
+                if (fresh && khw == 0 && ks == 0) {
+                  // first touch of plane sp: older planes accumulate, the fresh one is overwritten
+                  if (nblk > 1)
+                    umma_f16_lohi(d_lo, a_lo, a_hi, b_lo, b_hi, make_idesc_bf16(128, NT * (nblk - 1), 0, 0), 1u);
+                  umma_f16_lohi(d_lo + (nblk - 1) * NT, a_lo, a_hi, b_lo + (((nblk - 1) * Cfg::B_BYTES) >> 4), b_hi,
+                                make_idesc_bf16(128, NT, 0, 0), 0u);
+                } else {
+                  umma_f16_lohi(d_lo, a_lo + ((ks * 32) >> 4), a_hi, b_lo + ((ks * 32) >> 4), b_hi,
+                                make_idesc_bf16(128, NT * nblk, 0, 0), 1u);
+                }
+              }
+            }
+          }
+          umma_commit(&a_empty[sa]);
+        }
+        __syncwarp();
+        ++ita;
+      } else {
       uint32_t first = 1;
       for (int c = 0; c < chunks_per_item; ++c, ++ita) {
         const int par = G::PARITY_CHUNKS ? (c & 7) : pc;
@@ -268,6 +314,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         if (elect_one()) umma_commit(&a_empty[sa]);
         __syncwarp();
+      }
       }
       if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
