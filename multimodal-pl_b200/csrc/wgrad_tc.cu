@@ -71,7 +71,10 @@ struct WgParams {
   WgGroup groups[4][WG_MAX_GROUPS];     // per variant
 };
 
-template <int KC, int NCO, int TD, int HALO, int XB, int PDE>
+// PM (plane-major): only for the all-27-taps variant (HALO 2, PDE 2, one X block).  For X plane s, line pair hl and kh the
+// SAME A view pairs with the dY planes p = s - kd, so one MMA whose B operand spans those planes (N-chunks one dY
+// plane apart, LBO = plane pitch) accumulates into the adjacent accumulators (kh, 2-kd): half the MMAs and A reads.
+template <int KC, int NCO, int TD, int HALO, int XB, int PDE, bool PM>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                 const __grid_constant__ WgParams p) {
@@ -142,6 +145,42 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_wait(&full[s], ph);
       tc_fence_after();
       const uint32_t xs = xb0 + s * Cfg::X_STAGE, ys = yb0 + s * Cfg::Y_STAGE;
+      if (PM) {
+        if (elect_one()) {
+          constexpr uint32_t YPLANE = WG_TH * WG_TW * Cfg::RBY;           // bytes between dY planes
+          // B descriptor for the multi-plane operand: N-chunks (NCO channels each) are one dY plane apart
+          const uint64_t bp_fix = make_smem_desc(0, YPLANE, WG_TW * Cfg::RBY, Cfg::SWY, 0);
+          const uint32_t bp_hi = static_cast<uint32_t>(bp_fix >> 32), bp_lo_fix = static_cast<uint32_t>(bp_fix);
+#pragma unroll
+          for (int sp = 0; sp < TD + 2; ++sp) {
+            const int kd_hi = sp < 2 ? sp : 2;
+            const int kd_lo = sp - (TD - 1) > 0 ? sp - (TD - 1) : 0;
+            const int nblk = kd_hi - kd_lo + 1;
+            const int p_lo = sp - kd_hi;
+            const bool fresh = sp <= 2;          // accumulators (kd = sp, kh) see their first MMA at (sp, hl = 0)
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              const uint32_t acc = tmem_base + (kh * 3 + (2 - kd_hi)) * NCO;
+#pragma unroll
+              for (int hl = 0; hl < WG_TH; hl += 2) {
+                const uint32_t a_lo = a_lo_fix | ((xs + (((sp * Cfg::PH) + hl + kh) * Cfg::PW) * Cfg::RBX) >> 4);
+                const uint32_t b_lo = bp_lo_fix | ((ys + ((p_lo * WG_TH + hl) * WG_TW) * Cfg::RBY) >> 4);
+                if (fresh && hl == 0) {
+                  umma_f16_lohi(acc, a_lo, a_hi, b_lo, bp_hi, make_idesc_bf16(128, NCO, 1, 1), it != 0 ? 1u : 0u);
+                  if (nblk > 1)
+                    umma_f16_lohi(acc + NCO, a_lo, a_hi, b_lo + (YPLANE >> 4), bp_hi,
+                                  make_idesc_bf16(128, NCO * (nblk - 1), 1, 1), 1u);
+                } else {
+                  umma_f16_lohi(acc, a_lo, a_hi, b_lo, bp_hi, make_idesc_bf16(128, NCO * nblk, 1, 1), 1u);
+                }
+              }
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
+        continue;
+      }
       if (elect_one()) {
         for (int g = 0; g < ng; ++g) {
           const uint32_t acc = tmem_base + g * NCO;
@@ -172,8 +211,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tc_fence_after();
     const bool has_work = split < p.total_blocks;
 #pragma unroll 1
-    for (int g = 0; g < ng; ++g) {
-      const int tap = p.groups[var][g].tap[j & 3];
+    for (int g = 0; g < (PM ? 9 : ng); ++g) {
+      int tap = p.groups[var][PM ? 0 : g].tap[j & 3];
+      if (PM) tap = j < 3 ? ((2 - g % 3) * 3 + g / 3) * 3 + j : -1;
       const bool valid = has_work && tap >= 0;
 #pragma unroll
       for (int c0 = 0; c0 < NCO; c0 += 32) {
@@ -230,7 +270,7 @@ struct WgSource {
   int estride;
 };
 
-template <int KC, int NCO, int TD, int HALO, int XB, int PDE>
+template <int KC, int NCO, int TD, int HALO, int XB, int PDE, bool PM = false>
 int launch_wg(const WgSource& src, const void* dy, WgParams p, int taps, cudaStream_t s) {
   using Cfg = WgCfg<KC, NCO, TD, HALO, XB, PDE>;
   CUtensorMap tmX, tmY;
@@ -250,12 +290,12 @@ int launch_wg(const WgSource& src, const void* dy, WgParams p, int taps, cudaStr
   p.ksplit = ks;
   static bool attr_set = false;
   if (!attr_set) {
-    MMPL_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KC, NCO, TD, HALO, XB, PDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MMPL_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KC, NCO, TD, HALO, XB, PDE, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::SMEM_BYTES));
     attr_set = true;
   }
   MMPL_CUDA(cudaMemsetAsync(p.dw, 0, sizeof(float) * taps * p.cout * p.cin, s));
-  wgrad_tc_kernel<KC, NCO, TD, HALO, XB, PDE><<<p.combos * ks, WG_THREADS, Cfg::SMEM_BYTES, s>>>(tmX, tmY, p);
+  wgrad_tc_kernel<KC, NCO, TD, HALO, XB, PDE, PM><<<p.combos * ks, WG_THREADS, Cfg::SMEM_BYTES, s>>>(tmX, tmY, p);
   MMPL_CHECK_LAUNCH("wgrad_tc");
   return MMPL_OK;
 }
@@ -321,7 +361,7 @@ int conv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int d, int h,
           g.xblk = 0, g.row_shift = (kd * PH + kh) * PW;
           for (int j = 0; j < 3; ++j) g.tap[j] = (kd * 3 + kh) * 3 + j;
         }
-      return launch_wg<32, 32, 4, 2, 1, 2>(src, dy, p, taps, s);
+      return launch_wg<32, 32, 4, 2, 1, 2, true>(src, dy, p, taps, s);
     }
     // one kd per CTA variant (X block of TD planes at d0-1+kd): groups (kh, km)
     constexpr int PW = 10;
