@@ -68,8 +68,11 @@ int mmpl_ws_weight_bwd(const float* g_hat_tapmajor, const float* w_hat, const fl
 /* P[(p*N + n)][d'][h'][w'][c] = X[n][2d'+pd][2h'+ph][2w'+pw][c], p = pd*4+ph*2+pw, extents ceil(D/2) etc., zeros
  * where the source index is out of range.  bf16 only. */
 int mmpl_parity_split(const void* x, void* p_out, int n, int d, int h, int w, int c, int dtype, mmpl_stream_t stream);
+/* gn_stats_out (may be NULL): zero-initialised double [N][16][2]; receives the GroupNorm(16) raw sums of y -- fused into
+ * the tcgen05 epilogue when one tile spans all output channels, otherwise computed by a following streaming pass. */
 int mmpl_conv3d_fprop(const void* x, const void* w_fprop, const void* residual, void* y, int n, int d, int h, int w,
-                      int cin, int cout, int ksize, int stride, int dtype, int algo, mmpl_stream_t stream);
+                      int cin, int cout, int ksize, int stride, int dtype, int algo, double* gn_stats_out,
+                      mmpl_stream_t stream);
 int mmpl_conv3d_dgrad(const void* dy, const void* w_dgrad, const void* addend, void* dx, int n, int d, int h, int w,
                       int cin, int cout, int ksize, int stride, int dtype, int algo, mmpl_stream_t stream);
 int mmpl_conv3d_wgrad(const void* x, const void* dy, float* dw_tapmajor, int n, int d, int h, int w, int cin,

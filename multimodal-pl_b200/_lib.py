@@ -26,7 +26,7 @@ _SIGNATURES = {
     "mmpl_ws_weight_fwd": [_ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr],
     "mmpl_ws_weight_bwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
     "mmpl_parity_split": [_ptr, _ptr] + [_c_int] * 6 + [_ptr],
-    "mmpl_conv3d_fprop": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr],
+    "mmpl_conv3d_fprop": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr, _ptr],
     "mmpl_conv3d_dgrad": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr],
     "mmpl_conv3d_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr, _c_size, _ptr],
     "mmpl_conv3d_wgrad_workspace": [_c_int] * 9,

@@ -5,8 +5,10 @@ namespace mmpl {
 int conv_direct_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_direct_dgrad(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_direct_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int conv_tc_s1(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
-int conv_tc_s2_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int conv_tc_s1(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, double*, cudaStream_t);
+int conv_tc_s2_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, double*, cudaStream_t);
+bool conv_tc_can_fuse_stats(int nout);
+int conv_out_dim(int in, int k, int stride);
 int conv_tc_s2_dgrad(const void*, const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int parity_split(const void*, void*, int, int, int, int, int, cudaStream_t);
 int conv_tc_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -32,17 +34,28 @@ extern "C" int mmpl_parity_split(const void* x, void* p_out, int n, int d, int h
 
 extern "C" int mmpl_conv3d_fprop(const void* x, const void* w_fprop, const void* residual, void* y, int n, int d, int h,
                                  int w, int cin, int cout, int ksize, int stride, int dtype, int algo,
-                                 mmpl_stream_t stream) {
+                                 double* gn_stats_out, mmpl_stream_t stream) {
   if (int e = check_common(n, d, h, w, cin, cout, ksize, stride)) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t out_spatial = static_cast<int64_t>(conv_out_dim(d, ksize, stride)) * conv_out_dim(h, ksize, stride) *
+                              conv_out_dim(w, ksize, stride);
   if (algo == MMPL_ALGO_TCGEN05 || algo == MMPL_ALGO_TCGEN05_PSPLIT) {
     MMPL_REQUIRE(dtype == MMPL_BF16, MMPL_E_UNSUPPORTED, "conv3d_fprop: tcgen05 path needs bf16 (got dtype=%d)", dtype);
-    if (stride == 1) return conv_tc_s1(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, s);
-    MMPL_REQUIRE((ksize == 3) == (algo == MMPL_ALGO_TCGEN05_PSPLIT), MMPL_E_UNSUPPORTED,
-                 "conv3d_fprop: stride-2 3x3x3 takes the parity-split input (MMPL_ALGO_TCGEN05_PSPLIT), 1x1x1 takes x");
-    return conv_tc_s2_fprop(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, s);
+    double* fused = (gn_stats_out && conv_tc_can_fuse_stats(cout)) ? gn_stats_out : nullptr;
+    int rc;
+    if (stride == 1) {
+      rc = conv_tc_s1(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, fused, s);
+    } else {
+      MMPL_REQUIRE((ksize == 3) == (algo == MMPL_ALGO_TCGEN05_PSPLIT), MMPL_E_UNSUPPORTED,
+                   "conv3d_fprop: stride-2 3x3x3 takes the parity-split input (MMPL_ALGO_TCGEN05_PSPLIT), 1x1x1 takes x");
+      rc = conv_tc_s2_fprop(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, fused, s);
+    }
+    if (rc || !gn_stats_out || fused) return rc;
+    return mmpl_gn_stats(y, gn_stats_out, n, out_spatial, cout, 16, dtype, stream);
   }
-  return conv_direct_fprop(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, stride, dtype, s);
+  if (int e = conv_direct_fprop(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, stride, dtype, s)) return e;
+  if (gn_stats_out) return mmpl_gn_stats(y, gn_stats_out, n, out_spatial, cout, 16, dtype, stream);
+  return MMPL_OK;
 }
 
 extern "C" int mmpl_conv3d_dgrad(const void* dy, const void* w_dgrad, const void* addend, void* dx, int n, int d, int h,
@@ -53,7 +66,7 @@ extern "C" int mmpl_conv3d_dgrad(const void* dy, const void* w_dgrad, const void
   if (algo == MMPL_ALGO_TCGEN05) {
     MMPL_REQUIRE(dtype == MMPL_BF16, MMPL_E_UNSUPPORTED, "conv3d_dgrad: tcgen05 path needs bf16 (got dtype=%d)", dtype);
     // stride-1 dgrad is a correlation of dy with the flipped/transposed packing: channels swap roles
-    if (stride == 1) return conv_tc_s1(dy, w_dgrad, addend, dx, n, d, h, w, cout, cin, ksize, s);
+    if (stride == 1) return conv_tc_s1(dy, w_dgrad, addend, dx, n, d, h, w, cout, cin, ksize, nullptr, s);
     MMPL_REQUIRE(addend == nullptr, MMPL_E_UNSUPPORTED, "conv3d_dgrad: stride-2 tcgen05 path has no addend input");
     if (ksize == 1)  // only the even parity class receives gradient; the rest of dx is zero
       MMPL_CUDA(cudaMemsetAsync(dx, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(n) * d * h * w * cin, s));

@@ -86,6 +86,7 @@ struct TcParams {
   int cout_total;   // row stride of y in elements
   int DT, HT, WT, NTILES, NPAR;
   int total_items;
+  double* stats;    // optional GroupNorm(16) raw sums of the OUTPUT [N][16][2] (requires cout_total == NT), else NULL
 };
 
 // Tap enumeration shared by the weight producer and the MMA issuer.
@@ -324,10 +325,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int rh = row >> 3, rw = row & 7;
+    // fused GroupNorm statistics of the stored output: 16 groups of NT/16 channels; per-thread fp32 partials over this
+    // CTA's items, reduced across the warp and added to the fp64 buffer only when the sample changes / at the end
+    constexpr int CPG = NT / 16;
+    float gsum[16], gsq[16];
+#pragma unroll
+    for (int g = 0; g < 16; ++g) gsum[g] = gsq[g] = 0.f;
+    int stat_n = -1;
+    auto flush_stats = [&]() {
+      if (p.stats == nullptr || stat_n < 0) return;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        const float a = warp_sum(gsum[g]), b = warp_sum(gsq[g]);
+        if (lane == 0) {
+          atomicAdd(&p.stats[(static_cast<int64_t>(stat_n) * 16 + g) * 2 + 0], static_cast<double>(a));
+          atomicAdd(&p.stats[(static_cast<int64_t>(stat_n) * 16 + g) * 2 + 1], static_cast<double>(b));
+        }
+        gsum[g] = gsq[g] = 0.f;
+      }
+    };
     uint32_t iti = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++iti) {
       int nt, pc, n, d0, h0, w0;
       item_coords(item, nt, pc, n, d0, h0, w0);
+      if (p.stats != nullptr && n != stat_n) {
+        flush_stats();
+        stat_n = n;
+      }
       const uint32_t buf = iti & 1, bph = (iti >> 1) & 1;
       mbar_wait(&acc_full[buf], bph);
       tc_fence_after();
@@ -367,6 +391,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __nv_bfloat162 h2 =
                     __floats2bfloat162_rn(__uint_as_float(r[v * 8 + 2 * k]), __uint_as_float(r[v * 8 + 2 * k + 1]));
                 o[k] = *reinterpret_cast<uint32_t*>(&h2);
+                if (p.stats != nullptr) {   // statistics of the value as stored (bf16-rounded)
+                  const float x0 = __uint_as_float(o[k] << 16), x1 = __uint_as_float(o[k] & 0xFFFF0000u);
+                  constexpr int dummy_cpg = CPG;
+                  (void)dummy_cpg;
+                  const int g0 = (c0 + v * 8 + 2 * k) / CPG, g1 = (c0 + v * 8 + 2 * k + 1) / CPG;
+                  gsum[g0] += x0;
+                  gsq[g0] = fmaf(x0, x0, gsq[g0]);
+                  gsum[g1] += x1;
+                  gsq[g1] = fmaf(x1, x1, gsq[g1]);
+                }
               }
               *reinterpret_cast<uint4*>(p.y + off + c0 + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
@@ -377,6 +411,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
+    flush_stats();
   }
   tc_fence_before();
   __syncthreads();
@@ -441,6 +476,7 @@ struct TcProblem {
   void* y;
   int N, D, H, W;
   int kred, nout;
+  double* stats = nullptr;
 };
 
 template <int KC, int NT, int TD, int MODE, bool WRES, int NA_ = 2>
@@ -461,6 +497,7 @@ int launch_tc(const TcProblem& q, cudaStream_t s) {
   p.cout_total = q.nout;
   p.DT = ceil_div(p.Ds, TD), p.HT = ceil_div(p.Hs, TC_TH), p.WT = ceil_div(p.Ws, TC_TW), p.NTILES = q.nout / NT;
   p.NPAR = MODE == MODE_S2D ? 8 : 1;
+  p.stats = (q.stats != nullptr && q.nout == NT && !G::STRIDED_OUT) ? q.stats : nullptr;
   const int64_t items = static_cast<int64_t>(p.NTILES) * p.NPAR * q.N * p.DT * p.HT * p.WT;
   MMPL_REQUIRE(items < (1ll << 31), MMPL_E_SHAPE, "conv_tc: too many work items");
   p.total_items = static_cast<int>(items);
@@ -546,23 +583,26 @@ static int check_align(const void* a, const void* b, const void* c, const void* 
 }
 
 // ---- stride 1 (k = 3 or 1): x [N,D,H,W,cin] -> y [N,D,H,W,cout]; also stride-1 dgrad with swapped channel roles
+// GroupNorm statistics can be fused into the epilogue when one CTA tile spans all output channels
+bool conv_tc_can_fuse_stats(int nout) { return nout == 32 || nout == 64 || nout == 128 || nout == 256; }
+
 int conv_tc_s1(const void* x, const void* wp, const void* residual, void* y, int N, int D, int H, int W, int cin,
-               int cout, int ksize, cudaStream_t s) {
+               int cout, int ksize, double* stats, cudaStream_t s) {
   if (int e = check_align(x, wp, y, residual)) return e;
-  TcProblem q{x, N, D, H, W, wp, residual, y, N, D, H, W, cin, cout};
+  TcProblem q{x, N, D, H, W, wp, residual, y, N, D, H, W, cin, cout, stats};
   return ksize == 3 ? dispatch_tc<MODE_S1K3>(q, s) : dispatch_tc<MODE_S1K1>(q, s);
 }
 
 // ---- stride 2 fprop.  k=3: `src` is the parity-split tensor P [8N][Dp][Hp][Wp][cin]; k=1: `src` is x itself.
 int conv_tc_s2_fprop(const void* src, const void* wp, const void* residual, void* y, int N, int D, int H, int W, int cin,
-                     int cout, int ksize, cudaStream_t s) {
+                     int cout, int ksize, double* stats, cudaStream_t s) {
   if (int e = check_align(src, wp, y, residual)) return e;
   const int Do = (D + 1) / 2, Ho = (H + 1) / 2, Wo = (W + 1) / 2;   // == (in + 2*pad - k)/2 + 1 for k in {1,3}
   if (ksize == 3) {
-    TcProblem q{src, static_cast<int64_t>(8) * N, Do, Ho, Wo, wp, residual, y, N, Do, Ho, Wo, cin, cout};
+    TcProblem q{src, static_cast<int64_t>(8) * N, Do, Ho, Wo, wp, residual, y, N, Do, Ho, Wo, cin, cout, stats};
     return dispatch_tc<MODE_S2F>(q, s);
   }
-  TcProblem q{src, N, D, H, W, wp, residual, y, N, Do, Ho, Wo, cin, cout};
+  TcProblem q{src, N, D, H, W, wp, residual, y, N, Do, Ho, Wo, cin, cout, stats};
   return dispatch_tc<MODE_S2K1F>(q, s);
 }
 

@@ -129,7 +129,7 @@ class WSConv3dFn(torch.autograd.Function):
     """Weight-standardised (or plain) k^3 convolution, optional fused residual add.  unet3D.py:16-27."""
 
     @staticmethod
-    def forward(ctx, x, weight, residual, stride, standardise):
+    def forward(ctx, x, weight, residual, stride, standardise, want_stats=False):
         _lib.require_device()
         L = _lib.lib()
         dt = _cfg["dtype"]
@@ -164,9 +164,11 @@ class WSConv3dFn(torch.autograd.Function):
         flops = 2 * n * do * ho * wo * cout * cin * taps
         # fprop and stride-1 dgrad of a Cin==Cout layer are the same kernel instantiation on the same problem size
         ctx_key = ("conv_tc", min(cin, cout), max(cin, cout), k, stride, n * d * h * w)
+        # GroupNorm(16) raw sums of the output for the next GN+ReLU, produced by the conv epilogue
+        stats = torch.zeros(n * 16 * 2, dtype=torch.float64, device=dev) if (want_stats and cout % 16 == 0) else None
         with _timed(algo, flops, ctx_key):
             _lib.check(L.mmpl_conv3d_fprop(_p(src), _p(pf), _p(res), _p(y), n, d, h, w, cin, cout, k, stride, code, algo,
-                                           st), "conv3d_fprop")
+                                           _p(stats), st), "conv3d_fprop")
         # stride-2 3x3x3 on tensor cores: the parity-split copy is what wgrad reads, so keep it instead of x
         keep = src if (algo == _lib.ALGO_TCGEN05_PSPLIT and _tc_wgrad_supported(dt, k, stride, cin, cout)) else x
         ctx.save_for_backward(keep, w_hat, inv_std, pd)
@@ -174,10 +176,15 @@ class WSConv3dFn(torch.autograd.Function):
         ctx.meta = (n, d, h, w, cin, cout, k, stride, int(standardise), residual is not None, weight.dtype)
         ctx.flops = flops
         ctx.key = ctx_key
+        if want_stats:
+            if stats is None:
+                return y, torch.empty(0, dtype=torch.float64, device=dev)
+            ctx.mark_non_differentiable(stats)
+            return y, stats
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dstats=None):
         L = _lib.lib()
         x, w_hat, inv_std, pd = ctx.saved_tensors
         n, d, h, w, cin, cout, k, stride, standardise, has_res, wdtype = ctx.meta
@@ -213,7 +220,7 @@ class WSConv3dFn(torch.autograd.Function):
             dw = dw.to(wdtype)
         if has_res and ctx.needs_input_grad[2]:
             dres = dy
-        return dx, dw, dres, None, None
+        return dx, dw, dres, None, None, None
 
 
 _TC_WGRAD = {"enabled": os.environ.get("MMPL_TC_WGRAD", "1") != "0"}
@@ -229,8 +236,15 @@ def _tc_wgrad_supported(dtype, k, stride, cin, cout) -> bool:
     return cin % 64 == 0 and (cout == 32 or cout % 64 == 0)
 
 
-def ws_conv3d(x, weight, stride=1, standardise=True, residual=None):
-    return WSConv3dFn.apply(x, weight, residual, int(stride), bool(standardise))
+def ws_conv3d(x, weight, stride=1, standardise=True, residual=None, want_stats=False):
+    """want_stats=True additionally computes the GroupNorm(16) statistics of the output (fused into the tcgen05
+    epilogue) and attaches them to the returned tensor, where ``gn_relu`` picks them up."""
+    if not want_stats:
+        return WSConv3dFn.apply(x, weight, residual, int(stride), bool(standardise), False)
+    y, stats = WSConv3dFn.apply(x, weight, residual, int(stride), bool(standardise), True)
+    if stats.numel():
+        y._mmpl_gn_stats = (stats, 16)
+    return y
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -288,7 +302,7 @@ class GNReLUFn(torch.autograd.Function):
     block input, unet3D.py:59-60 and :69 / :645-646)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps):
+    def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps, stats_in=None):
         _lib.require_device()
         L = _lib.lib()
         dt = _cfg["dtype"]
@@ -296,14 +310,16 @@ class GNReLUFn(torch.autograd.Function):
         n, c, d, h, w = x.shape
         spatial = d * h * w
         dev = x.device
-        stats = torch.zeros(n * groups * 2, dtype=torch.float64, device=dev)
+        have_stats = stats_in is not None and stats_in.numel() == n * groups * 2
+        stats = stats_in if have_stats else torch.zeros(n * groups * 2, dtype=torch.float64, device=dev)
         code = _lib.dtype_code(dt)
         st = _lib.stream_ptr()
         g1, b1 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         dual = gamma2 is not None
         g2 = gamma2.detach().float().contiguous() if dual else None
         b2 = beta2.detach().float().contiguous() if dual else None
-        _lib.check(L.mmpl_gn_stats(_p(x), _p(stats), n, spatial, c, groups, code, st), "gn_stats")
+        if not have_stats:
+            _lib.check(L.mmpl_gn_stats(_p(x), _p(stats), n, spatial, c, groups, code, st), "gn_stats")
         y = empty_cl(n, c, d, h, w, dt, dev)
         y2 = empty_cl(n, c, d, h, w, dt, dev) if dual else None
         _lib.check(L.mmpl_gn_relu_fwd(_p(x), _p(stats), _p(g1), _p(b1), _p(y), _p(g2), _p(b2), _p(y2), n, spatial, c,
@@ -340,16 +356,21 @@ class GNReLUFn(torch.autograd.Function):
                                       None, _p(dx), _p(dg1), _p(db1), _p(dg2), _p(db2), _p(ws), n, spatial, c, groups,
                                       eps, code, st), "gn_relu_bwd")
         if dual:
-            return dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype), None, None
-        return dx, dg1.to(pdtype), db1.to(pdtype), None, None, None, None
+            return dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype), None, None, None
+        return dx, dg1.to(pdtype), db1.to(pdtype), None, None, None, None, None
+
+
+def _attached_stats(x, groups):
+    st = getattr(x, "_mmpl_gn_stats", None)
+    return st[0] if (st is not None and st[1] == groups) else None
 
 
 def gn_relu(x, gamma, beta, groups=16, eps=1e-5):
-    return GNReLUFn.apply(x, gamma, beta, None, None, int(groups), float(eps))
+    return GNReLUFn.apply(x, gamma, beta, None, None, int(groups), float(eps), _attached_stats(x, groups))
 
 
 def gn_relu_dual(x, gamma, beta, gamma2, beta2, groups=16, eps=1e-5):
-    return GNReLUFn.apply(x, gamma, beta, gamma2, beta2, int(groups), float(eps))
+    return GNReLUFn.apply(x, gamma, beta, gamma2, beta2, int(groups), float(eps), _attached_stats(x, groups))
 
 
 # --------------------------------------------------------------------------------------------------------------

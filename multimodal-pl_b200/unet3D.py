@@ -44,11 +44,11 @@ class Conv3d(nn.Conv3d):
                 f"got k={k} stride={s} padding={p} dilation={d} groups={groups} bias={self.bias is not None}")
         self._k, self._s = k, s
 
-    def forward(self, x, residual=None):
+    def forward(self, x, residual=None, want_stats=False):
         if self.in_channels == 1:
             assert residual is None
             return ops.stem_conv(x, self.weight, self._standardise)
-        return ops.ws_conv3d(x, self.weight, self._s, self._standardise, residual)
+        return ops.ws_conv3d(x, self.weight, self._s, self._standardise, residual, want_stats)
 
 
 class PlainConv3d(Conv3d):
@@ -115,9 +115,11 @@ class NoBottleneck(nn.Module):
         else:
             a1 = ops.gn_relu(x, self.gn1.weight, self.gn1.bias, self.gn1.num_groups, self.gn1.eps)
             residual = ds(x) if ds is not None else x
-        out = self.conv1(a1)
+        fuse = self.gn2.num_groups == 16
+        out = self.conv1(a1, want_stats=fuse)    # GroupNorm statistics of conv1's output come from its epilogue
         a2 = ops.gn_relu(out, self.gn2.weight, self.gn2.bias, self.gn2.num_groups, self.gn2.eps)
-        return self.conv2(a2, residual)          # residual add fused into conv2's epilogue
+        # residual add fused into conv2's epilogue; the block output usually feeds the next block's GroupNorm
+        return self.conv2(a2, residual, want_stats=fuse)
 
 
 class _Upsample2xAdd(nn.Upsample):
