@@ -151,6 +151,47 @@ stem_wgrad_kernel(const float* __restrict__ pad, const T* __restrict__ dy, float
   }
 }
 
+// ------------------------------------------------------------------------------------------------ stem im2col
+// X27[v][t] = image[v + tap(t) - 1] (zero padded), t = 0..26, channels 27..31 = 0, stored bf16 NDHWC with 32 channels.
+// With it the Cin = 1 stem becomes a 32 -> Cout 1x1x1 convolution that runs on the tcgen05 kernels (forward AND weight
+// gradient) at HBM speed instead of 864 CUDA-core FMAs per voxel.  One thread per voxel, 64-byte row per thread.
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int D, int H, int W) {
+  const int64_t total = static_cast<int64_t>(N) * D * H * W;
+  for (int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v < total;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(v % W);
+    int64_t r = v / W;
+    const int y = static_cast<int>(r % H);
+    r /= H;
+    const int z = static_cast<int>(r % D);
+    const int n = static_cast<int>(r / D);
+    const float* base = img + static_cast<int64_t>(n) * D * H * W;
+    float t[32];
+#pragma unroll
+    for (int i = 27; i < 32; ++i) t[i] = 0.f;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int zz = z + kd - 1, yy = y + kh - 1, xx = x + kw - 1;
+          float val = 0.f;
+          if (zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W)
+            val = base[(static_cast<int64_t>(zz) * H + yy) * W + xx];
+          t[(kd * 3 + kh) * 3 + kw] = val;
+        }
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 8) {
+      Vec<__nv_bfloat16> o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = t[c0 + k];
+      o.store(out + v * 32 + c0);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ classifier fwd
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256)
@@ -341,6 +382,16 @@ extern "C" int mmpl_stem_conv_fwd(const float* image, const float* w_hat, void* 
       stem_fwd_kernel<T, 64><<<blocks, 128, 0, s>>>(image, w_hat, static_cast<T*>(y), n, d, h, w);
   });
   MMPL_CHECK_LAUNCH("stem_conv_fwd");
+  return MMPL_OK;
+}
+
+extern "C" int mmpl_stem_im2col(const float* image, void* x27, int n, int d, int h, int w, mmpl_stream_t stream) {
+  MMPL_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0, MMPL_E_SHAPE, "stem_im2col: empty image");
+  const int64_t total = static_cast<int64_t>(n) * d * h * w;
+  const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(num_sms()) * 16));
+  stem_im2col_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(image, static_cast<__nv_bfloat16*>(x27), n, d,
+                                                                          h, w);
+  MMPL_CHECK_LAUNCH("stem_im2col");
   return MMPL_OK;
 }
 

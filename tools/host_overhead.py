@@ -49,4 +49,4 @@ if os.environ.get("TPROF"):
     gaps.sort(reverse=True)
     print("largest idle gaps (us):")
     for g in gaps[:15]: print("  %8.0f  after %-50s before %s" % g)
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=60))
