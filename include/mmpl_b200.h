@@ -83,9 +83,11 @@ size_t mmpl_conv3d_wgrad_workspace(int n, int d, int h, int w, int cin, int cout
 /* ---- stem (Cin = 1) and classifier (1x1x1 with bias, NCDHW fp32 logits): unet3D.py:594, :629-633 -------------- */
 int mmpl_stem_conv_fwd(const float* image, const float* w_hat /*[Cout][27]*/, void* y, int n, int d, int h, int w,
                        int cout, int dtype, mmpl_stream_t stream);
-/* bf16 path: x27 [N,D,H,W,32] bf16 = the 27 shifted copies of the image (+5 zero channels); the stem is then a
- * 32 -> Cout 1x1x1 convolution for mmpl_conv3d_fprop / mmpl_conv3d_wgrad (tcgen05). */
-int mmpl_stem_im2col(const float* image, void* x27, int n, int d, int h, int w, mmpl_stream_t stream);
+/* bf16 path: x27 [N,D,H,W,channels] bf16 = the 27 shifted copies of the image; the stem is then a channels -> Cout
+ * 1x1x1 convolution for mmpl_conv3d_fprop / mmpl_conv3d_wgrad (tcgen05).  channels = 32: taps in 0..26, zeros in
+ * 27..31.  channels = 64: hi bf16 part in 0..26 and the lo part (x - hi) in 32..58, i.e. the image keeps 16 mantissa
+ * bits and only the weights are rounded to bf16, as in every other layer. */
+int mmpl_stem_im2col(const float* image, void* x27, int n, int d, int h, int w, int channels, mmpl_stream_t stream);
 /* dw is tap-major [27][Cout] fp32; workspace (>= mmpl_stem_conv_wgrad_workspace bytes) holds a zero-padded image copy. */
 size_t mmpl_stem_conv_wgrad_workspace(int n, int d, int h, int w);
 int mmpl_stem_conv_wgrad(const float* image, const void* dy, float* dw_tapmajor /*[27][Cout]*/, int n, int d, int h,

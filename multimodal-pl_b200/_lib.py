@@ -30,7 +30,7 @@ _SIGNATURES = {
     "mmpl_conv3d_dgrad": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr],
     "mmpl_conv3d_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr, _c_size, _ptr],
     "mmpl_conv3d_wgrad_workspace": [_c_int] * 9,
-    "mmpl_stem_im2col": [_ptr, _ptr] + [_c_int] * 4 + [_ptr],
+    "mmpl_stem_im2col": [_ptr, _ptr] + [_c_int] * 5 + [_ptr],
     "mmpl_stem_conv_fwd": [_ptr, _ptr, _ptr] + [_c_int] * 6 + [_ptr],
     "mmpl_stem_conv_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 6 + [_ptr, _c_size, _ptr],
     "mmpl_stem_conv_wgrad_workspace": [_c_int] * 4,

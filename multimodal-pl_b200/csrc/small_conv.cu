@@ -152,11 +152,15 @@ stem_wgrad_kernel(const float* __restrict__ pad, const T* __restrict__ dy, float
 }
 
 // ------------------------------------------------------------------------------------------------ stem im2col
-// X27[v][t] = image[v + tap(t) - 1] (zero padded), t = 0..26, channels 27..31 = 0, stored bf16 NDHWC with 32 channels.
-// With it the Cin = 1 stem becomes a 32 -> Cout 1x1x1 convolution that runs on the tcgen05 kernels (forward AND weight
-// gradient) at HBM speed instead of 864 CUDA-core FMAs per voxel.  One thread per voxel, 64-byte row per thread.
+// X27[v][t] = image[v + tap(t) - 1] (zero padded), t = 0..26, stored bf16 NDHWC.  With it the Cin = 1 stem becomes a
+// 1x1x1 convolution that runs on the tcgen05 kernels (forward AND weight gradient) at HBM speed instead of 864
+// CUDA-core FMAs per voxel.  SPLIT = 0: 32 channels (27 taps + 5 zeros).  SPLIT = 1: 64 channels, the fp32 value is
+// carried as hi + lo bf16 parts (channels t and 32 + t; 16 mantissa bits), so only the weights are rounded to bf16 as
+// in every other layer.  One thread per voxel.
+template <int SPLIT>
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int D, int H, int W) {
+  constexpr int CH = SPLIT ? 64 : 32;
   const int64_t total = static_cast<int64_t>(N) * D * H * W;
   for (int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v < total;
        v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -187,7 +191,13 @@ stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ ou
       Vec<__nv_bfloat16> o;
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] = t[c0 + k];
-      o.store(out + v * 32 + c0);
+      o.store(out + v * CH + c0);
+      if (SPLIT) {
+        Vec<__nv_bfloat16> l;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) l.v[k] = t[c0 + k] - __bfloat162float(__float2bfloat16(t[c0 + k]));
+        l.store(out + v * CH + 32 + c0);
+      }
     }
   }
 }
@@ -385,12 +395,19 @@ extern "C" int mmpl_stem_conv_fwd(const float* image, const float* w_hat, void* 
   return MMPL_OK;
 }
 
-extern "C" int mmpl_stem_im2col(const float* image, void* x27, int n, int d, int h, int w, mmpl_stream_t stream) {
+extern "C" int mmpl_stem_im2col(const float* image, void* x27, int n, int d, int h, int w, int channels,
+                                mmpl_stream_t stream) {
   MMPL_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0, MMPL_E_SHAPE, "stem_im2col: empty image");
+  MMPL_REQUIRE(channels == 32 || channels == 64, MMPL_E_SHAPE, "stem_im2col: channels=%d (32, or 64 = hi/lo split)",
+               channels);
   const int64_t total = static_cast<int64_t>(n) * d * h * w;
   const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(num_sms()) * 16));
-  stem_im2col_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(image, static_cast<__nv_bfloat16*>(x27), n, d,
-                                                                          h, w);
+  if (channels == 64)
+    stem_im2col_kernel<1><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(image, static_cast<__nv_bfloat16*>(x27),
+                                                                               n, d, h, w);
+  else
+    stem_im2col_kernel<0><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(image, static_cast<__nv_bfloat16*>(x27),
+                                                                               n, d, h, w);
   MMPL_CHECK_LAUNCH("stem_im2col");
   return MMPL_OK;
 }

@@ -248,12 +248,23 @@ def ws_conv3d(x, weight, stride=1, standardise=True, residual=None, want_stats=F
 
 
 # --------------------------------------------------------------------------------------------------------------
+_STEM = {"mode": os.environ.get("MMPL_STEM", "split")}
+
+
+def set_stem_mode(mode: str):
+    """bf16 stem: 'split' (tcgen05, image carried as hi+lo bf16 parts, K = 64), 'tc32' (tcgen05, image rounded to bf16,
+    K = 32), 'fp32fwd' (CUDA-core fp32 forward, tcgen05 weight gradient) or 'direct' (CUDA cores only)."""
+    assert mode in ("split", "tc32", "fp32fwd", "direct")
+    _STEM["mode"] = mode
+
+
 class StemConvFn(torch.autograd.Function):
     """conv3x3x3(1 -> base) on the fp32 image (unet3D.py:594, :666).
 
-    bf16 / tcgen05 path: the image is expanded once into a bf16 [N,D,H,W,32] tensor holding its 27 shifted copies
-    (mmpl_stem_im2col); forward and weight gradient are then 32 -> base 1x1x1 convolutions on the tensor-core kernels
-    (HBM-bound) instead of 864 CUDA-core FMAs per voxel.  fp32 / 'direct' path: CUDA-core kernels on the fp32 image."""
+    bf16 / tcgen05 path: the image is expanded once into a bf16 [N,D,H,W,K] tensor holding its 27 shifted copies
+    (mmpl_stem_im2col; K = 64 carries each fp32 value as hi + lo bf16 parts so the image is not rounded); forward and
+    weight gradient are then K -> base 1x1x1 convolutions on the tensor-core kernels (HBM-bound) instead of 864
+    CUDA-core FMAs per voxel.  fp32 / 'direct' path: CUDA-core kernels on the fp32 image."""
 
     @staticmethod
     def forward(ctx, image, weight, standardise):
@@ -272,41 +283,53 @@ class StemConvFn(torch.autograd.Function):
         _lib.check(L.mmpl_ws_weight_fwd(_p(w32), cout, 1, 27, int(standardise), _p(w_hat), _p(inv_std), None, None,
                                         _lib.F32, st), "ws_weight_fwd")
         y = empty_cl(n, cout, d, h, w, dt, dev)
-        use_tc = _algo(dt, 32, cout) == _lib.ALGO_TCGEN05 and _tc_wgrad_supported(dt, 1, 1, 32, cout)
-        if use_tc:
-            x27 = torch.empty((n, d, h, w, 32), dtype=dt, device=dev)
-            _lib.check(L.mmpl_stem_im2col(_p(img), _p(x27), n, d, h, w, st), "stem_im2col")
-            pf = torch.zeros((cout, 32), dtype=dt, device=dev)
+        mode = _STEM["mode"]
+        kch = 64 if mode == "split" else 32
+        use_tc = (mode != "direct" and _algo(dt, kch, cout) == _lib.ALGO_TCGEN05
+                  and _tc_wgrad_supported(dt, 1, 1, kch, cout))
+        tc_fwd = use_tc and mode != "fp32fwd"
+        if tc_fwd:
+            x27 = torch.empty((n, d, h, w, kch), dtype=dt, device=dev)
+            _lib.check(L.mmpl_stem_im2col(_p(img), _p(x27), n, d, h, w, kch, st), "stem_im2col")
+            pf = torch.zeros((cout, kch), dtype=dt, device=dev)
             pf[:, :27] = w_hat.view(cout, 27)
+            if kch == 64:
+                pf[:, 32:59] = pf[:, :27]
             code = _lib.dtype_code(dt)
-            flops = 2 * n * d * h * w * cout * 32
-            with _timed(_lib.ALGO_TCGEN05, flops, ("conv_tc", 32, cout, 1, 1, n * d * h * w)):
-                _lib.check(L.mmpl_conv3d_fprop(_p(x27), _p(pf), None, _p(y), n, d, h, w, 32, cout, 1, 1, code,
+            flops = 2 * n * d * h * w * cout * kch
+            with _timed(_lib.ALGO_TCGEN05, flops, ("conv_tc", kch, cout, 1, 1, n * d * h * w)):
+                _lib.check(L.mmpl_conv3d_fprop(_p(x27), _p(pf), None, _p(y), n, d, h, w, kch, cout, 1, 1, code,
                                                _lib.ALGO_TCGEN05, None, st), "conv3d_fprop(stem)")
             ctx.save_for_backward(x27, w_hat, inv_std)
         else:
             _lib.check(L.mmpl_stem_conv_fwd(_p(img), _p(w_hat), _p(y), n, d, h, w, cout, _lib.dtype_code(dt), st),
                        "stem_conv_fwd")
             ctx.save_for_backward(img, w_hat, inv_std)
-        ctx.meta = (n, d, h, w, cout, int(standardise), weight.dtype, use_tc)
+        ctx.meta = (n, d, h, w, cout, int(standardise), weight.dtype, use_tc, tc_fwd, kch)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         L = _lib.lib()
         src, w_hat, inv_std = ctx.saved_tensors
-        n, d, h, w, cout, standardise, wdtype, use_tc = ctx.meta
+        n, d, h, w, cout, standardise, wdtype, use_tc, tc_fwd, kch = ctx.meta
         dy = to_cl(dy)
         st = _lib.stream_ptr()
         dev = src.device
         if use_tc:
+            if not tc_fwd:      # forward ran on the fp32 image: expand it now (bf16 rounding is fine for dW)
+                x27 = torch.empty((n, d, h, w, kch), dtype=dy.dtype, device=dev)
+                _lib.check(L.mmpl_stem_im2col(_p(src), _p(x27), n, d, h, w, kch, st), "stem_im2col")
+                src = x27
             code = _lib.dtype_code(dy.dtype)
-            g32 = torch.empty(cout * 32, dtype=torch.float32, device=dev)            # [1 tap][cout][32]
-            flops = 2 * n * d * h * w * cout * 32
-            with _timed(_lib.ALGO_TCGEN05, flops, ("wgrad_tc", 32, cout, 1, 1, n * d * h * w)):
-                _lib.check(L.mmpl_conv3d_wgrad(_p(src), _p(dy), _p(g32), n, d, h, w, 32, cout, 1, 1, code,
+            g32 = torch.empty(cout * kch, dtype=torch.float32, device=dev)            # [1 tap][cout][kch]
+            flops = 2 * n * d * h * w * cout * kch
+            with _timed(_lib.ALGO_TCGEN05, flops, ("wgrad_tc", kch, cout, 1, 1, n * d * h * w)):
+                _lib.check(L.mmpl_conv3d_wgrad(_p(src), _p(dy), _p(g32), n, d, h, w, kch, cout, 1, 1, code,
                                                _lib.ALGO_TCGEN05, None, 0, st), "conv3d_wgrad(stem)")
-            g_hat = g32.view(cout, 32)[:, :27].t().contiguous()                         # tap-major [27][cout]
+            g2 = g32.view(cout, kch)
+            g_hat = g2[:, :27] + g2[:, 32:59] if kch == 64 else g2[:, :27]
+            g_hat = g_hat.t().contiguous()                                              # tap-major [27][cout]
         else:
             g_hat = torch.empty(27 * cout, dtype=torch.float32, device=dev)
             wsb = int(L.mmpl_stem_conv_wgrad_workspace(n, d, h, w))
