@@ -263,6 +263,11 @@ def run_ours(args):
     launches_per_step = (_lib.launch_count() - launches_eager0) // 3
     prof = ops.collect_conv_profile()
     prof_steps = 3
+    if args.conv_table and rank == 0:
+        sys.stderr.write("tcgen05 conv launches per kernel key (op, Cmin, Cmax, k, stride, voxels): launches/step, ms/step, TFLOP/s\n")
+        for k, v in sorted(prof["per_key"].items(), key=lambda kv: -kv[1]["ms"]):
+            sys.stderr.write(f"  {k:52s} {v['launches'] // prof_steps:3d} {v['ms'] / prof_steps:8.3f} "
+                             f"{v['flops'] / max(v['ms'], 1e-9) / 1e9:8.1f}\n")
     ops.enable_conv_profile(False)
     if use_graph:
         launches = launches_per_step * args.steps      # kernels executed by the replayed graphs in the timed region
@@ -371,6 +376,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-table", action="store_true", help="print per-kernel-key tcgen05 conv timings to stderr")
     ap.add_argument("--eager", action="store_true", help="drive every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

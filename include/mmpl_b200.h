@@ -114,8 +114,10 @@ int mmpl_gn_relu_bwd(const void* x, const double* stats, const float* gamma, con
                      int64_t spatial, int c, int groups, float eps, int dtype, mmpl_stream_t stream);
 
 /* ---- trilinear x2 upsample (align_corners=False) + skip add: unet3D.py:608, :686-687 -------------------------- */
+/* gn_stats (optional, may be NULL): double [N][16][2], zeroed by the caller; receives the GroupNorm(16) raw sums
+ * (sum, sum of squares per group) of y, i.e. the statistics of the next block's gn1 / downsample.0 (unet3D.py:59, :645). */
 int mmpl_upsample2x_add_fwd(const void* x_lo, const void* skip, void* y, int n, int d, int h, int w, int c,
-                            int dtype, mmpl_stream_t stream);
+                            int dtype, void* gn_stats, mmpl_stream_t stream);
 int mmpl_upsample2x_bwd(const void* dy, void* dx_lo, int n, int d, int h, int w, int c, int dtype,
                         mmpl_stream_t stream);
 

@@ -213,164 +213,210 @@ cls_fwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
   if (threadIdx.x < 16) sb[threadIdx.x] = threadIdx.x < classes ? bias[threadIdx.x] : 0.f;
   __syncthreads();
   constexpr int VN = Vec<T>::N;
+  constexpr int VT = 2;   // voxels per thread: every weight LDS.128 feeds 8 FMAs (no grid-stride loop: keeps registers low)
   const int64_t total = static_cast<int64_t>(N) * S;
-  // one voxel per thread (no grid-stride loop: keeps the 16xCIN weights in shared memory instead of registers)
-  const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (v >= total) return;
-  const int64_t n = v / S, s = v - n * S;
-  float acc[16];
+  const int64_t vb = blockIdx.x * static_cast<int64_t>(blockDim.x) * VT + threadIdx.x;
+  float acc[VT][16];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = sb[c];
+  for (int u = 0; u < VT; ++u)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[u][c] = sb[c];
 #pragma unroll
   for (int k0 = 0; k0 < CIN; k0 += VN) {
-    Vec<T> x;
-    x.load(a + v * CIN + k0);
+    Vec<T> x[VT];
+#pragma unroll
+    for (int u = 0; u < VT; ++u) {
+      const int64_t v = vb + u * static_cast<int64_t>(blockDim.x);
+      if (v < total) {
+        x[u].load(a + v * CIN + k0);
+      } else {
+#pragma unroll
+        for (int k = 0; k < VN; ++k) x[u].v[k] = 0.f;
+      }
+    }
 #pragma unroll
     for (int k = 0; k < VN; ++k)
 #pragma unroll
       for (int c = 0; c < 16; c += 4) {
         const float4 w4 = *reinterpret_cast<const float4*>(&sw[k0 + k][c]);
-        acc[c] = fmaf(x.v[k], w4.x, acc[c]);
-        acc[c + 1] = fmaf(x.v[k], w4.y, acc[c + 1]);
-        acc[c + 2] = fmaf(x.v[k], w4.z, acc[c + 2]);
-        acc[c + 3] = fmaf(x.v[k], w4.w, acc[c + 3]);
+#pragma unroll
+        for (int u = 0; u < VT; ++u) {
+          acc[u][c] = fmaf(x[u].v[k], w4.x, acc[u][c]);
+          acc[u][c + 1] = fmaf(x[u].v[k], w4.y, acc[u][c + 1]);
+          acc[u][c + 2] = fmaf(x[u].v[k], w4.z, acc[u][c + 2]);
+          acc[u][c + 3] = fmaf(x[u].v[k], w4.w, acc[u][c + 3]);
+        }
       }
   }
 #pragma unroll
-  for (int c = 0; c < 16; ++c)
-    if (c < classes) logits[(n * classes + c) * S + s] = acc[c];
+  for (int u = 0; u < VT; ++u) {
+    const int64_t v = vb + u * static_cast<int64_t>(blockDim.x);
+    if (v >= total) continue;
+    const int64_t n = v / S, s = v - n * S;
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < classes) logits[(n * classes + c) * S + s] = acc[u][c];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ classifier bwd
 // One pass over dlogits and a: da[v][k] = sum_c dl[c][v] W[c][k];  dW[c][k] = sum_v dl[c][v] a[v][k];  db[c] = sum_v dl.
-// Tile of TV voxels staged in shared memory; dW accumulators are register-tiled 4(c) x 4(k) per thread.
+// 1024 FMAs per voxel (CIN = 32) next to 192 bytes of HBM traffic, so the kernel is laid out to be FMA-issue bound, not
+// shared-memory bound: tiles of 128 voxels are staged in shared memory (dl transposed to [voxel][class] with a 16-byte
+// swizzle, a as fp32); phase 1 keeps W in registers (thread = 4 input channels x 16 classes, 1 LDS.128 per 16 FMAs),
+// phase 2 register-tiles dW 4(c) x 4(k) per thread (1 LDS.128 per 8 FMAs).  The next tile's global loads are issued
+// before the current tile's arithmetic (register prefetch).
+template <typename T>
+struct Raw16 {   // 16 raw bytes of T (8 bf16 or 4 fp32), converted only when stored to shared memory
+  uint4 u;
+  __device__ __forceinline__ void load(const T* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void zero() { u = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void to_smem(float* dst) const;
+};
+template <>
+__device__ __forceinline__ void Raw16<float>::to_smem(float* dst) const {
+  *reinterpret_cast<uint4*>(dst) = u;
+}
+template <>
+__device__ __forceinline__ void Raw16<__nv_bfloat16>::to_smem(float* dst) const {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[2 * i] = __uint_as_float(w[i] << 16), f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void store4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
 template <typename T, int CIN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const float* __restrict__ dl, T* __restrict__ da,
                float* __restrict__ dwc, float* __restrict__ dbias, int N, int64_t S, int classes) {
-  constexpr int TV = 128;
-  constexpr int KB = CIN / 4;           // k-blocks of 4
-  constexpr int SLOTS = 4 * KB;         // (c-block, k-block) pairs
-  constexpr int REP = SLOTS / 32;       // pairs per lane (1 for CIN=32, 2 for CIN=64)
-  constexpr int DLP = TV + 1;            // odd pitch: conflict-free both for the staging stores and the phase-2 reads
-  __shared__ __align__(16) float sw[16][CIN];
-  __shared__ float s_dl[16 * DLP];
+  constexpr int TV = 128;               // voxels per tile
+  constexpr int KB = CIN / 4;           // blocks of 4 input channels
+  constexpr int VPP = 256 / KB;         // phase 1: voxels per pass over the block
+  constexpr int SLOTS = 4 * KB;         // phase 2: (class block, channel block) pairs
+  constexpr int VG = 256 / SLOTS;       // phase 2: voxel groups
+  constexpr int VN = Vec<T>::N;
+  constexpr int AV = TV * CIN / VN / 256;  // 16-byte loads of `a` per thread per tile
+  __shared__ __align__(16) float s_g[TV][16];
   __shared__ __align__(16) float s_a[TV][CIN];
-  for (int i = threadIdx.x; i < 16 * CIN; i += 256) sw[i / CIN][i % CIN] = (i / CIN) < classes ? wc[i] : 0.f;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float accw[REP][4][4];
+  const int tid = threadIdx.x;
+  const int kb1 = tid % KB, vs1 = tid / KB;
+  const int slot = tid % SLOTS, vg = tid / SLOTS, cb2 = slot / KB, kb2 = slot % KB;
+  const int sj = tid % TV, sc = (tid / TV) * 8;
+  float wreg[16][4];
+#pragma unroll
+  for (int c = 0; c < 16; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wreg[c][i] = c < classes ? wc[c * CIN + kb1 * 4 + i] : 0.f;
+  float accw[4][4];
   float accb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int r = 0; r < REP; ++r)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) accw[r][i][j] = 0.f;
-  constexpr int VN = Vec<T>::N;
+    for (int j = 0; j < 4; ++j) accw[i][j] = 0.f;
   const int64_t total = static_cast<int64_t>(N) * S;
   const int64_t ntiles = (total + TV - 1) / TV;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+
+  float pg[8];
+  Raw16<T> pa[AV];
+  auto prefetch = [&](int64_t tile) {
+    const int64_t v0 = tile * TV;
+    const int64_t v = v0 + sj;
+    const bool ok = v < total;
+    const int64_t n = ok ? v / S : 0, sp = ok ? v - n * S : 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pg[i] = (ok && sc + i < classes) ? dl[(n * classes + sc + i) * S + sp] : 0.f;
+#pragma unroll
+    for (int r = 0; r < AV; ++r) {
+      const int idx = tid + 256 * r;                 // 16-byte unit inside the tile
+      const int j = idx / (CIN / VN);
+      if (v0 + j < total)
+        pa[r].load(a + v0 * CIN + static_cast<int64_t>(idx) * VN);
+      else
+        pa[r].zero();
+    }
+  };
+
+  int64_t tile = blockIdx.x;
+  if (tile < ntiles) prefetch(tile);
+  for (; tile < ntiles; tile += gridDim.x) {
     const int64_t v0 = tile * TV;
     __syncthreads();
-    // stage dl (coalesced per class plane) and a (vector loads)
-    for (int i = threadIdx.x; i < 16 * TV; i += 256) {
-      const int c = i / TV, j = i % TV;
-      const int64_t v = v0 + j;
-      float val = 0.f;
-      if (c < classes && v < total) {
-        const int64_t n = v / S, s = v - n * S;
-        val = dl[(n * classes + c) * S + s];
-      }
-      s_dl[c * DLP + j] = val;
-    }
-    for (int i = threadIdx.x; i < TV * (CIN / VN); i += 256) {
-      const int j = i / (CIN / VN), k0 = (i % (CIN / VN)) * VN;
-      const int64_t v = v0 + j;
-      Vec<T> x;
-      if (v < total) {
-        x.load(a + v * CIN + k0);
-      } else {
+    {
+      const int sw = (sj >> 1) & 3;
+      *reinterpret_cast<float4*>(&s_g[sj][((sc / 4) ^ sw) * 4]) = make_float4(pg[0], pg[1], pg[2], pg[3]);
+      *reinterpret_cast<float4*>(&s_g[sj][((sc / 4 + 1) ^ sw) * 4]) = make_float4(pg[4], pg[5], pg[6], pg[7]);
 #pragma unroll
-        for (int k = 0; k < VN; ++k) x.v[k] = 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < VN; ++k) s_a[j][k0 + k] = x.v[k];
+      for (int r = 0; r < AV; ++r) pa[r].to_smem(&s_a[0][0] + static_cast<int64_t>(tid + 256 * r) * VN);
     }
     __syncthreads();
-    // phase 1: da for voxel j = threadIdx.x % TV, half of the channels per thread (256 threads / 128 voxels)
-    {
-      const int j = threadIdx.x % TV, half = threadIdx.x / TV;
-      const int64_t v = v0 + j;
-      if (v < total) {
-        float g[16];
+    if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);
+    // phase 1: da
+#pragma unroll 2
+    for (int p = 0; p < TV / VPP; ++p) {
+      const int j = p * VPP + vs1;
+      const int sw = (j >> 1) & 3;
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 16; ++c) g[c] = s_dl[c * DLP + j];
+      for (int cb = 0; cb < 4; ++cb) {
+        const float4 g4 = *reinterpret_cast<const float4*>(&s_g[j][(cb ^ sw) * 4]);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-        for (int k0 = half * (CIN / 2); k0 < (half + 1) * (CIN / 2); k0 += VN) {
-          Vec<T> o;
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int k = 0; k < VN; ++k) o.v[k] = 0.f;
-#pragma unroll
-          for (int c = 0; c < 16; ++c)
-#pragma unroll
-            for (int k = 0; k < VN; k += 4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(&sw[c][k0 + k]);
-              o.v[k] = fmaf(g[c], w4.x, o.v[k]);
-              o.v[k + 1] = fmaf(g[c], w4.y, o.v[k + 1]);
-              o.v[k + 2] = fmaf(g[c], w4.z, o.v[k + 2]);
-              o.v[k + 3] = fmaf(g[c], w4.w, o.v[k + 3]);
-            }
-          o.store(da + v * CIN + k0);
-        }
+          for (int i = 0; i < 4; ++i) o[i] = fmaf(g[c], wreg[cb * 4 + c][i], o[i]);
       }
+      if (v0 + j < total) store4(da + (v0 + j) * CIN + kb1 * 4, o);
     }
-    // phase 2: dW / dbias; warp w covers voxels w, w+8, ... of the tile
+    // phase 2: dW / dbias
+#pragma unroll 4
+    for (int j = vg; j < TV; j += VG) {
+      const float4 x4 = *reinterpret_cast<const float4*>(&s_a[j][kb2 * 4]);
+      const float4 g4 = *reinterpret_cast<const float4*>(&s_g[j][(cb2 ^ ((j >> 1) & 3)) * 4]);
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+      const float x[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-    for (int r = 0; r < REP; ++r) {
-      const int slot = lane + 32 * r, cb = slot / KB, kb = slot % KB;
-      for (int j = warp; j < TV; j += 8) {
-        const float4 x = *reinterpret_cast<const float4*>(&s_a[j][kb * 4]);
-        const float gg[4] = {s_dl[(cb * 4 + 0) * DLP + j], s_dl[(cb * 4 + 1) * DLP + j], s_dl[(cb * 4 + 2) * DLP + j],
-                             s_dl[(cb * 4 + 3) * DLP + j]};
-        const float xx[4] = {x.x, x.y, x.z, x.w};
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 4; ++k) accw[i][k] = fmaf(g[i], x[k], accw[i][k]);
+      if (kb2 == 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) accw[r][i][k] = fmaf(gg[i], xx[k], accw[r][i][k]);
-        if (r == 0 && kb == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) accb[i] += gg[i];
-        }
+        for (int i = 0; i < 4; ++i) accb[i] += g[i];
       }
     }
   }
-  // cross-warp reduction through shared memory (reuse the staging tiles), then one atomic per (c,k) per block
+  // cross-group reduction through shared memory (reuse the staging tiles), then one atomic per (c,k) per block
   __syncthreads();
-  float* red = &s_a[0][0];    // 8 warps x 16 classes x CIN floats == TV*CIN
-  float* redb = &s_dl[0];     // 8 warps x 16 classes
-  for (int r = 0; r < REP; ++r) {
-    const int slot = lane + 32 * r, cb = slot / KB, kb = slot % KB;
+  float* red = &s_a[0][0];    // VG x 16 classes x CIN floats <= TV*CIN
+  float* redb = &s_g[0][0];   // VG x 16 classes
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) red[(warp * 16 + cb * 4 + i) * CIN + kb * 4 + k] = accw[r][i][k];
-    if (r == 0 && kb == 0) {
+    for (int k = 0; k < 4; ++k) red[(vg * 16 + cb2 * 4 + i) * CIN + kb2 * 4 + k] = accw[i][k];
+  if (kb2 == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) redb[warp * 16 + cb * 4 + i] = accb[i];
-    }
+    for (int i = 0; i < 4; ++i) redb[vg * 16 + cb2 * 4 + i] = accb[i];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 16 * CIN; i += 256) {
+  for (int i = tid; i < 16 * CIN; i += 256) {
     const int c = i / CIN, k = i % CIN;
     if (c >= classes) continue;
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[(w * 16 + c) * CIN + k];
-    atomicAdd(&dwc[c * CIN + k], s);
+    float sum = 0.f;
+    for (int w = 0; w < VG; ++w) sum += red[(w * 16 + c) * CIN + k];
+    atomicAdd(&dwc[c * CIN + k], sum);
   }
-  if (threadIdx.x < classes) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += redb[w * 16 + threadIdx.x];
-    atomicAdd(&dbias[threadIdx.x], s);
+  if (tid < classes) {
+    float sum = 0.f;
+    for (int w = 0; w < VG; ++w) sum += redb[w * 16 + tid];
+    atomicAdd(&dbias[tid], sum);
   }
 }
 
@@ -445,7 +491,7 @@ extern "C" int mmpl_cls_fwd(const void* a, const float* wc, const float* bias, f
   MMPL_REQUIRE((cin == 32 || cin == 64) && classes >= 1 && classes <= 16, MMPL_E_SHAPE,
                "cls: cin=%d classes=%d (cin 32|64, classes<=16)", cin, classes);
   const int64_t total = static_cast<int64_t>(n) * spatial;
-  const int blocks = static_cast<int>((total + 255) / 256);
+  const int blocks = static_cast<int>((total + 511) / 512);   // 256 threads x 2 voxels
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   MMPL_DISPATCH_DTYPE(dtype, T, {
     if (cin == 32)
@@ -465,7 +511,7 @@ extern "C" int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits
   MMPL_CUDA(cudaMemsetAsync(dwc, 0, sizeof(float) * classes * cin, s));
   MMPL_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * classes, s));
   const int64_t ntiles = (static_cast<int64_t>(n) * spatial + 127) / 128;
-  const int blocks = static_cast<int>(std::min<int64_t>(ntiles, static_cast<int64_t>(num_sms()) * 4));
+  const int blocks = static_cast<int>(std::min<int64_t>(ntiles, static_cast<int64_t>(num_sms()) * 2));
   MMPL_DISPATCH_DTYPE(dtype, T, {
     if (cin == 32)
       cls_bwd_kernel<T, 32><<<blocks, 256, 0, s>>>(static_cast<const T*>(a), wc, dlogits, static_cast<T*>(da), dwc, dbias,

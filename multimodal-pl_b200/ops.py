@@ -58,6 +58,7 @@ def collect_conv_profile():
         e[2] += 1
     dom = max(per.items(), key=lambda kv: kv[1][0]) if per else (None, [0.0, 0.0, 0])
     return {"ms": tot_ms, "launches": len(_PROF["events"]), "flops": float(tot_fl),
+            "per_key": {str(k): {"ms": v[0], "flops": float(v[1]), "launches": v[2]} for k, v in per.items()},
             "dominant": {"key": dom[0], "ms": dom[1][0], "flops": float(dom[1][1]), "launches": dom[1][2]}}
 
 
@@ -297,19 +298,24 @@ class StemConvFn(torch.autograd.Function):
                 pf[:, 32:59] = pf[:, :27]
             code = _lib.dtype_code(dt)
             flops = 2 * n * d * h * w * cout * kch
+            # GroupNorm(16) raw sums of the stem output (layer0.0.gn1) come from the conv epilogue
+            stats = torch.zeros(n * 16 * 2, dtype=torch.float64, device=dev) if cout % 16 == 0 else None
             with _timed(_lib.ALGO_TCGEN05, flops, ("conv_tc", kch, cout, 1, 1, n * d * h * w)):
                 _lib.check(L.mmpl_conv3d_fprop(_p(x27), _p(pf), None, _p(y), n, d, h, w, kch, cout, 1, 1, code,
-                                               _lib.ALGO_TCGEN05, None, st), "conv3d_fprop(stem)")
+                                               _lib.ALGO_TCGEN05, _p(stats), st), "conv3d_fprop(stem)")
             ctx.save_for_backward(x27, w_hat, inv_std)
         else:
             _lib.check(L.mmpl_stem_conv_fwd(_p(img), _p(w_hat), _p(y), n, d, h, w, cout, _lib.dtype_code(dt), st),
                        "stem_conv_fwd")
             ctx.save_for_backward(img, w_hat, inv_std)
         ctx.meta = (n, d, h, w, cout, int(standardise), weight.dtype, use_tc, tc_fwd, kch)
-        return y
+        if not tc_fwd or stats is None:
+            stats = torch.empty(0, dtype=torch.float64, device=dev)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dstats=None):
         L = _lib.lib()
         src, w_hat, inv_std = ctx.saved_tensors
         n, d, h, w, cout, standardise, wdtype, use_tc, tc_fwd, kch = ctx.meta
@@ -343,16 +349,23 @@ class StemConvFn(torch.autograd.Function):
 
 
 def stem_conv(image, weight, standardise=True):
-    return StemConvFn.apply(image, weight, bool(standardise))
+    y, stats = StemConvFn.apply(image, weight, bool(standardise))
+    if stats.numel():
+        y._mmpl_gn_stats = (stats, 16)
+    return y
 
 
 # --------------------------------------------------------------------------------------------------------------
 class GNReLUFn(torch.autograd.Function):
     """GroupNorm(groups, C) + ReLU, optionally two affine heads on the same input (gn1 and downsample.0 share the
-    block input, unet3D.py:59-60 and :69 / :645-646)."""
+    block input, unet3D.py:59-60 and :69 / :645-646).
+
+    ``alias=True`` additionally returns the input itself as an extra output.  Callers route the *other* use of the
+    block input through it (the identity residual of unet3D.py:69-71, or the encoder skip of :669-677), so that its
+    gradient arrives here and is added inside the backward kernel instead of by a separate elementwise add."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps, stats_in=None):
+    def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps, stats_in=None, alias=False):
         _lib.require_device()
         L = _lib.lib()
         dt = _cfg["dtype"]
@@ -375,16 +388,23 @@ class GNReLUFn(torch.autograd.Function):
         _lib.check(L.mmpl_gn_relu_fwd(_p(x), _p(stats), _p(g1), _p(b1), _p(y), _p(g2), _p(b2), _p(y2), n, spatial, c,
                                       groups, eps, code, st), "gn_relu_fwd")
         ctx.save_for_backward(x, stats, g1, b1, g2, b2)
-        ctx.meta = (n, c, spatial, groups, eps, dual, gamma.dtype)
+        ctx.meta = (n, c, spatial, groups, eps, dual, gamma.dtype, bool(alias))
+        outs = [y]
         if dual:
-            return y, y2
-        return y
+            outs.append(y2)
+        if alias:
+            outs.append(x.view_as(x))
+        return outs[0] if len(outs) == 1 else tuple(outs)
 
     @staticmethod
-    def backward(ctx, dy, dy2=None):
+    def backward(ctx, *grads):
         L = _lib.lib()
         x, stats, g1, b1, g2, b2 = ctx.saved_tensors
-        n, c, spatial, groups, eps, dual, pdtype = ctx.meta
+        n, c, spatial, groups, eps, dual, pdtype, alias = ctx.meta
+        grads = list(grads)
+        dy = grads.pop(0)
+        dy2 = grads.pop(0) if dual else None
+        dres = grads.pop(0) if alias else None
         dt = x.dtype
         dev = x.device
         code = _lib.dtype_code(dt)
@@ -396,6 +416,8 @@ class GNReLUFn(torch.autograd.Function):
             if dy2 is None:
                 dy2 = torch.zeros_like(x)
             dy2 = to_cl(dy2, dt)
+        if dres is not None:
+            dres = to_cl(dres, dt)
         dx = torch.empty_like(x)
         dg1 = torch.empty(c, dtype=torch.float32, device=dev)
         db1 = torch.empty(c, dtype=torch.float32, device=dev)
@@ -403,11 +425,11 @@ class GNReLUFn(torch.autograd.Function):
         db2 = torch.empty(c, dtype=torch.float32, device=dev) if dual else None
         ws = torch.empty(n * c * 4, dtype=torch.float64, device=dev)
         _lib.check(L.mmpl_gn_relu_bwd(_p(x), _p(stats), _p(g1), _p(b1), _p(dy), _p(g2), _p(b2), _p(dy2) if dual else None,
-                                      None, _p(dx), _p(dg1), _p(db1), _p(dg2), _p(db2), _p(ws), n, spatial, c, groups,
+                                      _p(dres), _p(dx), _p(dg1), _p(db1), _p(dg2), _p(db2), _p(ws), n, spatial, c, groups,
                                       eps, code, st), "gn_relu_bwd")
         if dual:
-            return dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype), None, None, None
-        return dx, dg1.to(pdtype), db1.to(pdtype), None, None, None, None, None
+            return dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype), None, None, None, None
+        return dx, dg1.to(pdtype), db1.to(pdtype), None, None, None, None, None, None
 
 
 def _attached_stats(x, groups):
@@ -415,12 +437,15 @@ def _attached_stats(x, groups):
     return st[0] if (st is not None and st[1] == groups) else None
 
 
-def gn_relu(x, gamma, beta, groups=16, eps=1e-5):
-    return GNReLUFn.apply(x, gamma, beta, None, None, int(groups), float(eps), _attached_stats(x, groups))
+def gn_relu(x, gamma, beta, groups=16, eps=1e-5, alias=False):
+    """-> y, or (y, x_alias) with alias=True."""
+    return GNReLUFn.apply(x, gamma, beta, None, None, int(groups), float(eps), _attached_stats(x, groups), bool(alias))
 
 
-def gn_relu_dual(x, gamma, beta, gamma2, beta2, groups=16, eps=1e-5):
-    return GNReLUFn.apply(x, gamma, beta, gamma2, beta2, int(groups), float(eps), _attached_stats(x, groups))
+def gn_relu_dual(x, gamma, beta, gamma2, beta2, groups=16, eps=1e-5, alias=False):
+    """-> (y, y2), or (y, y2, x_alias) with alias=True."""
+    return GNReLUFn.apply(x, gamma, beta, gamma2, beta2, int(groups), float(eps), _attached_stats(x, groups),
+                          bool(alias))
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -436,13 +461,21 @@ class Upsample2xAddFn(torch.autograd.Function):
         n, c, d, h, w = x_lo.shape
         assert tuple(skip.shape) == (n, c, 2 * d, 2 * h, 2 * w), f"skip {tuple(skip.shape)} vs 2x of {tuple(x_lo.shape)}"
         y = empty_cl(n, c, 2 * d, 2 * h, 2 * w, dt, x_lo.device)
-        _lib.check(L.mmpl_upsample2x_add_fwd(_p(x_lo), _p(skip), _p(y), n, d, h, w, c, _lib.dtype_code(dt),
+        # GroupNorm(16) raw sums of the output (consumed by the next block's gn1 / downsample.0), when the channel
+        # vectors of a row tile evenly over a 256-thread block
+        vn = 8 if dt == torch.bfloat16 else 4
+        fuse = c % 16 == 0 and c <= 512 and 256 % (c // vn) == 0
+        stats = torch.zeros(n * 16 * 2, dtype=torch.float64, device=x_lo.device) if fuse else None
+        _lib.check(L.mmpl_upsample2x_add_fwd(_p(x_lo), _p(skip), _p(y), n, d, h, w, c, _lib.dtype_code(dt), _p(stats),
                                              _lib.stream_ptr()), "upsample2x_add_fwd")
         ctx.meta = (n, c, d, h, w, dt)
-        return y
+        if stats is None:
+            stats = torch.empty(0, dtype=torch.float64, device=x_lo.device)
+        ctx.mark_non_differentiable(stats)
+        return y, stats
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dstats=None):
         L = _lib.lib()
         n, c, d, h, w, dt = ctx.meta
         dy = to_cl(dy, dt)
@@ -455,7 +488,10 @@ class Upsample2xAddFn(torch.autograd.Function):
 
 
 def upsample2x_add(x_lo, skip):
-    return Upsample2xAddFn.apply(x_lo, skip)
+    y, stats = Upsample2xAddFn.apply(x_lo, skip)
+    if stats.numel():
+        y._mmpl_gn_stats = (stats, 16)
+    return y
 
 
 # --------------------------------------------------------------------------------------------------------------

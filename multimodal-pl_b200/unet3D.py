@@ -104,22 +104,36 @@ class NoBottleneck(nn.Module):
         self.dilation = dilation
         self.stride = stride
 
-    def forward(self, x):
+    def forward(self, x, want_alias=False):
+        """``want_alias=True`` -> (out, x_alias): x_alias is the block input routed through gn1's autograd node, so a
+        second consumer of the block input (the encoder skip, unet3D.py:669-677) has its gradient added inside the
+        GroupNorm backward kernel instead of by a separate elementwise add."""
         ds = self.downsample
         fused_ds = isinstance(ds, GNReLUConv) and ds[0].num_groups == self.gn1.num_groups and ds[0].eps == self.gn1.eps
+        x_alias = None
         if fused_ds:
             # gn1 and downsample.0 normalise the same tensor: one statistics pass, one read, two affine heads
-            a1, ads = ops.gn_relu_dual(x, self.gn1.weight, self.gn1.bias, ds[0].weight, ds[0].bias,
-                                       self.gn1.num_groups, self.gn1.eps)
+            outs = ops.gn_relu_dual(x, self.gn1.weight, self.gn1.bias, ds[0].weight, ds[0].bias,
+                                    self.gn1.num_groups, self.gn1.eps, alias=want_alias)
+            a1, ads = outs[0], outs[1]
+            if want_alias:
+                x_alias = outs[2]
             residual = ds[2](ads)
+        elif ds is None:
+            # identity residual: its gradient is folded into gn1's backward through the alias output
+            a1, x_alias = ops.gn_relu(x, self.gn1.weight, self.gn1.bias, self.gn1.num_groups, self.gn1.eps, alias=True)
+            residual = x_alias
         else:
             a1 = ops.gn_relu(x, self.gn1.weight, self.gn1.bias, self.gn1.num_groups, self.gn1.eps)
-            residual = ds(x) if ds is not None else x
+            residual = ds(x)
         fuse = self.gn2.num_groups == 16
         out = self.conv1(a1, want_stats=fuse)    # GroupNorm statistics of conv1's output come from its epilogue
         a2 = ops.gn_relu(out, self.gn2.weight, self.gn2.bias, self.gn2.num_groups, self.gn2.eps)
         # residual add fused into conv2's epilogue; the block output usually feeds the next block's GroupNorm
-        return self.conv2(a2, residual, want_stats=fuse)
+        out = self.conv2(a2, residual, want_stats=fuse)
+        if want_alias:
+            return out, (x_alias if x_alias is not None else x)
+        return out
 
 
 class _Upsample2xAdd(nn.Upsample):
@@ -182,17 +196,24 @@ class unet3D_baseline(nn.Module):
             layers.append(block(planes, planes, dilation=dilation, multi_grid=1, weight_std=self.weight_std))
         return nn.Sequential(*layers)
 
+    @staticmethod
+    def _stage_with_skip(layer, x):
+        """Run an encoder stage; also return its input as routed through the first block (see NoBottleneck.forward)."""
+        blocks = list(layer)
+        if not blocks or not isinstance(blocks[0], NoBottleneck):
+            return layer(x), x
+        out, skip = blocks[0](x, want_alias=True)
+        for blk in blocks[1:]:
+            out = blk(out)
+        return out, skip
+
     def forward(self, input, mask=None):
         x = self.conv1(input)
         x = self.layer0(x)
-        skip0 = x
-        x = self.layer1(x)
-        skip1 = x
-        x = self.layer2(x)
-        skip2 = x
-        x = self.layer3(x)
-        skip3 = x
-        x = self.layer4(x)
+        x, skip0 = self._stage_with_skip(self.layer1, x)     # skipN = the input of stage N+1 (reference :669-677)
+        x, skip1 = self._stage_with_skip(self.layer2, x)
+        x, skip2 = self._stage_with_skip(self.layer3, x)
+        x, skip3 = self._stage_with_skip(self.layer4, x)
         x = self.fusionConv(x)
         x = self.x8_resb(self.upsamplex2(x, skip3))
         x = self.x4_resb(self.upsamplex2(x, skip2))

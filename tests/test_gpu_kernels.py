@@ -70,6 +70,55 @@ def test_gn_relu(mm, dtype, tol_f, tol_b, shape):
         assert rel(pd2[i].grad, pr[i].grad) < tol_b, i
 
 
+@pytest.mark.parametrize("dtype,tol_b", [(torch.float32, 1e-4), (torch.bfloat16, 5e-2)])
+@pytest.mark.parametrize("dual", [False, True])
+def test_gn_relu_alias_folds_second_gradient(mm, dtype, tol_b, dual):
+    """alias=True returns the input as an extra output; the gradient arriving through it (identity residual /
+    encoder skip) must be added to dx inside the backward kernel: dx = dGN(dy) [+ dGN2(dy2)] + d_alias."""
+    mm.set_compute_dtype(dtype)
+    ops = mm.ops
+    shape = (2, 32, 4, 6, 10)
+    x = _rand(shape, 1) + 0.3
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    C = shape[1]
+    g1, b1, g2, b2 = 1 + 0.2 * _rand((C,), 2), 0.2 * _rand((C,), 3), 1 + 0.2 * _rand((C,), 4), 0.2 * _rand((C,), 5)
+    dy1, dy2, dres = _rand(shape, 6), _rand(shape, 7), _rand(shape, 8)
+    xr = x.clone().requires_grad_(True)
+    loss = (O.gn_relu(xr, g1, b1) * dy1).sum() + (xr * dres).sum()
+    if dual:
+        loss = loss + (O.gn_relu(xr, g2, b2) * dy2).sum()
+    loss.backward()
+    xd = x.cuda().requires_grad_(True)
+    if dual:
+        y1, y2, xa = ops.gn_relu_dual(xd, g1.cuda(), b1.cuda(), g2.cuda(), b2.cuda(), alias=True)
+        l = (y1.float() * dy1.cuda()).sum() + (y2.float() * dy2.cuda()).sum() + (xa.float() * dres.cuda()).sum()
+    else:
+        y1, xa = ops.gn_relu(xd, g1.cuda(), b1.cuda(), alias=True)
+        l = (y1.float() * dy1.cuda()).sum() + (xa.float() * dres.cuda()).sum()
+    assert torch.equal(xa.float().cpu(), x)
+    l.backward()
+    assert rel(xd.grad.float(), xr.grad) < tol_b
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-3)])
+@pytest.mark.parametrize("shape", [(2, 32, 3, 4, 5), (1, 64, 2, 2, 3), (1, 256, 2, 3, 1)])
+def test_upsample2x_add_fused_gn_statistics(mm, dtype, tol, shape):
+    """The up-sample kernel also emits the GroupNorm(16) raw sums of its output; they must equal the sums over the
+    stored output (what the stand-alone statistics kernel would read)."""
+    mm.set_compute_dtype(dtype)
+    n, c, d, h, w = shape
+    x, skip = _rand(shape, 1), _rand((n, c, 2 * d, 2 * h, 2 * w), 2)
+    y = mm.ops.upsample2x_add(x.cuda(), skip.cuda())
+    st = getattr(y, "_mmpl_gn_stats", None)
+    assert st is not None and st[1] == 16
+    got = st[0].view(n, 16, 2).cpu()
+    yy = y.detach().double().cpu().view(n, 16, c // 16, -1)
+    want = torch.stack([yy.sum(dim=(2, 3)), (yy * yy).sum(dim=(2, 3))], dim=-1)
+    assert torch.allclose(got[..., 1], want[..., 1], rtol=tol, atol=0)
+    assert torch.allclose(got[..., 0], want[..., 0], rtol=0, atol=tol * want[..., 1].sqrt().max().item() * 10)
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)])
 @pytest.mark.parametrize("shape", [(2, 32, 3, 4, 5), (1, 64, 1, 2, 2), (1, 256, 2, 3, 1)])
 def test_upsample2x_add(mm, dtype, tol, shape):
