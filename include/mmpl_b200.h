@@ -53,6 +53,20 @@ uint64_t mmpl_launch_count(void);
  * packings in `dtype` (either may be NULL).  standardise=0 copies/packs w unchanged (plain nn.Conv3d). */
 int mmpl_ws_weight_fwd(const float* w, int cout, int cin, int taps, int standardise, float* w_hat, float* inv_std,
                        void* packed_fprop, void* packed_dgrad, int dtype, mmpl_stream_t stream);
+/* The same for every convolution of a network in ONE launch.  `table_dev` is a DEVICE array of `count` entries sorted
+ * by first_block; entry i owns blocks [first_block, first_block + cout) of the grid, total_blocks = sum of cout.
+ * stem_kch > 0 (Cin = 1 stem only): packed_fprop is [cout][stem_kch] with the 27 taps in columns 0..26 and, for
+ * stem_kch = 64, again in 32..58 (the operand mmpl_stem_im2col pairs with); other columns are left untouched. */
+typedef struct mmpl_ws_entry {
+  const float* w;
+  float* w_hat;
+  float* inv_std;
+  void* packed_fprop;
+  void* packed_dgrad;
+  int32_t cout, cin, taps, standardise, first_block, stem_kch;
+} mmpl_ws_entry; /* 64 bytes */
+int mmpl_ws_weight_fwd_batched(const mmpl_ws_entry* table_dev, int count, int total_blocks, int dtype,
+                               mmpl_stream_t stream);
 /* Backward of the standardisation: g_hat = dL/dw_hat given tap-major [tap][Cout][Cin] fp32 (as wgrad writes it);
  * dw (reference layout, fp32) = (g - mean(g) - w_hat * sum(g*w_hat)/(n-1)) * inv_std.  standardise=0: un-pack. */
 int mmpl_ws_weight_bwd(const float* g_hat_tapmajor, const float* w_hat, const float* inv_std, int cout, int cin,

@@ -24,6 +24,7 @@ _SIGNATURES = {
     "mmpl_check_device": [],
     "mmpl_launch_count": [],
     "mmpl_ws_weight_fwd": [_ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr],
+    "mmpl_ws_weight_fwd_batched": [_ptr, _c_int, _c_int, _c_int, _ptr],
     "mmpl_ws_weight_bwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
     "mmpl_parity_split": [_ptr, _ptr] + [_c_int] * 6 + [_ptr],
     "mmpl_conv3d_fprop": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr, _ptr],

@@ -20,12 +20,14 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
   return t;
 }
 
+// One out-channel (co) of one convolution.  stem_kch > 0 selects the stem packing (Cin = 1): pf is [cout][stem_kch]
+// with the 27 taps in columns 0..26 and, for stem_kch = 64, again in columns 32..58 (hi/lo image split, see
+// mmpl_stem_im2col); the padding columns are never written and must be zero.
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
-ws_fwd_kernel(const float* __restrict__ w, int cout, int cin, int taps, int standardise, float* __restrict__ w_hat,
-              float* __restrict__ inv_std, T* __restrict__ pf, T* __restrict__ pd) {
-  __shared__ double scratch[kThreads / 32];
-  const int co = blockIdx.x, n = cin * taps;
+__device__ __forceinline__ void ws_fwd_one(const float* __restrict__ w, int cout, int cin, int taps, int standardise,
+                                           float* __restrict__ w_hat, float* __restrict__ inv_std, T* __restrict__ pf,
+                                           T* __restrict__ pd, int co, int stem_kch, double* scratch) {
+  const int n = cin * taps;
   const float* wr = w + static_cast<int64_t>(co) * n;
   float mean = 0.f, istd = 1.f;
   if (standardise) {
@@ -49,9 +51,43 @@ ws_fwd_kernel(const float* __restrict__ w, int cout, int cin, int taps, int stan
     const int ci = i / taps, t = i - ci * taps;
     const float wh = standardise ? (wr[i] - mean) * istd : wr[i];
     if (w_hat) w_hat[static_cast<int64_t>(co) * n + i] = wh;
-    if (pf) pf[(static_cast<int64_t>(t) * cout + co) * cin + ci] = from_f32<T>(wh);
-    if (pd) pd[(static_cast<int64_t>(taps - 1 - t) * cin + ci) * cout + co] = from_f32<T>(wh);
+    if (stem_kch > 0) {
+      if (pf) {
+        pf[static_cast<int64_t>(co) * stem_kch + t] = from_f32<T>(wh);
+        if (stem_kch >= 64) pf[static_cast<int64_t>(co) * stem_kch + 32 + t] = from_f32<T>(wh);
+      }
+    } else {
+      if (pf) pf[(static_cast<int64_t>(t) * cout + co) * cin + ci] = from_f32<T>(wh);
+      if (pd) pd[(static_cast<int64_t>(taps - 1 - t) * cin + ci) * cout + co] = from_f32<T>(wh);
+    }
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+ws_fwd_kernel(const float* __restrict__ w, int cout, int cin, int taps, int standardise, float* __restrict__ w_hat,
+              float* __restrict__ inv_std, T* __restrict__ pf, T* __restrict__ pd) {
+  __shared__ double scratch[kThreads / 32];
+  ws_fwd_one<T>(w, cout, cin, taps, standardise, w_hat, inv_std, pf, pd, blockIdx.x, 0, scratch);
+}
+
+// All convolutions of a network in ONE launch: block b serves out-channel (b - first_block) of the table entry that
+// contains b.  The table lives in device memory (mmpl_ws_entry, include/mmpl_b200.h).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+ws_fwd_batched_kernel(const mmpl_ws_entry* __restrict__ table, int count) {
+  __shared__ double scratch[kThreads / 32];
+  __shared__ mmpl_ws_entry e;
+  if (threadIdx.x == 0) {
+    int lo = 0;
+    const int b = blockIdx.x;
+    for (int i = 1; i < count; ++i)
+      if (table[i].first_block <= b) lo = i;
+    e = table[lo];
+  }
+  __syncthreads();
+  ws_fwd_one<T>(e.w, e.cout, e.cin, e.taps, e.standardise, e.w_hat, e.inv_std, static_cast<T*>(e.packed_fprop),
+                static_cast<T*>(e.packed_dgrad), blockIdx.x - e.first_block, e.stem_kch, scratch);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -94,6 +130,15 @@ extern "C" int mmpl_ws_weight_fwd(const float* w, int cout, int cin, int taps, i
                                                                         static_cast<T*>(packed_fprop),
                                                                         static_cast<T*>(packed_dgrad))));
   MMPL_CHECK_LAUNCH("ws_weight_fwd");
+  return MMPL_OK;
+}
+
+extern "C" int mmpl_ws_weight_fwd_batched(const mmpl_ws_entry* table_dev, int count, int total_blocks, int dtype,
+                                          mmpl_stream_t stream) {
+  MMPL_REQUIRE(table_dev != nullptr && count > 0 && total_blocks > 0, MMPL_E_SHAPE, "ws_weight_fwd_batched: empty table");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MMPL_DISPATCH_DTYPE(dtype, T, (ws_fwd_batched_kernel<T><<<total_blocks, kThreads, 0, s>>>(table_dev, count)));
+  MMPL_CHECK_LAUNCH("ws_weight_fwd_batched");
   return MMPL_OK;
 }
 

@@ -54,7 +54,10 @@ class DataParallelModel(torch.nn.Module):
         cur = {"hi": total, "lo": total, "pending": 0, "count": 0}
         for p in reversed(params):
             off -= p.numel()
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            # the backward kernels write parameter gradients straight into this slot (ops._grad_dst); gradients that
+            # arrive any other way are folded in by _adopt_grad
+            p._mmpl_grad_slot = (self.flat_grad, off, p.numel())
+            p.grad = None
             p._mmpl_bucket = len(self._buckets)
             cur["lo"] = off
             cur["count"] += 1
@@ -79,6 +82,8 @@ class DataParallelModel(torch.nn.Module):
 
     def all_reduce_flat(self):
         """One blocking all-reduce of the whole flat gradient buffer (used after a CUDA-graph replay)."""
+        for p in self._params:
+            _adopt_grad(p)
         if self.world_size > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
             if self.average:
@@ -87,6 +92,7 @@ class DataParallelModel(torch.nn.Module):
     def _on_grad(self, p):
         if not self.sync_in_backward:
             return
+        _adopt_grad(p)
         if not self._callback_queued:
             torch.autograd.Variable._execution_engine.queue_callback(self._finish)
             self._callback_queued = True
@@ -107,12 +113,33 @@ class DataParallelModel(torch.nn.Module):
             self.flat_grad.mul_(1.0 / self.world_size)
         self._reset()
 
-    def zero_grad(self, set_to_none: bool = False):
-        # gradients are views of the flat buffer: keep them, just clear
-        self.flat_grad.zero_()
+    def zero_grad(self, set_to_none: bool = True):
+        _zero_flat(self._params, self.flat_grad)
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
+
+
+def _adopt_grad(p):
+    """Make ``p.grad`` the view of p's slot in the flat gradient buffer.  The library's backward kernels write there
+    directly and autograd adopts that view (nothing to do); a gradient produced any other way (foreign autograd
+    function, cloned by autograd) is copied into the slot."""
+    slot = getattr(p, "_mmpl_grad_slot", None)
+    if slot is None or p.grad is None:
+        return
+    flat, off, n = slot
+    if p.grad.data_ptr() != flat.data_ptr() + 4 * off or p.grad.dtype != torch.float32:
+        view = flat[off:off + n].view_as(p)
+        view.copy_(p.grad)
+        p.grad = view
+
+
+def _zero_flat(params, flat):
+    """Start of a step: clear the flat buffer (parameters that receive no gradient must contribute zero) and drop the
+    per-parameter views so the next backward writes in place instead of accumulating."""
+    flat.zero_()
+    for p in params:
+        p.grad = None
 
 
 class FusedSGD(torch.optim.Optimizer):
@@ -135,18 +162,21 @@ class FusedSGD(torch.optim.Optimizer):
             self.flat_param[off:off + n].copy_(p.data.reshape(-1).float())
             p.data = self.flat_param[off:off + n].view_as(p)
             if own_grad:
-                p.grad = self.flat_grad[off:off + n].view_as(p)
+                p._mmpl_grad_slot = (self.flat_grad, off, n)
+                p.grad = None
             else:
-                assert p.grad is not None and p.grad.data_ptr() == self.flat_grad[off:off + n].data_ptr(), \
+                slot = getattr(p, "_mmpl_grad_slot", None)
+                assert slot is not None and slot[0] is self.flat_grad and slot[1] == off, \
                     "flat_grad must be laid out in parameter order (use DataParallelModel.flat_grad)"
             off += n
+        self._params = params
         self.momentum_buf = torch.zeros(total, dtype=torch.float32, device=dev)
         self._lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self._lr_host = None
         self._steps = 0
 
-    def zero_grad(self, set_to_none: bool = False):
-        self.flat_grad.zero_()
+    def zero_grad(self, set_to_none: bool = True):
+        _zero_flat(self._params, self.flat_grad)
 
     def _sync_lr(self):
         """Mirror param_groups[0]['lr'] into the device scalar the kernel reads (outside any graph capture)."""
@@ -160,6 +190,8 @@ class FusedSGD(torch.optim.Optimizer):
         g = self.param_groups[0]
         if not torch.cuda.is_current_stream_capturing():
             self._sync_lr()
+        for p in self._params:      # gradients that did not land in the flat buffer by themselves
+            _adopt_grad(p)
         _lib.require_device()
         _lib.check(_lib.lib().mmpl_sgd_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(),
                                             self.momentum_buf.data_ptr(), self.flat_param.numel(),

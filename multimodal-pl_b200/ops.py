@@ -83,6 +83,36 @@ class _timed:
         return False
 
 
+def _grad_dst(param, shape):
+    """Where a backward kernel writes a parameter gradient.  If the parameter has a slot in a flat gradient buffer
+    (engine.DataParallelModel / FusedSGD set ``_mmpl_grad_slot``) and no gradient yet this step, the kernel writes
+    straight into a fresh view of that slot and autograd's AccumulateGrad adopts the view as ``param.grad`` -- no copy,
+    no add kernel.  Otherwise (gradient accumulation, parameters without a slot, non-fp32 masters) a new tensor."""
+    slot = getattr(param, "_mmpl_grad_slot", None) if param is not None else None
+    if slot is not None and param.grad is None and param.dtype == torch.float32:
+        flat, off, n = slot
+        return flat[off:off + n].view(shape)
+    return torch.empty(shape, dtype=torch.float32, device=param.device if param is not None else None)
+
+
+_STATS_POOL = {"buf": None, "off": 0}
+
+
+def begin_forward(device, slots: int = 64, per_slot: int = 256):
+    """One zero-fill for all GroupNorm statistics accumulators of a forward pass (instead of one per layer).  A fresh
+    pool per forward: the slices are saved for the backward pass."""
+    _STATS_POOL["buf"] = torch.zeros(slots * per_slot, dtype=torch.float64, device=device)
+    _STATS_POOL["off"] = 0
+
+
+def _zero_stats(numel: int, device) -> torch.Tensor:
+    buf, off = _STATS_POOL["buf"], _STATS_POOL["off"]
+    if buf is not None and buf.device == device and off + numel <= buf.numel():
+        _STATS_POOL["off"] = off + numel
+        return buf[off:off + numel]
+    return torch.zeros(numel, dtype=torch.float64, device=device)
+
+
 def to_cl(x: torch.Tensor, dtype=None) -> torch.Tensor:
     """Logical NCDHW tensor -> compute dtype with physically dense NDHWC storage (no copy if already so)."""
     dtype = dtype or _cfg["dtype"]
@@ -126,6 +156,147 @@ def _out_dim(i, k, s):
 
 
 # --------------------------------------------------------------------------------------------------------------
+# Standardised weights.  The reference recomputes w_hat in every Conv3d.forward (unet3D.py:22-26), 8 ATen launches per
+# convolution.  Here each weight owns persistent buffers (w_hat, inv_std, the two tap-major packings) and ALL
+# convolutions of a network are refreshed by ONE launch (mmpl_ws_weight_fwd_batched) at the top of the model's forward
+# (``prepare_ws``).  The refresh is unconditional -- weights may be changed behind autograd's back (``p.data`` updates,
+# raw-pointer optimizers, CUDA-graph replays), so nothing is ever assumed fresh across forwards: ``prepare_ws`` marks
+# each entry as ready for exactly one use, and a convolution that finds its entry not ready (module called on its own,
+# or a weight shared by two layers) refreshes it itself.
+_WS_TABLES = {}
+
+
+class _WsEntry:
+    __slots__ = ("w_hat", "inv_std", "pf", "pd", "key", "shape_key")
+
+
+def _ws_key(weight, dt, standardise, stem_kch):
+    return (weight.data_ptr(), dt, bool(standardise), stem_kch)
+
+
+def _ws_entry(weight, dt, stem_kch=0, packed=True):
+    shape_key = (tuple(weight.shape), dt, weight.device, stem_kch, packed)
+    e = getattr(weight, "_mmpl_ws", None)
+    if e is None or e.shape_key != shape_key:
+        cout, cin = weight.shape[0], weight.shape[1]
+        taps = weight[0, 0].numel()
+        dev = weight.device
+        e = _WsEntry()
+        e.w_hat = torch.empty(weight.shape, dtype=torch.float32, device=dev)
+        e.inv_std = torch.empty(cout, dtype=torch.float32, device=dev)
+        if stem_kch:
+            e.pf = torch.zeros((cout, stem_kch), dtype=dt, device=dev)
+            e.pd = None
+        elif packed:
+            e.pf = torch.empty(taps * cout * cin, dtype=dt, device=dev)
+            e.pd = torch.empty(taps * cout * cin, dtype=dt, device=dev)
+        else:
+            e.pf = e.pd = None
+        e.key = None
+        e.shape_key = shape_key
+        weight._mmpl_ws = e
+    return e
+
+
+def _ws_cacheable(weight):
+    return weight.dtype == torch.float32 and weight.is_contiguous() and weight.is_cuda
+
+
+def _ws_refresh_one(weight, e, dt, standardise, stem_kch):
+    """Single-convolution refresh (fallback when prepare_ws was not called, e.g. a module used on its own)."""
+    L = _lib.lib()
+    cout, cin = weight.shape[0], weight.shape[1]
+    taps = weight[0, 0].numel()
+    w32 = weight.detach()
+    st = _lib.stream_ptr()
+    if stem_kch:
+        tab = _ws_table([(weight, standardise, stem_kch, e)], dt)
+        _lib.check(L.mmpl_ws_weight_fwd_batched(_p(tab[0]), tab[1], tab[2], _lib.dtype_code(dt), st), "ws_weight_fwd")
+    else:
+        _lib.check(L.mmpl_ws_weight_fwd(_p(w32), cout, cin, taps, int(standardise), _p(e.w_hat), _p(e.inv_std), _p(e.pf),
+                                        _p(e.pd), _lib.dtype_code(dt), st), "ws_weight_fwd")
+
+
+def _ws_table(items, dt):
+    """Device table of mmpl_ws_entry records (include/mmpl_b200.h) for ``items`` = [(weight, standardise, stem_kch,
+    entry)], cached by the pointers it contains."""
+    import numpy as np
+
+    rec = np.dtype([("w", "<u8"), ("w_hat", "<u8"), ("inv_std", "<u8"), ("pf", "<u8"), ("pd", "<u8"), ("cout", "<i4"),
+                    ("cin", "<i4"), ("taps", "<i4"), ("standardise", "<i4"), ("first_block", "<i4"), ("stem_kch", "<i4")])
+    assert rec.itemsize == 64
+    arr = np.zeros(len(items), dtype=rec)
+    first = 0
+    for i, (weight, standardise, stem_kch, e) in enumerate(items):
+        cout, cin = weight.shape[0], weight.shape[1]
+        arr[i] = (weight.data_ptr(), e.w_hat.data_ptr(), e.inv_std.data_ptr(), 0 if e.pf is None else e.pf.data_ptr(),
+                  0 if e.pd is None else e.pd.data_ptr(), cout, cin, weight[0, 0].numel(), int(standardise), first,
+                  stem_kch)
+        first += cout
+    key = arr.tobytes()
+    hit = _WS_TABLES.get(key)
+    if hit is None:
+        if len(_WS_TABLES) > 16:
+            _WS_TABLES.clear()
+        dev = items[0][0].device
+        t = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
+        hit = (t, len(items), first)
+        _WS_TABLES[key] = hit
+    return hit
+
+
+def _stem_plan(dt, cout):
+    """-> (use_tc, tc_fwd, kch) for the Cin = 1 stem under the current dtype / algo / stem mode."""
+    mode = _STEM["mode"]
+    kch = 64 if mode == "split" else 32
+    use_tc = (mode != "direct" and _algo(dt, kch, cout) == _lib.ALGO_TCGEN05
+              and _tc_wgrad_supported(dt, 1, 1, kch, cout))
+    return use_tc, use_tc and mode != "fp32fwd", kch
+
+
+def prepare_ws(convs):
+    """Refresh the standardised weights of ``convs`` = [(weight, standardise, is_stem)] with one launch.  Called at
+    the top of unet3D_baseline.forward."""
+    dt = _cfg["dtype"]
+    items, keys = [], []
+    for weight, standardise, is_stem in convs:
+        if not _ws_cacheable(weight):
+            continue
+        if is_stem:
+            _, tc_fwd, kch = _stem_plan(dt, weight.shape[0])
+            stem_kch = kch if tc_fwd else 0
+            e = _ws_entry(weight, dt, stem_kch, packed=False)
+        else:
+            stem_kch = 0
+            e = _ws_entry(weight, dt)
+        items.append((weight, standardise, stem_kch, e))
+        keys.append(_ws_key(weight, dt, standardise, stem_kch))
+    if not items:
+        return
+    _lib.require_device()
+    tab = _ws_table(items, dt)
+    _lib.check(_lib.lib().mmpl_ws_weight_fwd_batched(_p(tab[0]), tab[1], tab[2], _lib.dtype_code(dt), _lib.stream_ptr()),
+               "ws_weight_fwd_batched")
+    for (_, _, _, e), key in zip(items, keys):
+        e.key = key
+
+
+def _ws_get(weight, dt, standardise, stem_kch=0, packed=True):
+    """Standardised-weight buffers of ``weight`` for one use: those ``prepare_ws`` just refreshed, else refreshed here."""
+    if _ws_cacheable(weight):
+        e = _ws_entry(weight, dt, stem_kch, packed)
+        if e.key != _ws_key(weight, dt, standardise, stem_kch):
+            _ws_refresh_one(weight, e, dt, standardise, stem_kch)
+        e.key = None        # consumed: the next forward refreshes again
+        return e
+    # non-fp32 / non-contiguous master weight: one-off buffers
+    w32 = weight.detach().float().contiguous()
+    e = _ws_entry(w32, dt, stem_kch, packed)
+    _ws_refresh_one(w32, e, dt, standardise, stem_kch)
+    return e
+
+
+# --------------------------------------------------------------------------------------------------------------
 class WSConv3dFn(torch.autograd.Function):
     """Weight-standardised (or plain) k^3 convolution, optional fused residual add.  unet3D.py:16-27."""
 
@@ -139,16 +310,11 @@ class WSConv3dFn(torch.autograd.Function):
         taps = k * k * k
         n, _, d, h, w = x.shape
         assert x.shape[1] == cin, f"conv: input has {x.shape[1]} channels, weight expects {cin}"
-        w32 = weight.detach().float().contiguous()
         dev = x.device
-        w_hat = torch.empty_like(w32)
-        inv_std = torch.empty(cout, dtype=torch.float32, device=dev)
-        pf = torch.empty(taps * cout * cin, dtype=dt, device=dev)
-        pd = torch.empty(taps * cout * cin, dtype=dt, device=dev)
         code = _lib.dtype_code(dt)
         st = _lib.stream_ptr()
-        _lib.check(L.mmpl_ws_weight_fwd(_p(w32), cout, cin, taps, int(standardise), _p(w_hat), _p(inv_std), _p(pf),
-                                        _p(pd), code, st), "ws_weight_fwd")
+        ws = _ws_get(weight, dt, standardise)
+        w_hat, inv_std, pf, pd = ws.w_hat, ws.inv_std, ws.pf, ws.pd
         do, ho, wo = _out_dim(d, k, stride), _out_dim(h, k, stride), _out_dim(w, k, stride)
         y = empty_cl(n, cout, do, ho, wo, dt, dev)
         res = None
@@ -166,7 +332,7 @@ class WSConv3dFn(torch.autograd.Function):
         # fprop and stride-1 dgrad of a Cin==Cout layer are the same kernel instantiation on the same problem size
         ctx_key = ("conv_tc", min(cin, cout), max(cin, cout), k, stride, n * d * h * w)
         # GroupNorm(16) raw sums of the output for the next GN+ReLU, produced by the conv epilogue
-        stats = torch.zeros(n * 16 * 2, dtype=torch.float64, device=dev) if (want_stats and cout % 16 == 0) else None
+        stats = _zero_stats(n * 16 * 2, dev) if (want_stats and cout % 16 == 0) else None
         with _timed(algo, flops, ctx_key):
             _lib.check(L.mmpl_conv3d_fprop(_p(src), _p(pf), _p(res), _p(y), n, d, h, w, cin, cout, k, stride, code, algo,
                                            _p(stats), st), "conv3d_fprop")
@@ -175,6 +341,7 @@ class WSConv3dFn(torch.autograd.Function):
         ctx.save_for_backward(keep, w_hat, inv_std, pd)
         ctx.x_is_psplit = keep is not x
         ctx.meta = (n, d, h, w, cin, cout, k, stride, int(standardise), residual is not None, weight.dtype)
+        ctx.weight = weight
         ctx.flops = flops
         ctx.key = ctx_key
         if want_stats:
@@ -215,7 +382,7 @@ class WSConv3dFn(torch.autograd.Function):
             with _timed(algo, ctx.flops, ("wgrad_tc",) + ctx.key[1:]):
                 _lib.check(L.mmpl_conv3d_wgrad(_p(x), _p(dy), _p(g_hat), n, d, h, w, cin, cout, k, stride, code, algo,
                                                _p(ws), wsb, st), "conv3d_wgrad")
-            dw = torch.empty_like(w_hat)
+            dw = _grad_dst(ctx.weight, w_hat.shape)
             _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, cin, taps, standardise, _p(dw), st),
                        "ws_weight_bwd")
             dw = dw.to(wdtype)
@@ -276,30 +443,19 @@ class StemConvFn(torch.autograd.Function):
         n, c, d, h, w = img.shape
         assert c == 1 and tuple(weight.shape[1:]) == (1, 3, 3, 3)
         cout = weight.shape[0]
-        w32 = weight.detach().float().contiguous()
         dev = img.device
-        w_hat = torch.empty_like(w32)
-        inv_std = torch.empty(cout, dtype=torch.float32, device=dev)
         st = _lib.stream_ptr()
-        _lib.check(L.mmpl_ws_weight_fwd(_p(w32), cout, 1, 27, int(standardise), _p(w_hat), _p(inv_std), None, None,
-                                        _lib.F32, st), "ws_weight_fwd")
         y = empty_cl(n, cout, d, h, w, dt, dev)
-        mode = _STEM["mode"]
-        kch = 64 if mode == "split" else 32
-        use_tc = (mode != "direct" and _algo(dt, kch, cout) == _lib.ALGO_TCGEN05
-                  and _tc_wgrad_supported(dt, 1, 1, kch, cout))
-        tc_fwd = use_tc and mode != "fp32fwd"
+        use_tc, tc_fwd, kch = _stem_plan(dt, cout)
+        ws = _ws_get(weight, dt, standardise, kch if tc_fwd else 0, packed=False)
+        w_hat, inv_std, pf = ws.w_hat, ws.inv_std, ws.pf
         if tc_fwd:
             x27 = torch.empty((n, d, h, w, kch), dtype=dt, device=dev)
             _lib.check(L.mmpl_stem_im2col(_p(img), _p(x27), n, d, h, w, kch, st), "stem_im2col")
-            pf = torch.zeros((cout, kch), dtype=dt, device=dev)
-            pf[:, :27] = w_hat.view(cout, 27)
-            if kch == 64:
-                pf[:, 32:59] = pf[:, :27]
             code = _lib.dtype_code(dt)
             flops = 2 * n * d * h * w * cout * kch
             # GroupNorm(16) raw sums of the stem output (layer0.0.gn1) come from the conv epilogue
-            stats = torch.zeros(n * 16 * 2, dtype=torch.float64, device=dev) if cout % 16 == 0 else None
+            stats = _zero_stats(n * 16 * 2, dev) if cout % 16 == 0 else None
             with _timed(_lib.ALGO_TCGEN05, flops, ("conv_tc", kch, cout, 1, 1, n * d * h * w)):
                 _lib.check(L.mmpl_conv3d_fprop(_p(x27), _p(pf), None, _p(y), n, d, h, w, kch, cout, 1, 1, code,
                                                _lib.ALGO_TCGEN05, _p(stats), st), "conv3d_fprop(stem)")
@@ -309,6 +465,7 @@ class StemConvFn(torch.autograd.Function):
                        "stem_conv_fwd")
             ctx.save_for_backward(img, w_hat, inv_std)
         ctx.meta = (n, d, h, w, cout, int(standardise), weight.dtype, use_tc, tc_fwd, kch)
+        ctx.weight = weight
         if not tc_fwd or stats is None:
             stats = torch.empty(0, dtype=torch.float64, device=dev)
         ctx.mark_non_differentiable(stats)
@@ -342,7 +499,7 @@ class StemConvFn(torch.autograd.Function):
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             _lib.check(L.mmpl_stem_conv_wgrad(_p(src), _p(dy), _p(g_hat), n, d, h, w, cout, _lib.dtype_code(dy.dtype),
                                               _p(ws), wsb, st), "stem_conv_wgrad")
-        dw = torch.empty_like(w_hat)
+        dw = _grad_dst(ctx.weight, w_hat.shape)
         _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, 1, 27, standardise, _p(dw), st),
                    "ws_weight_bwd")
         return None, dw.to(wdtype), None
@@ -374,7 +531,7 @@ class GNReLUFn(torch.autograd.Function):
         spatial = d * h * w
         dev = x.device
         have_stats = stats_in is not None and stats_in.numel() == n * groups * 2
-        stats = stats_in if have_stats else torch.zeros(n * groups * 2, dtype=torch.float64, device=dev)
+        stats = stats_in if have_stats else _zero_stats(n * groups * 2, dev)
         code = _lib.dtype_code(dt)
         st = _lib.stream_ptr()
         g1, b1 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
@@ -389,6 +546,7 @@ class GNReLUFn(torch.autograd.Function):
                                       groups, eps, code, st), "gn_relu_fwd")
         ctx.save_for_backward(x, stats, g1, b1, g2, b2)
         ctx.meta = (n, c, spatial, groups, eps, dual, gamma.dtype, bool(alias))
+        ctx.params = (gamma, beta, gamma2, beta2)
         outs = [y]
         if dual:
             outs.append(y2)
@@ -419,10 +577,10 @@ class GNReLUFn(torch.autograd.Function):
         if dres is not None:
             dres = to_cl(dres, dt)
         dx = torch.empty_like(x)
-        dg1 = torch.empty(c, dtype=torch.float32, device=dev)
-        db1 = torch.empty(c, dtype=torch.float32, device=dev)
-        dg2 = torch.empty(c, dtype=torch.float32, device=dev) if dual else None
-        db2 = torch.empty(c, dtype=torch.float32, device=dev) if dual else None
+        pg, pb, pg2, pb2 = ctx.params
+        dg1, db1 = _grad_dst(pg, (c,)), _grad_dst(pb, (c,))
+        dg2 = _grad_dst(pg2, (c,)) if dual else None
+        db2 = _grad_dst(pb2, (c,)) if dual else None
         ws = torch.empty(n * c * 4, dtype=torch.float64, device=dev)
         _lib.check(L.mmpl_gn_relu_bwd(_p(x), _p(stats), _p(g1), _p(b1), _p(dy), _p(g2), _p(b2), _p(dy2) if dual else None,
                                       _p(dres), _p(dx), _p(dg1), _p(db1), _p(dg2), _p(db2), _p(ws), n, spatial, c, groups,
@@ -465,7 +623,7 @@ class Upsample2xAddFn(torch.autograd.Function):
         # vectors of a row tile evenly over a 256-thread block
         vn = 8 if dt == torch.bfloat16 else 4
         fuse = c % 16 == 0 and c <= 512 and 256 % (c // vn) == 0
-        stats = torch.zeros(n * 16 * 2, dtype=torch.float64, device=x_lo.device) if fuse else None
+        stats = _zero_stats(n * 16 * 2, x_lo.device) if fuse else None
         _lib.check(L.mmpl_upsample2x_add_fwd(_p(x_lo), _p(skip), _p(y), n, d, h, w, c, _lib.dtype_code(dt), _p(stats),
                                              _lib.stream_ptr()), "upsample2x_add_fwd")
         ctx.meta = (n, c, d, h, w, dt)
@@ -514,6 +672,7 @@ class ClassifierFn(torch.autograd.Function):
                                   _lib.stream_ptr()), "cls_fwd")
         ctx.save_for_backward(a, wc)
         ctx.meta = (n, cin, d, h, w, classes, weight.dtype, tuple(weight.shape))
+        ctx.params = (weight, bias)
         return logits
 
     @staticmethod
@@ -523,11 +682,11 @@ class ClassifierFn(torch.autograd.Function):
         n, cin, d, h, w, classes, wdtype, wshape = ctx.meta
         dl = dl.float().contiguous()
         da = torch.empty_like(a)
-        dwc = torch.empty(classes * cin, dtype=torch.float32, device=a.device)
-        db = torch.empty(classes, dtype=torch.float32, device=a.device)
+        dwc = _grad_dst(ctx.params[0], wshape)
+        db = _grad_dst(ctx.params[1], (classes,))
         _lib.check(L.mmpl_cls_bwd(_p(a), _p(wc), _p(dl), _p(da), _p(dwc), _p(db), n, d * h * w, cin, classes,
                                   _lib.dtype_code(a.dtype), _lib.stream_ptr()), "cls_bwd")
-        return da, dwc.reshape(wshape).to(wdtype), db.to(wdtype)
+        return da, dwc.to(wdtype), db.to(wdtype)
 
 
 def classifier(a, weight, bias):

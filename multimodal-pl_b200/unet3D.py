@@ -207,7 +207,18 @@ class unet3D_baseline(nn.Module):
             out = blk(out)
         return out, skip
 
+    def _ws_convs(self):
+        convs = getattr(self, "_ws_conv_list", None)
+        if convs is None:
+            convs = [m for m in self.modules() if isinstance(m, Conv3d)]
+            object.__setattr__(self, "_ws_conv_list", convs)
+        return [(m.weight, m._standardise, m.in_channels == 1) for m in convs]
+
     def forward(self, input, mask=None):
+        # one launch standardises + packs the weights of every convolution (the reference does it per Conv3d.forward,
+        # unet3D.py:22-26); one zero-fill serves all GroupNorm statistics accumulators
+        ops.prepare_ws(self._ws_convs())
+        ops.begin_forward(input.device)
         x = self.conv1(input)
         x = self.layer0(x)
         x, skip0 = self._stage_with_skip(self.layer1, x)     # skipN = the input of stage N+1 (reference :669-677)

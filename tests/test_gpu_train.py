@@ -49,6 +49,37 @@ def test_fused_sgd_matches_torch_sgd_on_model():
         mm.set_compute_dtype(torch.bfloat16)
 
 
+def test_parameter_gradients_land_in_the_flat_buffer_without_copies():
+    """Backward kernels write every parameter gradient straight into its slot of the flat buffer and autograd adopts
+    the view (no per-parameter add/copy launches); a second backward before zero_grad accumulates (p.grad += new)."""
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.engine import DataParallelModel, FusedSGD
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    mm.set_compute_dtype(torch.bfloat16)
+    torch.manual_seed(0)
+    model = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True).cuda()
+    dp = DataParallelModel(model, 1)
+    opt = FusedSGD(dp.parameters(), lr=0.0, momentum=0.0, weight_decay=0.0, flat_grad=dp.flat_grad)
+    x = O.synth_patch((1, 1, 16, 32, 32), 5, "ct").cuda()
+    lab = O.synth_labels((1, 16, 32, 32), 6, 16, 32).cuda()
+    crit = EDiceLoss_partial(16)
+    opt.zero_grad()
+    assert all(p.grad is None for p in model.parameters())
+    crit(dp(x, lab)[0], lab.squeeze(1), mask=[torch.ones(16)]).backward()
+    base = dp.flat_grad.data_ptr()
+    for k, p in model.named_parameters():
+        _, off, n = p._mmpl_grad_slot
+        assert p.grad is not None and p.grad.data_ptr() == base + 4 * off, k
+    once = dp.flat_grad.clone()
+    assert once.abs().max().item() > 0
+    crit(dp(x, lab)[0], lab.squeeze(1), mask=[torch.ones(16)]).backward()      # accumulate
+    assert torch.allclose(dp.flat_grad, 2 * once, rtol=1e-3, atol=1e-6 * once.abs().max().item())
+    opt.zero_grad()
+    assert dp.flat_grad.abs().max().item() == 0 and all(p.grad is None for p in model.parameters())
+
+
 def test_bf16_training_reduces_loss():
     import multimodal_pl_b200 as mm
     from multimodal_pl_b200.engine import DataParallelModel, FusedSGD
