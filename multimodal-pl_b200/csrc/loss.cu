@@ -48,15 +48,19 @@ __device__ __forceinline__ void softmax_regs(const float* __restrict__ logits, i
   for (int c = 0; c < MAXC; ++c) p[c] *= inv;
 }
 
-template <int MAXC>
-__global__ void __launch_bounds__(kThreads)
+template <int MAXC, int NTHR>
+__global__ void __launch_bounds__(NTHR, MAXC <= 16 ? 3 : 1)
 partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                         const float* __restrict__ cw, const float* __restrict__ lut, double* __restrict__ sums,
                         float* __restrict__ loss, unsigned int* __restrict__ ticket, int N, int64_t S, int C, int uce) {
   __shared__ float s_lut[MAXC];
-  __shared__ float s_part[kThreads / 32][4 * MAXC];
+  __shared__ float s_part[NTHR / 32][4 * MAXC];
   __shared__ bool s_last;
   __shared__ unsigned int s_ce_mask;   // classes whose BCE term is needed (weight != 0)
+  // I_c and Y_c only ever receive the voxel's own class: per-thread accumulators in shared memory ([class][thread],
+  // conflict-free) take a dynamic class index, which registers cannot; Z_c and E_c stay in registers.  One slot more
+  // than MAXC collects voxels whose label is not a class id.
+  __shared__ float s_I[MAXC + 1][NTHR], s_Y[MAXC + 1][NTHR];
   if (threadIdx.x < MAXC) s_lut[threadIdx.x] = (lut && threadIdx.x < C) ? lut[threadIdx.x] : static_cast<float>(threadIdx.x);
   if (threadIdx.x == 0) {
     unsigned int m = 0;
@@ -64,25 +68,27 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
       if (uce && cw[c] != 0.f) m |= 1u << c;
     s_ce_mask = m;
   }
+#pragma unroll
+  for (int c = 0; c <= MAXC; ++c) s_I[c][threadIdx.x] = s_Y[c][threadIdx.x] = 0.f;
   __syncthreads();
   const unsigned int ce_mask = s_ce_mask;
-  float aI[MAXC], aZ[MAXC], aY[MAXC], aE[MAXC];
+  float aZ[MAXC], aE[MAXC];
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c) aI[c] = aZ[c] = aY[c] = aE[c] = 0.f;
+  for (int c = 0; c < MAXC; ++c) aZ[c] = aE[c] = 0.f;
   const int64_t total = static_cast<int64_t>(N) * S;
-  for (int64_t v = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; v < total;
-       v += static_cast<int64_t>(gridDim.x) * kThreads) {
+  for (int64_t v = blockIdx.x * static_cast<int64_t>(NTHR) + threadIdx.x; v < total;
+       v += static_cast<int64_t>(gridDim.x) * NTHR) {
     const int64_t n = v / S, s = v - n * S;
     float p[MAXC];
     softmax_regs<MAXC>(logits, n * C * S + s, S, C, p);
     const int tc = class_of(target[v], lut ? s_lut : nullptr, C);
+    float ptc = 0.f;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
       if (c < C) {
         const bool t = (c == tc);
-        aI[c] += t ? p[c] : 0.f;
+        ptc = t ? p[c] : ptc;
         aZ[c] = fmaf(p[c], p[c], aZ[c]);
-        aY[c] += t ? 1.f : 0.f;
         if (ce_mask & (1u << c)) {
           // nn.BCELoss semantics: log() of the fp32 probability, clamped at -100
           const float l = t ? logf(p[c]) : logf(1.0f - p[c]);
@@ -90,7 +96,13 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
         }
       }
     }
+    const int slot = tc >= 0 ? tc : MAXC;
+    s_I[slot][threadIdx.x] += ptc;
+    s_Y[slot][threadIdx.x] += 1.f;
   }
+  float aI[MAXC], aY[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) aI[c] = s_I[c][threadIdx.x], aY[c] = s_Y[c][threadIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
@@ -107,7 +119,7 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
     const int k = threadIdx.x / MAXC, c = threadIdx.x % MAXC;
     if (c < C) {
       double t = 0;
-      for (int w = 0; w < kThreads / 32; ++w) t += static_cast<double>(s_part[w][threadIdx.x]);
+      for (int w = 0; w < NTHR / 32; ++w) t += static_cast<double>(s_part[w][threadIdx.x]);
       atomicAdd(&sums[k * C + c], t);
     }
   }
@@ -131,7 +143,7 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
 }
 
 template <int MAXC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MAXC <= 16 ? 3 : 1)
 partial_loss_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                         const float* __restrict__ cw, const float* __restrict__ lut, const double* __restrict__ sums,
                         const float* __restrict__ grad_out, float* __restrict__ dlogits, int N, int64_t S, int C,
@@ -155,21 +167,23 @@ partial_loss_bwd_kernel(const float* __restrict__ logits, const float* __restric
   for (int64_t v = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; v < total;
        v += static_cast<int64_t>(gridDim.x) * kThreads) {
     const int64_t n = v / S, s = v - n * S;
-    float p[MAXC], g[MAXC];
+    float p[MAXC];
     softmax_regs<MAXC>(logits, n * C * S + s, S, C, p);
     const int tc = class_of(target[v], lut ? s_lut : nullptr, C);
-    float dot = 0.f;
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
+    // g_c is cheap: evaluate it twice (once for the dot product, once for the output) instead of keeping 16 more
+    // registers live -- the kernel is bound by loads in flight, i.e. by occupancy
+    auto gfun = [&](int c) {
       const float t = (c == tc) ? 1.f : 0.f;
       float gc = t * s_a[c] + p[c] * s_b[c];
       if (s_e[c] != 0.f) gc += s_e[c] * (p[c] - t) / fmaxf(p[c] * (1.0f - p[c]), 1e-12f);   // warp-uniform branch
-      g[c] = gc;
-      dot = fmaf(gc, p[c], dot);
-    }
+      return gc;
+    };
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) dot = fmaf(gfun(c), p[c], dot);
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
-      if (c < C) dlogits[n * C * S + c * S + s] = p[c] * (g[c] - dot);
+      if (c < C) dlogits[n * C * S + c * S + s] = p[c] * (gfun(c) - dot);
   }
 }
 
@@ -197,13 +211,15 @@ extern "C" int mmpl_partial_loss_fwd(const float* logits, const float* target, c
   MMPL_REQUIRE(ticket != nullptr, MMPL_E_CUDA, "partial_loss: ticket allocation failed");
   MMPL_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * classes, s));
   const int64_t total = static_cast<int64_t>(n) * spatial;
-  const int blocks = static_cast<int>(std::min<int64_t>((total + kThreads - 1) / kThreads, static_cast<int64_t>(num_sms()) * 8));
-  if (classes <= 16)
-    partial_loss_fwd_kernel<16><<<blocks, kThreads, 0, s>>>(logits, target, class_weight, lut, sums, loss, ticket, n,
+  if (classes <= 16) {
+    const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(num_sms()) * 6));
+    partial_loss_fwd_kernel<16, 256><<<blocks, 256, 0, s>>>(logits, target, class_weight, lut, sums, loss, ticket, n,
                                                            spatial, classes, uce);
-  else
-    partial_loss_fwd_kernel<32><<<blocks, kThreads, 0, s>>>(logits, target, class_weight, lut, sums, loss, ticket, n,
+  } else {
+    const int blocks = static_cast<int>(std::min<int64_t>((total + 127) / 128, static_cast<int64_t>(num_sms()) * 8));
+    partial_loss_fwd_kernel<32, 128><<<blocks, 128, 0, s>>>(logits, target, class_weight, lut, sums, loss, ticket, n,
                                                            spatial, classes, uce);
+  }
   MMPL_CHECK_LAUNCH("partial_loss_fwd");
   return MMPL_OK;
 }
