@@ -87,8 +87,23 @@ int mmpl_parity_split(const void* x, void* p_out, int n, int d, int h, int w, in
 int mmpl_conv3d_fprop(const void* x, const void* w_fprop, const void* residual, void* y, int n, int d, int h, int w,
                       int cin, int cout, int ksize, int stride, int dtype, int algo, double* gn_stats_out,
                       mmpl_stream_t stream);
+/* Optional fusion of the first pass of the GroupNorm+ReLU backward into the dgrad epilogue.  dx is the gradient
+ * w.r.t. a = relu(gn(.)), this convolution's forward input (NoBottleneck.forward, unet3D.py:59-66).  Since
+ * a = gamma*xhat + beta where the ReLU passes and 0 elsewhere, the sums the GroupNorm backward needs are
+ *   S1_c = sum_v dx*[a > 0]      and      Q_c = gamma_c * sum_v g*xhat = sum_v dx*a - beta_c*S1_c,
+ * which the epilogue accumulates while dx is still in registers (one extra row read of `a`).  `ws` is the
+ * double [N][Cin][6] workspace of mmpl_gn_relu_bwd (zero on entry); head selects columns {0,1} or {2,3}.
+ * *gn_fused_out = 1 if the request was honoured (tcgen05 algorithms), 0 if the caller must run the reduction pass. */
+typedef struct mmpl_gn_bwd_fuse {
+  const void* a;           /* forward input of this convolution, dtype of dx: [N,D,H,W,Cin], or its parity-split copy */
+  const float* beta;       /* [Cin] GroupNorm bias of the node that produced a */
+  double* ws;              /* [N][Cin][6], accumulated into */
+  int a_is_parity_split;   /* 1: `a` is the mmpl_parity_split tensor (stride-2 3x3x3 convolutions keep only that) */
+  int head;                /* 0, or 1 for the second head of a dual GroupNorm */
+} mmpl_gn_bwd_fuse;
 int mmpl_conv3d_dgrad(const void* dy, const void* w_dgrad, const void* addend, void* dx, int n, int d, int h, int w,
-                      int cin, int cout, int ksize, int stride, int dtype, int algo, mmpl_stream_t stream);
+                      int cin, int cout, int ksize, int stride, int dtype, int algo, const mmpl_gn_bwd_fuse* gn,
+                      int* gn_fused_out, mmpl_stream_t stream);
 int mmpl_conv3d_wgrad(const void* x, const void* dy, float* dw_tapmajor, int n, int d, int h, int w, int cin,
                       int cout, int ksize, int stride, int dtype, int algo, void* workspace, size_t workspace_bytes,
                       mmpl_stream_t stream);
@@ -108,8 +123,11 @@ int mmpl_stem_conv_wgrad(const float* image, const void* dy, float* dw_tapmajor 
                          int w, int cout, int dtype, void* workspace, size_t workspace_bytes, mmpl_stream_t stream);
 int mmpl_cls_fwd(const void* a, const float* wc /*[C][Cin]*/, const float* bias, float* logits, int n, int64_t spatial,
                  int cin, int classes, int dtype, mmpl_stream_t stream);
-int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits, void* da, float* dwc, float* dbias, int n,
-                 int64_t spatial, int cin, int classes, int dtype, mmpl_stream_t stream);
+/* gn_beta / gn_ws (both NULL or both set): `a` is the output of precls_conv.0/1 = GroupNorm+ReLU (unet3D.py:629-631);
+ * the kernel then also accumulates that node's backward sums S1, Q into gn_ws[N][Cin][6] (see mmpl_gn_bwd_fuse). */
+int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits, void* da, float* dwc, float* dbias,
+                 const float* gn_beta, double* gn_ws, int n, int64_t spatial, int cin, int classes, int dtype,
+                 mmpl_stream_t stream);
 
 /* ---- GroupNorm(16)+ReLU: NoBottleneck.forward, unet3D.py:59-60,64-65 and downsample.0/1, :645-646 -------------
  * stats: double [N][G][2], must be zero before mmpl_gn_stats accumulates into it. */
@@ -121,10 +139,14 @@ int mmpl_gn_relu_fwd(const void* x, const double* stats, const float* gamma, con
                      const float* gamma2, const float* beta2, void* y2, int n, int64_t spatial, int c, int groups,
                      float eps, int dtype, mmpl_stream_t stream);
 /* dx = d/dx of the one or two GN+ReLU heads (+ addend if non-NULL); dgamma/dbeta per head (fp32 [C]).
- * workspace: double [N][C][4], zeroed by the call. */
+ * workspace: N*C*6 + 1 doubles: [N][C][6] = per head {S1 = sum g, Q = gamma * sum g*xhat} (g = dy*[relu gate]) in columns 0..3 and
+ * scratch in 4..5.  reduced = 0: the call zeroes it and runs the reduction pass over (x, dy[, dy2]); reduced = 1: the
+ * producers of dy (and dy2) already accumulated S1 and Q (mmpl_gn_bwd_fuse, mmpl_cls_bwd), only the apply pass runs.
+ * In both cases the workspace is zero again when the call's work completes.  Channels with gamma == 0 (where Q
+ * carries no information about sum g*xhat) get their dgamma from an exact accumulation inside the apply pass. */
 int mmpl_gn_relu_bwd(const void* x, const double* stats, const float* gamma, const float* beta, const void* dy,
                      const float* gamma2, const float* beta2, const void* dy2, const void* addend, void* dx,
-                     float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, double* workspace, int n,
+                     float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, double* workspace, int reduced, int n,
                      int64_t spatial, int c, int groups, float eps, int dtype, mmpl_stream_t stream);
 
 /* ---- trilinear x2 upsample (align_corners=False) + skip add: unet3D.py:608, :686-687 -------------------------- */

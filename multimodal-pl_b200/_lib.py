@@ -28,7 +28,7 @@ _SIGNATURES = {
     "mmpl_ws_weight_bwd": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr],
     "mmpl_parity_split": [_ptr, _ptr] + [_c_int] * 6 + [_ptr],
     "mmpl_conv3d_fprop": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr, _ptr],
-    "mmpl_conv3d_dgrad": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr],
+    "mmpl_conv3d_dgrad": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr, _ptr, _ptr],
     "mmpl_conv3d_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr, _c_size, _ptr],
     "mmpl_conv3d_wgrad_workspace": [_c_int] * 9,
     "mmpl_stem_im2col": [_ptr, _ptr] + [_c_int] * 5 + [_ptr],
@@ -36,10 +36,10 @@ _SIGNATURES = {
     "mmpl_stem_conv_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 6 + [_ptr, _c_size, _ptr],
     "mmpl_stem_conv_wgrad_workspace": [_c_int] * 4,
     "mmpl_cls_fwd": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
-    "mmpl_cls_bwd": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
+    "mmpl_cls_bwd": [_ptr] * 8 + [_c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_gn_stats": [_ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_gn_relu_fwd": [_ptr] * 8 + [_c_int, _c_i64, _c_int, _c_int, _c_f32, _c_int, _ptr],
-    "mmpl_gn_relu_bwd": [_ptr] * 15 + [_c_int, _c_i64, _c_int, _c_int, _c_f32, _c_int, _ptr],
+    "mmpl_gn_relu_bwd": [_ptr] * 15 + [_c_int, _c_int, _c_i64, _c_int, _c_int, _c_f32, _c_int, _ptr],
     "mmpl_upsample2x_add_fwd": [_ptr, _ptr, _ptr] + [_c_int] * 6 + [_ptr, _ptr],
     "mmpl_upsample2x_bwd": [_ptr, _ptr] + [_c_int] * 6 + [_ptr],
     "mmpl_partial_loss_fwd": [_ptr] * 6 + [_c_int, _c_i64, _c_int, _c_int, _ptr],
@@ -52,6 +52,11 @@ _RESTYPES = {"mmpl_last_error": ctypes.c_char_p, "mmpl_launch_count": ctypes.c_u
              "mmpl_conv3d_wgrad_workspace": ctypes.c_size_t, "mmpl_stem_conv_wgrad_workspace": ctypes.c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class GnBwdFuse(ctypes.Structure):
+    """mmpl_gn_bwd_fuse (include/mmpl_b200.h)."""
+    _fields_ = [("a", _ptr), ("beta", _ptr), ("ws", _ptr), ("a_is_parity_split", _c_int), ("head", _c_int)]
 
 
 def build(verbose: bool = False) -> str:

@@ -5,11 +5,13 @@ namespace mmpl {
 int conv_direct_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_direct_dgrad(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_direct_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int conv_tc_s1(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, double*, cudaStream_t);
+int conv_tc_s1(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, double*,
+               const mmpl_gn_bwd_fuse*, cudaStream_t);
+bool conv_tc_can_fuse_gn_bwd(int nout);
 int conv_tc_s2_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, double*, cudaStream_t);
 bool conv_tc_can_fuse_stats(int nout);
 int conv_out_dim(int in, int k, int stride);
-int conv_tc_s2_dgrad(const void*, const void*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int conv_tc_s2_dgrad(const void*, const void*, void*, int, int, int, int, int, int, int, const mmpl_gn_bwd_fuse*, cudaStream_t);
 int parity_split(const void*, void*, int, int, int, int, int, cudaStream_t);
 int conv_tc_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 size_t conv_tc_wgrad_workspace(int, int, int, int, int, int);
@@ -44,7 +46,7 @@ extern "C" int mmpl_conv3d_fprop(const void* x, const void* w_fprop, const void*
     double* fused = (gn_stats_out && conv_tc_can_fuse_stats(cout)) ? gn_stats_out : nullptr;
     int rc;
     if (stride == 1) {
-      rc = conv_tc_s1(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, fused, s);
+      rc = conv_tc_s1(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, fused, nullptr, s);
     } else {
       MMPL_REQUIRE((ksize == 3) == (algo == MMPL_ALGO_TCGEN05_PSPLIT), MMPL_E_UNSUPPORTED,
                    "conv3d_fprop: stride-2 3x3x3 takes the parity-split input (MMPL_ALGO_TCGEN05_PSPLIT), 1x1x1 takes x");
@@ -60,17 +62,31 @@ extern "C" int mmpl_conv3d_fprop(const void* x, const void* w_fprop, const void*
 
 extern "C" int mmpl_conv3d_dgrad(const void* dy, const void* w_dgrad, const void* addend, void* dx, int n, int d, int h,
                                  int w, int cin, int cout, int ksize, int stride, int dtype, int algo,
-                                 mmpl_stream_t stream) {
+                                 const mmpl_gn_bwd_fuse* gn, int* gn_fused_out, mmpl_stream_t stream) {
+  if (gn_fused_out) *gn_fused_out = 0;
   if (int e = check_common(n, d, h, w, cin, cout, ksize, stride)) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (algo == MMPL_ALGO_TCGEN05) {
     MMPL_REQUIRE(dtype == MMPL_BF16, MMPL_E_UNSUPPORTED, "conv3d_dgrad: tcgen05 path needs bf16 (got dtype=%d)", dtype);
+    const mmpl_gn_bwd_fuse* fuse = nullptr;
+    if (gn != nullptr && gn->ws != nullptr && conv_tc_can_fuse_gn_bwd(cin)) {
+      MMPL_REQUIRE(gn->a && gn->beta && (gn->head == 0 || gn->head == 1), MMPL_E_SHAPE,
+                   "conv3d_dgrad: incomplete GroupNorm-backward fusion request");
+      // the parity-split copy only exists for (and is only indexed by) the stride-2 3x3x3 dgrad
+      if (!gn->a_is_parity_split || (stride == 2 && ksize == 3)) fuse = gn;
+    }
+    int rc;
     // stride-1 dgrad is a correlation of dy with the flipped/transposed packing: channels swap roles
-    if (stride == 1) return conv_tc_s1(dy, w_dgrad, addend, dx, n, d, h, w, cout, cin, ksize, nullptr, s);
-    MMPL_REQUIRE(addend == nullptr, MMPL_E_UNSUPPORTED, "conv3d_dgrad: stride-2 tcgen05 path has no addend input");
-    if (ksize == 1)  // only the even parity class receives gradient; the rest of dx is zero
-      MMPL_CUDA(cudaMemsetAsync(dx, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(n) * d * h * w * cin, s));
-    return conv_tc_s2_dgrad(dy, w_dgrad, dx, n, d, h, w, cin, cout, ksize, s);
+    if (stride == 1) {
+      rc = conv_tc_s1(dy, w_dgrad, addend, dx, n, d, h, w, cout, cin, ksize, nullptr, fuse, s);
+    } else {
+      MMPL_REQUIRE(addend == nullptr, MMPL_E_UNSUPPORTED, "conv3d_dgrad: stride-2 tcgen05 path has no addend input");
+      if (ksize == 1)  // only the even parity class receives gradient; the rest of dx is zero
+        MMPL_CUDA(cudaMemsetAsync(dx, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(n) * d * h * w * cin, s));
+      rc = conv_tc_s2_dgrad(dy, w_dgrad, dx, n, d, h, w, cin, cout, ksize, fuse, s);
+    }
+    if (rc == MMPL_OK && fuse && gn_fused_out) *gn_fused_out = 1;
+    return rc;
   }
   return conv_direct_dgrad(dy, w_dgrad, addend, dx, n, d, h, w, cin, cout, ksize, stride, dtype, s);
 }

@@ -87,6 +87,18 @@ struct TcParams {
   int DT, HT, WT, NTILES, NPAR;
   int total_items;
   double* stats;    // optional GroupNorm(16) raw sums of the OUTPUT [N][16][2] (requires cout_total == NT), else NULL
+  // Optional fused first pass of the GroupNorm+ReLU backward (dgrad launches): the output of this launch is dA, the
+  // gradient w.r.t. a = relu(gn(x)) = this convolution's forward input, still available as gn_a (NDHWC like y, or the
+  // parity-split copy P when gn_psplit).  Because a = gamma*xhat + beta where the ReLU passes and 0 elsewhere,
+  //   S1_c = sum_v g = sum_v dA*[a > 0]          and          gamma_c * sum_v g*xhat = sum_v dA*a - beta_c * S1_c,
+  // so the epilogue needs one extra row read and 4 instructions per element, no per-channel constants.  It accumulates
+  // S1 and Q = gamma*sum(g*xhat) into gn_ws[n][c][gn_head*2 + {0,1}] (the workspace of mmpl_gn_relu_bwd).
+  const __nv_bfloat16* gn_a;
+  const float* gn_beta;
+  double* gn_ws;
+  int gn_ws_stride;   // doubles per (n, c) entry of gn_ws
+  int gn_head;
+  int gn_psplit;
 };
 
 // Tap enumeration shared by the weight producer and the MMA issuer.
@@ -344,73 +356,181 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         gsum[g] = gsq[g] = 0.f;
       }
     };
+    // ---- fused GroupNorm+ReLU backward reduction (see TcParams::gn_*)
+    // p1[j] / p2[j]: this thread's (= output row's) partial S1 and sum dA*a for column j of the current chunk.  Summing over
+    // the warp's 32 rows is a 31-shuffle transpose-reduce; with a single column chunk (NT == 32) the partials simply
+    // keep accumulating over all items of the CTA and are reduced once per sample, otherwise once per item and chunk.
+    const bool gn_on = p.gn_ws != nullptr;
+    constexpr bool GN_PERSIST = NT == 32;
+    float gacc1[NT / 32], gacc2[NT / 32];
+#pragma unroll
+    for (int i = 0; i < NT / 32; ++i) gacc1[i] = gacc2[i] = 0.f;
+    float p1[32], p2[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) p1[j] = p2[j] = 0.f;
+    int gn_n = -1, gn_nt = -1;
+    // sum over the warp's 32 rows of each of 32 per-lane values; afterwards v[0] of lane l is the total of index l
+    auto transpose_reduce = [&](float (&v)[32]) {
+#pragma unroll
+      for (int sft = 16; sft >= 1; sft >>= 1) {
+        const bool up = (lane & sft) != 0;
+#pragma unroll
+        for (int i = 0; i < sft; ++i) {
+          const float send = up ? v[i] : v[i + sft];
+          const float keep = up ? v[i + sft] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+        }
+      }
+    };
+    auto gn_flush = [&]() {
+      if (!gn_on || gn_n < 0) return;
+      if (GN_PERSIST) {
+        transpose_reduce(p1);
+        transpose_reduce(p2);
+        gacc1[0] = p1[0], gacc2[0] = p2[0];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) p1[j] = p2[j] = 0.f;
+      }
+#pragma unroll
+      for (int ci = 0; ci < NT / 32; ++ci) {
+        const int c = gn_nt * NT + ci * 32 + lane;
+        double* w = p.gn_ws + (static_cast<int64_t>(gn_n) * p.cout_total + c) * p.gn_ws_stride + p.gn_head * 2;
+        const double s1 = static_cast<double>(gacc1[ci]);
+        atomicAdd(w, s1);
+        atomicAdd(w + 1, static_cast<double>(gacc2[ci]) - static_cast<double>(p.gn_beta[c]) * s1);
+        gacc1[ci] = gacc2[ci] = 0.f;
+      }
+    };
+    // The epilogue reads one auxiliary row per output row (the residual of conv2, or the activation for the fused
+    // GroupNorm-backward reduction).  With a single epilogue warp per scheduler a ~1 us load latency per (chunk, plane)
+    // step would be fully exposed, so the rows run through a 2-step register ring that is kept two steps AHEAD of the
+    // arithmetic across item boundaries (the coordinates of the next item are known in advance).
+    constexpr int TOT = TD * (NT / 32);          // (column chunk, plane) steps per item, chunk-major
+    static_assert(TOT % 2 == 0, "the 2-deep ring needs an even number of steps per item");
+    const __nv_bfloat16* aux = gn_on ? p.gn_a : p.residual;
+    const bool res_direct = gn_on && p.residual != nullptr;   // both present: the residual takes the unpipelined path
+    struct ItemPos {
+      int nt, pc, n, d0, h0, w0;
+      bool ok;
+    };
+    auto locate = [&](int item) {
+      ItemPos t;
+      t.ok = item < p.total_items;
+      if (t.ok) item_coords(item, t.nt, t.pc, t.n, t.d0, t.h0, t.w0);
+      return t;
+    };
+    // element offset of step i of an item in y (and in a same-layout aux tensor); valid = row inside the tensor
+    auto step_off = [&](const ItemPos& t, int i, bool& valid) -> int64_t {
+      const int c0 = (i / TD) * 32, pl = i % TD;
+      int dd = t.d0 + pl, hh = t.h0 + rh, ww = t.w0 + rw;
+      if (G::STRIDED_OUT) dd = 2 * dd + (t.pc >> 2), hh = 2 * hh + ((t.pc >> 1) & 1), ww = 2 * ww + (t.pc & 1);
+      valid = t.ok && hh < p.H && ww < p.W && dd < p.D;
+      return ((((static_cast<int64_t>(t.n) * p.D + dd) * p.H + hh) * p.W + ww) * p.cout_total) + t.nt * NT + c0;
+    };
+    uint4 ring[2][4];
+    auto prefetch = [&](const ItemPos& t, int i, uint4 (&dst)[4]) {
+      bool valid;
+      int64_t off = step_off(t, i, valid);
+      if (G::STRIDED_OUT && gn_on && p.gn_psplit)   // a lives in the parity-split copy: plane (pc, n), sub-grid coordinates
+        off = ((((static_cast<int64_t>(t.pc) * p.N + t.n) * p.Ds + t.d0 + (i % TD)) * p.Hs + t.h0 + rh) * p.Ws + t.w0 + rw) *
+                  p.cout_total + t.nt * NT + (i / TD) * 32;
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        dst[v] = (aux != nullptr && valid) ? *reinterpret_cast<const uint4*>(aux + off + v * 8) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    ItemPos cur = locate(blockIdx.x);
+    prefetch(cur, 0, ring[0]);
+    prefetch(cur, 1, ring[1]);
     uint32_t iti = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++iti) {
-      int nt, pc, n, d0, h0, w0;
-      item_coords(item, nt, pc, n, d0, h0, w0);
+      const ItemPos nxt = locate(item + gridDim.x);
+      const int nt = cur.nt, n = cur.n;
       if (p.stats != nullptr && n != stat_n) {
         flush_stats();
         stat_n = n;
       }
+      if (gn_on && (n != gn_n || nt != gn_nt)) {
+        gn_flush();
+        gn_n = n, gn_nt = nt;
+      }
       const uint32_t buf = iti & 1, bph = (iti >> 1) & 1;
       mbar_wait(&acc_full[buf], bph);
       tc_fence_after();
-      int hh = h0 + rh, ww = w0 + rw;
-      if (G::STRIDED_OUT) hh = 2 * hh + ((pc >> 1) & 1), ww = 2 * ww + (pc & 1);
-      const bool in_hw = hh < p.H && ww < p.W;
 #pragma unroll
-      for (int pl = 0; pl < TD; ++pl) {
-        int dd = d0 + pl;
-        if (G::STRIDED_OUT) dd = 2 * dd + (pc >> 2);
-        const bool valid = in_hw && dd < p.D;
-        const int64_t off = ((((static_cast<int64_t>(n) * p.D + dd) * p.H + hh) * p.W + ww) * p.cout_total) + nt * NT;
+      for (int i = 0; i < TOT; ++i) {
+        const int c0 = (i / TD) * 32, pl = i % TD;
+        if (!GN_PERSIST && pl == 0) {
 #pragma unroll
-        for (int c0 = 0; c0 < NT; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::ACC_COLS + pl * NT + c0, r);
-          tmem_ld_wait();
-          if (valid) {
-            if (p.residual) {
+          for (int j = 0; j < 32; ++j) p1[j] = p2[j] = 0.f;
+        }
+        bool valid;
+        const int64_t off = step_off(cur, i, valid);
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::ACC_COLS + pl * NT + c0, r);
+        tmem_ld_wait();
+        uint4 row[4];
 #pragma unroll
-              for (int v = 0; v < 4; ++v) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + off + c0 + v * 8);
-                const uint32_t u[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  r[v * 8 + 2 * k] = __float_as_uint(__uint_as_float(r[v * 8 + 2 * k]) + __uint_as_float(u[k] << 16));
-                  r[v * 8 + 2 * k + 1] =
-                      __float_as_uint(__uint_as_float(r[v * 8 + 2 * k + 1]) + __uint_as_float(u[k] & 0xFFFF0000u));
-                }
-              }
-            }
+        for (int v = 0; v < 4; ++v) row[v] = ring[i % 2][v];
+        if (i + 2 < TOT)
+          prefetch(cur, i + 2, ring[i % 2]);
+        else
+          prefetch(nxt, i + 2 - TOT, ring[i % 2]);
+        if (valid) {
+          if (p.residual) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-              uint32_t o[4];
+              const uint4 rv = res_direct ? *reinterpret_cast<const uint4*>(p.residual + off + v * 8) : row[v];
+              const uint32_t u[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                __nv_bfloat162 h2 =
-                    __floats2bfloat162_rn(__uint_as_float(r[v * 8 + 2 * k]), __uint_as_float(r[v * 8 + 2 * k + 1]));
-                o[k] = *reinterpret_cast<uint32_t*>(&h2);
-                if (p.stats != nullptr) {   // statistics of the value as stored (bf16-rounded)
-                  const float x0 = __uint_as_float(o[k] << 16), x1 = __uint_as_float(o[k] & 0xFFFF0000u);
-                  constexpr int dummy_cpg = CPG;
-                  (void)dummy_cpg;
-                  const int g0 = (c0 + v * 8 + 2 * k) / CPG, g1 = (c0 + v * 8 + 2 * k + 1) / CPG;
-                  gsum[g0] += x0;
-                  gsq[g0] = fmaf(x0, x0, gsq[g0]);
-                  gsum[g1] += x1;
-                  gsq[g1] = fmaf(x1, x1, gsq[g1]);
-                }
+                r[v * 8 + 2 * k] = __float_as_uint(__uint_as_float(r[v * 8 + 2 * k]) + __uint_as_float(u[k] << 16));
+                r[v * 8 + 2 * k + 1] =
+                    __float_as_uint(__uint_as_float(r[v * 8 + 2 * k + 1]) + __uint_as_float(u[k] & 0xFFFF0000u));
               }
-              *reinterpret_cast<uint4*>(p.y + off + c0 + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint32_t o[4];
+            const uint32_t xu[4] = {row[v].x, row[v].y, row[v].z, row[v].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float e0 = __uint_as_float(r[v * 8 + 2 * k]), e1 = __uint_as_float(r[v * 8 + 2 * k + 1]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+              o[k] = *reinterpret_cast<uint32_t*>(&h2);
+              if (p.stats != nullptr) {   // statistics of the value as stored (bf16-rounded)
+                const float x0 = __uint_as_float(o[k] << 16), x1 = __uint_as_float(o[k] & 0xFFFF0000u);
+                const int g0 = (c0 + v * 8 + 2 * k) / CPG, g1 = (c0 + v * 8 + 2 * k + 1) / CPG;
+                gsum[g0] += x0;
+                gsq[g0] = fmaf(x0, x0, gsq[g0]);
+                gsum[g1] += x1;
+                gsq[g1] = fmaf(x1, x1, gsq[g1]);
+              }
+              if (gn_on) {   // dA (fp32, before the bf16 rounding of the store) against a = relu(gn(x)): gate = [a > 0]
+                const int j = v * 8 + 2 * k;
+                const float a0 = __uint_as_float(xu[k] << 16), a1 = __uint_as_float(xu[k] & 0xFFFF0000u);
+                p2[j] = fmaf(e0, a0, p2[j]);
+                p2[j + 1] = fmaf(e1, a1, p2[j + 1]);
+                if (a0 > 0.f) p1[j] += e0;
+                if (a1 > 0.f) p1[j + 1] += e1;
+              }
+            }
+            *reinterpret_cast<uint4*>(p.y + off + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        if (gn_on && !GN_PERSIST && pl == TD - 1) {
+          transpose_reduce(p1);
+          transpose_reduce(p2);
+          gacc1[c0 / 32] += p1[0];
+          gacc2[c0 / 32] += p2[0];
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      cur = nxt;
     }
+    gn_flush();
     flush_stats();
   }
   tc_fence_before();
@@ -477,6 +597,7 @@ struct TcProblem {
   int N, D, H, W;
   int kred, nout;
   double* stats = nullptr;
+  const mmpl_gn_bwd_fuse* gn = nullptr;   // fused GroupNorm-backward reduction over the OUTPUT (dgrad launches)
 };
 
 template <int KC, int NT, int TD, int MODE, bool WRES, int NA_ = 2>
@@ -498,6 +619,13 @@ int launch_tc(const TcProblem& q, cudaStream_t s) {
   p.DT = ceil_div(p.Ds, TD), p.HT = ceil_div(p.Hs, TC_TH), p.WT = ceil_div(p.Ws, TC_TW), p.NTILES = q.nout / NT;
   p.NPAR = MODE == MODE_S2D ? 8 : 1;
   p.stats = (q.stats != nullptr && q.nout == NT && !G::STRIDED_OUT) ? q.stats : nullptr;
+  p.gn_a = nullptr, p.gn_beta = nullptr, p.gn_ws = nullptr, p.gn_ws_stride = 6, p.gn_head = 0, p.gn_psplit = 0;
+  if (q.gn != nullptr) {
+    MMPL_REQUIRE(!q.gn->a_is_parity_split || MODE == MODE_S2D, MMPL_E_UNSUPPORTED,
+                 "conv_tc: a parity-split activation only pairs with the stride-2 3x3x3 dgrad");
+    p.gn_a = static_cast<const __nv_bfloat16*>(q.gn->a);
+    p.gn_beta = q.gn->beta, p.gn_ws = q.gn->ws, p.gn_head = q.gn->head, p.gn_psplit = q.gn->a_is_parity_split;
+  }
   const int64_t items = static_cast<int64_t>(p.NTILES) * p.NPAR * q.N * p.DT * p.HT * p.WT;
   MMPL_REQUIRE(items < (1ll << 31), MMPL_E_SHAPE, "conv_tc: too many work items");
   p.total_items = static_cast<int>(items);
@@ -585,11 +713,16 @@ static int check_align(const void* a, const void* b, const void* c, const void* 
 // ---- stride 1 (k = 3 or 1): x [N,D,H,W,cin] -> y [N,D,H,W,cout]; also stride-1 dgrad with swapped channel roles
 // GroupNorm statistics can be fused into the epilogue when one CTA tile spans all output channels
 bool conv_tc_can_fuse_stats(int nout) { return nout == 32 || nout == 64 || nout == 128 || nout == 256; }
+// The GroupNorm-backward reduction rides on the dgrad epilogue where that is cheaper than a separate streaming pass:
+// wide-and-shallow outputs (<= 64 channels: the full- and half-resolution layers, 85 % of the reduction traffic).  With
+// more channels a work item has 8+ column chunks to transpose-reduce while the tensors are small enough that the
+// stand-alone pass costs little (measured on B200: fusing everywhere loses 0.9 ms/step of MMA time to save 0.5 ms).
+bool conv_tc_can_fuse_gn_bwd(int nout) { return nout == 32 || nout == 64; }
 
 int conv_tc_s1(const void* x, const void* wp, const void* residual, void* y, int N, int D, int H, int W, int cin,
-               int cout, int ksize, double* stats, cudaStream_t s) {
+               int cout, int ksize, double* stats, const mmpl_gn_bwd_fuse* gn, cudaStream_t s) {
   if (int e = check_align(x, wp, y, residual)) return e;
-  TcProblem q{x, N, D, H, W, wp, residual, y, N, D, H, W, cin, cout, stats};
+  TcProblem q{x, N, D, H, W, wp, residual, y, N, D, H, W, cin, cout, stats, gn};
   return ksize == 3 ? dispatch_tc<MODE_S1K3>(q, s) : dispatch_tc<MODE_S1K1>(q, s);
 }
 
@@ -608,10 +741,10 @@ int conv_tc_s2_fprop(const void* src, const void* wp, const void* residual, void
 
 // ---- stride 2 dgrad: dy [N,Do,Ho,Wo,cout] -> dx [N,D,H,W,cin] (k=1: dx must be zero-filled by the caller)
 int conv_tc_s2_dgrad(const void* dy, const void* wp_dgrad, void* dx, int N, int D, int H, int W, int cin, int cout,
-                     int ksize, cudaStream_t s) {
+                     int ksize, const mmpl_gn_bwd_fuse* gn, cudaStream_t s) {
   if (int e = check_align(dy, wp_dgrad, dx, nullptr)) return e;
   const int Do = (D + 1) / 2, Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  TcProblem q{dy, N, Do, Ho, Wo, wp_dgrad, nullptr, dx, N, D, H, W, cout, cin};
+  TcProblem q{dy, N, Do, Ho, Wo, wp_dgrad, nullptr, dx, N, D, H, W, cout, cin, nullptr, gn};
   return ksize == 3 ? dispatch_tc<MODE_S2D>(q, s) : dispatch_tc<MODE_S2K1D>(q, s);
 }
 

@@ -124,7 +124,14 @@ gn_relu_fwd_kernel(const T* __restrict__ x, const double* __restrict__ stats, co
   }
 }
 
-// Pass 1 of the backward: per (n, c) sums of g = dy*[y>0] and g*xhat for each head -> ws[N][C][4] (fp64).
+// Workspace of the backward: double ws[N][C][6] (+ one trailing double used as the last-block ticket).  Per head h:
+//   ws[n][c][2h]   = S1 = sum_v g            (g = dy * [relu gate])
+//   ws[n][c][2h+1] = Q  = gamma_c * sum_v g*xhat
+//   ws[n][c][4+h]  = sum_v g*xhat, accumulated by the apply pass only for channels with gamma_c == 0 (Q is useless there)
+// The sums come either from pass 1 below or from the epilogue of the kernel that produced dy (conv_tc.cu, cls_bwd).
+constexpr int kWs = 6;
+
+// Pass 1 of the backward: per (n, c) sums S1 and Q for each head -> ws (fp64).
 template <typename T, bool DUAL>
 __global__ void __launch_bounds__(kThreads)
 gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
@@ -199,18 +206,20 @@ gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ st
   __syncthreads();
   for (int i = threadIdx.x; i < C * 2 * NH; i += kThreads) {
     const int c = i / (2 * NH), k = i % (2 * NH);
-    atomicAdd(&ws[(static_cast<int64_t>(n) * C + c) * 4 + k], sc[c][k]);
+    const double gam = (k & 1) ? static_cast<double>((k >> 1) == 0 ? gamma[c] : gamma2[c]) : 1.0;
+    atomicAdd(&ws[(static_cast<int64_t>(n) * C + c) * kWs + k], sc[c][k] * gam);
   }
 }
 
-// Pass 2: dx = sum_heads rstd*(gamma*g - m1 - xhat*m2) (+ addend); block (0,0) also emits dgamma/dbeta.
+// Pass 2: dx = sum_heads rstd*(gamma*g - m1 - xhat*m2) (+ addend), m1 = mean_group(gamma*S1), m2 = mean_group(Q).
+// The last block to finish emits dbeta = sum_n S1 and dgamma = sum_n Q / gamma.
 template <typename T, bool DUAL, bool ADD>
 __global__ void __launch_bounds__(kThreads)
 gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                          const float* __restrict__ beta, const T* __restrict__ dy, const float* __restrict__ gamma2,
                          const float* __restrict__ beta2, const T* __restrict__ dy2, const T* __restrict__ addend,
                          T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                         float* __restrict__ dgamma2, float* __restrict__ dbeta2, const double* __restrict__ ws,
+                         float* __restrict__ dgamma2, float* __restrict__ dbeta2, double* __restrict__ ws,
                          int N, int64_t spatial, int C, int groups, float eps, int64_t vox_per_block) {
   using V = VecH<T>;
   constexpr int VN = V::N;
@@ -221,40 +230,35 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
   const int cpg = C / groups;
   const double m = static_cast<double>(cpg) * static_cast<double>(spatial);
   __shared__ float gm[32][4];  // per group: m1,m2 per head (already divided by m)
+  __shared__ bool s_last;
   if (threadIdx.x < groups * NH) {
     const int g = threadIdx.x / NH, hh = threadIdx.x % NH;
     const float* gam = hh == 0 ? gamma : gamma2;
     double a = 0, b = 0;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      const double* w = ws + (static_cast<int64_t>(n) * C + c) * 4 + hh * 2;
+      const double* w = ws + (static_cast<int64_t>(n) * C + c) * kWs + hh * 2;
       a += static_cast<double>(gam[c]) * w[0];
-      b += static_cast<double>(gam[c]) * w[1];
+      b += w[1];
     }
     gm[g][hh * 2 + 0] = static_cast<float>(a / m);
     gm[g][hh * 2 + 1] = static_cast<float>(b / m);
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0) {
-    for (int i = threadIdx.x; i < C * NH; i += kThreads) {
-      const int c = i / NH, hh = i % NH;
-      double a = 0, b = 0;
-      for (int nn = 0; nn < N; ++nn) {
-        const double* w = ws + (static_cast<int64_t>(nn) * C + c) * 4 + hh * 2;
-        a += w[0];
-        b += w[1];
-      }
-      (hh == 0 ? dbeta : dbeta2)[c] = static_cast<float>(a);
-      (hh == 0 ? dgamma : dgamma2)[c] = static_cast<float>(b);
-    }
-  }
   __syncthreads();
   float mu[VN], rs[VN], ga[NH][VN], be[NH][VN], m1[NH][VN], m2[NH][VN];
+  bool any_zero_gamma = false;
 #pragma unroll
   for (int i = 0; i < VN; ++i) {
     const int c = cv * VN + i, g = c / cpg;
     mean_rstd(stats + (static_cast<int64_t>(n) * groups + g) * 2, m, eps, mu[i], rs[i]);
     ga[0][i] = gamma[c], be[0][i] = beta[c], m1[0][i] = gm[g][0], m2[0][i] = gm[g][1];
     if (DUAL) ga[NH - 1][i] = gamma2[c], be[NH - 1][i] = beta2[c], m1[NH - 1][i] = gm[g][2], m2[NH - 1][i] = gm[g][3];
+    any_zero_gamma |= ga[0][i] == 0.f || (DUAL && ga[NH - 1][i] == 0.f);
   }
+  float ex[NH][VN];   // sum g*xhat of this thread's channels, only maintained when one of them has gamma == 0
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+    for (int i = 0; i < VN; ++i) ex[hh][i] = 0.f;
   const int64_t v0 = static_cast<int64_t>(blockIdx.x) * vox_per_block;
   const int64_t v1 = min(v0 + vox_per_block, spatial);
   const int64_t off = (static_cast<int64_t>(n) * spatial) * C + cv * VN;
@@ -268,6 +272,7 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
       const float xh = (a.v[i] - mu[i]) * rs[i];
       const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[0][i], be[0][i]) ? g.v[i] : 0.f;
       o.v[i] = rs[i] * (ga[0][i] * gg - m1[0][i] - xh * m2[0][i]);
+      if (any_zero_gamma) ex[0][i] = fmaf(gg, xh, ex[0][i]);
     }
     if (DUAL) {
       g.load(dy2 + off + v * C);
@@ -276,6 +281,7 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
         const float xh = (a.v[i] - mu[i]) * rs[i];
         const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[NH - 1][i], be[NH - 1][i]) ? g.v[i] : 0.f;
         o.v[i] += rs[i] * (ga[NH - 1][i] * gg - m1[NH - 1][i] - xh * m2[NH - 1][i]);
+        if (any_zero_gamma) ex[NH - 1][i] = fmaf(gg, xh, ex[NH - 1][i]);
       }
     }
     if (ADD) {
@@ -284,6 +290,36 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
       for (int i = 0; i < VN; ++i) o.v[i] += g.v[i];
     }
     o.store(dx + off + v * C);
+  }
+  if (any_zero_gamma) {
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+      for (int i = 0; i < VN; ++i)
+        if (ga[hh][i] == 0.f)
+          atomicAdd(&ws[(static_cast<int64_t>(n) * C + cv * VN + i) * kWs + 4 + hh], static_cast<double>(ex[hh][i]));
+  }
+  // last block: parameter gradients
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + static_cast<int64_t>(N) * C * kWs);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const volatile double* vws = ws;
+    for (int i = threadIdx.x; i < C * NH; i += kThreads) {
+      const int c = i / NH, hh = i % NH;
+      const float gam = (hh == 0 ? gamma : gamma2)[c];
+      double a = 0, b = 0;
+      for (int nn = 0; nn < N; ++nn) {
+        const volatile double* w = vws + (static_cast<int64_t>(nn) * C + c) * kWs;
+        a += w[hh * 2];
+        b += gam != 0.f ? w[hh * 2 + 1] / static_cast<double>(gam) : w[4 + hh];
+      }
+      (hh == 0 ? dbeta : dbeta2)[c] = static_cast<float>(a);
+      (hh == 0 ? dgamma : dgamma2)[c] = static_cast<float>(b);
+    }
   }
 }
 
@@ -314,7 +350,7 @@ void plan(int n, int64_t spatial, int c, int dtype, int& blocks_x, int64_t& vox_
 template <typename T>
 int launch_gn_bwd(const void* x, const double* stats, const float* gamma, const float* beta, const void* dy,
                   const float* gamma2, const float* beta2, const void* dy2, const void* addend, void* dx,
-                  float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, double* workspace, int n,
+                  float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, double* workspace, int reduced, int n,
                   int64_t spatial, int c, int groups, float eps, int bx, int64_t vpb, cudaStream_t s) {
   const bool dual = gamma2 != nullptr;
   const bool add = addend != nullptr;
@@ -324,13 +360,15 @@ int launch_gn_bwd(const void* x, const double* stats, const float* gamma, const 
   const T* ad = static_cast<const T*>(addend);
   T* out = static_cast<T*>(dx);
   const dim3 grid(bx, n);
-  if (dual)
-    gn_relu_bwd_reduce_kernel<T, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
-                                                                workspace, spatial, c, groups, eps, vpb);
-  else
-    gn_relu_bwd_reduce_kernel<T, false><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, nullptr, nullptr,
-                                                                 nullptr, workspace, spatial, c, groups, eps, vpb);
-  MMPL_CHECK_LAUNCH("gn_relu_bwd_reduce");
+  if (!reduced) {
+    if (dual)
+      gn_relu_bwd_reduce_kernel<T, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
+                                                                  workspace, spatial, c, groups, eps, vpb);
+    else
+      gn_relu_bwd_reduce_kernel<T, false><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, nullptr, nullptr,
+                                                                   nullptr, workspace, spatial, c, groups, eps, vpb);
+    MMPL_CHECK_LAUNCH("gn_relu_bwd_reduce");
+  }
   if (dual && add)
     gn_relu_bwd_apply_kernel<T, true, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
         ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, eps, vpb);
@@ -390,19 +428,22 @@ extern "C" int mmpl_gn_relu_fwd(const void* x, const double* stats, const float*
 extern "C" int mmpl_gn_relu_bwd(const void* x, const double* stats, const float* gamma, const float* beta,
                                 const void* dy, const float* gamma2, const float* beta2, const void* dy2,
                                 const void* addend, void* dx, float* dgamma, float* dbeta, float* dgamma2,
-                                float* dbeta2, double* workspace, int n, int64_t spatial, int c, int groups, float eps,
-                                int dtype, mmpl_stream_t stream) {
+                                float* dbeta2, double* workspace, int reduced, int n, int64_t spatial, int c, int groups,
+                                float eps, int dtype, mmpl_stream_t stream) {
   if (int e = check_shape(c, groups, dtype, true)) return e;
   int bx;
   int64_t vpb;
   plan(n, spatial, c, dtype, bx, vpb, true);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  MMPL_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 4 * n * c, s));
+  const size_t ws_bytes = sizeof(double) * (static_cast<size_t>(kWs) * n * c + 1);
+  if (!reduced) MMPL_CUDA(cudaMemsetAsync(workspace, 0, ws_bytes, s));
   int rc = MMPL_OK;
   MMPL_DISPATCH_DTYPE(dtype, T, rc = (launch_gn_bwd<T>(x, stats, gamma, beta, dy, gamma2, beta2, dy2, addend, dx, dgamma,
-                                                     dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, eps, bx,
-                                                     vpb, s)));
+                                                     dbeta, dgamma2, dbeta2, workspace, reduced, n, spatial, c, groups,
+                                                     eps, bx, vpb, s)));
   if (rc) return rc;
   MMPL_CHECK_LAUNCH("gn_relu_bwd_apply");
+  // leave the workspace clean: producers of a later backward through the same node accumulate into it again
+  MMPL_CUDA(cudaMemsetAsync(workspace, 0, ws_bytes, s));
   return MMPL_OK;
 }

@@ -297,7 +297,8 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&v)[4]) {
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256, 2)
 cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const float* __restrict__ dl, T* __restrict__ da,
-               float* __restrict__ dwc, float* __restrict__ dbias, int N, int64_t S, int classes) {
+               float* __restrict__ dwc, float* __restrict__ dbias, const float* __restrict__ gn_beta,
+               double* __restrict__ gn_ws, int N, int64_t S, int classes) {
   constexpr int TV = 128;               // voxels per tile
   constexpr int KB = CIN / 4;           // blocks of 4 input channels
   constexpr int VPP = 256 / KB;         // phase 1: voxels per pass over the block
@@ -322,24 +323,47 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) accw[i][j] = 0.f;
-  const int64_t total = static_cast<int64_t>(N) * S;
-  const int64_t ntiles = (total + TV - 1) / TV;
+  // tiles never straddle samples (tile -> (n, t)): the fused GroupNorm-backward sums below are per sample
+  const int64_t tps = (S + TV - 1) / TV;              // tiles per sample
+  const int64_t ntiles = static_cast<int64_t>(N) * tps;
+  // Fused first pass of the backward of precls_conv.0/1 = GroupNorm+ReLU (unet3D.py:629-631): `a` is its output, so
+  // S1_c = sum_v da*[a > 0] and Q_c = sum_v da*a - beta_c*S1_c (see mmpl_gn_bwd_fuse) accumulate per thread in phase 1.
+  const bool gn_on = gn_ws != nullptr;
+  float gs1[4] = {0.f, 0.f, 0.f, 0.f}, gs2[4] = {0.f, 0.f, 0.f, 0.f};
+  int64_t gn_n = -1;
+  auto gn_flush = [&]() {
+    if (!gn_on || gn_n < 0) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float s1 = gs1[i], s2 = gs2[i];
+      for (int o = 16; o >= KB; o >>= 1) {          // lanes KB apart own the same 4 channels
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if ((tid & 31) < KB) {
+        const int c = kb1 * 4 + i;
+        double* w = gn_ws + (gn_n * CIN + c) * 6;
+        atomicAdd(w, static_cast<double>(s1));
+        atomicAdd(w + 1, static_cast<double>(s2) - static_cast<double>(gn_beta[c]) * static_cast<double>(s1));
+      }
+      gs1[i] = gs2[i] = 0.f;
+    }
+  };
 
   float pg[8];
   Raw16<T> pa[AV];
   auto prefetch = [&](int64_t tile) {
-    const int64_t v0 = tile * TV;
-    const int64_t v = v0 + sj;
-    const bool ok = v < total;
-    const int64_t n = ok ? v / S : 0, sp = ok ? v - n * S : 0;
+    const int64_t n = tile / tps, sp0 = (tile - n * tps) * TV;
+    const int64_t sp = sp0 + sj;
+    const bool ok = sp < S;
 #pragma unroll
     for (int i = 0; i < 8; ++i) pg[i] = (ok && sc + i < classes) ? dl[(n * classes + sc + i) * S + sp] : 0.f;
 #pragma unroll
     for (int r = 0; r < AV; ++r) {
       const int idx = tid + 256 * r;                 // 16-byte unit inside the tile
       const int j = idx / (CIN / VN);
-      if (v0 + j < total)
-        pa[r].load(a + v0 * CIN + static_cast<int64_t>(idx) * VN);
+      if (sp0 + j < S)
+        pa[r].load(a + (n * S + sp0) * CIN + static_cast<int64_t>(idx) * VN);
       else
         pa[r].zero();
     }
@@ -348,7 +372,13 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
   int64_t tile = blockIdx.x;
   if (tile < ntiles) prefetch(tile);
   for (; tile < ntiles; tile += gridDim.x) {
-    const int64_t v0 = tile * TV;
+    const int64_t tn = tile / tps, sp0 = (tile - tn * tps) * TV;
+    const int64_t v0 = tn * S + sp0;
+    const int64_t total = (tn + 1) * S;              // end of this sample
+    if (gn_on && tn != gn_n) {
+      gn_flush();
+      gn_n = tn;
+    }
     __syncthreads();
     {
       const int sw = (sj >> 1) & 3;
@@ -374,7 +404,19 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
 #pragma unroll
           for (int i = 0; i < 4; ++i) o[i] = fmaf(g[c], wreg[cb * 4 + c][i], o[i]);
       }
-      if (v0 + j < total) store4(da + (v0 + j) * CIN + kb1 * 4, o);
+      if (v0 + j < total) {
+        store4(da + (v0 + j) * CIN + kb1 * 4, o);
+        if (gn_on) {
+          const float4 a4 = *reinterpret_cast<const float4*>(&s_a[j][kb1 * 4]);
+          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float e = to_f32<T>(from_f32<T>(o[i]));     // da as stored
+            gs2[i] = fmaf(e, av[i], gs2[i]);
+            gs1[i] += av[i] > 0.f ? e : 0.f;
+          }
+        }
+      }
     }
     // phase 2: dW / dbias
 #pragma unroll 4
@@ -393,6 +435,7 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
       }
     }
   }
+  gn_flush();
   // cross-group reduction through shared memory (reuse the staging tiles), then one atomic per (c,k) per block
   __syncthreads();
   float* red = &s_a[0][0];    // VG x 16 classes x CIN floats <= TV*CIN
@@ -504,21 +547,23 @@ extern "C" int mmpl_cls_fwd(const void* a, const float* wc, const float* bias, f
 }
 
 extern "C" int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits, void* da, float* dwc, float* dbias,
-                            int n, int64_t spatial, int cin, int classes, int dtype, mmpl_stream_t stream) {
+                            const float* gn_beta, double* gn_ws, int n, int64_t spatial, int cin, int classes, int dtype,
+                            mmpl_stream_t stream) {
+  MMPL_REQUIRE((gn_beta == nullptr) == (gn_ws == nullptr), MMPL_E_SHAPE, "cls_bwd: gn_beta and gn_ws go together");
   MMPL_REQUIRE((cin == 32 || cin == 64) && classes >= 1 && classes <= 16, MMPL_E_SHAPE,
                "cls: cin=%d classes=%d (cin 32|64, classes<=16)", cin, classes);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   MMPL_CUDA(cudaMemsetAsync(dwc, 0, sizeof(float) * classes * cin, s));
   MMPL_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * classes, s));
-  const int64_t ntiles = (static_cast<int64_t>(n) * spatial + 127) / 128;
+  const int64_t ntiles = static_cast<int64_t>(n) * ((spatial + 127) / 128);
   const int blocks = static_cast<int>(std::min<int64_t>(ntiles, static_cast<int64_t>(num_sms()) * 2));
   MMPL_DISPATCH_DTYPE(dtype, T, {
     if (cin == 32)
       cls_bwd_kernel<T, 32><<<blocks, 256, 0, s>>>(static_cast<const T*>(a), wc, dlogits, static_cast<T*>(da), dwc, dbias,
-                                                 n, spatial, classes);
+                                                 gn_beta, gn_ws, n, spatial, classes);
     else
       cls_bwd_kernel<T, 64><<<blocks, 256, 0, s>>>(static_cast<const T*>(a), wc, dlogits, static_cast<T*>(da), dwc, dbias,
-                                                 n, spatial, classes);
+                                                 gn_beta, gn_ws, n, spatial, classes);
   });
   MMPL_CHECK_LAUNCH("cls_bwd");
   return MMPL_OK;

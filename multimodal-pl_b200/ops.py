@@ -4,6 +4,7 @@ Activations travel as logical NCDHW tensors in ``torch.channels_last_3d`` memory
 the layout the kernels want -- so the reference's module interfaces (NCDHW in, NCDHW out) are kept without any
 transpose kernels.  Gradients use the same convention.  Every function enqueues on torch's current stream.
 """
+import ctypes
 import os
 
 import torch
@@ -13,7 +14,14 @@ from ._lib import p as _p
 
 _CL = torch.channels_last_3d
 
-_cfg = {"dtype": torch.bfloat16, "conv_algo": os.environ.get("MMPL_CONV_ALGO", "auto")}
+_cfg = {"dtype": torch.bfloat16, "conv_algo": os.environ.get("MMPL_CONV_ALGO", "auto"),
+        "fuse_gn_bwd": os.environ.get("MMPL_FUSE_GN_BWD", "1") != "0"}
+
+
+def set_fuse_gn_bwd(on: bool):
+    """Fold the reduction pass of every GroupNorm+ReLU backward into the epilogue of the kernel that produces its dY
+    (conv dgrad / classifier backward).  On by default; off = separate reduction kernel (used by the parity tests)."""
+    _cfg["fuse_gn_bwd"] = bool(on)
 
 
 def set_compute_dtype(dt: torch.dtype):
@@ -98,14 +106,24 @@ def _grad_dst(param, shape):
 _STATS_POOL = {"buf": None, "off": 0}
 
 
-def begin_forward(device, slots: int = 64, per_slot: int = 256):
-    """One zero-fill for all GroupNorm statistics accumulators of a forward pass (instead of one per layer).  A fresh
-    pool per forward: the slices are saved for the backward pass."""
-    _STATS_POOL["buf"] = torch.zeros(slots * per_slot, dtype=torch.float64, device=device)
+# dX tensors whose producer (conv dgrad / classifier backward) already accumulated the GroupNorm-backward sums:
+# data_ptr -> (workspace data_ptr, head).  Consumed by GNReLUFn.backward.
+_GN_REDUCED = {}
+
+
+def begin_forward(device, doubles: int = 1 << 16):
+    """One zero-fill for all GroupNorm accumulators of a forward pass (statistics [N][16][2] and backward workspaces
+    [N][C][4] per layer) instead of one per layer.  A fresh pool per forward: the slices live until the backward."""
+    # sized by what the previous forward asked for (the wide cfg5 network needs more than the default)
+    doubles = max(doubles, _STATS_POOL.get("demand", 0))
+    _STATS_POOL["buf"] = torch.zeros(doubles, dtype=torch.float64, device=device)
     _STATS_POOL["off"] = 0
+    _STATS_POOL["demand"] = 0
+    _GN_REDUCED.clear()
 
 
 def _zero_stats(numel: int, device) -> torch.Tensor:
+    _STATS_POOL["demand"] = _STATS_POOL.get("demand", 0) + numel
     buf, off = _STATS_POOL["buf"], _STATS_POOL["off"]
     if buf is not None and buf.device == device and off + numel <= buf.numel():
         _STATS_POOL["off"] = off + numel
@@ -305,6 +323,7 @@ class WSConv3dFn(torch.autograd.Function):
         _lib.require_device()
         L = _lib.lib()
         dt = _cfg["dtype"]
+        ctx.gn_bwd = getattr(x, "_mmpl_gn_bwd", None)      # x = relu(gn(.)): its backward reduction rides on our dgrad
         x = to_cl(x, dt)
         cout, cin, k = weight.shape[0], weight.shape[1], weight.shape[2]
         taps = k * k * k
@@ -365,9 +384,18 @@ class WSConv3dFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = empty_cl(n, cin, d, h, w, dt, dev)
             algo = _algo(dt, cout, cin)
+            fuse, fused = None, None
+            if ctx.gn_bwd is not None and algo == _lib.ALGO_TCGEN05 and x.dtype == dt:
+                # x (our forward input, or its parity-split copy) is a = relu(gn(.)) itself
+                gb, gws, ghead = ctx.gn_bwd
+                fuse = _lib.GnBwdFuse(_p(x), _p(gb), _p(gws), int(ctx.x_is_psplit), int(ghead))
+                fused = ctypes.c_int(0)
             with _timed(algo, ctx.flops, ctx.key):
                 _lib.check(L.mmpl_conv3d_dgrad(_p(dy), _p(pd), None, _p(dx), n, d, h, w, cin, cout, k, stride, code,
-                                               algo, st), "conv3d_dgrad")
+                                               algo, ctypes.byref(fuse) if fuse is not None else None,
+                                               ctypes.byref(fused) if fused is not None else None, st), "conv3d_dgrad")
+            if fused is not None and fused.value:
+                _GN_REDUCED[dx.data_ptr()] = (gws.data_ptr(), ghead)
         if ctx.needs_input_grad[1]:
             taps = k * k * k
             g_hat = torch.empty(taps * cout * cin, dtype=torch.float32, device=dev)
@@ -522,7 +550,7 @@ class GNReLUFn(torch.autograd.Function):
     gradient arrives here and is added inside the backward kernel instead of by a separate elementwise add."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps, stats_in=None, alias=False):
+    def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps, stats_in=None, alias=False, ws=None):
         _lib.require_device()
         L = _lib.lib()
         dt = _cfg["dtype"]
@@ -547,6 +575,11 @@ class GNReLUFn(torch.autograd.Function):
         ctx.save_for_backward(x, stats, g1, b1, g2, b2)
         ctx.meta = (n, c, spatial, groups, eps, dual, gamma.dtype, bool(alias))
         ctx.params = (gamma, beta, gamma2, beta2)
+        ctx.ws = ws
+        # what a consumer convolution needs to fold the first backward pass of this node into its dgrad epilogue
+        ctx.fuse_info = None
+        if ws is not None:
+            ctx.fuse_info = [(b1, ws, 0)] + ([(b2, ws, 1)] if dual else [])
         outs = [y]
         if dual:
             outs.append(y2)
@@ -581,13 +614,22 @@ class GNReLUFn(torch.autograd.Function):
         dg1, db1 = _grad_dst(pg, (c,)), _grad_dst(pb, (c,))
         dg2 = _grad_dst(pg2, (c,)) if dual else None
         db2 = _grad_dst(pb2, (c,)) if dual else None
-        ws = torch.empty(n * c * 4, dtype=torch.float64, device=dev)
+        ws = ctx.ws
+        reduced = 0
+        if ws is not None:
+            # the producers of dy (and dy2) may already have accumulated the reduction sums into ws
+            t1 = _GN_REDUCED.pop(dy.data_ptr(), None)
+            t2 = _GN_REDUCED.pop(dy2.data_ptr(), None) if dual else None
+            if t1 == (ws.data_ptr(), 0) and (not dual or t2 == (ws.data_ptr(), 1)):
+                reduced = 1
+        else:
+            ws = torch.empty(n * c * 6 + 2, dtype=torch.float64, device=dev)
         _lib.check(L.mmpl_gn_relu_bwd(_p(x), _p(stats), _p(g1), _p(b1), _p(dy), _p(g2), _p(b2), _p(dy2) if dual else None,
-                                      _p(dres), _p(dx), _p(dg1), _p(db1), _p(dg2), _p(db2), _p(ws), n, spatial, c, groups,
-                                      eps, code, st), "gn_relu_bwd")
+                                      _p(dres), _p(dx), _p(dg1), _p(db1), _p(dg2), _p(db2), _p(ws), reduced, n, spatial, c,
+                                      groups, eps, code, st), "gn_relu_bwd")
         if dual:
-            return dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype), None, None, None, None
-        return dx, dg1.to(pdtype), db1.to(pdtype), None, None, None, None, None, None
+            return dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype), None, None, None, None, None
+        return dx, dg1.to(pdtype), db1.to(pdtype), None, None, None, None, None, None, None
 
 
 def _attached_stats(x, groups):
@@ -595,15 +637,37 @@ def _attached_stats(x, groups):
     return st[0] if (st is not None and st[1] == groups) else None
 
 
+def _gn_bwd_ws(x):
+    """Backward workspace [N][C][4] (fp64, zero) of a GroupNorm node, taken from the forward's zero pool."""
+    if not (_cfg["fuse_gn_bwd"] and torch.is_grad_enabled() and x.is_cuda):
+        return None
+    return _zero_stats(x.shape[0] * x.shape[1] * 6 + 2, x.device)     # [N][C][6] + ticket (mmpl_gn_relu_bwd)
+
+
+def _tag_gn_outputs(outs, n_heads):
+    """Attach to each GN+ReLU output what its consumer needs to fuse this node's backward reduction (head h)."""
+    first = outs[0] if isinstance(outs, tuple) else outs
+    fn = first.grad_fn
+    info = getattr(fn, "fuse_info", None) if fn is not None else None
+    if info:
+        ys = outs if isinstance(outs, tuple) else (outs,)
+        for h in range(n_heads):
+            ys[h]._mmpl_gn_bwd = info[h]
+    return outs
+
+
 def gn_relu(x, gamma, beta, groups=16, eps=1e-5, alias=False):
     """-> y, or (y, x_alias) with alias=True."""
-    return GNReLUFn.apply(x, gamma, beta, None, None, int(groups), float(eps), _attached_stats(x, groups), bool(alias))
+    outs = GNReLUFn.apply(x, gamma, beta, None, None, int(groups), float(eps), _attached_stats(x, groups), bool(alias),
+                          _gn_bwd_ws(x))
+    return _tag_gn_outputs(outs, 1)
 
 
 def gn_relu_dual(x, gamma, beta, gamma2, beta2, groups=16, eps=1e-5, alias=False):
     """-> (y, y2), or (y, y2, x_alias) with alias=True."""
-    return GNReLUFn.apply(x, gamma, beta, gamma2, beta2, int(groups), float(eps), _attached_stats(x, groups),
-                          bool(alias))
+    outs = GNReLUFn.apply(x, gamma, beta, gamma2, beta2, int(groups), float(eps), _attached_stats(x, groups),
+                          bool(alias), _gn_bwd_ws(x))
+    return _tag_gn_outputs(outs, 2)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -661,6 +725,7 @@ class ClassifierFn(torch.autograd.Function):
         _lib.require_device()
         L = _lib.lib()
         dt = _cfg["dtype"]
+        ctx.gn_bwd = getattr(a, "_mmpl_gn_bwd", None)      # a = relu(gn(.)): its backward reduction rides on cls_bwd
         a = to_cl(a, dt)
         n, cin, d, h, w = a.shape
         classes = weight.shape[0]
@@ -684,8 +749,13 @@ class ClassifierFn(torch.autograd.Function):
         da = torch.empty_like(a)
         dwc = _grad_dst(ctx.params[0], wshape)
         db = _grad_dst(ctx.params[1], (classes,))
-        _lib.check(L.mmpl_cls_bwd(_p(a), _p(wc), _p(dl), _p(da), _p(dwc), _p(db), n, d * h * w, cin, classes,
-                                  _lib.dtype_code(a.dtype), _lib.stream_ptr()), "cls_bwd")
+        gb = gws = None
+        if ctx.gn_bwd is not None and ctx.gn_bwd[2] == 0:
+            gb, gws, _ = ctx.gn_bwd
+        _lib.check(L.mmpl_cls_bwd(_p(a), _p(wc), _p(dl), _p(da), _p(dwc), _p(db), _p(gb), _p(gws), n, d * h * w, cin,
+                                  classes, _lib.dtype_code(a.dtype), _lib.stream_ptr()), "cls_bwd")
+        if gws is not None:
+            _GN_REDUCED[da.data_ptr()] = (gws.data_ptr(), 0)
         return da, dwc.to(wdtype), db.to(wdtype)
 
 

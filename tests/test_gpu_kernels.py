@@ -101,6 +101,94 @@ def test_gn_relu_alias_folds_second_gradient(mm, dtype, tol_b, dual):
     assert rel(xd.grad.float(), xr.grad) < tol_b
 
 
+@pytest.mark.parametrize("dtype,tol_b", [(torch.float32, 1e-4), (torch.bfloat16, 5e-2)])
+@pytest.mark.parametrize("through_conv", [False, True])
+def test_gn_relu_backward_with_zero_gamma_channels(mm, dtype, tol_b, through_conv):
+    """gamma_c == 0 makes Q_c = gamma_c * sum(g*xhat) useless for dgamma_c; the apply pass then accumulates it
+    exactly.  Checked stand-alone (reduction pass) and behind a tcgen05 convolution (fused reduction)."""
+    if through_conv and dtype != torch.bfloat16:
+        pytest.skip("the fused reduction rides on the tcgen05 dgrad (bf16)")
+    mm.set_compute_dtype(dtype)
+    ops = mm.ops
+    shape = (2, 32, 4, 9, 10)
+    x = _rand(shape, 1) + 0.3
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    g1, b1 = 1 + 0.2 * _rand((32,), 2), 0.2 * _rand((32,), 3)
+    g1[3] = 0.0
+    b1[3] = 0.4          # gate open everywhere: dgamma_3 = sum dy * xhat != 0
+    g1[17] = 0.0
+    b1[17] = -0.4        # gate closed everywhere: dgamma_17 = 0
+    w = _rand((32, 32, 3, 3, 3), 4)
+    xr = x.clone().requires_grad_(True)
+    pr = [g1.clone().requires_grad_(True), b1.clone().requires_grad_(True)]
+    yr = O.gn_relu(xr, pr[0], pr[1])
+    if through_conv:
+        yr = O.ws_conv3d(yr.bfloat16().float(), w, 1, 1)
+    dy = _rand(tuple(yr.shape), 5)
+    (yr * dy).sum().backward()
+    ops.begin_forward(torch.device("cuda"))
+    xd = x.cuda().requires_grad_(True)
+    pd = [g1.cuda().requires_grad_(True), b1.cuda().requires_grad_(True)]
+    y = ops.gn_relu(xd, pd[0], pd[1])
+    if through_conv:
+        y = ops.ws_conv3d(y, w.cuda(), 1)
+    (y.float() * dy.cuda()).sum().backward()
+    assert rel(pd[0].grad, pr[0].grad) < tol_b and rel(pd[1].grad, pr[1].grad) < tol_b
+    assert abs(pd[0].grad[3].item() - pr[0].grad[3].item()) < tol_b * abs(pr[0].grad[3].item()) + 1e-6
+    assert pd[0].grad[17].item() == 0.0
+    assert rel(xd.grad.float(), xr.grad) < tol_b
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,sp,dual", [
+    (32, 32, 3, 1, (5, 18, 11), False),     # resident-weight plane-major kernel, ragged tiles
+    (64, 64, 3, 1, (6, 17, 9), False),
+    (256, 256, 3, 1, (2, 5, 7), False),     # 8 column chunks per tile
+    (64, 128, 3, 2, (6, 10, 12), True),     # dual GN: 3x3x3 stride-2 dgrad (8 parity classes) + 1x1x1 stride-2 dgrad
+    (128, 64, 3, 1, (3, 9, 8), True),       # dual GN: decoder block (3x3x3 + 1x1x1, stride 1)
+])
+def test_gn_backward_reduction_fused_into_dgrad_epilogue(mm, cin, cout, k, stride, sp, dual):
+    """conv(relu(gn(x))) on the tcgen05 path: with the GroupNorm-backward reduction folded into the dgrad epilogue the
+    gradients must equal those of the unfused path (same kernels + separate reduction pass) to fp32 summation-order
+    noise, and the fused path must actually be taken."""
+    mm.set_compute_dtype(torch.bfloat16)
+    ops = mm.ops
+    x = (_rand((2, cin) + sp, 1) + 0.2).bfloat16().float()
+    g1, b1 = 1 + 0.2 * _rand((cin,), 2), 0.2 * _rand((cin,), 3)
+    g2, b2 = 1 + 0.2 * _rand((cin,), 4), 0.2 * _rand((cin,), 5)
+    w1 = _rand((cout, cin, k, k, k), 6)
+    w2 = _rand((cout, cin, 1, 1, 1), 7)
+
+    def run(fuse):
+        ops.set_fuse_gn_bwd(fuse)
+        try:
+            ops.begin_forward(torch.device("cuda"))
+            xd = x.cuda().requires_grad_(True)
+            ps = [t.cuda().requires_grad_(True) for t in (g1, b1, g2, b2)]
+            if dual:
+                a1, a2 = ops.gn_relu_dual(xd, *ps)
+                y = ops.ws_conv3d(a1, w1.cuda(), stride) + ops.ws_conv3d(a2, w2.cuda(), stride)
+            else:
+                a1 = ops.gn_relu(xd, ps[0], ps[1])
+                y = ops.ws_conv3d(a1, w1.cuda(), stride)
+            dy = _rand(tuple(y.shape), 8).cuda().to(y.dtype)
+            launches = mm._lib.launch_count()
+            y.backward(dy)
+            launches = mm._lib.launch_count() - launches
+            return xd.grad.float().cpu(), [p.grad.cpu() for p in ps[:4 if dual else 2]], launches
+        finally:
+            ops.set_fuse_gn_bwd(True)
+
+    gx_f, gp_f, n_f = run(True)
+    gx_u, gp_u, n_u = run(False)
+    assert n_f == n_u - 1, (n_f, n_u)          # exactly the reduction launch disappeared
+    assert rel(gx_f, gx_u) < 2e-3               # dx is stored in bf16 (rounding of ~identical fp32 values)
+    # the fused sums see xhat through a = relu(gn(x)) as stored in bf16 (relative rounding 2^-9 per element, random):
+    # parameter gradients agree with the separate fp32 reduction pass to a few 1e-3, well inside the bf16 tolerance
+    for a, b in zip(gp_f, gp_u):
+        assert rel(a, b) < 1e-2
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-3)])
 @pytest.mark.parametrize("shape", [(2, 32, 3, 4, 5), (1, 64, 2, 2, 3), (1, 256, 2, 3, 1)])
 def test_upsample2x_add_fused_gn_statistics(mm, dtype, tol, shape):
