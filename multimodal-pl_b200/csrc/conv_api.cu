@@ -5,11 +5,11 @@ namespace mmpl {
 int conv_direct_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_direct_dgrad(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int conv_direct_wgrad(const void*, const void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int conv_tc_s1(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, double*,
+int conv_tc_s1(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, double*, int*,
                const mmpl_gn_bwd_fuse*, cudaStream_t);
 bool conv_tc_can_fuse_gn_bwd(int nout);
-int conv_tc_s2_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, double*, cudaStream_t);
-bool conv_tc_can_fuse_stats(int nout);
+int conv_tc_s2_fprop(const void*, const void*, const void*, void*, int, int, int, int, int, int, int, double*, int*,
+                     cudaStream_t);
 int conv_out_dim(int in, int k, int stride);
 int conv_tc_s2_dgrad(const void*, const void*, void*, int, int, int, int, int, int, int, const mmpl_gn_bwd_fuse*, cudaStream_t);
 int parity_split(const void*, void*, int, int, int, int, int, cudaStream_t);
@@ -43,14 +43,14 @@ extern "C" int mmpl_conv3d_fprop(const void* x, const void* w_fprop, const void*
                               conv_out_dim(w, ksize, stride);
   if (algo == MMPL_ALGO_TCGEN05 || algo == MMPL_ALGO_TCGEN05_PSPLIT) {
     MMPL_REQUIRE(dtype == MMPL_BF16, MMPL_E_UNSUPPORTED, "conv3d_fprop: tcgen05 path needs bf16 (got dtype=%d)", dtype);
-    double* fused = (gn_stats_out && conv_tc_can_fuse_stats(cout)) ? gn_stats_out : nullptr;
+    int fused = 0;   // set by the launch when its epilogue produced the statistics (one tile spans all output channels)
     int rc;
     if (stride == 1) {
-      rc = conv_tc_s1(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, fused, nullptr, s);
+      rc = conv_tc_s1(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, gn_stats_out, &fused, nullptr, s);
     } else {
       MMPL_REQUIRE((ksize == 3) == (algo == MMPL_ALGO_TCGEN05_PSPLIT), MMPL_E_UNSUPPORTED,
                    "conv3d_fprop: stride-2 3x3x3 takes the parity-split input (MMPL_ALGO_TCGEN05_PSPLIT), 1x1x1 takes x");
-      rc = conv_tc_s2_fprop(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, fused, s);
+      rc = conv_tc_s2_fprop(x, w_fprop, residual, y, n, d, h, w, cin, cout, ksize, gn_stats_out, &fused, s);
     }
     if (rc || !gn_stats_out || fused) return rc;
     return mmpl_gn_stats(y, gn_stats_out, n, out_spatial, cout, 16, dtype, stream);
@@ -78,7 +78,7 @@ extern "C" int mmpl_conv3d_dgrad(const void* dy, const void* w_dgrad, const void
     int rc;
     // stride-1 dgrad is a correlation of dy with the flipped/transposed packing: channels swap roles
     if (stride == 1) {
-      rc = conv_tc_s1(dy, w_dgrad, addend, dx, n, d, h, w, cout, cin, ksize, nullptr, fuse, s);
+      rc = conv_tc_s1(dy, w_dgrad, addend, dx, n, d, h, w, cout, cin, ksize, nullptr, nullptr, fuse, s);
     } else {
       MMPL_REQUIRE(addend == nullptr, MMPL_E_UNSUPPORTED, "conv3d_dgrad: stride-2 tcgen05 path has no addend input");
       if (ksize == 1)  // only the even parity class receives gradient; the rest of dx is zero

@@ -143,7 +143,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   // item -> (nt, parity class, n, tile origin in the tile-grid domain)
+  // The parity class is the FASTEST index: the 8 classes of a stride-2 dgrad tile run on neighbouring CTAs at the same
+  // time, so their interleaved 64-byte stores merge into full lines in L2 and the dY tile is fetched from HBM once.
   auto item_coords = [&](int item, int& nt, int& pc, int& n, int& d0, int& h0, int& w0) {
+    pc = item % p.NPAR;
+    item /= p.NPAR;
     w0 = (item % p.WT) * TC_TW;
     item /= p.WT;
     h0 = (item % p.HT) * TC_TH;
@@ -151,9 +155,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     d0 = (item % p.DT) * TD;
     item /= p.DT;
     n = item % p.N;
-    item /= p.N;
-    pc = item % p.NPAR;
-    nt = item / p.NPAR;
+    nt = item / p.N;
   };
   // number of (A-chunk) loads per item and taps per chunk
   const int chunks_per_item = G::PARITY_CHUNKS ? p.nch * 8 : p.nch;
@@ -598,6 +600,7 @@ struct TcProblem {
   int kred, nout;
   double* stats = nullptr;
   const mmpl_gn_bwd_fuse* gn = nullptr;   // fused GroupNorm-backward reduction over the OUTPUT (dgrad launches)
+  int* stats_fused = nullptr;             // out: 1 if the launch computed `stats` (one tile spans all output channels)
 };
 
 template <int KC, int NT, int TD, int MODE, bool WRES, int NA_ = 2>
@@ -619,6 +622,7 @@ int launch_tc(const TcProblem& q, cudaStream_t s) {
   p.DT = ceil_div(p.Ds, TD), p.HT = ceil_div(p.Hs, TC_TH), p.WT = ceil_div(p.Ws, TC_TW), p.NTILES = q.nout / NT;
   p.NPAR = MODE == MODE_S2D ? 8 : 1;
   p.stats = (q.stats != nullptr && q.nout == NT && !G::STRIDED_OUT) ? q.stats : nullptr;
+  if (q.stats_fused) *q.stats_fused = p.stats != nullptr;
   p.gn_a = nullptr, p.gn_beta = nullptr, p.gn_ws = nullptr, p.gn_ws_stride = 6, p.gn_head = 0, p.gn_psplit = 0;
   if (q.gn != nullptr) {
     MMPL_REQUIRE(!q.gn->a_is_parity_split || MODE == MODE_S2D, MMPL_E_UNSUPPORTED,
@@ -663,6 +667,14 @@ int dispatch_tc(const TcProblem& q, cudaStream_t s) {
   // ring (the weight tiles, one TMA round trip per tap, are the latency-critical stream).  MMPL_TC_DEEPB=0 selects
   // the double-buffered-activation variant instead.
   static const bool deep_b = [] { const char* e = getenv("MMPL_TC_DEEPB"); return !(e && e[0] == '0'); }();
+  if (MODE == MODE_S1K3 && nt >= 128) {
+    // Lowest-resolution layers (cfg2: 2 x 4 x 12 x 12 voxels, 256 channels): a 128-row x 256-column tiling yields 16
+    // work items for 148 SMs.  Narrow column tiles and single planes give 4-8x the items; the extra A-operand traffic is
+    // irrelevant at this size.
+    const int64_t sp = static_cast<int64_t>(q.N) * ceil_div(q.H, TC_TH) * ceil_div(q.W, TC_TW);
+    const int64_t items_default = sp * ceil_div(q.D, nt == 128 ? 2 : 1) * (nout / nt);
+    if (items_default * 2 <= num_sms()) return launch_tc<64, 64, 1, MODE, false, 1>(q, s);
+  }
   if (deep_b && MODE == MODE_S1K3) {
     if (nt == 32) return launch_tc<64, 32, 4, MODE, false, 1>(q, s);
     if (nt == 64) return launch_tc<64, 64, 4, MODE, false, 1>(q, s);
@@ -712,7 +724,6 @@ static int check_align(const void* a, const void* b, const void* c, const void* 
 
 // ---- stride 1 (k = 3 or 1): x [N,D,H,W,cin] -> y [N,D,H,W,cout]; also stride-1 dgrad with swapped channel roles
 // GroupNorm statistics can be fused into the epilogue when one CTA tile spans all output channels
-bool conv_tc_can_fuse_stats(int nout) { return nout == 32 || nout == 64 || nout == 128 || nout == 256; }
 // The GroupNorm-backward reduction rides on the dgrad epilogue where that is cheaper than a separate streaming pass:
 // wide-and-shallow outputs (<= 64 channels: the full- and half-resolution layers, 85 % of the reduction traffic).  With
 // more channels a work item has 8+ column chunks to transpose-reduce while the tensors are small enough that the
@@ -720,22 +731,23 @@ bool conv_tc_can_fuse_stats(int nout) { return nout == 32 || nout == 64 || nout 
 bool conv_tc_can_fuse_gn_bwd(int nout) { return nout == 32 || nout == 64; }
 
 int conv_tc_s1(const void* x, const void* wp, const void* residual, void* y, int N, int D, int H, int W, int cin,
-               int cout, int ksize, double* stats, const mmpl_gn_bwd_fuse* gn, cudaStream_t s) {
+               int cout, int ksize, double* stats, int* stats_fused, const mmpl_gn_bwd_fuse* gn, cudaStream_t s) {
   if (int e = check_align(x, wp, y, residual)) return e;
-  TcProblem q{x, N, D, H, W, wp, residual, y, N, D, H, W, cin, cout, stats, gn};
+  TcProblem q{x, N, D, H, W, wp, residual, y, N, D, H, W, cin, cout, stats, gn, stats_fused};
   return ksize == 3 ? dispatch_tc<MODE_S1K3>(q, s) : dispatch_tc<MODE_S1K1>(q, s);
 }
 
 // ---- stride 2 fprop.  k=3: `src` is the parity-split tensor P [8N][Dp][Hp][Wp][cin]; k=1: `src` is x itself.
 int conv_tc_s2_fprop(const void* src, const void* wp, const void* residual, void* y, int N, int D, int H, int W, int cin,
-                     int cout, int ksize, double* stats, cudaStream_t s) {
+                     int cout, int ksize, double* stats, int* stats_fused, cudaStream_t s) {
   if (int e = check_align(src, wp, y, residual)) return e;
   const int Do = (D + 1) / 2, Ho = (H + 1) / 2, Wo = (W + 1) / 2;   // == (in + 2*pad - k)/2 + 1 for k in {1,3}
   if (ksize == 3) {
-    TcProblem q{src, static_cast<int64_t>(8) * N, Do, Ho, Wo, wp, residual, y, N, Do, Ho, Wo, cin, cout, stats};
+    TcProblem q{src, static_cast<int64_t>(8) * N, Do, Ho, Wo, wp, residual, y, N, Do, Ho, Wo, cin, cout, stats, nullptr,
+                stats_fused};
     return dispatch_tc<MODE_S2F>(q, s);
   }
-  TcProblem q{src, N, D, H, W, wp, residual, y, N, Do, Ho, Wo, cin, cout, stats};
+  TcProblem q{src, N, D, H, W, wp, residual, y, N, Do, Ho, Wo, cin, cout, stats, nullptr, stats_fused};
   return dispatch_tc<MODE_S2K1F>(q, s);
 }
 

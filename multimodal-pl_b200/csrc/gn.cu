@@ -244,15 +244,28 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
     gm[g][hh * 2 + 1] = static_cast<float>(b / m);
   }
   __syncthreads();
-  float mu[VN], rs[VN], ga[NH][VN], be[NH][VN], m1[NH][VN], m2[NH][VN];
+  // Per channel and head the whole update folds into   dx += cA * g + cB * x + cC   with
+  //   cA = rstd*gamma,  cB = -rstd^2 * m2,  cC = rstd * (rstd*mean*m2 - m1),
+  // and the ReLU gate is the forward's own fused multiply-add (sc = rstd*gamma = cA, sh = beta - mean*sc):
+  // 2 FMAs for the gate/select and 2 for the update per element and head.
+  float mu[VN], rs[VN], ga[NH][VN], sh[NH][VN], cB[NH][VN], cC[NH][VN];
+  float cA[NH][VN];
   bool any_zero_gamma = false;
 #pragma unroll
   for (int i = 0; i < VN; ++i) {
     const int c = cv * VN + i, g = c / cpg;
     mean_rstd(stats + (static_cast<int64_t>(n) * groups + g) * 2, m, eps, mu[i], rs[i]);
-    ga[0][i] = gamma[c], be[0][i] = beta[c], m1[0][i] = gm[g][0], m2[0][i] = gm[g][1];
-    if (DUAL) ga[NH - 1][i] = gamma2[c], be[NH - 1][i] = beta2[c], m1[NH - 1][i] = gm[g][2], m2[NH - 1][i] = gm[g][3];
-    any_zero_gamma |= ga[0][i] == 0.f || (DUAL && ga[NH - 1][i] == 0.f);
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) {
+      const float gam = (hh == 0 ? gamma : gamma2)[c], bet = (hh == 0 ? beta : beta2)[c];
+      const float m1 = gm[g][hh * 2 + 0], m2 = gm[g][hh * 2 + 1];
+      ga[hh][i] = gam;
+      cA[hh][i] = rs[i] * gam;                      // == the forward's scale
+      sh[hh][i] = bet - mu[i] * cA[hh][i];          // == the forward's shift
+      cB[hh][i] = -rs[i] * rs[i] * m2;
+      cC[hh][i] = rs[i] * (rs[i] * mu[i] * m2 - m1);
+      any_zero_gamma |= gam == 0.f;
+    }
   }
   float ex[NH][VN];   // sum g*xhat of this thread's channels, only maintained when one of them has gamma == 0
 #pragma unroll
@@ -264,30 +277,25 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
   const int64_t off = (static_cast<int64_t>(n) * spatial) * C + cv * VN;
 #pragma unroll 2
   for (int64_t v = v0 + vl; v < v1; v += vstep) {
-    V a, g, o;
+    V a, g, g2, ad, o;
     a.load(x + off + v * C);
     g.load(dy + off + v * C);
+    if (DUAL) g2.load(dy2 + off + v * C);
+    if (ADD) ad.load(addend + off + v * C);
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
-      const float xh = (a.v[i] - mu[i]) * rs[i];
-      const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[0][i], be[0][i]) ? g.v[i] : 0.f;
-      o.v[i] = rs[i] * (ga[0][i] * gg - m1[0][i] - xh * m2[0][i]);
-      if (any_zero_gamma) ex[0][i] = fmaf(gg, xh, ex[0][i]);
-    }
-    if (DUAL) {
-      g.load(dy2 + off + v * C);
-#pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        const float xh = (a.v[i] - mu[i]) * rs[i];
-        const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[NH - 1][i], be[NH - 1][i]) ? g.v[i] : 0.f;
-        o.v[i] += rs[i] * (ga[NH - 1][i] * gg - m1[NH - 1][i] - xh * m2[NH - 1][i]);
-        if (any_zero_gamma) ex[NH - 1][i] = fmaf(gg, xh, ex[NH - 1][i]);
+      float r = fmaf(cB[0][i], a.v[i], cC[0][i]);
+      const float gg = fmaf(a.v[i], cA[0][i], sh[0][i]) > 0.f ? g.v[i] : 0.f;
+      r = fmaf(cA[0][i], gg, r);
+      if (DUAL) {
+        r += fmaf(cB[NH - 1][i], a.v[i], cC[NH - 1][i]);
+        const float gg2 = fmaf(a.v[i], cA[NH - 1][i], sh[NH - 1][i]) > 0.f ? g2.v[i] : 0.f;
+        r = fmaf(cA[NH - 1][i], gg2, r);
+        if (any_zero_gamma) ex[NH - 1][i] = fmaf(gg2, (a.v[i] - mu[i]) * rs[i], ex[NH - 1][i]);
       }
-    }
-    if (ADD) {
-      g.load(addend + off + v * C);
-#pragma unroll
-      for (int i = 0; i < VN; ++i) o.v[i] += g.v[i];
+      if (any_zero_gamma) ex[0][i] = fmaf(gg, (a.v[i] - mu[i]) * rs[i], ex[0][i]);
+      if (ADD) r += ad.v[i];
+      o.v[i] = r;
     }
     o.store(dx + off + v * C);
   }

@@ -18,7 +18,7 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, ops
 
 
 def _env_int(name, default):
@@ -99,6 +99,7 @@ class DataParallelModel(torch.nn.Module):
         b = self._buckets[p._mmpl_bucket]
         b["pending"] -= 1
         if b["pending"] == 0:
+            ops.join_side_stream()      # weight gradients are finished on a side stream (ops._ws_bwd_launch)
             view = self.flat_grad[b["lo"]:b["hi"]]
             self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True))
 

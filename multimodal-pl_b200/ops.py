@@ -15,7 +15,8 @@ from ._lib import p as _p
 _CL = torch.channels_last_3d
 
 _cfg = {"dtype": torch.bfloat16, "conv_algo": os.environ.get("MMPL_CONV_ALGO", "auto"),
-        "fuse_gn_bwd": os.environ.get("MMPL_FUSE_GN_BWD", "1") != "0"}
+        "fuse_gn_bwd": os.environ.get("MMPL_FUSE_GN_BWD", "1") != "0",
+        "ws_bwd_side_stream": os.environ.get("MMPL_WS_BWD_SIDE_STREAM", "1") != "0"}
 
 
 def set_fuse_gn_bwd(on: bool):
@@ -96,11 +97,55 @@ def _grad_dst(param, shape):
     (engine.DataParallelModel / FusedSGD set ``_mmpl_grad_slot``) and no gradient yet this step, the kernel writes
     straight into a fresh view of that slot and autograd's AccumulateGrad adopts the view as ``param.grad`` -- no copy,
     no add kernel.  Otherwise (gradient accumulation, parameters without a slot, non-fp32 masters) a new tensor."""
-    slot = getattr(param, "_mmpl_grad_slot", None) if param is not None else None
-    if slot is not None and param.grad is None and param.dtype == torch.float32:
-        flat, off, n = slot
+    if _grad_is_direct(param):
+        flat, off, n = param._mmpl_grad_slot
         return flat[off:off + n].view(shape)
     return torch.empty(shape, dtype=torch.float32, device=param.device if param is not None else None)
+
+
+def _grad_is_direct(param) -> bool:
+    """True if ``_grad_dst`` hands out the flat-buffer view, i.e. autograd will adopt the gradient without launching
+    anything that reads it."""
+    slot = getattr(param, "_mmpl_grad_slot", None) if param is not None else None
+    return slot is not None and param.grad is None and param.dtype == torch.float32
+
+
+# ---- side stream for the weight-standardisation backward --------------------------------------------------------
+# dW of a convolution has no consumer inside the backward pass (only the optimizer / gradient all-reduce read it), but
+# its two small kernels (wgrad -> ws_weight_bwd) would sit on the critical path 35 times per step.  ws_weight_bwd is
+# therefore launched on a side stream that forks after the wgrad kernel and is joined once, when the backward pass
+# ends (autograd engine callback) -- inside a CUDA-graph capture this becomes a parallel branch of the graph.
+_SIDE = {"stream": None, "pending": False}
+
+
+def _side_stream():
+    if _SIDE["stream"] is None:
+        _SIDE["stream"] = torch.cuda.Stream()
+    return _SIDE["stream"]
+
+
+def join_side_stream():
+    """Make the current stream wait for everything launched on the side stream (no-op if nothing is pending)."""
+    if _SIDE["pending"]:
+        torch.cuda.current_stream().wait_stream(_SIDE["stream"])
+        _SIDE["pending"] = False
+
+
+def _ws_bwd_launch(g_hat, w_hat, inv_std, cout, cin, taps, standardise, dw, off_critical_path):
+    L = _lib.lib()
+    if not (off_critical_path and _cfg["ws_bwd_side_stream"]):
+        _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, cin, taps, standardise, _p(dw),
+                                        _lib.stream_ptr()), "ws_weight_bwd")
+        return
+    cur, side = torch.cuda.current_stream(), _side_stream()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, cin, taps, standardise, _p(dw),
+                                        _lib.stream_ptr()), "ws_weight_bwd")
+    g_hat.record_stream(side)
+    if not _SIDE["pending"]:
+        _SIDE["pending"] = True
+        torch.autograd.Variable._execution_engine.queue_callback(join_side_stream)
 
 
 _STATS_POOL = {"buf": None, "off": 0}
@@ -410,9 +455,9 @@ class WSConv3dFn(torch.autograd.Function):
             with _timed(algo, ctx.flops, ("wgrad_tc",) + ctx.key[1:]):
                 _lib.check(L.mmpl_conv3d_wgrad(_p(x), _p(dy), _p(g_hat), n, d, h, w, cin, cout, k, stride, code, algo,
                                                _p(ws), wsb, st), "conv3d_wgrad")
+            direct = _grad_is_direct(ctx.weight)
             dw = _grad_dst(ctx.weight, w_hat.shape)
-            _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, cin, taps, standardise, _p(dw), st),
-                       "ws_weight_bwd")
+            _ws_bwd_launch(g_hat, w_hat, inv_std, cout, cin, taps, standardise, dw, direct)
             dw = dw.to(wdtype)
         if has_res and ctx.needs_input_grad[2]:
             dres = dy
@@ -527,9 +572,9 @@ class StemConvFn(torch.autograd.Function):
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             _lib.check(L.mmpl_stem_conv_wgrad(_p(src), _p(dy), _p(g_hat), n, d, h, w, cout, _lib.dtype_code(dy.dtype),
                                               _p(ws), wsb, st), "stem_conv_wgrad")
+        direct = _grad_is_direct(ctx.weight)
         dw = _grad_dst(ctx.weight, w_hat.shape)
-        _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, 1, 27, standardise, _p(dw), st),
-                   "ws_weight_bwd")
+        _ws_bwd_launch(g_hat, w_hat, inv_std, cout, 1, 27, standardise, dw, direct)
         return None, dw.to(wdtype), None
 
 
