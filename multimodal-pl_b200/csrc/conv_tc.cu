@@ -19,7 +19,8 @@
 //             mmpl_parity_split); tap k of parity p is P_p shifted by (k != 0) -> 8 chunks x (1..8 taps) per item;
 //      dgrad  runs per parity class of dX: a 1..8-tap stride-1 correlation over dY whose epilogue stores to 2i+p.
 //  * Warp roles: 0 = activation TMA producer, 1 = weight TMA producer, 2 = MMA issuer (warp-uniform loop, one elected
-//    lane issues) and TMEM allocator, 3..6 = epilogue (tcgen05.ld -> +residual -> bf16 -> 16-byte global stores).
+//    lane issues) and TMEM allocator, 4..7 / 8..11 = two epilogue warpgroups on alternate items (tcgen05.ld ->
+//    +residual -> bf16 -> 16-byte global stores, plus the fused GroupNorm statistics / backward reduction).
 //  * WRES: for 32->32 layers all 27 weight tiles (55 KB) stay resident in shared memory for the life of the CTA.
 #include <stdlib.h>
 
@@ -32,7 +33,12 @@ namespace {
 using namespace ptx;
 
 constexpr int TC_TH = 16, TC_TW = 8;
-constexpr int TC_THREADS = 224;
+// 12 warps: 0 = activation TMA, 1 = weight TMA, 2 = MMA issuer, 3 = idle, 4..7 and 8..11 = two epilogue warpgroups that
+// take alternate work items (one per TMEM accumulator buffer), so an epilogue has two MMA periods to finish.  The
+// register file is re-partitioned with setmaxnreg: 64 for warps 0..3, 216 for the epilogue warpgroups
+// (launch: 384 x 168; the decrease must free more than the increase takes, or the second group waits forever).
+constexpr int TC_THREADS = 384;
+constexpr int TC_REGS_SPECIAL = 64, TC_REGS_EPILOGUE = 216;
 
 enum : int {
   MODE_S1K3 = 0,   // 3x3x3 stride 1 (fprop, or dgrad with the flipped/transposed packing)
@@ -160,6 +166,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // number of (A-chunk) loads per item and taps per chunk
   const int chunks_per_item = G::PARITY_CHUNKS ? p.nch * 8 : p.nch;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SPECIAL));
   if (warp == 0) {
     // ===================================================== activation producer
     if (lane == 0) {
@@ -334,28 +342,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (elect_one()) umma_commit(&acc_full[buf]);
       __syncwarp();
     }
+  }
   } else {
-    // ===================================================== epilogue warps 3..6 (TMEM lane quarter = warp % 4)
+    // ===================================================== epilogue warpgroups (TMEM lane quarter = warp % 4)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPILOGUE));
     const int q = warp & 3;
+    const int eg = (warp - 4) >> 2;        // epilogue group: owns accumulator buffer eg and the items of parity eg
     const int row = q * 32 + lane;
     const int rh = row >> 3, rw = row & 7;
     // fused GroupNorm statistics of the stored output: 16 groups of NT/16 channels; per-thread fp32 partials over this
     // CTA's items, reduced across the warp and added to the fp64 buffer only when the sample changes / at the end
     constexpr int CPG = NT / 16;
-    float gsum[16], gsq[16];
+    // p1/p2: per-thread partials of the fused GroupNorm-backward reduction (dgrad launches).  The forward statistics
+    // (fprop launches) never coexist with them and live in the first half of p1: gsum = p1[0..15], gsq = p1[16..31].
+    float p1[32], p2[32];
 #pragma unroll
-    for (int g = 0; g < 16; ++g) gsum[g] = gsq[g] = 0.f;
+    for (int j = 0; j < 32; ++j) p1[j] = p2[j] = 0.f;
+    float (&gstat)[32] = p1;
     int stat_n = -1;
     auto flush_stats = [&]() {
       if (p.stats == nullptr || stat_n < 0) return;
 #pragma unroll
       for (int g = 0; g < 16; ++g) {
-        const float a = warp_sum(gsum[g]), b = warp_sum(gsq[g]);
+        const float a = warp_sum(gstat[g]), b = warp_sum(gstat[16 + g]);
         if (lane == 0) {
           atomicAdd(&p.stats[(static_cast<int64_t>(stat_n) * 16 + g) * 2 + 0], static_cast<double>(a));
           atomicAdd(&p.stats[(static_cast<int64_t>(stat_n) * 16 + g) * 2 + 1], static_cast<double>(b));
         }
-        gsum[g] = gsq[g] = 0.f;
+        gstat[g] = gstat[16 + g] = 0.f;
       }
     };
     // ---- fused GroupNorm+ReLU backward reduction (see TcParams::gn_*)
@@ -367,9 +381,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float gacc1[NT / 32], gacc2[NT / 32];
 #pragma unroll
     for (int i = 0; i < NT / 32; ++i) gacc1[i] = gacc2[i] = 0.f;
-    float p1[32], p2[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) p1[j] = p2[j] = 0.f;
     int gn_n = -1, gn_nt = -1;
     // sum over the warp's 32 rows of each of 32 per-lane values; afterwards v[0] of lane l is the total of index l
     auto transpose_reduce = [&](float (&v)[32]) {
@@ -440,12 +451,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int v = 0; v < 4; ++v)
         dst[v] = (aux != nullptr && valid) ? *reinterpret_cast<const uint4*>(aux + off + v * 8) : make_uint4(0u, 0u, 0u, 0u);
     };
-    ItemPos cur = locate(blockIdx.x);
+    const int item_step = 2 * gridDim.x;
+    ItemPos cur = locate(blockIdx.x + eg * gridDim.x);
     prefetch(cur, 0, ring[0]);
     prefetch(cur, 1, ring[1]);
-    uint32_t iti = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++iti) {
-      const ItemPos nxt = locate(item + gridDim.x);
+    uint32_t iti = eg;
+    for (int item = blockIdx.x + eg * gridDim.x; item < p.total_items; item += item_step, iti += 2) {
+      const ItemPos nxt = locate(item + item_step);
       const int nt = cur.nt, n = cur.n;
       if (p.stats != nullptr && n != stat_n) {
         flush_stats();
@@ -461,7 +473,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int i = 0; i < TOT; ++i) {
         const int c0 = (i / TD) * 32, pl = i % TD;
-        if (!GN_PERSIST && pl == 0) {
+        if (gn_on && !GN_PERSIST && pl == 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) p1[j] = p2[j] = 0.f;
         }
@@ -470,13 +482,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::ACC_COLS + pl * NT + c0, r);
         tmem_ld_wait();
-        uint4 row[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) row[v] = ring[i % 2][v];
-        if (i + 2 < TOT)
-          prefetch(cur, i + 2, ring[i % 2]);
-        else
-          prefetch(nxt, i + 2 - TOT, ring[i % 2]);
+        uint4 (&row)[4] = ring[i % 2];
         if (valid) {
           if (p.residual) {
 #pragma unroll
@@ -503,10 +509,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (p.stats != nullptr) {   // statistics of the value as stored (bf16-rounded)
                 const float x0 = __uint_as_float(o[k] << 16), x1 = __uint_as_float(o[k] & 0xFFFF0000u);
                 const int g0 = (c0 + v * 8 + 2 * k) / CPG, g1 = (c0 + v * 8 + 2 * k + 1) / CPG;
-                gsum[g0] += x0;
-                gsq[g0] = fmaf(x0, x0, gsq[g0]);
-                gsum[g1] += x1;
-                gsq[g1] = fmaf(x1, x1, gsq[g1]);
+                gstat[g0] += x0;
+                gstat[16 + g0] = fmaf(x0, x0, gstat[16 + g0]);
+                gstat[g1] += x1;
+                gstat[16 + g1] = fmaf(x1, x1, gstat[16 + g1]);
               }
               if (gn_on) {   // dA (fp32, before the bf16 rounding of the store) against a = relu(gn(x)): gate = [a > 0]
                 const int j = v * 8 + 2 * k;
@@ -520,6 +526,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *reinterpret_cast<uint4*>(p.y + off + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
+        if (i + 2 < TOT)          // the slot is consumed: refill it two steps ahead
+          prefetch(cur, i + 2, ring[i % 2]);
+        else
+          prefetch(nxt, i + 2 - TOT, ring[i % 2]);
         if (gn_on && !GN_PERSIST && pl == TD - 1) {
           transpose_reduce(p1);
           transpose_reduce(p2);

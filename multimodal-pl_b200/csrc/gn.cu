@@ -5,6 +5,8 @@
 // Thread mapping shared by all kernels: a block of 256 threads covers 256/VPV voxels per iteration, where
 // VPV = C / (channels per 16-byte vector); thread t owns vector column t % VPV for the whole kernel, so per-channel
 // parameters and partial sums live in registers.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mmpl {
@@ -267,46 +269,55 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
       any_zero_gamma |= gam == 0.f;
     }
   }
-  float ex[NH][VN];   // sum g*xhat of this thread's channels, only maintained when one of them has gamma == 0
-#pragma unroll
-  for (int hh = 0; hh < NH; ++hh)
-#pragma unroll
-    for (int i = 0; i < VN; ++i) ex[hh][i] = 0.f;
   const int64_t v0 = static_cast<int64_t>(blockIdx.x) * vox_per_block;
   const int64_t v1 = min(v0 + vox_per_block, spatial);
   const int64_t off = (static_cast<int64_t>(n) * spatial) * C + cv * VN;
-#pragma unroll 2
-  for (int64_t v = v0 + vl; v < v1; v += vstep) {
-    V a, g, g2, ad, o;
-    a.load(x + off + v * C);
-    g.load(dy + off + v * C);
-    if (DUAL) g2.load(dy2 + off + v * C);
-    if (ADD) ad.load(addend + off + v * C);
-#pragma unroll
-    for (int i = 0; i < VN; ++i) {
-      float r = fmaf(cB[0][i], a.v[i], cC[0][i]);
-      const float gg = fmaf(a.v[i], cA[0][i], sh[0][i]) > 0.f ? g.v[i] : 0.f;
-      r = fmaf(cA[0][i], gg, r);
-      if (DUAL) {
-        r += fmaf(cB[NH - 1][i], a.v[i], cC[NH - 1][i]);
-        const float gg2 = fmaf(a.v[i], cA[NH - 1][i], sh[NH - 1][i]) > 0.f ? g2.v[i] : 0.f;
-        r = fmaf(cA[NH - 1][i], gg2, r);
-        if (any_zero_gamma) ex[NH - 1][i] = fmaf(gg2, (a.v[i] - mu[i]) * rs[i], ex[NH - 1][i]);
-      }
-      if (any_zero_gamma) ex[0][i] = fmaf(gg, (a.v[i] - mu[i]) * rs[i], ex[0][i]);
-      if (ADD) r += ad.v[i];
-      o.v[i] = r;
-    }
-    o.store(dx + off + v * C);
-  }
-  if (any_zero_gamma) {
+  // The streaming loop exists twice: the plain one, and (block-uniform choice, practically never taken) one that also
+  // accumulates sum g*xhat for the channels of this block whose gamma is exactly 0.
+  auto stream = [&](auto exc_tag) {
+    constexpr bool EXC = decltype(exc_tag)::value;
+    float ex[NH][VN];
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
-      for (int i = 0; i < VN; ++i)
-        if (ga[hh][i] == 0.f)
-          atomicAdd(&ws[(static_cast<int64_t>(n) * C + cv * VN + i) * kWs + 4 + hh], static_cast<double>(ex[hh][i]));
-  }
+      for (int i = 0; i < VN; ++i) ex[hh][i] = 0.f;
+#pragma unroll 2
+    for (int64_t v = v0 + vl; v < v1; v += vstep) {
+      V a, g, g2, ad, o;
+      a.load(x + off + v * C);
+      g.load(dy + off + v * C);
+      if (DUAL) g2.load(dy2 + off + v * C);
+      if (ADD) ad.load(addend + off + v * C);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        float r = fmaf(cB[0][i], a.v[i], cC[0][i]);
+        const float gg = fmaf(a.v[i], cA[0][i], sh[0][i]) > 0.f ? g.v[i] : 0.f;
+        r = fmaf(cA[0][i], gg, r);
+        if (EXC) ex[0][i] = fmaf(gg, (a.v[i] - mu[i]) * rs[i], ex[0][i]);
+        if (DUAL) {
+          r += fmaf(cB[NH - 1][i], a.v[i], cC[NH - 1][i]);
+          const float gg2 = fmaf(a.v[i], cA[NH - 1][i], sh[NH - 1][i]) > 0.f ? g2.v[i] : 0.f;
+          r = fmaf(cA[NH - 1][i], gg2, r);
+          if (EXC) ex[NH - 1][i] = fmaf(gg2, (a.v[i] - mu[i]) * rs[i], ex[NH - 1][i]);
+        }
+        if (ADD) r += ad.v[i];
+        o.v[i] = r;
+      }
+      o.store(dx + off + v * C);
+    }
+    if (EXC) {
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+        for (int i = 0; i < VN; ++i)
+          if (ga[hh][i] == 0.f)
+            atomicAdd(&ws[(static_cast<int64_t>(n) * C + cv * VN + i) * kWs + 4 + hh], static_cast<double>(ex[hh][i]));
+    }
+  };
+  if (__syncthreads_or(any_zero_gamma ? 1 : 0))
+    stream(std::true_type{});
+  else
+    stream(std::false_type{});
   // last block: parameter gradients
   unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + static_cast<int64_t>(N) * C * kWs);
   __threadfence();

@@ -294,7 +294,7 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&v)[4]) {
   *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
 }
 
-template <typename T, int CIN>
+template <typename T, int CIN, bool GN>
 __global__ void __launch_bounds__(256, 2)
 cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const float* __restrict__ dl, T* __restrict__ da,
                float* __restrict__ dwc, float* __restrict__ dbias, const float* __restrict__ gn_beta,
@@ -324,11 +324,11 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
 #pragma unroll
     for (int j = 0; j < 4; ++j) accw[i][j] = 0.f;
   // tiles never straddle samples (tile -> (n, t)): the fused GroupNorm-backward sums below are per sample
-  const int64_t tps = (S + TV - 1) / TV;              // tiles per sample
-  const int64_t ntiles = static_cast<int64_t>(N) * tps;
+  const int tps = static_cast<int>((S + TV - 1) / TV);   // tiles per sample (32-bit tile arithmetic: no 64-bit divisions)
+  const int ntiles = N * tps;
   // Fused first pass of the backward of precls_conv.0/1 = GroupNorm+ReLU (unet3D.py:629-631): `a` is its output, so
   // S1_c = sum_v da*[a > 0] and Q_c = sum_v da*a - beta_c*S1_c (see mmpl_gn_bwd_fuse) accumulate per thread in phase 1.
-  const bool gn_on = gn_ws != nullptr;
+  constexpr bool gn_on = GN;
   float gs1[4] = {0.f, 0.f, 0.f, 0.f}, gs2[4] = {0.f, 0.f, 0.f, 0.f};
   int64_t gn_n = -1;
   auto gn_flush = [&]() {
@@ -352,8 +352,9 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
 
   float pg[8];
   Raw16<T> pa[AV];
-  auto prefetch = [&](int64_t tile) {
-    const int64_t n = tile / tps, sp0 = (tile - n * tps) * TV;
+  auto prefetch = [&](int tile) {
+    const int tn_ = tile / tps;
+    const int64_t n = tn_, sp0 = static_cast<int64_t>(tile - tn_ * tps) * TV;
     const int64_t sp = sp0 + sj;
     const bool ok = sp < S;
 #pragma unroll
@@ -369,10 +370,11 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
     }
   };
 
-  int64_t tile = blockIdx.x;
+  int tile = blockIdx.x;
   if (tile < ntiles) prefetch(tile);
   for (; tile < ntiles; tile += gridDim.x) {
-    const int64_t tn = tile / tps, sp0 = (tile - tn * tps) * TV;
+    const int tni = tile / tps;
+    const int64_t tn = tni, sp0 = static_cast<int64_t>(tile - tni * tps) * TV;
     const int64_t v0 = tn * S + sp0;
     const int64_t total = (tn + 1) * S;              // end of this sample
     if (gn_on && tn != gn_n) {
@@ -460,6 +462,22 @@ cls_bwd_kernel(const T* __restrict__ a, const float* __restrict__ wc, const floa
     float sum = 0.f;
     for (int w = 0; w < VG; ++w) sum += redb[w * 16 + tid];
     atomicAdd(&dbias[tid], sum);
+  }
+}
+
+template <typename T>
+void launch_cls_bwd(int cin, int blocks, cudaStream_t s, const T* a, const float* wc, const float* dl, T* da, float* dwc,
+                    float* dbias, const float* gn_beta, double* gn_ws, int n, int64_t spatial, int classes) {
+  if (cin == 32) {
+    if (gn_ws)
+      cls_bwd_kernel<T, 32, true><<<blocks, 256, 0, s>>>(a, wc, dl, da, dwc, dbias, gn_beta, gn_ws, n, spatial, classes);
+    else
+      cls_bwd_kernel<T, 32, false><<<blocks, 256, 0, s>>>(a, wc, dl, da, dwc, dbias, gn_beta, gn_ws, n, spatial, classes);
+  } else {
+    if (gn_ws)
+      cls_bwd_kernel<T, 64, true><<<blocks, 256, 0, s>>>(a, wc, dl, da, dwc, dbias, gn_beta, gn_ws, n, spatial, classes);
+    else
+      cls_bwd_kernel<T, 64, false><<<blocks, 256, 0, s>>>(a, wc, dl, da, dwc, dbias, gn_beta, gn_ws, n, spatial, classes);
   }
 }
 
@@ -557,14 +575,8 @@ extern "C" int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits
   MMPL_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * classes, s));
   const int64_t ntiles = static_cast<int64_t>(n) * ((spatial + 127) / 128);
   const int blocks = static_cast<int>(std::min<int64_t>(ntiles, static_cast<int64_t>(num_sms()) * 2));
-  MMPL_DISPATCH_DTYPE(dtype, T, {
-    if (cin == 32)
-      cls_bwd_kernel<T, 32><<<blocks, 256, 0, s>>>(static_cast<const T*>(a), wc, dlogits, static_cast<T*>(da), dwc, dbias,
-                                                 gn_beta, gn_ws, n, spatial, classes);
-    else
-      cls_bwd_kernel<T, 64><<<blocks, 256, 0, s>>>(static_cast<const T*>(a), wc, dlogits, static_cast<T*>(da), dwc, dbias,
-                                                 gn_beta, gn_ws, n, spatial, classes);
-  });
+  MMPL_DISPATCH_DTYPE(dtype, T, (launch_cls_bwd<T>(cin, blocks, s, static_cast<const T*>(a), wc, dlogits,
+                                                   static_cast<T*>(da), dwc, dbias, gn_beta, gn_ws, n, spatial, classes)));
   MMPL_CHECK_LAUNCH("cls_bwd");
   return MMPL_OK;
 }
