@@ -37,7 +37,15 @@ constexpr int TC_TH = 16, TC_TW = 8;
 // take alternate work items (one per TMEM accumulator buffer), so an epilogue has two MMA periods to finish.  The
 // register file is re-partitioned with setmaxnreg: 64 for warps 0..3, 216 for the epilogue warpgroups
 // (launch: 384 x 168; the decrease must free more than the increase takes, or the second group waits forever).
-constexpr int TC_THREADS = 384;
+// MMPL_TC_TWO_GROUPS = 0 (default) keeps ONE epilogue warpgroup (warps 3..6, 7 warps, no register re-partition): measured
+// on B200 the register-lean epilogue keeps up with the MMAs on its own, and the 12-warp layout costs the plain
+// launches ~18 % (profiles/r01_ncu_summary.md).
+#ifndef MMPL_TC_TWO_GROUPS
+#define MMPL_TC_TWO_GROUPS 0
+#endif
+constexpr bool TC_TWO_GROUPS = MMPL_TC_TWO_GROUPS != 0;
+constexpr int TC_THREADS = TC_TWO_GROUPS ? 384 : 224;
+constexpr int TC_EPI0 = TC_TWO_GROUPS ? 4 : 3;      // first epilogue warp
 constexpr int TC_REGS_SPECIAL = 64, TC_REGS_EPILOGUE = 216;
 
 enum : int {
@@ -105,6 +113,7 @@ struct TcParams {
   int gn_ws_stride;   // doubles per (n, c) entry of gn_ws
   int gn_head;
   int gn_psplit;
+  int epi_groups;     // 1 or 2 epilogue warpgroups in use
 };
 
 // Tap enumeration shared by the weight producer and the MMA issuer.
@@ -166,8 +175,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // number of (A-chunk) loads per item and taps per chunk
   const int chunks_per_item = G::PARITY_CHUNKS ? p.nch * 8 : p.nch;
 
-  if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SPECIAL));
+  if (warp < TC_EPI0) {
+  if (TC_TWO_GROUPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_SPECIAL));
   if (warp == 0) {
     // ===================================================== activation producer
     if (lane == 0) {
@@ -345,9 +354,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   } else {
     // ===================================================== epilogue warpgroups (TMEM lane quarter = warp % 4)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPILOGUE));
+    if (TC_TWO_GROUPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPILOGUE));
     const int q = warp & 3;
-    const int eg = (warp - 4) >> 2;        // epilogue group: owns accumulator buffer eg and the items of parity eg
+    // epilogue group: with p.epi_groups == 2 group g owns accumulator buffer g and the items of parity g; with 1 the
+    // first group takes every item (plain launches: the second group would only add scheduler pressure)
+    const int eg = (warp - TC_EPI0) >> 2;
+    const int epi_groups = TC_TWO_GROUPS ? p.epi_groups : 1;
+    if (eg < epi_groups) {
     const int row = q * 32 + lane;
     const int rh = row >> 3, rw = row & 7;
     // fused GroupNorm statistics of the stored output: 16 groups of NT/16 channels; per-thread fp32 partials over this
@@ -451,12 +464,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int v = 0; v < 4; ++v)
         dst[v] = (aux != nullptr && valid) ? *reinterpret_cast<const uint4*>(aux + off + v * 8) : make_uint4(0u, 0u, 0u, 0u);
     };
-    const int item_step = 2 * gridDim.x;
+    const int item_step = epi_groups * gridDim.x;
     ItemPos cur = locate(blockIdx.x + eg * gridDim.x);
     prefetch(cur, 0, ring[0]);
     prefetch(cur, 1, ring[1]);
     uint32_t iti = eg;
-    for (int item = blockIdx.x + eg * gridDim.x; item < p.total_items; item += item_step, iti += 2) {
+    for (int item = blockIdx.x + eg * gridDim.x; item < p.total_items; item += item_step, iti += epi_groups) {
       const ItemPos nxt = locate(item + item_step);
       const int nt = cur.nt, n = cur.n;
       if (p.stats != nullptr && n != stat_n) {
@@ -544,6 +557,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     gn_flush();
     flush_stats();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -634,6 +648,9 @@ int launch_tc(const TcProblem& q, cudaStream_t s) {
   p.stats = (q.stats != nullptr && q.nout == NT && !G::STRIDED_OUT) ? q.stats : nullptr;
   if (q.stats_fused) *q.stats_fused = p.stats != nullptr;
   p.gn_a = nullptr, p.gn_beta = nullptr, p.gn_ws = nullptr, p.gn_ws_stride = 6, p.gn_head = 0, p.gn_psplit = 0;
+  // two epilogue groups pay off when the epilogue has extra work per row (residual read, fused GroupNorm reduction)
+  static const int force_groups = [] { const char* e = getenv("MMPL_TC_EPI_GROUPS"); return e ? atoi(e) : 0; }();
+  p.epi_groups = force_groups == 1 || force_groups == 2 ? force_groups : ((q.gn != nullptr || q.residual != nullptr) ? 2 : 1);
   if (q.gn != nullptr) {
     MMPL_REQUIRE(!q.gn->a_is_parity_split || MODE == MODE_S2D, MMPL_E_UNSUPPORTED,
                  "conv_tc: a parity-split activation only pairs with the stride-2 3x3x3 dgrad");

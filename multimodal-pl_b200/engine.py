@@ -259,6 +259,42 @@ class GraphedTrainStep:
         return self.static_loss
 
 
+class GraphedInference:
+    """Eval-mode forward of ``model`` captured ONCE into a CUDA graph for the shape of ``example`` and replayed per
+    call: the ~140 kernel launches of a tile cost one graph launch on the host.  Use as a network in
+    ``evaluate.predict_sliding(..., net_list=[GraphedInference(model, tile)], ...)``: ``net(img, task_id) -> logits``.
+    The returned tensor is a static buffer that the next call overwrites (the sliding-window blend consumes it first,
+    in stream order).  Inputs of any other shape fall back to the eager module."""
+
+    def __init__(self, model: torch.nn.Module, example: torch.Tensor, warmup: int = 2):
+        self.model = model
+        self.static_in = example.detach().clone()
+        was_training = model.training
+        model.eval()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(warmup, 1)):
+                model(self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            out = model(self.static_in)
+            self.static_out = out[0] if isinstance(out, (tuple, list)) else out
+        if was_training:
+            model.train()
+
+    def __call__(self, img, task_id=None):
+        if tuple(img.shape) != tuple(self.static_in.shape) or self.model.training:
+            with torch.no_grad():
+                out = self.model(img)
+            return out[0] if isinstance(out, (tuple, list)) else out
+        self.static_in.copy_(img, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
+
+
 def extant_file(x):
     if not os.path.exists(x):
         raise argparse.ArgumentTypeError("{0} does not exist".format(x))

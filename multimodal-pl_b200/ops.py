@@ -398,7 +398,7 @@ class WSConv3dFn(torch.autograd.Function):
         ctx_key = ("conv_tc", min(cin, cout), max(cin, cout), k, stride, n * d * h * w)
         # GroupNorm(16) raw sums of the output for the next GN+ReLU, produced by the conv epilogue
         stats = _zero_stats(n * 16 * 2, dev) if (want_stats and cout % 16 == 0) else None
-        with _timed(algo, flops, ctx_key):
+        with _timed(algo, flops, ctx_key + ("fprop+res" if res is not None else "fprop",)):
             _lib.check(L.mmpl_conv3d_fprop(_p(src), _p(pf), _p(res), _p(y), n, d, h, w, cin, cout, k, stride, code, algo,
                                            _p(stats), st), "conv3d_fprop")
         # stride-2 3x3x3 on tensor cores: the parity-split copy is what wgrad reads, so keep it instead of x
@@ -436,7 +436,7 @@ class WSConv3dFn(torch.autograd.Function):
                 gb, gws, ghead = ctx.gn_bwd
                 fuse = _lib.GnBwdFuse(_p(x), _p(gb), _p(gws), int(ctx.x_is_psplit), int(ghead))
                 fused = ctypes.c_int(0)
-            with _timed(algo, ctx.flops, ctx.key):
+            with _timed(algo, ctx.flops, ctx.key + ("dgrad+gn" if fuse is not None else "dgrad",)):
                 _lib.check(L.mmpl_conv3d_dgrad(_p(dy), _p(pd), None, _p(dx), n, d, h, w, cin, cout, k, stride, code,
                                                algo, ctypes.byref(fuse) if fuse is not None else None,
                                                ctypes.byref(fused) if fused is not None else None, st), "conv3d_dgrad")
