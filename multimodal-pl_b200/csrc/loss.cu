@@ -10,6 +10,8 @@
 //   dz_c = p_c (g_c - sum_k g_k p_k) * grad_out
 // No one-hot tensor, no host synchronisation (the reference does 16 .item() syncs, loss_partial.py:55).
 // Algorithmic HBM bytes per voxel (fp32 logits, fp32 labels): fwd 4C+4, bwd 8C+4.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mmpl {
@@ -28,6 +30,12 @@ __device__ __forceinline__ int class_of(float tv, const float* lut, int C) {
   return ti;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int MAXC>
 __device__ __forceinline__ void softmax_regs(const float* __restrict__ logits, int64_t base, int64_t S, int C,
                                              float (&p)[MAXC]) {
@@ -37,10 +45,14 @@ __device__ __forceinline__ void softmax_regs(const float* __restrict__ logits, i
     p[c] = c < C ? logits[base + c * S] : -INFINITY;
     mx = fmaxf(mx, p[c]);
   }
+  // exp(z - mx) as one FMA + one MUFU: 2^(z*log2(e) - mx*log2(e)), ex2.approx (max rel. error 2^-22; the arguments are
+  // <= 0 so flush-to-zero only affects probabilities below 1e-38).  The kernels are instruction-issue bound.
+  constexpr float kLog2e = 1.4426950408889634f;
+  const float mxs = mx * kLog2e;
   float sum = 0.f;
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
-    p[c] = c < C ? expf(p[c] - mx) : 0.f;
+    p[c] = c < C ? ex2_approx(fmaf(p[c], kLog2e, -mxs)) : 0.f;
     sum += p[c];
   }
   const float inv = 1.0f / sum;
@@ -76,12 +88,13 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) aZ[c] = aE[c] = 0.f;
   const int64_t total = static_cast<int64_t>(N) * S;
-  for (int64_t v = blockIdx.x * static_cast<int64_t>(NTHR) + threadIdx.x; v < total;
-       v += static_cast<int64_t>(gridDim.x) * NTHR) {
-    const int64_t n = v / S, s = v - n * S;
+  // grid = (blocks per sample, N): no 64-bit division per voxel
+  const int64_t n = blockIdx.y;
+  for (int64_t s = blockIdx.x * static_cast<int64_t>(NTHR) + threadIdx.x; s < S;
+       s += static_cast<int64_t>(gridDim.x) * NTHR) {
     float p[MAXC];
     softmax_regs<MAXC>(logits, n * C * S + s, S, C, p);
-    const int tc = class_of(target[v], lut ? s_lut : nullptr, C);
+    const int tc = class_of(target[n * S + s], lut ? s_lut : nullptr, C);
     float ptc = 0.f;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
@@ -125,7 +138,7 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1);
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     __threadfence();
@@ -143,13 +156,13 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
 }
 
 template <int MAXC>
-__global__ void __launch_bounds__(kThreads, MAXC <= 16 ? 3 : 1)
+__global__ void __launch_bounds__(kThreads, MAXC <= 16 ? 2 : 1)
 partial_loss_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                         const float* __restrict__ cw, const float* __restrict__ lut, const double* __restrict__ sums,
                         const float* __restrict__ grad_out, float* __restrict__ dlogits, int N, int64_t S, int C,
                         int uce) {
   __shared__ float s_lut[MAXC], s_a[MAXC], s_b[MAXC], s_e[MAXC];
-  const int64_t total = static_cast<int64_t>(N) * S;
+  const int64_t total = static_cast<int64_t>(N) * S;   // voxels in the BCE mean
   if (threadIdx.x < MAXC) {
     const int c = threadIdx.x;
     s_lut[c] = (lut && c < C) ? lut[c] : static_cast<float>(c);
@@ -164,12 +177,12 @@ partial_loss_bwd_kernel(const float* __restrict__ logits, const float* __restric
     }
   }
   __syncthreads();
-  for (int64_t v = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; v < total;
-       v += static_cast<int64_t>(gridDim.x) * kThreads) {
-    const int64_t n = v / S, s = v - n * S;
+  const int64_t n = blockIdx.y;
+  for (int64_t s = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; s < S;
+       s += static_cast<int64_t>(gridDim.x) * kThreads) {
     float p[MAXC];
     softmax_regs<MAXC>(logits, n * C * S + s, S, C, p);
-    const int tc = class_of(target[v], lut ? s_lut : nullptr, C);
+    const int tc = class_of(target[n * S + s], lut ? s_lut : nullptr, C);
     // g_c is cheap: evaluate it twice (once for the dot product, once for the output) instead of keeping 16 more
     // registers live -- the kernel is bound by loads in flight, i.e. by occupancy
     auto gfun = [&](int c) {
@@ -211,12 +224,15 @@ extern "C" int mmpl_partial_loss_fwd(const float* logits, const float* target, c
   MMPL_REQUIRE(ticket != nullptr, MMPL_E_CUDA, "partial_loss: ticket allocation failed");
   MMPL_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * classes, s));
   const int64_t total = static_cast<int64_t>(n) * spatial;
+  MMPL_REQUIRE(n <= 65535, MMPL_E_SHAPE, "partial_loss: batch %d exceeds the grid limit", n);
   if (classes <= 16) {
-    const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(num_sms()) * 6));
+    const int bx = static_cast<int>(std::min<int64_t>((spatial + 255) / 256, std::max(1, num_sms() * 6 / n)));
+    const dim3 blocks(bx, n);
     partial_loss_fwd_kernel<16, 256><<<blocks, 256, 0, s>>>(logits, target, class_weight, lut, sums, loss, ticket, n,
                                                            spatial, classes, uce);
   } else {
-    const int blocks = static_cast<int>(std::min<int64_t>((total + 127) / 128, static_cast<int64_t>(num_sms()) * 8));
+    const int bx = static_cast<int>(std::min<int64_t>((spatial + 127) / 128, std::max(1, num_sms() * 8 / n)));
+    const dim3 blocks(bx, n);
     partial_loss_fwd_kernel<32, 128><<<blocks, 128, 0, s>>>(logits, target, class_weight, lut, sums, loss, ticket, n,
                                                            spatial, classes, uce);
   }
@@ -230,8 +246,9 @@ extern "C" int mmpl_partial_loss_bwd(const float* logits, const float* target, c
   MMPL_REQUIRE(classes >= 1 && classes <= 32, MMPL_E_SHAPE, "partial_loss: classes=%d (1..32 supported)", classes);
   MMPL_REQUIRE(n > 0 && spatial > 0, MMPL_E_SHAPE, "partial_loss: empty input");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t total = static_cast<int64_t>(n) * spatial;
-  const int blocks = static_cast<int>(std::min<int64_t>((total + kThreads - 1) / kThreads, static_cast<int64_t>(num_sms()) * 8));
+  MMPL_REQUIRE(n <= 65535, MMPL_E_SHAPE, "partial_loss: batch %d exceeds the grid limit", n);
+  const int bx = static_cast<int>(std::min<int64_t>((spatial + kThreads - 1) / kThreads, std::max(1, num_sms() * 8 / n)));
+  const dim3 blocks(bx, n);
   if (classes <= 16)
     partial_loss_bwd_kernel<16><<<blocks, kThreads, 0, s>>>(logits, target, class_weight, lut, sums, grad_out, dlogits, n,
                                                            spatial, classes, uce);
