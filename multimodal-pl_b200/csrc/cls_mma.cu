@@ -1,0 +1,265 @@
+// bf16 classifier kernels on warp-level tensor-core MMAs (mma.sync m16n8k16, fp32 accumulate).
+// Reference op: precls_conv.2 = nn.Conv3d(base, classes, 1) with bias and its autograd (unet3D.py:632, :713).
+//
+// Why not tcgen05: the contraction lengths are 32/64 (forward, dA) or 16 (classes), the GEMMs are skinny and the
+// kernels are bound by HBM traffic and instruction issue, not by tensor throughput -- the CUDA-core versions in
+// small_conv.cu spend ~1000 FMAs per voxel and are issue-bound at 2-3x the HBM time.  Warp MMAs cut the instruction
+// count ~15x with no shared-memory staging: every fragment is loaded straight from global memory in the layout the
+// instruction wants.
+//
+// Precision: activations are bf16 already; fp32 operands (W, dlogits) are split into hi + lo bf16 parts and
+// multiplied in 2-3 MMAs, so the products carry 16 mantissa bits (logits within 1e-5 of the fp32 computation).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace mmpl {
+namespace {
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// (x, y) -> bf16x2 with x in the low half; hi = round-to-nearest part, lo = what is left of the fp32 values
+__device__ __forceinline__ uint32_t pack_hi(float x, float y) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack_hi(x, y);
+  const float xh = __uint_as_float(hi << 16), yh = __uint_as_float(hi & 0xFFFF0000u);
+  lo = pack_hi(x - xh, y - yh);
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+// logits[n][c][s] = bias[c] + sum_k a[n][s][k] W[c][k].  A warp owns chunks of 32 voxels of one sample (2 m16 tiles);
+// A fragments come from `a` (row = voxel), B fragments (W^T, hi/lo) live in registers for the whole kernel.
+template <int CIN>
+__global__ void __launch_bounds__(256)
+cls_fwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ wc, const float* __restrict__ bias,
+                   float* __restrict__ logits, int N, int64_t S, int classes) {
+  constexpr int KS = CIN / 16;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  uint32_t bh[KS][2][2], bl[KS][2][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = nt * 8 + g, k = ks * 16 + h * 8 + 2 * t;
+        const float w0 = c < classes ? wc[c * CIN + k] : 0.f, w1 = c < classes ? wc[c * CIN + k + 1] : 0.f;
+        split2(w0, w1, bh[ks][nt][h], bl[ks][nt][h]);
+      }
+  float bia[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) bia[nt][j] = (nt * 8 + 2 * t + j) < classes ? bias[nt * 8 + 2 * t + j] : 0.f;
+  const int cps = static_cast<int>((S + 31) / 32);          // 32-voxel chunks per sample
+  const int nchunks = N * cps;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warps) {
+    const int n = chunk / cps;
+    const int64_t s0 = static_cast<int64_t>(chunk - n * cps) * 32;
+    const __nv_bfloat16* an = a + (static_cast<int64_t>(n) * S) * CIN;
+    float acc[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+        acc[mt][nt][0] = acc[mt][nt][2] = bia[nt][0], acc[mt][nt][1] = acc[mt][nt][3] = bia[nt][1];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int64_t r0 = s0 + mt * 16 + g, r1 = r0 + 8;
+      const bool ok0 = r0 < S, ok1 = r1 < S;
+      uint32_t af[KS][4];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int k = ks * 16 + 2 * t;
+        af[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(an + r0 * CIN + k) : 0u;
+        af[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(an + r1 * CIN + k) : 0u;
+        af[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(an + r0 * CIN + k + 8) : 0u;
+        af[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(an + r1 * CIN + k + 8) : 0u;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          mma_bf16(acc[mt][nt], af[ks][0], af[ks][1], af[ks][2], af[ks][3], bh[ks][nt][0], bh[ks][nt][1]);
+          mma_bf16(acc[mt][nt], af[ks][0], af[ks][1], af[ks][2], af[ks][3], bl[ks][nt][0], bl[ks][nt][1]);
+        }
+    }
+    float* ln = logits + static_cast<int64_t>(n) * classes * S;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t r = s0 + mt * 16 + g + (j >> 1) * 8;
+          const int c = nt * 8 + 2 * t + (j & 1);
+          if (r < S && c < classes) ln[static_cast<int64_t>(c) * S + r] = acc[mt][nt][j];
+        }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// One pass over dlogits and a per 16-voxel tile (one tile per warp iteration):
+//   dA[v][k]  = sum_c dl[c][v] W[c][k]       M = voxels, N = CIN, K = 16 classes   (dl hi/lo x W hi/lo, 3 MMAs)
+//   dW[c][k] += sum_v dl[c][v] a[v][k]       M = classes, N = CIN, K = 16 voxels   (dl hi/lo, 2 MMAs)
+//   db[c]    += sum_v dl[c][v]
+// dW / db stay in registers for the whole kernel, are summed over the block's warps in shared memory and leave with
+// one fp32 atomic per element per block.
+template <int CIN>
+__global__ void __launch_bounds__(256)
+cls_bwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ wc, const float* __restrict__ dl,
+                   __nv_bfloat16* __restrict__ da, float* __restrict__ dwc, float* __restrict__ dbias, int N,
+                   int64_t S, int classes) {
+  constexpr int NT = CIN / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  // B operand of the dA product: W[c][k] as (K = class) x (N = channel), hi/lo
+  uint32_t wh[NT][2], wl[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = h * 8 + 2 * t, k = nt * 8 + g;
+      const float w0 = c < classes ? wc[c * CIN + k] : 0.f, w1 = (c + 1) < classes ? wc[(c + 1) * CIN + k] : 0.f;
+      split2(w0, w1, wh[nt][h], wl[nt][h]);
+    }
+  float dw[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dw[nt][j] = 0.f;
+  float db0 = 0.f, db1 = 0.f;          // classes g and g + 8
+  const int tps = static_cast<int>((S + 15) / 16);            // 16-voxel tiles per sample
+  const int ntiles = N * tps;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles; tile += warps) {
+    const int n = tile / tps;
+    const int64_t s0 = static_cast<int64_t>(tile - n * tps) * 16;
+    const float* dln = dl + static_cast<int64_t>(n) * classes * S;
+    const __nv_bfloat16* an = a + (static_cast<int64_t>(n) * S) * CIN;
+    __nv_bfloat16* dan = da + (static_cast<int64_t>(n) * S) * CIN;
+    // ---- dA: A[row v][col c] = dl[c][v]
+    {
+      const int64_t r0 = s0 + g, r1 = r0 + 8;
+      const bool ok0 = r0 < S, ok1 = r1 < S;
+      float e[4][2];     // [fragment register][class 2t+j (+8)]
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c0 = 2 * t + j, c1 = c0 + 8;
+        e[0][j] = (ok0 && c0 < classes) ? dln[static_cast<int64_t>(c0) * S + r0] : 0.f;
+        e[1][j] = (ok1 && c0 < classes) ? dln[static_cast<int64_t>(c0) * S + r1] : 0.f;
+        e[2][j] = (ok0 && c1 < classes) ? dln[static_cast<int64_t>(c1) * S + r0] : 0.f;
+        e[3][j] = (ok1 && c1 < classes) ? dln[static_cast<int64_t>(c1) * S + r1] : 0.f;
+      }
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split2(e[i][0], e[i][1], ah[i], al[i]);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16(o, ah[0], ah[1], ah[2], ah[3], wh[nt][0], wh[nt][1]);
+        mma_bf16(o, al[0], al[1], al[2], al[3], wh[nt][0], wh[nt][1]);
+        mma_bf16(o, ah[0], ah[1], ah[2], ah[3], wl[nt][0], wl[nt][1]);
+        if (ok0) *reinterpret_cast<uint32_t*>(dan + r0 * CIN + nt * 8 + 2 * t) = pack_hi(o[0], o[1]);
+        if (ok1) *reinterpret_cast<uint32_t*>(dan + r1 * CIN + nt * 8 + 2 * t) = pack_hi(o[2], o[3]);
+      }
+    }
+    // ---- dW / db: A[row c][col v] = dl[c][v], B[row v][col k] = a[v][k]
+    {
+      const int64_t v0 = s0 + 2 * t;            // fragment columns: voxels v0, v0+1, v0+8, v0+9
+      const bool okc0 = g < classes, okc1 = (g + 8) < classes;
+      float e[4][2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int64_t va = v0 + j, vb = v0 + 8 + j;
+        e[0][j] = (okc0 && va < S) ? dln[static_cast<int64_t>(g) * S + va] : 0.f;
+        e[1][j] = (okc1 && va < S) ? dln[static_cast<int64_t>(g + 8) * S + va] : 0.f;
+        e[2][j] = (okc0 && vb < S) ? dln[static_cast<int64_t>(g) * S + vb] : 0.f;
+        e[3][j] = (okc1 && vb < S) ? dln[static_cast<int64_t>(g + 8) * S + vb] : 0.f;
+      }
+      db0 += (e[0][0] + e[0][1]) + (e[2][0] + e[2][1]);
+      db1 += (e[1][0] + e[1][1]) + (e[3][0] + e[3][1]);
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split2(e[i][0], e[i][1], ah[i], al[i]);
+      const unsigned short* au = reinterpret_cast<const unsigned short*>(an);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int k = nt * 8 + g;
+        uint32_t x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t v = v0 + (i >> 1) * 8 + (i & 1);
+          x[i] = v < S ? static_cast<uint32_t>(au[v * CIN + k]) : 0u;
+        }
+        const uint32_t b0 = x[0] | (x[1] << 16), b1 = x[2] | (x[3] << 16);
+        mma_bf16(dw[nt], ah[0], ah[1], ah[2], ah[3], b0, b1);
+        mma_bf16(dw[nt], al[0], al[1], al[2], al[3], b0, b1);
+      }
+    }
+  }
+  // ---- block reduction of dW (fragment: rows c = g, g+8; cols k = nt*8 + 2t, +1) and db
+  __shared__ float red[16 * CIN];
+  __shared__ float redb[16];
+  for (int i = threadIdx.x; i < 16 * CIN; i += 256) red[i] = 0.f;
+  if (threadIdx.x < 16) redb[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(&red[(g + (j >> 1) * 8) * CIN + nt * 8 + 2 * t + (j & 1)], dw[nt][j]);
+  db0 += __shfl_xor_sync(0xffffffffu, db0, 1);
+  db0 += __shfl_xor_sync(0xffffffffu, db0, 2);
+  db1 += __shfl_xor_sync(0xffffffffu, db1, 1);
+  db1 += __shfl_xor_sync(0xffffffffu, db1, 2);
+  if (t == 0) {
+    atomicAdd(&redb[g], db0);
+    atomicAdd(&redb[g + 8], db1);
+  }
+  __syncthreads();
+  (void)warp;
+  for (int i = threadIdx.x; i < 16 * CIN; i += 256)
+    if (i / CIN < classes) atomicAdd(&dwc[i], red[i]);
+  if (threadIdx.x < classes) atomicAdd(&dbias[threadIdx.x], redb[threadIdx.x]);
+}
+
+}  // namespace
+
+int cls_fwd_mma(const void* a, const float* wc, const float* bias, float* logits, int n, int64_t spatial, int cin,
+                int classes, cudaStream_t s) {
+  const int64_t chunks = static_cast<int64_t>(n) * ((spatial + 31) / 32);
+  MMPL_REQUIRE(chunks < (1ll << 31), MMPL_E_SHAPE, "cls_fwd: too many voxels");
+  const int blocks = static_cast<int>(std::min<int64_t>((chunks + 7) / 8, static_cast<int64_t>(num_sms()) * 8));
+  const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(a);
+  if (cin == 32)
+    cls_fwd_mma_kernel<32><<<blocks, 256, 0, s>>>(ap, wc, bias, logits, n, spatial, classes);
+  else
+    cls_fwd_mma_kernel<64><<<blocks, 256, 0, s>>>(ap, wc, bias, logits, n, spatial, classes);
+  return MMPL_OK;
+}
+
+// dwc / dbias must be zero on entry
+int cls_bwd_mma(const void* a, const float* wc, const float* dlogits, void* da, float* dwc, float* dbias, int n,
+                int64_t spatial, int cin, int classes, cudaStream_t s) {
+  const int64_t tiles = static_cast<int64_t>(n) * ((spatial + 15) / 16);
+  MMPL_REQUIRE(tiles < (1ll << 31), MMPL_E_SHAPE, "cls_bwd: too many voxels");
+  const int blocks = static_cast<int>(std::min<int64_t>((tiles + 7) / 8, static_cast<int64_t>(num_sms()) * 4));
+  const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(a);
+  __nv_bfloat16* dap = static_cast<__nv_bfloat16*>(da);
+  if (cin == 32)
+    cls_bwd_mma_kernel<32><<<blocks, 256, 0, s>>>(ap, wc, dlogits, dap, dwc, dbias, n, spatial, classes);
+  else
+    cls_bwd_mma_kernel<64><<<blocks, 256, 0, s>>>(ap, wc, dlogits, dap, dwc, dbias, n, spatial, classes);
+  return MMPL_OK;
+}
+
+}  // namespace mmpl

@@ -484,6 +484,11 @@ void launch_cls_bwd(int cin, int blocks, cudaStream_t s, const T* a, const float
 }  // namespace
 }  // namespace mmpl
 
+namespace mmpl {
+int cls_fwd_mma(const void*, const float*, const float*, float*, int, int64_t, int, int, cudaStream_t);
+int cls_bwd_mma(const void*, const float*, const float*, void*, float*, float*, int, int64_t, int, int, cudaStream_t);
+}  // namespace mmpl
+
 using namespace mmpl;
 
 extern "C" int mmpl_stem_conv_fwd(const float* image, const float* w_hat, void* y, int n, int d, int h, int w, int cout,
@@ -554,6 +559,11 @@ extern "C" int mmpl_cls_fwd(const void* a, const float* wc, const float* bias, f
   const int64_t total = static_cast<int64_t>(n) * spatial;
   const int blocks = static_cast<int>((total + 511) / 512);   // 256 threads x 2 voxels
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MMPL_BF16) {   // warp-MMA kernel (cls_mma.cu); the CUDA-core kernel below is the fp32 exact path
+    if (int e = cls_fwd_mma(a, wc, bias, logits, n, spatial, cin, classes, s)) return e;
+    MMPL_CHECK_LAUNCH("cls_fwd");
+    return MMPL_OK;
+  }
   MMPL_DISPATCH_DTYPE(dtype, T, {
     if (cin == 32)
       cls_fwd_kernel<T, 32><<<blocks, 256, 0, s>>>(static_cast<const T*>(a), wc, bias, logits, n, spatial, classes);
@@ -573,7 +583,13 @@ extern "C" int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   MMPL_CUDA(cudaMemsetAsync(dwc, 0, sizeof(float) * classes * cin, s));
   MMPL_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * classes, s));
+  if (dtype == MMPL_BF16 && gn_ws == nullptr) {   // warp-MMA kernel (cls_mma.cu)
+    if (int e = cls_bwd_mma(a, wc, dlogits, da, dwc, dbias, n, spatial, cin, classes, s)) return e;
+    MMPL_CHECK_LAUNCH("cls_bwd");
+    return MMPL_OK;
+  }
   const int64_t ntiles = static_cast<int64_t>(n) * ((spatial + 127) / 128);
+  MMPL_REQUIRE(ntiles < (1ll << 31), MMPL_E_SHAPE, "cls_bwd: too many voxels");
   const int blocks = static_cast<int>(std::min<int64_t>(ntiles, static_cast<int64_t>(num_sms()) * 2));
   MMPL_DISPATCH_DTYPE(dtype, T, (launch_cls_bwd<T>(cin, blocks, s, static_cast<const T*>(a), wc, dlogits,
                                                    static_cast<T*>(da), dwc, dbias, gn_beta, gn_ws, n, spatial, classes)));
