@@ -54,7 +54,9 @@ uint64_t mmpl_launch_count(void);
 int mmpl_ws_weight_fwd(const float* w, int cout, int cin, int taps, int standardise, float* w_hat, float* inv_std,
                        void* packed_fprop, void* packed_dgrad, int dtype, mmpl_stream_t stream);
 /* The same for every convolution of a network in ONE launch.  `table_dev` is a DEVICE array of `count` entries sorted
- * by first_block; entry i owns blocks [first_block, first_block + cout) of the grid, total_blocks = sum of cout.
+ * by first_block; a block serves 8 consecutive out-channels, entry i owns blocks [first_block, first_block +
+ * ceil(cout/8)) of the grid, total_blocks = sum of ceil(cout/8).  16-byte aligned packings, cout % 8 == 0 for the
+ * vectorised dgrad packing (any cout works, narrower stores).
  * stem_kch > 0 (Cin = 1 stem only): packed_fprop is [cout][stem_kch] with the 27 taps in columns 0..26 and, for
  * stem_kch = 64, again in 32..58 (the operand mmpl_stem_im2col pairs with); other columns are left untouched. */
 typedef struct mmpl_ws_entry {

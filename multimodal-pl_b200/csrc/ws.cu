@@ -71,13 +71,20 @@ ws_fwd_kernel(const float* __restrict__ w, int cout, int cin, int taps, int stan
   ws_fwd_one<T>(w, cout, cin, taps, standardise, w_hat, inv_std, pf, pd, blockIdx.x, 0, scratch);
 }
 
-// All convolutions of a network in ONE launch: block b serves out-channel (b - first_block) of the table entry that
-// contains b.  The table lives in device memory (mmpl_ws_entry, include/mmpl_b200.h).
+// All convolutions of a network in ONE launch.  A block serves EIGHT consecutive out-channels of the table entry that
+// contains it (entry i owns blocks [first_block, first_block + ceil(cout/8))), so that both packings are written with
+// coalesced stores: warp q computes mean / inv_std of out-channel co0+q, then the block walks the input channels in
+// chunks of 32, stages the standardised values of the 8 x 32 x taps sub-filter in shared memory and writes
+//   pf [tap][co][ci]   as 32 consecutive ci per (tap, co)            (64-byte segments)
+//   pd [tap'][ci][co]  as 8 consecutive co per (tap', ci)            (16-byte vectors).
+constexpr int kCoPerBlock = 8, kCiChunk = 32;
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 ws_fwd_batched_kernel(const mmpl_ws_entry* __restrict__ table, int count) {
-  __shared__ double scratch[kThreads / 32];
   __shared__ mmpl_ws_entry e;
+  __shared__ float s_stat[kCoPerBlock][2];
+  __shared__ float s_w[kCoPerBlock][kCiChunk * 27 + 1];
   if (threadIdx.x == 0) {
     int lo = 0;
     const int b = blockIdx.x;
@@ -86,8 +93,86 @@ ws_fwd_batched_kernel(const mmpl_ws_entry* __restrict__ table, int count) {
     e = table[lo];
   }
   __syncthreads();
-  ws_fwd_one<T>(e.w, e.cout, e.cin, e.taps, e.standardise, e.w_hat, e.inv_std, static_cast<T*>(e.packed_fprop),
-                static_cast<T*>(e.packed_dgrad), blockIdx.x - e.first_block, e.stem_kch, scratch);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = (blockIdx.x - e.first_block) * kCoPerBlock;
+  const int cout = e.cout, cin = e.cin, taps = e.taps, n = cin * taps;
+  const int nco = min(kCoPerBlock, cout - co0);
+  T* pf = static_cast<T*>(e.packed_fprop);
+  T* pd = static_cast<T*>(e.packed_dgrad);
+  // ---- statistics: warp q <-> out-channel co0 + q
+  if (warp < nco) {
+    const float* wr = e.w + static_cast<int64_t>(co0 + warp) * n;
+    float mean = 0.f, istd = 1.f;
+    if (e.standardise) {
+      double sum = 0;
+      for (int i = lane; i < n; i += 32) sum += wr[i];
+      mean = static_cast<float>(warp_sum(sum) / n);
+      double s1 = 0, s2 = 0;      // variance of the centred fp32 weight (unbiased), as torch.var(w.view(O,-1), dim=1) sees it
+      for (int i = lane; i < n; i += 32) {
+        const double c = static_cast<double>(wr[i] - mean);
+        s1 += c;
+        s2 += c * c;
+      }
+      const double t1 = warp_sum(s1), t2 = warp_sum(s2);
+      const double var = (t2 - t1 * t1 / n) / (n > 1 ? n - 1 : 1);
+      istd = static_cast<float>(1.0 / sqrt(var + 1e-12));
+    }
+    if (lane == 0) {
+      s_stat[warp][0] = mean, s_stat[warp][1] = istd;
+      if (e.inv_std) e.inv_std[co0 + warp] = istd;
+    }
+  }
+  __syncthreads();
+  if (e.stem_kch > 0) {   // Cin = 1 stem: [cout][stem_kch] with the taps in columns 0..26 (and 32..58)
+    if (warp < nco && lane < taps) {
+      const int co = co0 + warp;
+      const float wv = e.w[static_cast<int64_t>(co) * n + lane];
+      const float wh = e.standardise ? (wv - s_stat[warp][0]) * s_stat[warp][1] : wv;
+      if (e.w_hat) e.w_hat[static_cast<int64_t>(co) * n + lane] = wh;
+      if (pf) {
+        pf[static_cast<int64_t>(co) * e.stem_kch + lane] = from_f32<T>(wh);
+        if (e.stem_kch >= 64) pf[static_cast<int64_t>(co) * e.stem_kch + 32 + lane] = from_f32<T>(wh);
+      }
+    }
+    return;
+  }
+  for (int ci0 = 0; ci0 < cin; ci0 += kCiChunk) {
+    const int cic = min(kCiChunk, cin - ci0), m = cic * taps;     // sub-filter: nco x cic x taps
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nco * m; idx += kThreads) {
+      const int q = idx / m, r = idx - q * m;
+      const int64_t src = static_cast<int64_t>(co0 + q) * n + static_cast<int64_t>(ci0) * taps + r;
+      const float wv = e.w[src];
+      const float wh = e.standardise ? (wv - s_stat[q][0]) * s_stat[q][1] : wv;
+      if (e.w_hat) e.w_hat[src] = wh;
+      s_w[q][r] = wh;
+    }
+    __syncthreads();
+    if (pf) {
+      for (int idx = threadIdx.x; idx < taps * nco * cic; idx += kThreads) {
+        const int cil = idx % cic, q = (idx / cic) % nco, t = idx / (cic * nco);
+        pf[(static_cast<int64_t>(t) * cout + co0 + q) * cin + ci0 + cil] = from_f32<T>(s_w[q][cil * taps + t]);
+      }
+    }
+    if (pd) {
+      for (int idx = threadIdx.x; idx < taps * cic; idx += kThreads) {
+        const int cil = idx % cic, t = idx / cic;
+        T* dst = pd + (static_cast<int64_t>(taps - 1 - t) * cin + ci0 + cil) * cout + co0;
+        if (nco == kCoPerBlock) {
+          constexpr int VN = Vec<T>::N;     // 8 bf16 = one 16-byte store, 2 x 4 fp32 = two
+#pragma unroll
+          for (int h = 0; h < kCoPerBlock / VN; ++h) {
+            Vec<T> v;
+#pragma unroll
+            for (int k = 0; k < VN; ++k) v.v[k] = s_w[h * VN + k][cil * taps + t];
+            v.store(dst + h * VN);
+          }
+        } else {
+          for (int q = 0; q < nco; ++q) dst[q] = from_f32<T>(s_w[q][cil * taps + t]);
+        }
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -137,6 +222,7 @@ extern "C" int mmpl_ws_weight_fwd_batched(const mmpl_ws_entry* table_dev, int co
                                           mmpl_stream_t stream) {
   MMPL_REQUIRE(table_dev != nullptr && count > 0 && total_blocks > 0, MMPL_E_SHAPE, "ws_weight_fwd_batched: empty table");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // total_blocks = sum over the entries of ceil(cout / 8) (a block serves 8 out-channels)
   MMPL_DISPATCH_DTYPE(dtype, T, (ws_fwd_batched_kernel<T><<<total_blocks, kThreads, 0, s>>>(table_dev, count)));
   MMPL_CHECK_LAUNCH("ws_weight_fwd_batched");
   return MMPL_OK;

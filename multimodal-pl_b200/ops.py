@@ -296,7 +296,7 @@ def _ws_table(items, dt):
         arr[i] = (weight.data_ptr(), e.w_hat.data_ptr(), e.inv_std.data_ptr(), 0 if e.pf is None else e.pf.data_ptr(),
                   0 if e.pd is None else e.pd.data_ptr(), cout, cin, weight[0, 0].numel(), int(standardise), first,
                   stem_kch)
-        first += cout
+        first += (cout + 7) // 8          # a block of the batched kernel serves 8 out-channels
     key = arr.tobytes()
     hit = _WS_TABLES.get(key)
     if hit is None:
