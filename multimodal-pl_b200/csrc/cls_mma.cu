@@ -115,11 +115,13 @@ cls_fwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict_
 //   db[c]    += sum_v dl[c][v]
 // dW / db stay in registers for the whole kernel, are summed over the block's warps in shared memory and leave with
 // one fp32 atomic per element per block.
-template <int CIN>
+// GN = true additionally folds in the first pass of the backward of precls_conv.0/1 (GroupNorm+ReLU, unet3D.py:629-631),
+// whose output is `a`: S1_c = sum_v dA*[a > 0], Q_c = sum_v dA*a - beta_c*S1_c (see mmpl_gn_bwd_fuse) -> gn_ws[N][CIN][6].
+template <int CIN, bool GN>
 __global__ void __launch_bounds__(256)
 cls_bwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ wc, const float* __restrict__ dl,
-                   __nv_bfloat16* __restrict__ da, float* __restrict__ dwc, float* __restrict__ dbias, int N,
-                   int64_t S, int classes) {
+                   __nv_bfloat16* __restrict__ da, float* __restrict__ dwc, float* __restrict__ dbias,
+                   const float* __restrict__ gn_beta, double* __restrict__ gn_ws, int N, int64_t S, int classes) {
   constexpr int NT = CIN / 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   // B operand of the dA product: W[c][k] as (K = class) x (N = channel), hi/lo
@@ -138,11 +140,40 @@ cls_bwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) dw[nt][j] = 0.f;
   float db0 = 0.f, db1 = 0.f;          // classes g and g + 8
+  float gs1[NT][2], gs2[NT][2];        // GN: partial S1 / sum dA*a of channels nt*8 + 2t + j over this thread's rows
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) gs1[nt][0] = gs1[nt][1] = gs2[nt][0] = gs2[nt][1] = 0.f;
+  int gn_n = -1;
+  auto gn_flush = [&]() {
+    if (!GN || gn_n < 0) return;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float s1 = gs1[nt][j], s2 = gs2[nt][j];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {      // rows live on the lanes that share t
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (g == 0) {
+          const int c = nt * 8 + 2 * t + j;
+          double* w = gn_ws + (static_cast<int64_t>(gn_n) * CIN + c) * 6;
+          atomicAdd(w, static_cast<double>(s1));
+          atomicAdd(w + 1, static_cast<double>(s2) - static_cast<double>(gn_beta[c]) * static_cast<double>(s1));
+        }
+        gs1[nt][j] = gs2[nt][j] = 0.f;
+      }
+  };
   const int tps = static_cast<int>((S + 15) / 16);            // 16-voxel tiles per sample
   const int ntiles = N * tps;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles; tile += warps) {
     const int n = tile / tps;
+    if (GN && n != gn_n) {
+      gn_flush();
+      gn_n = n;
+    }
     const int64_t s0 = static_cast<int64_t>(tile - n * tps) * 16;
     const float* dln = dl + static_cast<int64_t>(n) * classes * S;
     const __nv_bfloat16* an = a + (static_cast<int64_t>(n) * S) * CIN;
@@ -171,6 +202,18 @@ cls_bwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict_
         mma_bf16(o, ah[0], ah[1], ah[2], ah[3], wl[nt][0], wl[nt][1]);
         if (ok0) *reinterpret_cast<uint32_t*>(dan + r0 * CIN + nt * 8 + 2 * t) = pack_hi(o[0], o[1]);
         if (ok1) *reinterpret_cast<uint32_t*>(dan + r1 * CIN + nt * 8 + 2 * t) = pack_hi(o[2], o[3]);
+        if (GN) {
+          const uint32_t u0 = ok0 ? *reinterpret_cast<const uint32_t*>(an + r0 * CIN + nt * 8 + 2 * t) : 0u;
+          const uint32_t u1 = ok1 ? *reinterpret_cast<const uint32_t*>(an + r1 * CIN + nt * 8 + 2 * t) : 0u;
+          const float a00 = __uint_as_float(u0 << 16), a01 = __uint_as_float(u0 & 0xFFFF0000u);
+          const float a10 = __uint_as_float(u1 << 16), a11 = __uint_as_float(u1 & 0xFFFF0000u);
+          gs2[nt][0] = fmaf(o[0], a00, fmaf(o[2], a10, gs2[nt][0]));
+          gs2[nt][1] = fmaf(o[1], a01, fmaf(o[3], a11, gs2[nt][1]));
+          if (a00 > 0.f) gs1[nt][0] += o[0];
+          if (a10 > 0.f) gs1[nt][0] += o[2];
+          if (a01 > 0.f) gs1[nt][1] += o[1];
+          if (a11 > 0.f) gs1[nt][1] += o[3];
+        }
       }
     }
     // ---- dW / db: A[row c][col v] = dl[c][v], B[row v][col k] = a[v][k]
@@ -207,6 +250,7 @@ cls_bwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict_
       }
     }
   }
+  gn_flush();
   // ---- block reduction of dW (fragment: rows c = g, g+8; cols k = nt*8 + 2t, +1) and db
   __shared__ float red[16 * CIN];
   __shared__ float redb[16];
@@ -248,17 +292,24 @@ int cls_fwd_mma(const void* a, const float* wc, const float* bias, float* logits
 }
 
 // dwc / dbias must be zero on entry
-int cls_bwd_mma(const void* a, const float* wc, const float* dlogits, void* da, float* dwc, float* dbias, int n,
-                int64_t spatial, int cin, int classes, cudaStream_t s) {
+int cls_bwd_mma(const void* a, const float* wc, const float* dlogits, void* da, float* dwc, float* dbias,
+                const float* gn_beta, double* gn_ws, int n, int64_t spatial, int cin, int classes, cudaStream_t s) {
   const int64_t tiles = static_cast<int64_t>(n) * ((spatial + 15) / 16);
   MMPL_REQUIRE(tiles < (1ll << 31), MMPL_E_SHAPE, "cls_bwd: too many voxels");
   const int blocks = static_cast<int>(std::min<int64_t>((tiles + 7) / 8, static_cast<int64_t>(num_sms()) * 4));
   const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(a);
   __nv_bfloat16* dap = static_cast<__nv_bfloat16*>(da);
-  if (cin == 32)
-    cls_bwd_mma_kernel<32><<<blocks, 256, 0, s>>>(ap, wc, dlogits, dap, dwc, dbias, n, spatial, classes);
-  else
-    cls_bwd_mma_kernel<64><<<blocks, 256, 0, s>>>(ap, wc, dlogits, dap, dwc, dbias, n, spatial, classes);
+  if (cin == 32) {
+    if (gn_ws)
+      cls_bwd_mma_kernel<32, true><<<blocks, 256, 0, s>>>(ap, wc, dlogits, dap, dwc, dbias, gn_beta, gn_ws, n, spatial, classes);
+    else
+      cls_bwd_mma_kernel<32, false><<<blocks, 256, 0, s>>>(ap, wc, dlogits, dap, dwc, dbias, gn_beta, gn_ws, n, spatial, classes);
+  } else {
+    if (gn_ws)
+      cls_bwd_mma_kernel<64, true><<<blocks, 256, 0, s>>>(ap, wc, dlogits, dap, dwc, dbias, gn_beta, gn_ws, n, spatial, classes);
+    else
+      cls_bwd_mma_kernel<64, false><<<blocks, 256, 0, s>>>(ap, wc, dlogits, dap, dwc, dbias, gn_beta, gn_ws, n, spatial, classes);
+  }
   return MMPL_OK;
 }
 

@@ -715,29 +715,24 @@ int dispatch_tc(const TcProblem& q, cudaStream_t s) {
 }
 
 // parity split: P[p*N + n][d'][h'][w'][c] = X[n][2d'+pd][2h'+ph][2w'+pw][c]  (zero where the source is out of range)
+// Grid (ceil(Wp*C/8 / 256), Hp, 8*N*Dp): rows are block-uniform, all index arithmetic is 32-bit.
 __global__ void __launch_bounds__(256)
 parity_split_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ pout, int N, int D, int H, int W,
                     int C, int Dp, int Hp, int Wp) {
   const int vpv = C / 8;
-  const int64_t total = static_cast<int64_t>(8) * N * Dp * Hp * Wp * vpv;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(idx % vpv);
-    int64_t r = idx / vpv;
-    const int w = static_cast<int>(r % Wp);
-    r /= Wp;
-    const int h = static_cast<int>(r % Hp);
-    r /= Hp;
-    const int d = static_cast<int>(r % Dp);
-    r /= Dp;
-    const int n = static_cast<int>(r % N);
-    const int pc = static_cast<int>(r / N);
-    const int sd = 2 * d + (pc >> 2), sh = 2 * h + ((pc >> 1) & 1), sw = 2 * w + (pc & 1);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (sd < D && sh < H && sw < W)
-      v = *reinterpret_cast<const uint4*>(x + ((((static_cast<int64_t>(n) * D + sd) * H + sh) * W + sw) * C) + cv * 8);
-    *reinterpret_cast<uint4*>(pout + idx * 8) = v;
-  }
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= Wp * vpv) return;
+  const int w = e / vpv, cv = e - w * vpv;
+  const int h = blockIdx.y;
+  int r = blockIdx.z;
+  const int d = r % Dp;
+  r /= Dp;
+  const int n = r % N, pc = r / N;
+  const int sd = 2 * d + (pc >> 2), sh = 2 * h + ((pc >> 1) & 1), sw = 2 * w + (pc & 1);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (sd < D && sh < H && sw < W)
+    v = *reinterpret_cast<const uint4*>(x + ((((static_cast<int64_t>(n) * D + sd) * H + sh) * W + sw) * C) + cv * 8);
+  *reinterpret_cast<uint4*>(pout + (((static_cast<int64_t>(blockIdx.z) * Hp + h) * Wp + w) * C) + cv * 8) = v;
 }
 
 }  // namespace
@@ -751,11 +746,13 @@ static int check_align(const void* a, const void* b, const void* c, const void* 
 
 // ---- stride 1 (k = 3 or 1): x [N,D,H,W,cin] -> y [N,D,H,W,cout]; also stride-1 dgrad with swapped channel roles
 // GroupNorm statistics can be fused into the epilogue when one CTA tile spans all output channels
-// The GroupNorm-backward reduction rides on the dgrad epilogue where that is cheaper than a separate streaming pass:
-// wide-and-shallow outputs (<= 64 channels: the full- and half-resolution layers, 85 % of the reduction traffic).  With
-// more channels a work item has 8+ column chunks to transpose-reduce while the tensors are small enough that the
-// stand-alone pass costs little (measured on B200: fusing everywhere loses 0.9 ms/step of MMA time to save 0.5 ms).
-bool conv_tc_can_fuse_gn_bwd(int nout) { return nout == 32 || nout == 64; }
+// The GroupNorm-backward reduction rides on every dgrad launch whose output has <= 512 channels in 16 groups.  Measured
+// on B200 (cfg2) with the register-lean epilogue: fusing all layers 14.34 ms/step, only the <= 64-channel layers 14.66,
+// none 15.5.  MMPL_GN_FUSE_MAXC narrows it for experiments.
+bool conv_tc_can_fuse_gn_bwd(int nout) {
+  static const int maxc = [] { const char* e = getenv("MMPL_GN_FUSE_MAXC"); return e ? atoi(e) : 512; }();
+  return nout % 32 == 0 && nout <= maxc && nout <= 512;
+}
 
 int conv_tc_s1(const void* x, const void* wp, const void* residual, void* y, int N, int D, int H, int W, int cin,
                int cout, int ksize, double* stats, int* stats_fused, const mmpl_gn_bwd_fuse* gn, cudaStream_t s) {
@@ -790,8 +787,8 @@ int conv_tc_s2_dgrad(const void* dy, const void* wp_dgrad, void* dx, int N, int 
 int parity_split(const void* x, void* pout, int N, int D, int H, int W, int C, cudaStream_t s) {
   MMPL_REQUIRE(C % 8 == 0, MMPL_E_SHAPE, "parity_split: C=%d", C);
   const int Dp = (D + 1) / 2, Hp = (H + 1) / 2, Wp = (W + 1) / 2;
-  const int64_t total = static_cast<int64_t>(8) * N * Dp * Hp * Wp * (C / 8);
-  const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(num_sms()) * 16));
+  MMPL_REQUIRE(Hp <= 65535 && static_cast<int64_t>(8) * N * Dp <= 65535, MMPL_E_SHAPE, "parity_split: grid limits");
+  const dim3 blocks((Wp * (C / 8) + 255) / 256, Hp, 8 * N * Dp);
   parity_split_kernel<<<blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(pout), N, D,
                                             H, W, C, Dp, Hp, Wp);
   MMPL_CHECK_LAUNCH("parity_split");

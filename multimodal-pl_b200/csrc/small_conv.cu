@@ -157,47 +157,45 @@ stem_wgrad_kernel(const float* __restrict__ pad, const T* __restrict__ dy, float
 // CUDA-core FMAs per voxel.  SPLIT = 0: 32 channels (27 taps + 5 zeros).  SPLIT = 1: 64 channels, the fp32 value is
 // carried as hi + lo bf16 parts (channels t and 32 + t; 16 mantissa bits), so only the weights are rounded to bf16 as
 // in every other layer.  One thread per voxel.
+// Grid (ceil(W/256), H, N*D): rows are block-uniform, all index arithmetic is 32-bit.
 template <int SPLIT>
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int N, int D, int H, int W) {
   constexpr int CH = SPLIT ? 64 : 32;
-  const int64_t total = static_cast<int64_t>(N) * D * H * W;
-  for (int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v < total;
-       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(v % W);
-    int64_t r = v / W;
-    const int y = static_cast<int>(r % H);
-    r /= H;
-    const int z = static_cast<int>(r % D);
-    const int n = static_cast<int>(r / D);
-    const float* base = img + static_cast<int64_t>(n) * D * H * W;
-    float t[32];
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  if (x >= W) return;
+  const int y = blockIdx.y, z = blockIdx.z % D, n = blockIdx.z / D;
+  const float* base = img + static_cast<int64_t>(n) * D * H * W;
+  float t[32];
 #pragma unroll
-    for (int i = 27; i < 32; ++i) t[i] = 0.f;
+  for (int i = 27; i < 32; ++i) t[i] = 0.f;
 #pragma unroll
-    for (int kd = 0; kd < 3; ++kd)
+  for (int kd = 0; kd < 3; ++kd) {
+    const int zz = z + kd - 1;
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
+    for (int kh = 0; kh < 3; ++kh) {
+      const int yy = y + kh - 1;
+      const bool row_ok = zz >= 0 && zz < D && yy >= 0 && yy < H;
+      const float* row = base + (static_cast<int64_t>(row_ok ? zz : 0) * H + (row_ok ? yy : 0)) * W;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int zz = z + kd - 1, yy = y + kh - 1, xx = x + kw - 1;
-          float val = 0.f;
-          if (zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W)
-            val = base[(static_cast<int64_t>(zz) * H + yy) * W + xx];
-          t[(kd * 3 + kh) * 3 + kw] = val;
-        }
-#pragma unroll
-    for (int c0 = 0; c0 < 32; c0 += 8) {
-      Vec<__nv_bfloat16> o;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = t[c0 + k];
-      o.store(out + v * CH + c0);
-      if (SPLIT) {
-        Vec<__nv_bfloat16> l;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) l.v[k] = t[c0 + k] - __bfloat162float(__float2bfloat16(t[c0 + k]));
-        l.store(out + v * CH + 32 + c0);
+      for (int kw = 0; kw < 3; ++kw) {
+        const int xx = x + kw - 1;
+        t[(kd * 3 + kh) * 3 + kw] = (row_ok && xx >= 0 && xx < W) ? row[xx] : 0.f;
       }
+    }
+  }
+  __nv_bfloat16* dst = out + (((static_cast<int64_t>(n) * D + z) * H + y) * W + x) * CH;
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 8) {
+    Vec<__nv_bfloat16> o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = t[c0 + k];
+    o.store(dst + c0);
+    if (SPLIT) {
+      Vec<__nv_bfloat16> l;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) l.v[k] = t[c0 + k] - __bfloat162float(__float2bfloat16(t[c0 + k]));
+      l.store(dst + 32 + c0);
     }
   }
 }
@@ -486,7 +484,8 @@ void launch_cls_bwd(int cin, int blocks, cudaStream_t s, const T* a, const float
 
 namespace mmpl {
 int cls_fwd_mma(const void*, const float*, const float*, float*, int, int64_t, int, int, cudaStream_t);
-int cls_bwd_mma(const void*, const float*, const float*, void*, float*, float*, int, int64_t, int, int, cudaStream_t);
+int cls_bwd_mma(const void*, const float*, const float*, void*, float*, float*, const float*, double*, int, int64_t, int,
+                int, cudaStream_t);
 }  // namespace mmpl
 
 using namespace mmpl;
@@ -512,8 +511,9 @@ extern "C" int mmpl_stem_im2col(const float* image, void* x27, int n, int d, int
   MMPL_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0, MMPL_E_SHAPE, "stem_im2col: empty image");
   MMPL_REQUIRE(channels == 32 || channels == 64, MMPL_E_SHAPE, "stem_im2col: channels=%d (32, or 64 = hi/lo split)",
                channels);
-  const int64_t total = static_cast<int64_t>(n) * d * h * w;
-  const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(num_sms()) * 16));
+  MMPL_REQUIRE(h <= 65535 && static_cast<int64_t>(n) * d <= 65535, MMPL_E_SHAPE, "stem_im2col: H=%d, N*D=%lld exceed the grid",
+               h, static_cast<long long>(n) * d);
+  const dim3 blocks((w + 255) / 256, h, n * d);
   if (channels == 64)
     stem_im2col_kernel<1><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(image, static_cast<__nv_bfloat16*>(x27),
                                                                                n, d, h, w);
@@ -583,8 +583,8 @@ extern "C" int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   MMPL_CUDA(cudaMemsetAsync(dwc, 0, sizeof(float) * classes * cin, s));
   MMPL_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * classes, s));
-  if (dtype == MMPL_BF16 && gn_ws == nullptr) {   // warp-MMA kernel (cls_mma.cu)
-    if (int e = cls_bwd_mma(a, wc, dlogits, da, dwc, dbias, n, spatial, cin, classes, s)) return e;
+  if (dtype == MMPL_BF16) {   // warp-MMA kernel (cls_mma.cu)
+    if (int e = cls_bwd_mma(a, wc, dlogits, da, dwc, dbias, gn_beta, gn_ws, n, spatial, cin, classes, s)) return e;
     MMPL_CHECK_LAUNCH("cls_bwd");
     return MMPL_OK;
   }

@@ -17,7 +17,7 @@ _CL = torch.channels_last_3d
 _cfg = {"dtype": torch.bfloat16, "conv_algo": os.environ.get("MMPL_CONV_ALGO", "auto"),
         "fuse_gn_bwd": os.environ.get("MMPL_FUSE_GN_BWD", "1") != "0",
         "ws_bwd_side_stream": os.environ.get("MMPL_WS_BWD_SIDE_STREAM", "1") != "0",
-        "fuse_gn_bwd_cls": os.environ.get("MMPL_FUSE_GN_BWD_CLS", "0") != "0"}
+        "fuse_gn_bwd_cls": {"0": False, "1": True}.get(os.environ.get("MMPL_FUSE_GN_BWD_CLS", ""), None)}
 
 
 def set_fuse_gn_bwd(on: bool):
@@ -796,10 +796,10 @@ class ClassifierFn(torch.autograd.Function):
         dwc = _grad_dst(ctx.params[0], wshape)
         db = _grad_dst(ctx.params[1], (classes,))
         gb = gws = None
-        # Folding the backward reduction of precls_conv.0/1 into this kernel is supported by the library but off by
-        # default: cls_bwd is issue-bound, and the extra accumulation costs more (0.17 ms) than the stand-alone
-        # reduction pass it replaces (0.13 ms) at cfg2 sizes.
-        if _cfg["fuse_gn_bwd_cls"] and ctx.gn_bwd is not None and ctx.gn_bwd[2] == 0:
+        # The backward reduction of precls_conv.0/1 rides on the bf16 warp-MMA kernel (8 extra loads + 12 FMAs per 16x8
+        # fragment); the fp32 CUDA-core kernel is issue-bound, there the stand-alone reduction pass is cheaper.
+        fuse_cls = _cfg["fuse_gn_bwd_cls"] if _cfg["fuse_gn_bwd_cls"] is not None else a.dtype == torch.bfloat16
+        if fuse_cls and ctx.gn_bwd is not None and ctx.gn_bwd[2] == 0:
             gb, gws, _ = ctx.gn_bwd
         _lib.check(L.mmpl_cls_bwd(_p(a), _p(wc), _p(dl), _p(da), _p(dwc), _p(db), _p(gb), _p(gws), n, d * h * w, cin,
                                   classes, _lib.dtype_code(a.dtype), _lib.stream_ptr()), "cls_bwd")
