@@ -170,6 +170,17 @@ int mmpl_partial_loss_bwd(const float* logits, const float* target, const float*
                           const double* sums, const float* grad_out /*device scalar*/, float* dlogits, int n,
                           int64_t spatial, int classes, int uce, mmpl_stream_t stream);
 
+/* ---- binary Dice over a voxel gate (+ BCE-with-logits): DiceLoss._dice_loss / EDiceLoss_full2.forward,
+ * loss_partial.py:24-36, :150-170 (the pseudo-label terms of get_loss, losses.py:165-176) --------------------------
+ * x, target, gate: fp32 [voxels]; gate may be NULL (= all voxels) and is a 0/1 mask otherwise.  sigmoid = 1: the score
+ * is sigmoid(x), else x itself.  uce = 1 adds mean BCE-with-logits over ALL voxels.  sums: double[4] = {I, Y, Z, E},
+ * written by fwd and read by bwd.  dtarget may be NULL. */
+int mmpl_masked_dice_fwd(const float* x, const float* target, const float* gate, double* sums, float* loss,
+                         int64_t voxels, int sigmoid, int uce, mmpl_stream_t stream);
+int mmpl_masked_dice_bwd(const float* x, const float* target, const float* gate, const double* sums,
+                         const float* grad_out, float* dx, float* dtarget, int64_t voxels, int sigmoid, int uce,
+                         mmpl_stream_t stream);
+
 /* ---- SGD with momentum: torch.optim.SGD at train_amos_atlas_final.py:132-135,378 ------------------------------
  * d = grad*grad_scale + wd*p; buf = first ? d : mom*buf + d; p -= lr*buf.  lr is read from a device scalar so a
  * captured CUDA graph can be replayed while the poly schedule (utils.py:53-60) changes it. */

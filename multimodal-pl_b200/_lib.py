@@ -44,6 +44,8 @@ _SIGNATURES = {
     "mmpl_upsample2x_bwd": [_ptr, _ptr] + [_c_int] * 6 + [_ptr],
     "mmpl_partial_loss_fwd": [_ptr] * 6 + [_c_int, _c_i64, _c_int, _c_int, _ptr],
     "mmpl_partial_loss_bwd": [_ptr] * 7 + [_c_int, _c_i64, _c_int, _c_int, _ptr],
+    "mmpl_masked_dice_fwd": [_ptr] * 5 + [_c_i64, _c_int, _c_int, _ptr],
+    "mmpl_masked_dice_bwd": [_ptr] * 7 + [_c_i64, _c_int, _c_int, _ptr],
     "mmpl_sgd_step": [_ptr, _ptr, _ptr, _c_i64, _ptr, _c_f32, _c_f32, _c_f32, _c_int, _ptr],
     "mmpl_sw_blend": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 11 + [_ptr],
     "mmpl_sw_finalize": [_ptr] * 6 + [_c_int, _c_i64, _c_int, _ptr],

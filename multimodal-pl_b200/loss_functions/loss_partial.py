@@ -48,7 +48,10 @@ class DiceLoss(nn.Module):
         return (input_tensor.unsqueeze(1) == idx.view(shape)).float()
 
     def _dice_loss(self, score, target, mask):
-        """Binary Dice over the voxels where ``mask`` is true (loss_partial.py:24-36)."""
+        """Binary Dice over the voxels where ``mask`` is true (loss_partial.py:24-36): one fused kernel on the device
+        (ops.masked_dice); plain torch ops only for inputs whose shapes do not line up element by element."""
+        if score.is_cuda and score.numel() == target.numel() == mask.numel():
+            return ops.masked_dice(score, target, mask, sigmoid=False, uce=False)
         target = target.float()
         m = mask.bool()
         score = score[m]
@@ -117,6 +120,9 @@ class EDiceLoss_full2(nn.Module):
         self.bce = nn.BCEWithLogitsLoss()
 
     def forward(self, inputs, target, uce=True, mask=None, sigmoid=True):
+        if inputs.is_cuda and inputs.numel() == target.numel() and (mask is None or mask.numel() == target.numel()):
+            # fused: sigmoid, gated Dice sums and BCE-with-logits (always on the raw inputs, :168) in one pass
+            return ops.masked_dice(inputs, target, mask, sigmoid=sigmoid, uce=uce)
         p = torch.sigmoid(inputs) if sigmoid else inputs
         if mask is None:
             mask = torch.ones_like(target).unsqueeze(0)

@@ -852,3 +852,47 @@ class PartialLossFn(torch.autograd.Function):
 
 def partial_label_loss(logits, target, class_weight, lut=None, uce=True):
     return PartialLossFn.apply(logits, target, class_weight, lut, bool(uce))
+
+
+# --------------------------------------------------------------------------------------------------------------
+class MaskedDiceFn(torch.autograd.Function):
+    """DiceLoss._dice_loss over a voxel gate, optionally on sigmoid(x) and with the BCE-with-logits term of
+    EDiceLoss_full2.forward (loss_partial.py:24-36, :150-170): one fused pass forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, x, target, gate, sigmoid, uce):
+        _lib.require_device()
+        L = _lib.lib()
+        xf = x.detach().float().contiguous()
+        tf = target.detach().float().contiguous()
+        v = xf.numel()
+        assert tf.numel() == v, f"masked dice: score {tuple(x.shape)} vs target {tuple(target.shape)}"
+        gf = None
+        if gate is not None:
+            gf = gate.detach().to(torch.float32).contiguous()
+            assert gf.numel() == v, f"masked dice: gate {tuple(gate.shape)} vs score {tuple(x.shape)}"
+        dev = xf.device
+        sums = torch.empty(4, dtype=torch.float64, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        _lib.check(L.mmpl_masked_dice_fwd(_p(xf), _p(tf), _p(gf), _p(sums), _p(loss), v, int(sigmoid), int(uce),
+                                          _lib.stream_ptr()), "masked_dice_fwd")
+        ctx.save_for_backward(xf, tf, gf, sums)
+        ctx.meta = (v, int(sigmoid), int(uce), x.dtype, tuple(x.shape), target.dtype, tuple(target.shape))
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        L = _lib.lib()
+        xf, tf, gf, sums = ctx.saved_tensors
+        v, sigmoid, uce, xdt, xshape, tdt, tshape = ctx.meta
+        g = gout.detach().float().contiguous()
+        dx = torch.empty_like(xf)
+        dt = torch.empty_like(tf) if ctx.needs_input_grad[1] else None
+        _lib.check(L.mmpl_masked_dice_bwd(_p(xf), _p(tf), _p(gf), _p(sums), _p(g), _p(dx), _p(dt), v, sigmoid, uce,
+                                          _lib.stream_ptr()), "masked_dice_bwd")
+        return (dx.view(xshape).to(xdt) if ctx.needs_input_grad[0] else None,
+                dt.view(tshape).to(tdt) if dt is not None else None, None, None, None)
+
+
+def masked_dice(x, target, gate=None, sigmoid=False, uce=False):
+    return MaskedDiceFn.apply(x, target, gate, bool(sigmoid), bool(uce))

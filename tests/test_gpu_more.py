@@ -117,6 +117,64 @@ def test_dice_and_gated_losses_match_oracle():
         assert abs(a - b) < 1e-6, (uce, sig)
 
 
+@pytest.mark.parametrize("uce,sig", [(False, True), (False, False), (True, True), (True, False)])
+def test_gated_dice_fused_kernel_gradients(uce, sig):
+    """mmpl_masked_dice_{fwd,bwd}: value and gradients w.r.t. the score AND the soft target vs the oracle's autograd
+    (EDiceLoss_full2 / DiceLoss._dice_loss, loss_partial.py:24-36, :150-170), ragged size, partial gate."""
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_full2
+
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((1, 1, 5, 7, 9), generator=g)
+    if not sig:
+        x = torch.sigmoid(x)
+    t = torch.rand((1, 5, 7, 9), generator=g)
+    m = (torch.rand((1, 1, 5, 7, 9), generator=g) > 0.4).float()
+    xr, tr = x.clone().requires_grad_(True), t.clone().requires_grad_(True)
+    ref = O.binary_gated_dice(xr, tr, m, uce=uce, sigmoid=sig)
+    ref.backward()
+    xd, td = x.cuda().requires_grad_(True), t.cuda().requires_grad_(True)
+    got = EDiceLoss_full2(2)(xd, td, uce=uce, mask=m.cuda(), sigmoid=sig)
+    got.backward()
+    assert abs(got.item() - ref.item()) < 1e-6
+    assert (xd.grad.cpu() - xr.grad).abs().max().item() < 1e-6 * max(1.0, xr.grad.abs().max().item()) + 1e-8
+    assert (td.grad.cpu() - tr.grad).abs().max().item() < 1e-6 * max(1.0, tr.grad.abs().max().item()) + 1e-8
+    # no gate == all voxels
+    a = EDiceLoss_full2(2)(x.cuda(), t.cuda(), uce=uce, mask=None, sigmoid=sig).item()
+    b = O.binary_gated_dice(x, t, None, uce=uce, sigmoid=sig).item()
+    assert abs(a - b) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["mixed", "none_supervised"])
+def test_get_loss_refiner_branch_matches_reference_fixture(golden_dir, tag):
+    """get_loss with a refiner output (reference losses.py:131-178): value and gradients w.r.t. the logits, the three
+    attention maps and the refiner output vs tests/golden/get_loss_refine.npz, written by oracle/make_golden_get_loss.py
+    from the UNMODIFIED reference function."""
+    import importlib.util
+    import os
+
+    from multimodal_pl_b200.loss_functions.losses import get_loss
+
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_get_loss", os.path.join(os.path.dirname(golden_dir), "..", "oracle", "make_golden_get_loss.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)                      # only its seeded input generator is used (no reference import)
+    g = np.load(os.path.join(golden_dir, "get_loss_refine.npz"))
+    output, target, attns, refine, deep = gen.inputs()
+    leaves = [output.cuda().requires_grad_(True)] + [a.cuda().requires_grad_(True) for a in attns] + \
+             [refine.cuda().requires_grad_(True)]
+    label_t = [bool(v) for v in g[tag + ":label_t"]]
+    loss, confi = get_loss(leaves[0], 0, [d.cuda() for d in deep], target.cuda(),
+                           mask=[torch.from_numpy(g[tag + ":wmask"])], attns=leaves[1:4], refine_output=leaves[4],
+                           label_t=label_t, aux_weight=0.7, weight_feature=0.3)
+    loss.backward()
+    assert abs(loss.item() - float(g[tag + ":loss"])) < 2e-6 and confi == float(g[tag + ":confi"])
+    for name, t in zip(["output", "attn0", "attn1", "attn2", "refine"], leaves):
+        ref = torch.from_numpy(g[tag + ":grad:" + name])
+        got = t.grad.cpu()
+        assert (got - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item()) + 1e-8, name
+        assert ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item() < 1e-4, name
+
+
 def test_poly_lr_drives_fused_sgd():
     from multimodal_pl_b200.engine import FusedSGD
     from multimodal_pl_b200.utils import adjust_learning_rate, lr_poly
