@@ -17,6 +17,7 @@ _CL = torch.channels_last_3d
 _cfg = {"dtype": torch.bfloat16, "conv_algo": os.environ.get("MMPL_CONV_ALGO", "auto"),
         "fuse_gn_bwd": os.environ.get("MMPL_FUSE_GN_BWD", "1") != "0",
         "ws_bwd_side_stream": os.environ.get("MMPL_WS_BWD_SIDE_STREAM", "1") != "0",
+        "wgrad_side_stream": os.environ.get("MMPL_WGRAD_SIDE_STREAM", "1") != "0",
         "fuse_gn_bwd_cls": {"0": False, "1": True}.get(os.environ.get("MMPL_FUSE_GN_BWD_CLS", ""), None)}
 
 
@@ -116,7 +117,7 @@ def _grad_is_direct(param) -> bool:
 # its two small kernels (wgrad -> ws_weight_bwd) would sit on the critical path 35 times per step.  ws_weight_bwd is
 # therefore launched on a side stream that forks after the wgrad kernel and is joined once, when the backward pass
 # ends (autograd engine callback) -- inside a CUDA-graph capture this becomes a parallel branch of the graph.
-_SIDE = {"stream": None, "pending": False}
+_SIDE = {"stream": None, "pending": False, "keep": []}
 
 
 def _side_stream():
@@ -130,6 +131,7 @@ def join_side_stream():
     if _SIDE["pending"]:
         torch.cuda.current_stream().wait_stream(_SIDE["stream"])
         _SIDE["pending"] = False
+    _SIDE["keep"].clear()      # tensors the side stream was still reading may be recycled from here on
 
 
 def _ws_bwd_launch(g_hat, w_hat, inv_std, cout, cin, taps, standardise, dw, off_critical_path):
@@ -144,6 +146,10 @@ def _ws_bwd_launch(g_hat, w_hat, inv_std, cout, cin, taps, standardise, dw, off_
         _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, cin, taps, standardise, _p(dw),
                                         _lib.stream_ptr()), "ws_weight_bwd")
     g_hat.record_stream(side)
+    _side_mark_pending()
+
+
+def _side_mark_pending():
     if not _SIDE["pending"]:
         _SIDE["pending"] = True
         torch.autograd.Variable._execution_engine.queue_callback(join_side_stream)
@@ -427,6 +433,15 @@ class WSConv3dFn(torch.autograd.Function):
         dy = to_cl(dy, dt)
         dev = x.device
         dx = dw = dres = None
+        # The weight-gradient chain (wgrad -> ws_weight_bwd) has no consumer inside the backward pass.  When autograd
+        # will simply adopt dW (flat-buffer slot), the chain runs on the side stream, forked HERE -- before the data
+        # gradient is enqueued -- so the critical path (dgrad -> GN backward -> previous layer) does not wait for it and
+        # its CTAs fill the SMs that tails and low-resolution kernels leave idle.
+        direct = ctx.needs_input_grad[1] and _grad_is_direct(ctx.weight)
+        wgrad_side = (direct and ctx.needs_input_grad[0] and _cfg["wgrad_side_stream"] and _cfg["ws_bwd_side_stream"]
+                      and not _PROF["on"])
+        if wgrad_side:
+            _side_stream().wait_stream(torch.cuda.current_stream())
         if ctx.needs_input_grad[0]:
             dx = empty_cl(n, cin, d, h, w, dt, dev)
             algo = _algo(dt, cout, cin)
@@ -444,21 +459,34 @@ class WSConv3dFn(torch.autograd.Function):
                 _GN_REDUCED[dx.data_ptr()] = (gws.data_ptr(), ghead)
         if ctx.needs_input_grad[1]:
             taps = k * k * k
-            g_hat = torch.empty(taps * cout * cin, dtype=torch.float32, device=dev)
             algo = _lib.ALGO_DIRECT
             if ctx.x_is_psplit:
                 algo = _lib.ALGO_TCGEN05_PSPLIT
             elif _cfg["conv_algo"] != "direct" and _tc_wgrad_supported(dt, k, stride, cin, cout) and not (
                     stride == 2 and k == 3):
                 algo = _lib.ALGO_TCGEN05
-            wsb = int(L.mmpl_conv3d_wgrad_workspace(n, d, h, w, cin, cout, k, stride, algo))
-            ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev) if wsb else None
-            with _timed(algo, ctx.flops, ("wgrad_tc",) + ctx.key[1:]):
-                _lib.check(L.mmpl_conv3d_wgrad(_p(x), _p(dy), _p(g_hat), n, d, h, w, cin, cout, k, stride, code, algo,
-                                               _p(ws), wsb, st), "conv3d_wgrad")
-            direct = _grad_is_direct(ctx.weight)
             dw = _grad_dst(ctx.weight, w_hat.shape)
-            _ws_bwd_launch(g_hat, w_hat, inv_std, cout, cin, taps, standardise, dw, direct)
+
+            def chain(on_side):
+                g_hat = torch.empty(taps * cout * cin, dtype=torch.float32, device=dev)
+                wsb = int(L.mmpl_conv3d_wgrad_workspace(n, d, h, w, cin, cout, k, stride, algo))
+                ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev) if wsb else None
+                with _timed(algo, ctx.flops, ("wgrad_tc",) + ctx.key[1:]):
+                    _lib.check(L.mmpl_conv3d_wgrad(_p(x), _p(dy), _p(g_hat), n, d, h, w, cin, cout, k, stride, code, algo,
+                                                   _p(ws), wsb, _lib.stream_ptr()), "conv3d_wgrad")
+                if on_side:
+                    _lib.check(L.mmpl_ws_weight_bwd(_p(g_hat), _p(w_hat), _p(inv_std), cout, cin, taps, standardise,
+                                                    _p(dw), _lib.stream_ptr()), "ws_weight_bwd")
+                    _SIDE["keep"].append((x, dy, g_hat, ws))     # alive until the join
+                else:
+                    _ws_bwd_launch(g_hat, w_hat, inv_std, cout, cin, taps, standardise, dw, direct)
+
+            if wgrad_side:
+                with torch.cuda.stream(_side_stream()):
+                    chain(True)
+                _side_mark_pending()
+            else:
+                chain(False)
             dw = dw.to(wdtype)
         if has_res and ctx.needs_input_grad[2]:
             dres = dy
