@@ -134,6 +134,10 @@ cls_bwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict_
       const float w0 = c < classes ? wc[c * CIN + k] : 0.f, w1 = (c + 1) < classes ? wc[(c + 1) * CIN + k] : 0.f;
       split2(w0, w1, wh[nt][h], wl[nt][h]);
     }
+  constexpr int PITCH = CIN * 2 + 16;                           // bytes per voxel row of the per-warp activation tile
+  __shared__ __align__(16) uint8_t s_tile[8][16 * PITCH];
+  uint8_t* tile = s_tile[warp];
+  const uint32_t tile_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
   float dw[NT][4];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
@@ -234,19 +238,30 @@ cls_bwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict_
       uint32_t ah[4], al[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) split2(e[i][0], e[i][1], ah[i], al[i]);
-      const unsigned short* au = reinterpret_cast<const unsigned short*>(an);
+      // B fragments: the 16 x CIN activation tile goes through a per-warp shared-memory tile (two coalesced 16-byte
+      // loads per lane, row pitch CIN*2+16 bytes -> conflict-free) and comes back transposed with ldmatrix.x4.trans:
+      // matrices (v 0..7 | 8..15) x (n-tile nt | nt+1) are exactly b0, b1 of two n-tiles.
+      __syncwarp();
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const int k = nt * 8 + g;
-        uint32_t x[4];
+      for (int i = 0; i < (16 * CIN * 2) / (32 * 16); ++i) {
+        const int u = lane + 32 * i, row = u / (CIN / 8), c16 = u % (CIN / 8);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (s0 + row < S) v = *reinterpret_cast<const uint4*>(an + (s0 + row) * CIN + c16 * 8);
+        *reinterpret_cast<uint4*>(tile + row * PITCH + c16 * 16) = v;
+      }
+      __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int64_t v = v0 + (i >> 1) * 8 + (i & 1);
-          x[i] = v < S ? static_cast<uint32_t>(au[v * CIN + k]) : 0u;
-        }
-        const uint32_t b0 = x[0] | (x[1] << 16), b1 = x[2] | (x[3] << 16);
-        mma_bf16(dw[nt], ah[0], ah[1], ah[2], ah[3], b0, b1);
-        mma_bf16(dw[nt], al[0], al[1], al[2], al[3], b0, b1);
+      for (int nt = 0; nt < NT; nt += 2) {
+        const int mi = lane >> 3, r = lane & 7;
+        const uint32_t addr = tile_u32 + ((mi & 1) * 8 + r) * PITCH + (nt + (mi >> 1)) * 16;
+        uint32_t b[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
+                     : "r"(addr));
+        mma_bf16(dw[nt], ah[0], ah[1], ah[2], ah[3], b[0], b[1]);
+        mma_bf16(dw[nt], al[0], al[1], al[2], al[3], b[0], b[1]);
+        mma_bf16(dw[nt + 1], ah[0], ah[1], ah[2], ah[3], b[2], b[3]);
+        mma_bf16(dw[nt + 1], al[0], al[1], al[2], al[3], b[2], b[3]);
       }
     }
   }
@@ -270,7 +285,6 @@ cls_bwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict_
     atomicAdd(&redb[g + 8], db1);
   }
   __syncthreads();
-  (void)warp;
   for (int i = threadIdx.x; i < 16 * CIN; i += 256)
     if (i / CIN < classes) atomicAdd(&dwc[i], red[i]);
   if (threadIdx.x < classes) atomicAdd(&dbias[threadIdx.x], redb[threadIdx.x]);

@@ -264,7 +264,9 @@ class GraphedInference:
     call: the ~140 kernel launches of a tile cost one graph launch on the host.  Use as a network in
     ``evaluate.predict_sliding(..., net_list=[GraphedInference(model, tile)], ...)``: ``net(img, task_id) -> logits``.
     The returned tensor is a static buffer that the next call overwrites (the sliding-window blend consumes it first,
-    in stream order).  Inputs of any other shape fall back to the eager module."""
+    in stream order).  Inputs of any other shape fall back to the eager module.  The weights are treated as frozen:
+    their standardised copies are computed once here, not per tile (``ops.frozen_weights``) -- build a new
+    GraphedInference after the weights change."""
 
     def __init__(self, model: torch.nn.Module, example: torch.Tensor, warmup: int = 2):
         self.model = model
@@ -273,13 +275,13 @@ class GraphedInference:
         model.eval()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side), torch.no_grad():
+        with torch.cuda.stream(side), torch.no_grad(), ops.frozen_weights():
             for _ in range(max(warmup, 1)):
                 model(self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph), torch.no_grad():
+        with torch.cuda.graph(self.graph), torch.no_grad(), ops.frozen_weights():
             out = model(self.static_in)
             self.static_out = out[0] if isinstance(out, (tuple, list)) else out
         if was_training:

@@ -18,6 +18,7 @@ _cfg = {"dtype": torch.bfloat16, "conv_algo": os.environ.get("MMPL_CONV_ALGO", "
         "fuse_gn_bwd": os.environ.get("MMPL_FUSE_GN_BWD", "1") != "0",
         "ws_bwd_side_stream": os.environ.get("MMPL_WS_BWD_SIDE_STREAM", "1") != "0",
         "wgrad_side_stream": os.environ.get("MMPL_WGRAD_SIDE_STREAM", "1") != "0",
+        "ws_fwd_side_stream": os.environ.get("MMPL_WS_FWD_SIDE_STREAM", "1") != "0",
         "fuse_gn_bwd_cls": {"0": False, "1": True}.get(os.environ.get("MMPL_FUSE_GN_BWD_CLS", ""), None)}
 
 
@@ -237,7 +238,7 @@ _WS_TABLES = {}
 
 
 class _WsEntry:
-    __slots__ = ("w_hat", "inv_std", "pf", "pd", "key", "shape_key")
+    __slots__ = ("w_hat", "inv_std", "pf", "pd", "key", "shape_key", "on_side")
 
 
 def _ws_key(weight, dt, standardise, stem_kch):
@@ -263,6 +264,7 @@ def _ws_entry(weight, dt, stem_kch=0, packed=True):
         else:
             e.pf = e.pd = None
         e.key = None
+        e.on_side = False
         e.shape_key = shape_key
         weight._mmpl_ws = e
     return e
@@ -324,6 +326,22 @@ def _stem_plan(dt, cout):
     return use_tc, use_tc and mode != "fp32fwd", kch
 
 
+class frozen_weights:
+    """Context manager for inference with weights that do not change: inside it the standardised weights are computed
+    by the first forward and reused by the following ones (the reference recomputes them in every Conv3d.forward,
+    unet3D.py:22-26; with frozen weights that is the same values 96 times per volume).  Leave the context -- or call
+    ``ops.invalidate_weights()`` -- before the weights change."""
+
+    def __enter__(self):
+        self.prev = _cfg.get("ws_frozen", False)
+        _cfg["ws_frozen"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _cfg["ws_frozen"] = self.prev
+        return False
+
+
 def prepare_ws(convs):
     """Refresh the standardised weights of ``convs`` = [(weight, standardise, is_stem)] with one launch.  Called at
     the top of unet3D_baseline.forward."""
@@ -343,12 +361,40 @@ def prepare_ws(convs):
         keys.append(_ws_key(weight, dt, standardise, stem_kch))
     if not items:
         return
+    if _cfg.get("ws_frozen", False) and all(it[3].key == k for it, k in zip(items, keys)):
+        return                       # frozen weights: what the previous forward computed is still valid
     _lib.require_device()
-    tab = _ws_table(items, dt)
-    _lib.check(_lib.lib().mmpl_ws_weight_fwd_batched(_p(tab[0]), tab[1], tab[2], _lib.dtype_code(dt), _lib.stream_ptr()),
-               "ws_weight_fwd_batched")
+    L = _lib.lib()
+    code = _lib.dtype_code(dt)
+    first = [it for it in items if it[2] or it[0].shape[1] == 1]        # the stem: needed immediately
+    rest = [it for it in items if not (it[2] or it[0].shape[1] == 1)]
+    if _cfg["ws_fwd_side_stream"] and first and rest:
+        # the stem's weights on the current stream; everything else on a side stream, concurrently with the stem
+        # (im2col + 1x1x1 conv are HBM-bound).  The first convolution that needs them joins (``_ws_get``).
+        tab = _ws_table(first, dt)
+        _lib.check(L.mmpl_ws_weight_fwd_batched(_p(tab[0]), tab[1], tab[2], code, _lib.stream_ptr()),
+                   "ws_weight_fwd_batched")
+        if _WS_SIDE["stream"] is None:
+            _WS_SIDE["stream"] = torch.cuda.Stream()
+        side = _WS_SIDE["stream"]
+        side.wait_stream(torch.cuda.current_stream())
+        tab = _ws_table(rest, dt)
+        with torch.cuda.stream(side):
+            _lib.check(L.mmpl_ws_weight_fwd_batched(_p(tab[0]), tab[1], tab[2], code, _lib.stream_ptr()),
+                       "ws_weight_fwd_batched")
+        _WS_SIDE["pending"] = True
+        side_ids = {id(it[3]) for it in rest}
+    else:
+        tab = _ws_table(items, dt)
+        _lib.check(L.mmpl_ws_weight_fwd_batched(_p(tab[0]), tab[1], tab[2], code, _lib.stream_ptr()),
+                   "ws_weight_fwd_batched")
+        side_ids = set()
     for (_, _, _, e), key in zip(items, keys):
         e.key = key
+        e.on_side = id(e) in side_ids
+
+
+_WS_SIDE = {"stream": None, "pending": False}
 
 
 def _ws_get(weight, dt, standardise, stem_kch=0, packed=True):
@@ -357,7 +403,12 @@ def _ws_get(weight, dt, standardise, stem_kch=0, packed=True):
         e = _ws_entry(weight, dt, stem_kch, packed)
         if e.key != _ws_key(weight, dt, standardise, stem_kch):
             _ws_refresh_one(weight, e, dt, standardise, stem_kch)
-        e.key = None        # consumed: the next forward refreshes again
+        elif e.on_side and _WS_SIDE["pending"]:
+            torch.cuda.current_stream().wait_stream(_WS_SIDE["stream"])      # join the side-stream refresh once
+            _WS_SIDE["pending"] = False
+        if not _cfg.get("ws_frozen", False):
+            e.key = None    # consumed: the next forward refreshes again
+        e.on_side = False
         return e
     # non-fp32 / non-contiguous master weight: one-off buffers
     w32 = weight.detach().float().contiguous()
