@@ -136,8 +136,8 @@ cls_bwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict_
     }
   constexpr int PITCH = CIN * 2 + 16;                           // bytes per voxel row of the per-warp activation tile
   __shared__ __align__(16) uint8_t s_tile[8][16 * PITCH];
-  uint8_t* tile = s_tile[warp];
-  const uint32_t tile_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+  uint8_t* stage = s_tile[warp];
+  const uint32_t stage_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(stage));
   float dw[NT][4];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
@@ -247,13 +247,13 @@ cls_bwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict_
         const int u = lane + 32 * i, row = u / (CIN / 8), c16 = u % (CIN / 8);
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (s0 + row < S) v = *reinterpret_cast<const uint4*>(an + (s0 + row) * CIN + c16 * 8);
-        *reinterpret_cast<uint4*>(tile + row * PITCH + c16 * 16) = v;
+        *reinterpret_cast<uint4*>(stage + row * PITCH + c16 * 16) = v;
       }
       __syncwarp();
 #pragma unroll
       for (int nt = 0; nt < NT; nt += 2) {
         const int mi = lane >> 3, r = lane & 7;
-        const uint32_t addr = tile_u32 + ((mi & 1) * 8 + r) * PITCH + (nt + (mi >> 1)) * 16;
+        const uint32_t addr = stage_u32 + ((mi & 1) * 8 + r) * PITCH + (nt + (mi >> 1)) * 16;
         uint32_t b[4];
         asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                      : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
