@@ -82,7 +82,15 @@ class GNReLUClassifier(nn.Sequential):
     def forward(self, x):
         gn, conv = self[0], self[2]
         a = ops.gn_relu(x, gn.weight, gn.bias, gn.num_groups, gn.eps)
-        return ops.classifier(a, conv.weight, conv.bias)
+        if conv.in_channels in (32, 64) and conv.out_channels <= 16:
+            return ops.classifier(a, conv.weight, conv.bias)
+        # deepout1 of unet3D_with_feam3 (128 channels, 1/8 resolution, 9 216 voxels per sample at cfg2): outside the
+        # width the classifier kernels are built for; a plain fp32 library GEMM on this tiny tensor (a matmul, not a
+        # cuDNN convolution: those default to TF32)
+        n, c = a.shape[0], a.shape[1]
+        rows = a.permute(0, 2, 3, 4, 1).reshape(n, -1, c).float()                 # view of the NDHWC storage
+        out = rows @ conv.weight.view(conv.out_channels, c).t().float() + conv.bias.float()
+        return out.permute(0, 2, 1).reshape((n, conv.out_channels) + tuple(a.shape[2:])).contiguous()
 
 
 class NoBottleneck(nn.Module):
@@ -234,3 +242,129 @@ class unet3D_baseline(nn.Module):
         if self.training:
             return logits, [], []
         return logits
+
+
+class EAM(nn.Module):
+    """Class-token cross attention of the reference (unet3D.py:142-212), same constructor, parameters and outputs:
+    ``forward(x [B,N,C], modality_token [B,Nt,C]) -> (x_out [B,Nt,C], attn [B,heads,Nt,N])`` with ``attn`` the UNSCALED
+    q.k^T logits (the model averages them over the heads into its attention maps, :1133-1137).  Tiny next to the
+    backbone (<= 2.4 GFLOP per call at cfg2): LayerNorm + library GEMMs in fp32."""
+
+    def __init__(self, dim, input_resolution, num_heads, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop=0.,
+                 attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, upsample=None, use_checkpoint=False):
+        super(EAM, self).__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.use_checkpoint = use_checkpoint
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        self.kv = nn.Linear(dim, dim * 2, bias=False)
+        self.q = nn.Linear(dim, dim, bias=False)
+        self.softmax = nn.Softmax(dim=-1)
+        self.proj = nn.Linear(dim, dim)
+        self.norm2 = norm_layer(dim)
+        self.norm3 = norm_layer(dim)
+
+    def forward(self, x, modality_token):
+        B_, N, C = x.shape
+        B_, Nt, ct = modality_token.shape
+        x = self.norm2(x.float())
+        modality_token = self.norm3(modality_token.float())
+        kv = self.kv(x).reshape(B_, N, 2, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        k, v = kv[0], kv[1]
+        q = self.q(modality_token).reshape(B_, Nt, self.num_heads, C // self.num_heads).permute(0, 2, 1, 3)
+        attn = (q @ k.transpose(-2, -1))
+        attnf = self.softmax(attn * self.scale)
+        x = (attnf @ v).transpose(1, 2).reshape(B_, Nt, C)
+        x = self.proj(self.norm2(x)) + x
+        return x, attn
+
+
+class unet3D_with_feam3(unet3D_baseline):
+    """Reference unet3D.py:938-1190: the baseline backbone plus three deep-supervision heads (GN-ReLU-1x1x1, :969-993),
+    three class-token attention modules (EAM) and EMA class tokens.  ``forward(input, mask=None)`` returns
+    ``(logits, atten_map[3], deep_map[3], feature_stored[3])`` in train mode and ``logits`` in eval mode;
+    ``renew_token(features, mask)`` is the EMA update of :1051-1068.  Same ``state_dict`` keys as the reference."""
+
+    def __init__(self, layers, num_classes=12, weight_std=False, ema=False, use_cm=[True, True, True], deep_up=False):
+        super(unet3D_with_feam3, self).__init__(layers, num_classes=num_classes, weight_std=weight_std, ema=False,
+                                                use_cm=use_cm, deep_up=deep_up, base=32)
+        self.upsamplex3 = nn.Upsample(scale_factor=4, mode='trilinear')
+        self.upsamplex4 = nn.Upsample(scale_factor=8, mode='trilinear')
+        self.deepout1 = GNReLUClassifier(nn.GroupNorm(16, 128), nn.ReLU(inplace=in_place),
+                                         nn.Conv3d(128, num_classes, kernel_size=1))
+        self.eam84 = EAM(128, input_resolution=None, num_heads=4)
+        self.deepout2 = GNReLUClassifier(nn.GroupNorm(16, 64), nn.ReLU(inplace=in_place),
+                                         nn.Conv3d(64, num_classes, kernel_size=1))
+        self.eam42 = EAM(64, input_resolution=None, num_heads=4)
+        self.deepout3 = GNReLUClassifier(nn.GroupNorm(16, 32), nn.ReLU(inplace=in_place),
+                                         nn.Conv3d(32, num_classes, kernel_size=1))
+        self.eam21 = EAM(32, input_resolution=None, num_heads=4)
+        # class tokens are plain tensors in the reference (not parameters, not in the state_dict), :1006-1011
+        self.class_token1 = torch.randn(num_classes - 1, 128)
+        self.class_token2 = torch.randn(num_classes - 1, 64)
+        self.class_token3 = torch.randn(num_classes - 1, 32)
+        if ema:
+            for param in self.parameters():
+                param.detach_()
+
+    def _attend(self, eam, token, x, up):
+        """attention map of one decoder scale (:1131-1137): mean over heads of the q.k^T logits, as a volume"""
+        n, c = x.shape[0], x.shape[1]
+        x_t = x.permute(0, 2, 3, 4, 1).reshape(n, -1, c)          # [B, voxels, C]: a view of the NDHWC storage
+        _, cattn = eam(x_t, token.view(1, self.num_classes - 1, c).detach())
+        amap = cattn.mean(1).reshape((n, self.num_classes - 1) + tuple(x.shape[2:]))
+        return up(amap) if self.deep_up else amap
+
+    def forward(self, input, mask=None):
+        dev = input.device
+        self.class_token1 = self.class_token1.to(dev)
+        self.class_token2 = self.class_token2.to(dev)
+        self.class_token3 = self.class_token3.to(dev)
+        atten_map, deep_map, feature_stored = [], [], []
+        ops.prepare_ws(self._ws_convs())
+        ops.begin_forward(dev)
+        x = self.conv1(input)
+        x = self.layer0(x)
+        x, skip0 = self._stage_with_skip(self.layer1, x)
+        x, skip1 = self._stage_with_skip(self.layer2, x)
+        x, skip2 = self._stage_with_skip(self.layer3, x)
+        x, skip3 = self._stage_with_skip(self.layer4, x)
+        x = self.fusionConv(x)
+        stages = [(self.x8_resb, skip3, self.deepout1, self.eam84, "class_token1", self.upsamplex4, 0),
+                  (self.x4_resb, skip2, self.deepout2, self.eam42, "class_token2", self.upsamplex3, 1),
+                  (self.x2_resb, skip1, self.deepout3, self.eam21, "class_token3", nn.Upsample(scale_factor=2, mode='trilinear'), 2)]
+        for resb, skip, deepout, eam, tok, up, i in stages:
+            x = resb(self.upsamplex2(x, skip))
+            deep_map.append(deepout(x))
+            feature_stored.append(x.detach().clone())
+            if self.use_cm[i]:
+                atten_map.append(self._attend(eam, getattr(self, tok), x, up))
+        x = self.x1_resb(self.upsamplex2(x, skip0))
+        logits = self.precls_conv(x)
+        if self.training:
+            return logits, atten_map, deep_map, feature_stored
+        return logits
+
+    @torch.no_grad()
+    def renew_token(self, features, mask):
+        """EMA of the per-class mean feature into the class tokens (:1051-1068), without the reference's host
+        synchronisations: classes absent from ``mask`` (or from its nearest-neighbour down-sampling) keep their token.
+        Per-channel means pool over the batch (the reference's reshape is only meaningful for batch 1)."""
+        tokens = [self.class_token1, self.class_token2, self.class_token3]
+        for index, x in enumerate(features):
+            tok = tokens[min(index, 2)].to(x.device)
+            xf = x.float()
+            for l in range(self.num_classes - 1):
+                cm = torch.nn.functional.interpolate((mask == (l + 1)).float(), xf.shape[2:], mode="nearest")
+                cnt = cm.sum()
+                mean = (xf * cm).sum(dim=(0, 2, 3, 4)) / cnt.clamp_min(1.0)
+                upd = tok[l] * (1 - self.alpha) + mean * self.alpha
+                tok[l] = torch.where(cnt > 0, upd, tok[l])
+            if index == 0:
+                self.class_token1 = tok
+            elif index == 1:
+                self.class_token2 = tok
+            else:
+                self.class_token3 = tok

@@ -117,6 +117,39 @@ def synth_state_dict(base: int = 32, num_classes: int = 16, seed: int = 0) -> Di
     return sd
 
 
+def synth_feam3_state_dict(num_classes: int = 16, seed: int = 0):
+    """Deterministic weights for unet3D_with_feam3 (reference unet3D.py:938-1017): the baseline backbone weights of
+    ``synth_state_dict`` plus the three deep-supervision heads and the three EAM modules; also returns the three class
+    tokens (plain tensors in the reference, :1006-1011).  -> (state_dict, [token1, token2, token3])."""
+    sd = synth_state_dict(32, num_classes, seed)
+    extra = {}
+    for name, c in (("1", 128), ("2", 64), ("3", 32)):
+        extra[f"deepout{name}.0.weight"] = (c,)
+        extra[f"deepout{name}.0.bias"] = (c,)
+        extra[f"deepout{name}.2.weight"] = (num_classes, c, 1, 1, 1)
+        extra[f"deepout{name}.2.bias"] = (num_classes,)
+    for name, c in (("eam84", 128), ("eam42", 64), ("eam21", 32)):
+        extra[name + ".kv.weight"] = (2 * c, c)
+        extra[name + ".q.weight"] = (c, c)
+        extra[name + ".proj.weight"] = (c, c)
+        extra[name + ".proj.bias"] = (c,)
+        for nrm in ("norm2", "norm3"):
+            extra[f"{name}.{nrm}.weight"] = (c,)
+            extra[f"{name}.{nrm}.bias"] = (c,)
+    for i, (k, shp) in enumerate(sorted(extra.items())):
+        g = torch.Generator().manual_seed(seed * 100003 + 5000 + i)
+        if k.endswith(".0.weight") or k.endswith("norm2.weight") or k.endswith("norm3.weight"):
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif k.endswith("bias"):
+            t = 0.1 * torch.randn(shp, generator=g)
+        else:
+            t = torch.randn(shp, generator=g) / math.sqrt(int(np.prod(shp[1:])))
+        sd[k] = t.float()
+    tokens = [torch.randn((num_classes - 1, c), generator=torch.Generator().manual_seed(seed * 100003 + 7000 + j))
+              for j, c in enumerate((128, 64, 32))]
+    return sd, tokens
+
+
 def no_bottleneck(x: torch.Tensor, sd: Dict[str, torch.Tensor], p: str, stride: int) -> torch.Tensor:
     """NoBottleneck.forward (unet3D.py:56-73): pre-activation residual block; the residual branch is
     downsample(x) = WSconv1x1(relu(GN(x))) computed from the block input when present (:68-69, :643-649)."""

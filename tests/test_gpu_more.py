@@ -175,6 +175,94 @@ def test_get_loss_refiner_branch_matches_reference_fixture(golden_dir, tag):
         assert ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item() < 1e-4, name
 
 
+def test_unet3d_with_feam3_matches_reference_fixture(golden_dir):
+    """unet3D_with_feam3 (reference unet3D.py:938-1190) on the fp32 exact path vs tests/golden/feam3.npz, written by
+    oracle/make_golden_feam3.py from the UNMODIFIED reference model: the four train-mode outputs, gradients under a fixed
+    objective (including that parameters the forward never uses get no gradient), eval-mode logits and the EMA class
+    tokens after renew_token()."""
+    import importlib.util
+    import os
+
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.unet3D import unet3D_with_feam3
+
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_feam3", os.path.join(os.path.dirname(golden_dir), "..", "oracle", "make_golden_feam3.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)                       # seeded objective / constants only (no reference import)
+    g = np.load(os.path.join(golden_dir, "feam3.npz"))
+    mm.set_compute_dtype(torch.float32)
+    mm.set_conv_algo("direct")
+    try:
+        sd, tokens = O.synth_feam3_state_dict(gen.CLASSES, gen.SEED)
+        model = unet3D_with_feam3([1, 2, 2, 2, 2], num_classes=gen.CLASSES, weight_std=True).cuda()
+        model.load_state_dict(sd)
+        model.class_token1, model.class_token2, model.class_token3 = [t.clone() for t in tokens]
+        model.train()
+        x = O.synth_patch(gen.SHAPE, 1000 + gen.SEED, "ct").cuda()
+        lab = O.synth_labels((gen.SHAPE[0],) + gen.SHAPE[2:], 2000 + gen.SEED, gen.CLASSES, 32).cuda()
+        logits, attn, deep, feats = model(x, lab)
+        assert len(attn) == len(deep) == len(feats) == 3
+
+        def rel(a, b):
+            a, b = a.detach().double().cpu(), torch.from_numpy(b).double()
+            return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+        assert rel(logits, g["logits"]) < 1e-5
+        for i in range(3):
+            assert rel(attn[i], g[f"attn{i}"]) < 1e-4, i
+            assert rel(deep[i], g[f"deep{i}"]) < 1e-5, i
+            assert rel(feats[i], g[f"feat{i}"]) < 1e-5, i
+        dys = gen.seeded_dys([tuple(logits.shape)] + [tuple(a.shape) for a in attn] + [tuple(d.shape) for d in deep])
+        gen.objective(logits, attn, deep, dys).backward()
+        params = dict(model.named_parameters())
+        # whole-network gradients: 1e-2, the bound test_gpu_unet.py documents (a ReLU gate within fp32 rounding of zero
+        # may resolve differently in two fp32 implementations; one flip moves upstream rel-L2 by ~2e-3)
+        errs = {k: rel(params[k].grad, g["grad:" + k]) for k in gen.GRAD_KEYS}
+        assert all(v < 1e-2 for v in errs.values()), errs
+        assert (params["eam84.proj.weight"].grad is None) == bool(g["unused_grad_is_none"][0])
+        model.renew_token(feats, lab)
+        for i, t in enumerate([model.class_token1, model.class_token2, model.class_token3]):
+            assert rel(t, g[f"token{i}"]) < 1e-5, i
+        model.eval()
+        with torch.no_grad():
+            ev = model(x)
+        assert torch.equal(ev, logits.detach()) == bool(g["eval_equals_train_logits"][0])
+    finally:
+        mm.set_conv_algo("auto")
+        mm.set_compute_dtype(torch.bfloat16)
+
+
+def test_unet3d_with_feam3_bf16_train_step_runs():
+    """bf16 / tcgen05 path of the full train-loop model: finite outputs and gradients, logits close to the fixture."""
+    import os
+
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.loss_functions.losses import get_loss
+    from multimodal_pl_b200.unet3D import unet3D_with_feam3
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "feam3.npz"))
+    mm.set_compute_dtype(torch.bfloat16)
+    sd, tokens = O.synth_feam3_state_dict(16, 3)
+    model = unet3D_with_feam3([1, 2, 2, 2, 2], num_classes=16, weight_std=True).cuda()
+    model.load_state_dict(sd)
+    model.class_token1, model.class_token2, model.class_token3 = [t.clone() for t in tokens]
+    model.train()
+    x = O.synth_patch((1, 1, 16, 32, 32), 1003, "ct").cuda()
+    lab = O.synth_labels((1, 16, 32, 32), 2003, 16, 32).cuda()
+    logits, attn, deep, feats = model(x, lab)
+    ref = torch.from_numpy(g["logits"])
+    assert ((logits.float().cpu() - ref).norm() / ref.norm()).item() < 2e-2
+    loss, _ = get_loss(logits, 0, deep, lab, [torch.ones(16)])
+    (loss + sum(a.float().mean() for a in attn) + sum(d.float().mean() for d in deep)).backward()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            assert torch.isfinite(p.grad).all(), k
+    assert model.eam84.kv.weight.grad is not None and model.deepout2[2].weight.grad is not None
+    model.renew_token(feats, lab)
+    assert torch.isfinite(model.class_token3).all()
+
+
 def test_poly_lr_drives_fused_sgd():
     from multimodal_pl_b200.engine import FusedSGD
     from multimodal_pl_b200.utils import adjust_learning_rate, lr_poly
