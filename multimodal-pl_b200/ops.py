@@ -68,7 +68,15 @@ def collect_conv_profile():
         e[0] += t
         e[1] += f
         e[2] += 1
-    dom = max(per.items(), key=lambda kv: kv[1][0]) if per else (None, [0.0, 0.0, 0])
+    # the dominant KERNEL is one template instantiation: fprop / fprop+res / dgrad / dgrad+gn launches of the same
+    # (op, Cin, Cout, k, stride, voxels) problem are the same conv_tc kernel -> group by the first six key fields
+    inst = {}
+    for k, v in per.items():
+        e = inst.setdefault(tuple(k[:6]), [0.0, 0.0, 0])
+        e[0] += v[0]
+        e[1] += v[1]
+        e[2] += v[2]
+    dom = max(inst.items(), key=lambda kv: kv[1][0]) if inst else (None, [0.0, 0.0, 0])
     return {"ms": tot_ms, "launches": len(_PROF["events"]), "flops": float(tot_fl),
             "per_key": {str(k): {"ms": v[0], "flops": float(v[1]), "launches": v[2]} for k, v in per.items()},
             "dominant": {"key": dom[0], "ms": dom[1][0], "flops": float(dom[1][1]), "launches": dom[1][2]}}
