@@ -231,7 +231,13 @@ class GraphedTrainStep:
         except AttributeError:
             pass
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on a HIGH-priority stream: the critical path (forward, dgrad, GroupNorm backward) then wins the SMs
+        # over the weight-gradient branch that ops forks onto its default-priority side stream
+        hp = None
+        if os.environ.get("MMPL_GRAPH_PRIORITY", "1") != "0":
+            lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+            hp = torch.cuda.Stream(priority=hi)
+        with torch.cuda.graph(self.graph, stream=hp):
             self.static_loss = self._body(in_graph=True)
         self._prev_sync = prev
 
