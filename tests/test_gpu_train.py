@@ -80,6 +80,74 @@ def test_parameter_gradients_land_in_the_flat_buffer_without_copies():
     assert dp.flat_grad.abs().max().item() == 0 and all(p.grad is None for p in model.parameters())
 
 
+def test_graphed_train_step_matches_eager_steps():
+    """engine.GraphedTrainStep (what bench.py times): constructor warm-up step + 2 replays == 3 eager steps -- same losses
+    and parameters up to the summation-order noise of the fp32/fp64 atomics (the captured graph contains the side-stream
+    weight-gradient branch, the batched weight standardisation and the fused SGD)."""
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.engine import DataParallelModel, FusedSGD, GraphedTrainStep
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    mm.set_compute_dtype(torch.bfloat16)
+    sd = O.synth_state_dict(32, 16, 0)
+    x = O.synth_patch((2, 1, 16, 32, 32), 5, "ct").cuda()
+    lab = O.synth_labels((2, 16, 32, 32), 6, 16, 32).cuda()
+    crit = EDiceLoss_partial(16)
+    w = [torch.ones(16)] * 2
+
+    def loss_fn(logits, l):
+        return crit(logits, l.squeeze(1), mask=w)
+
+    def make():
+        m = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True).cuda()
+        m.load_state_dict(sd)
+        m.train()
+        dp = DataParallelModel(m, 1)
+        return m, dp, FusedSGD(dp.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, flat_grad=dp.flat_grad)
+
+    ma, dpa, opta = make()
+    eager_losses = []
+    for _ in range(3):
+        opta.zero_grad()
+        loss = loss_fn(dpa(x, lab)[0], lab)
+        loss.backward()
+        opta.step()
+        eager_losses.append(loss.item())
+    mb, dpb, optb = make()
+    step = GraphedTrainStep(dpb, loss_fn, optb, x, lab, warmup=1)
+    graph_losses = [step(x, lab).item() for _ in range(2)]
+    assert abs(graph_losses[0] - eager_losses[1]) < 2e-3 * abs(eager_losses[1])
+    assert abs(graph_losses[1] - eager_losses[2]) < 2e-3 * abs(eager_losses[2])
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert torch.allclose(pa, pb, rtol=2e-2, atol=2e-4), k
+
+
+def test_graphed_inference_matches_eager_forward():
+    """engine.GraphedInference (sliding-window tiles): the replayed forward with frozen standardised weights equals the
+    eager eval-mode forward; other input shapes fall back to the eager module."""
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.engine import GraphedInference
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    mm.set_compute_dtype(torch.bfloat16)
+    model = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True).cuda()
+    model.load_state_dict(O.synth_state_dict(32, 16, 1))
+    model.eval()
+    x1 = O.synth_patch((1, 1, 16, 32, 32), 7, "ct").cuda()
+    x2 = O.synth_patch((1, 1, 16, 32, 32), 8, "mri").cuda()
+    with torch.no_grad():
+        r1, r2 = model(x1).clone(), model(x2).clone()
+    net = GraphedInference(model, x1)
+    for xin, ref in ((x1, r1), (x2, r2), (x1, r1)):
+        out = net(xin, None)
+        assert ((out - ref).norm() / ref.norm()).item() < 1e-3
+    small = O.synth_patch((1, 1, 16, 16, 32), 9, "ct").cuda()
+    with torch.no_grad():
+        ref_small = model(small)
+    assert ((net(small, None) - ref_small).norm() / ref_small.norm()).item() < 1e-3
+
+
 def test_bf16_training_reduces_loss():
     import multimodal_pl_b200 as mm
     from multimodal_pl_b200.engine import DataParallelModel, FusedSGD
