@@ -19,8 +19,9 @@
 //             mmpl_parity_split); tap k of parity p is P_p shifted by (k != 0) -> 8 chunks x (1..8 taps) per item;
 //      dgrad  runs per parity class of dX: a 1..8-tap stride-1 correlation over dY whose epilogue stores to 2i+p.
 //  * Warp roles: 0 = activation TMA producer, 1 = weight TMA producer, 2 = MMA issuer (warp-uniform loop, one elected
-//    lane issues) and TMEM allocator, 4..7 / 8..11 = two epilogue warpgroups on alternate items (tcgen05.ld ->
-//    +residual -> bf16 -> 16-byte global stores, plus the fused GroupNorm statistics / backward reduction).
+//    lane issues) and TMEM allocator, 3..6 = epilogue (tcgen05.ld -> +residual -> bf16 -> 16-byte global stores, plus
+//    the fused GroupNorm statistics / GroupNorm-backward reduction).  A 12-warp variant with two epilogue warpgroups on
+//    alternate items and a setmaxnreg register re-partition is kept behind MMPL_TC_TWO_GROUPS (see below).
 //  * WRES: for 32->32 layers all 27 weight tiles (55 KB) stay resident in shared memory for the life of the CTA.
 #include <stdlib.h>
 
@@ -33,10 +34,10 @@ namespace {
 using namespace ptx;
 
 constexpr int TC_TH = 16, TC_TW = 8;
-// 12 warps: 0 = activation TMA, 1 = weight TMA, 2 = MMA issuer, 3 = idle, 4..7 and 8..11 = two epilogue warpgroups that
-// take alternate work items (one per TMEM accumulator buffer), so an epilogue has two MMA periods to finish.  The
-// register file is re-partitioned with setmaxnreg: 64 for warps 0..3, 216 for the epilogue warpgroups
-// (launch: 384 x 168; the decrease must free more than the increase takes, or the second group waits forever).
+// Optional 12-warp layout (MMPL_TC_TWO_GROUPS=1): 0 = activation TMA, 1 = weight TMA, 2 = MMA issuer, 3 = idle, 4..7 and
+// 8..11 = two epilogue warpgroups that take alternate work items (one per TMEM accumulator buffer), so an epilogue has two
+// MMA periods to finish.  The register file is re-partitioned with setmaxnreg: 64 for warps 0..3, 216 for the epilogue
+// warpgroups (launch: 384 x 168; the decrease must free more than the increase takes, or the second group waits forever).
 // MMPL_TC_TWO_GROUPS = 0 (default) keeps ONE epilogue warpgroup (warps 3..6, 7 warps, no register re-partition): measured
 // on B200 the register-lean epilogue keeps up with the MMAs on its own, and the 12-warp layout costs the plain
 // launches ~18 % (profiles/r01_ncu_summary.md).
