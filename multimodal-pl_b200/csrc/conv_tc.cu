@@ -709,6 +709,13 @@ int dispatch_tc(const TcProblem& q, cudaStream_t s) {
     if (nt == 128) return launch_tc<64, 128, 2, MODE, false, 1>(q, s);
     return launch_tc<64, 256, 1, MODE, false, 1>(q, s);
   }
+  if constexpr (MODE == MODE_S2D) {
+    // stride-2 dgrad: every parity class re-reads the dY halo block, so deeper tiles (4 planes, one activation stage)
+    // cut the L2->SMEM traffic per output voxel; MMPL_TC_S2D_TD4=0 selects the 2-plane double-buffered variant
+    static const bool td4 = [] { const char* e = getenv("MMPL_TC_S2D_TD4"); return !(e && e[0] == '0'); }();
+    if (td4 && nt == 32) return launch_tc<64, 32, 4, MODE, false, 1>(q, s);
+    if (td4 && nt == 64) return launch_tc<64, 64, 4, MODE, false, 1>(q, s);
+  }
   if (nt == 32) return launch_tc<64, 32, 2, MODE, false>(q, s);
   if (nt == 64) return launch_tc<64, 64, 2, MODE, false>(q, s);
   if (nt == 128) return launch_tc<64, 128, 2, MODE, false>(q, s);
