@@ -177,11 +177,11 @@ def senc_score(preds, labels):
 
 
 def get_dice(preds, labels, t_id, atlas=None, num_class=13):
-    """Reference evaluate_amos.py:128-154 without atlas: argmax over classes, then per class l = 1..num_class
-    Dice / sensitivity / specificity-like scores with +1 smoothing.  One fused kernel (argmax of softmax == argmax of
-    logits).  Returns (dices, senc, spec, preds) with ``preds`` the argmax volume."""
-    if atlas is not None:
-        raise NotImplementedError("get_dice(atlas=...) (reference evaluate_amos.py:142-151) is outside the hot path")
+    """Reference evaluate_amos.py:128-154: argmax over classes, then per class l = 1..num_class Dice / sensitivity /
+    specificity-like scores with +1 smoothing -- one fused kernel (argmax of softmax == argmax of logits).  With an
+    ``atlas`` prior [B, num_class, D, H, W] the per-class prediction is ``softmax(preds)[:, l+1] + 0.15 > 1 - atlas[:, l]``
+    instead (:142-151; a validation-time option of the reference, plain tensor ops here).  Returns
+    (dices, senc, spec, preds) with ``preds`` the argmax volume."""
     _lib.require_device()
     dev = torch.device("cuda", torch.cuda.current_device())
     x = preds.to(dev)
@@ -189,4 +189,15 @@ def get_dice(preds, labels, t_id, atlas=None, num_class=13):
         x = x.float()
     x = x.contiguous()
     dices, senc, spec, amax = _finalize(x, None, labels, x.shape[1], num_class)
+    if atlas is not None:
+        preds_r = F.softmax(x, dim=1)
+        lab = labels.to(dev)
+        atlas = atlas.to(dev)
+        dices, senc, spec = [], [], []
+        for l in range(num_class):
+            cpred = (preds_r[:, l + 1] + 0.15) > (1 - atlas[:, l])
+            tgt = (lab == (l + 1)).reshape(cpred.shape) if lab.numel() == cpred.numel() else lab == (l + 1)
+            dices.append(dice_score(cpred, tgt))
+            senc.append(senc_score(cpred, tgt))
+            spec.append(spec_score(cpred, tgt))
     return dices, senc, spec, amax.long()

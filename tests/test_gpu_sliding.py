@@ -57,6 +57,26 @@ def test_get_dice_exact_counts():
     assert np.allclose([float(d) for d in spec], [float(d) for d in rp], atol=1e-12)
 
 
+def test_get_dice_with_atlas_prior():
+    """get_dice(atlas=...) (reference evaluate_amos.py:142-151): cpred_l = softmax(x)[:, l+1] + 0.15 > 1 - atlas[:, l]."""
+    from multimodal_pl_b200.evaluate import get_dice
+
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn((1, 6, 5, 7, 9), generator=g)
+    lab = torch.randint(0, 6, (1, 5, 7, 9), generator=g).float()
+    atlas = torch.rand((1, 5, 5, 7, 9), generator=g)
+    dices, senc, spec, am = get_dice(logits.cuda(), lab.cuda(), None, atlas=atlas.cuda(), num_class=5)
+    pr = torch.softmax(logits, 1)
+    assert torch.equal(am.cpu(), pr.argmax(1))
+    for l in range(5):
+        cp = ((pr[:, l + 1] + 0.15) > (1 - atlas[:, l])).double().view(1, -1)
+        t = (lab == (l + 1)).double().view(1, -1)
+        inter = (cp * t).sum(1)
+        assert abs(float(dices[l]) - float((2 * inter / (cp.sum(1) + t.sum(1) + 1)).mean())) < 1e-9
+        assert abs(float(senc[l]) - float((inter / (t.sum(1) + 1)).mean())) < 1e-9
+        assert abs(float(spec[l]) - float((inter / (cp.sum(1) + 1)).mean())) < 1e-9
+
+
 def test_unet_sliding_window_fp32_argmax_identical():
     """Full path on a small volume (2x2x2 tiles of 16x32x32): fp32 exact kernels vs the CPU oracle; argmax identical
     outside near-ties (reference top-2 gap < 1e-4), Dice within 1e-3."""
