@@ -75,6 +75,69 @@ def test_state_dict_contract_and_signatures():
         unet3D.Conv3d(32, 32, kernel_size=(5, 5, 5), padding=(2, 2, 2))
 
 
+def test_feam3_contract_eam_and_tokens_on_cpu(golden_dir):
+    """unet3D_with_feam3: reference state_dict keys/shapes (143 tensors), constructor signature, and the parts that are
+    plain tensor ops and therefore run on the CPU -- the EAM module against its formula and renew_token against the
+    class tokens the unmodified reference produced (tests/golden/feam3.npz, oracle/make_golden_feam3.py)."""
+    from multimodal_pl_b200 import unet3D
+
+    net = unet3D.unet3D_with_feam3([1, 2, 2, 2, 2], num_classes=16, weight_std=True)
+    sd_ref, tokens = O.synth_feam3_state_dict(16, 3)
+    sd = net.state_dict()
+    assert len(sd) == 143 and set(sd) == set(sd_ref)
+    assert all(tuple(sd[k].shape) == tuple(sd_ref[k].shape) for k in sd_ref)
+    net.load_state_dict(sd_ref)
+    assert list(inspect.signature(unet3D.unet3D_with_feam3.__init__).parameters)[1:7] == \
+        ["layers", "num_classes", "weight_std", "ema", "use_cm", "deep_up"]
+    # EAM: attn = q k^T (unscaled), per head; returned x = proj(norm2(softmax(attn*scale) v)) + softmax(...) v
+    eam = net.eam21
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((1, 40, 32), generator=g)
+    tok = torch.randn((1, 15, 32), generator=g)
+    out, attn = eam(x, tok)
+    xn = torch.nn.functional.layer_norm(x, (32,), eam.norm2.weight, eam.norm2.bias)
+    tn = torch.nn.functional.layer_norm(tok, (32,), eam.norm3.weight, eam.norm3.bias)
+    kv = xn @ eam.kv.weight.t()
+    k, v = kv[..., :32].reshape(1, 40, 4, 8), kv[..., 32:].reshape(1, 40, 4, 8)
+    q = (tn @ eam.q.weight.t()).reshape(1, 15, 4, 8)
+    ref_attn = torch.einsum("bthd,bnhd->bhtn", q, k)
+    assert tuple(attn.shape) == (1, 4, 15, 40) and torch.allclose(attn, ref_attn, atol=1e-5)
+    av = torch.einsum("bhtn,bnhd->bthd", torch.softmax(ref_attn * eam.scale, -1), v).reshape(1, 15, 32)
+    ref_out = torch.nn.functional.layer_norm(av, (32,), eam.norm2.weight, eam.norm2.bias) @ eam.proj.weight.t() \
+        + eam.proj.bias + av
+    assert torch.allclose(out, ref_out, atol=1e-5)
+    # renew_token on the reference's own stored features
+    fix = np.load(os.path.join(golden_dir, "feam3.npz"))
+    net.class_token1, net.class_token2, net.class_token3 = [t.clone() for t in tokens]
+    lab = O.synth_labels((1, 16, 32, 32), 2003, 16, 32)
+    net.renew_token([torch.from_numpy(fix[f"feat{i}"]) for i in range(3)], lab)
+    for i, t in enumerate([net.class_token1, net.class_token2, net.class_token3]):
+        assert torch.allclose(t, torch.from_numpy(fix[f"token{i}"]), rtol=1e-5, atol=1e-6), i
+
+
+def test_flat_gradient_adoption_on_cpu():
+    """engine.DataParallelModel keeps gradients in one flat buffer: gradients that autograd produced elsewhere are
+    folded into their slots (engine._adopt_grad), zero_grad drops the views and clears the buffer."""
+    from multimodal_pl_b200.engine import DataParallelModel
+
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+    dp = DataParallelModel(m, 1)
+    assert all(p.grad is None for p in m.parameters())
+    x = torch.randn(4, 5)
+    dp(x).square().sum().backward()
+    ref = torch.cat([p.grad.reshape(-1).clone() for p in m.parameters()])
+    dp.all_reduce_flat()                                   # world 1: only adopts
+    assert torch.allclose(dp.flat_grad, ref)
+    for p in m.parameters():
+        _, off, n = p._mmpl_grad_slot
+        assert p.grad.data_ptr() == dp.flat_grad.data_ptr() + 4 * off
+    dp(x).square().sum().backward()                        # accumulates in place, inside the flat buffer
+    assert torch.allclose(dp.flat_grad, 2 * ref)
+    dp.zero_grad()
+    assert dp.flat_grad.abs().max().item() == 0 and all(p.grad is None for p in m.parameters())
+
+
 def test_tile_grid_matches_oracle():
     from multimodal_pl_b200.evaluate import _get_gaussian, tile_origins
 
