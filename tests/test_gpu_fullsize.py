@@ -115,3 +115,38 @@ def test_sliding_window_cfg4_partition_of_unity():
         p, t = (ref_am == l), (labc == l)
         ref_d = 2.0 * (p & t).sum().double() / (p.sum().double() + t.sum().double() + 1)
         assert abs(float(dices[l - 1]) - ref_d.item()) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 48, 176, 144), (3, 1, 32, 80, 112)])
+def test_unet_ragged_patch_bf16_vs_fp32_paths(shape):
+    """Patch sizes that are not multiples of the 4x16x8 conv tiles (only of the network's 16x down-sampling) and an odd
+    batch: the bf16 tcgen05 path agrees with the fp32 exact CUDA-core path (itself pinned to the reference at 1e-5 in
+    test_gpu_unet.py) within the bf16 tolerance, forward and loss; all parameter gradients finite."""
+    import mmpl_oracle as O
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    sd = O.synth_state_dict(32, 16, 2)
+    x = O.synth_patch(shape, 11, "ct").cuda()
+    lab = O.synth_labels((shape[0],) + shape[2:], 12, 16, 32).cuda()
+    w = [torch.ones(16)] * shape[0]
+    outs = {}
+    try:
+        for dt, algo in ((torch.float32, "direct"), (torch.bfloat16, "auto")):
+            mm.set_compute_dtype(dt)
+            mm.set_conv_algo(algo)
+            model = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True).cuda()
+            model.load_state_dict(sd)
+            model.train()
+            logits = model(x, lab)[0]
+            loss = EDiceLoss_partial(16)(logits, lab.squeeze(1), mask=w)
+            loss.backward()
+            assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+            outs[dt] = (logits.detach().float(), loss.item())
+    finally:
+        mm.set_conv_algo("auto")
+        mm.set_compute_dtype(torch.bfloat16)
+    ref, got = outs[torch.float32], outs[torch.bfloat16]
+    assert ((got[0] - ref[0]).norm() / ref[0].norm()).item() < 2e-2
+    assert abs(got[1] - ref[1]) < 1e-2 * abs(ref[1])
