@@ -205,6 +205,79 @@ def unet3d_forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, base: int =
     return F.conv3d(x, sd["precls_conv.2.weight"], sd["precls_conv.2.bias"])         # :629-633, :713
 
 
+def eam_attention_logits(sd: Dict[str, torch.Tensor], p: str, x_tokens: torch.Tensor, class_token: torch.Tensor,
+                         heads: int = 4) -> torch.Tensor:
+    """The part of EAM.forward (unet3D.py:190-212) the model uses: attn = q k^T per head (UNSCALED, :203), with
+    k = kv(norm2(x))[..., :C], q = q(norm3(token)).  x_tokens [B, N, C], class_token [B, Nt, C] -> [B, heads, Nt, N]."""
+    B, N, C = x_tokens.shape
+    xn = F.layer_norm(x_tokens, (C,), sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+    tn = F.layer_norm(class_token, (C,), sd[p + "norm3.weight"], sd[p + "norm3.bias"])
+    kv = F.linear(xn, sd[p + "kv.weight"]).reshape(B, N, 2, heads, C // heads).permute(2, 0, 3, 1, 4)
+    q = F.linear(tn, sd[p + "q.weight"]).reshape(B, class_token.shape[1], heads, C // heads).permute(0, 2, 1, 3)
+    return q @ kv[0].transpose(-2, -1)
+
+
+def unet3d_feam3_forward(sd: Dict[str, torch.Tensor], tokens: Sequence[torch.Tensor], image: torch.Tensor):
+    """unet3D_with_feam3.forward in train mode (unet3D.py:1095-1190, use_cm all True, deep_up False):
+    -> (logits, atten_map[3], deep_map[3], feature_stored[3])."""
+    spec = {p: (cin, cout, s) for p, cin, cout, s in backbone_spec(32)}
+
+    def blk(x, p):
+        return no_bottleneck(x, sd, p, spec[p][2])
+
+    def head(x, p):        # GroupNorm -> ReLU -> 1x1x1 conv with bias (:969-993)
+        return F.conv3d(gn_relu(x, sd[p + "0.weight"], sd[p + "0.bias"]), sd[p + "2.weight"], sd[p + "2.bias"])
+
+    x = blk(ws_conv3d(image, sd["conv1.weight"], 1, 1), "layer0.0.")
+    skip0 = x
+    x = blk(blk(x, "layer1.0."), "layer1.1.")
+    skip1 = x
+    x = blk(blk(x, "layer2.0."), "layer2.1.")
+    skip2 = x
+    x = blk(blk(x, "layer3.0."), "layer3.1.")
+    skip3 = x
+    x = blk(blk(x, "layer4.0."), "layer4.1.")
+    x = ws_conv3d(gn_relu(x, sd["fusionConv.0.weight"], sd["fusionConv.0.bias"]), sd["fusionConv.2.weight"], 1, 0)
+    attn, deep, feats = [], [], []
+    for resb, skip, dp, eam, tok in (("x8_resb.0.", skip3, "deepout1.", "eam84.", tokens[0]),
+                                     ("x4_resb.0.", skip2, "deepout2.", "eam42.", tokens[1]),
+                                     ("x2_resb.0.", skip1, "deepout3.", "eam21.", tokens[2])):
+        x = blk(upsample2x_add(x, skip), resb)
+        deep.append(head(x, dp))
+        feats.append(x.detach().clone())
+        B, C = x.shape[0], x.shape[1]
+        x_t = x.view(B, C, -1).permute(0, 2, 1)                                        # :1131
+        a = eam_attention_logits(sd, eam, x_t, tok.view(1, tok.shape[0], C).detach())
+        attn.append(a.mean(1).reshape((B, tok.shape[0]) + tuple(x.shape[2:])))        # :1134
+    x = blk(upsample2x_add(x, skip0), "x1_resb.0.")
+    return head(x, "precls_conv."), attn, deep, feats
+
+
+def get_loss_refine(output, deep_out, target, class_weight, attns, refine_output, label_t, confi=0.10, aux_weight=1.0,
+                    weight_feature=0.1):
+    """get_loss with a refiner output (losses.py:107-178): base partial-label term + deep-supervision terms +
+    pseudo-label gated-Dice terms; single-sample batches (the reference indexes mask[0])."""
+    num_classes = output.shape[1] - 1
+    loss = partial_label_loss(output, target.squeeze(1), class_weight)
+    aux = 0.0
+    weights = [0.125, 0.25, 0.5, 1]
+    for idx, l in enumerate(deep_out):
+        ct = F.interpolate(target, l.shape[2:], mode="nearest").float()
+        aux = aux + partial_label_loss(l, ct.squeeze(1), class_weight, uce=False) * weights[idx]
+    rp = torch.softmax(refine_output, 1)
+    cmask = torch.logical_or(rp > (1 - confi), rp < confi).float()
+    sup = sum(1 for v in label_t if v)
+    maps = list(attns) + [torch.softmax(output, 1)[:, 1:]]
+    for idx, l in enumerate(maps):
+        for gan in range(num_classes):
+            if label_t[gan]:
+                continue
+            cd = binary_gated_dice(l[:, gan:gan + 1], rp[gan:gan + 1, 1], cmask[gan:gan + 1, 1:], uce=False,
+                                   sigmoid=(idx != 3))
+            aux = aux + cd / (num_classes - sup) * weights[idx] * weight_feature
+    return loss + aux * aux_weight
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # Partial-label loss                                                                      loss_partial.py:10-99
 # ----------------------------------------------------------------------------------------------------------------

@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 import torch
 
 import mmpl_oracle as O
@@ -138,3 +139,49 @@ def test_sgd_matches_torch():
         q, buf = O.sgd_step(q, g, buf, 0.01)
     assert torch.allclose(p.detach(), q, atol=1e-7)
     assert abs(O.lr_poly(0.01, 250, 500) - 0.01 * 0.5 ** 0.9) < 1e-12
+
+
+def test_feam3_oracle_matches_reference_fixture(golden_dir):
+    """O.unet3d_feam3_forward (restatement of unet3D_with_feam3.forward, unet3D.py:1095-1190) vs tests/golden/feam3.npz
+    written from the unmodified reference model: logits, attention maps, deep-supervision maps, stored features."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_feam3", os.path.join(os.path.dirname(golden_dir), "..", "oracle", "make_golden_feam3.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = np.load(os.path.join(golden_dir, "feam3.npz"))
+    sd, tokens = O.synth_feam3_state_dict(gen.CLASSES, gen.SEED)
+    x = O.synth_patch(gen.SHAPE, 1000 + gen.SEED, "ct")
+    with torch.no_grad():
+        logits, attn, deep, feats = O.unet3d_feam3_forward(sd, tokens, x)
+
+    def rel(a, b):
+        b = torch.from_numpy(b).double()
+        return ((a.double() - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+    assert rel(logits, g["logits"]) < 1e-5
+    for i in range(3):
+        assert rel(attn[i], g[f"attn{i}"]) < 1e-5 and rel(deep[i], g[f"deep{i}"]) < 1e-5 and rel(feats[i], g[f"feat{i}"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["mixed", "none_supervised"])
+def test_get_loss_refine_oracle_matches_reference_fixture(golden_dir, tag):
+    """O.get_loss_refine (restatement of the refiner branch of get_loss, losses.py:107-178) vs the value and the gradients
+    the unmodified reference function produced (tests/golden/get_loss_refine.npz)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_get_loss", os.path.join(os.path.dirname(golden_dir), "..", "oracle", "make_golden_get_loss.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = np.load(os.path.join(golden_dir, "get_loss_refine.npz"))
+    output, target, attns, refine, deep = gen.inputs()
+    leaves = [output.requires_grad_(True)] + [a.requires_grad_(True) for a in attns] + [refine.requires_grad_(True)]
+    loss = O.get_loss_refine(leaves[0], deep, target, g[tag + ":wmask"].tolist(), leaves[1:4], leaves[4],
+                             [bool(v) for v in g[tag + ":label_t"]], aux_weight=0.7, weight_feature=0.3)
+    loss.backward()
+    assert abs(loss.item() - float(g[tag + ":loss"])) < 1e-6
+    for name, t in zip(["output", "attn0", "attn1", "attn2", "refine"], leaves):
+        ref = torch.from_numpy(g[tag + ":grad:" + name])
+        assert (t.grad - ref).abs().max().item() < 1e-6 * max(1.0, ref.abs().max().item()) + 1e-9, name
