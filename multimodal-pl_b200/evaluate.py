@@ -77,9 +77,12 @@ def tile_origins(image_size, tile_size):
 def _tile_logits(net_list, img, task_id, tta):
     pred = multi_net(net_list, img, task_id)
     if tta:                                                                       # reference :247-255
+        # a network may hand out a static buffer that its next call overwrites (engine.GraphedInference): take a
+        # private copy of the un-flipped prediction before asking for the next one
+        pred = pred.clone()
         for dims in ([2], [3], [4], [2, 3], [2, 4], [3, 4], [2, 3, 4]):
-            pred = pred + torch.flip(multi_net(net_list, torch.flip(img, dims), task_id), dims)
-        pred = pred / 8.
+            pred += torch.flip(multi_net(net_list, torch.flip(img, dims), task_id), dims)
+        pred /= 8.
     return pred
 
 

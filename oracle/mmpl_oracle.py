@@ -48,6 +48,40 @@ def gn_relu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: in
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Storage-precision emulation (test infrastructure for the bf16 production path; nothing in the reference)
+# ----------------------------------------------------------------------------------------------------------------
+# The reference computes everything in fp32.  The B200 path stores every activation tensor between
+# kernels -- and every gradient tensor between backward kernels -- in bf16 while accumulating in fp32, and feeds the
+# tensor cores bf16 copies of the standardised weights.  ``store_dtype=torch.bfloat16`` makes this oracle round at
+# exactly those points (round-to-nearest-even, like the kernels' cvt.rn.bf16x2.f32), so the CUDA path can be held to a
+# real per-tensor gradient tolerance instead of the "a few ReLU gates resolve differently" argument: both sides then
+# see the same stored values up to fp32 summation order.
+
+
+class _RoundStored(torch.autograd.Function):
+    """y = round_to(dtype)(x) in the forward pass; the incoming gradient is rounded the same way in the backward pass
+    (a tensor that is stored in bf16 has its gradient stored in bf16 by the backward kernel that produces it)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype, round_grad):
+        ctx.dtype, ctx.round_grad = dtype, round_grad
+        return x.to(dtype).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.round_grad:
+            g = g.to(ctx.dtype).to(g.dtype)
+        return g, None, None
+
+
+def stored(x: torch.Tensor, store_dtype: Optional[torch.dtype], round_grad: bool = True) -> torch.Tensor:
+    """Identity for ``store_dtype`` None / float32, else the value as it is after a round trip through HBM."""
+    if store_dtype is None or store_dtype == x.dtype:
+        return x
+    return _RoundStored.apply(x, store_dtype, round_grad)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # Topology of unet3D_baseline                                                            unet3D.py:585-718
 # ----------------------------------------------------------------------------------------------------------------
 
@@ -150,19 +184,27 @@ def synth_feam3_state_dict(num_classes: int = 16, seed: int = 0):
     return sd, tokens
 
 
-def no_bottleneck(x: torch.Tensor, sd: Dict[str, torch.Tensor], p: str, stride: int) -> torch.Tensor:
+def no_bottleneck(x: torch.Tensor, sd: Dict[str, torch.Tensor], p: str, stride: int,
+                  store_dtype: Optional[torch.dtype] = None, groups: int = 16) -> torch.Tensor:
     """NoBottleneck.forward (unet3D.py:56-73): pre-activation residual block; the residual branch is
-    downsample(x) = WSconv1x1(relu(GN(x))) computed from the block input when present (:68-69, :643-649)."""
-    out = gn_relu(x, sd[p + "gn1.weight"], sd[p + "gn1.bias"])
-    out = ws_conv3d(out, sd[p + "conv1.weight"], stride, 1)
-    out = gn_relu(out, sd[p + "gn2.weight"], sd[p + "gn2.bias"])
-    out = ws_conv3d(out, sd[p + "conv2.weight"], 1, 1)
+    downsample(x) = WSconv1x1(relu(GN(x))) computed from the block input when present (:68-69, :643-649).
+    ``store_dtype``: see ``stored`` (each tensor a kernel writes to HBM is rounded; the residual is added to the fp32
+    accumulator before the one rounding of the block output)."""
+    st = store_dtype
+
+    def conv(a, key, s_, pad):
+        return F.conv3d(a, stored(ws_weight(sd[key]), st, round_grad=False), None, s_, pad, 1, 1)
+
+    out = stored(gn_relu(x, sd[p + "gn1.weight"], sd[p + "gn1.bias"], groups), st)
+    out = stored(conv(out, p + "conv1.weight", stride, 1), st)
+    out = stored(gn_relu(out, sd[p + "gn2.weight"], sd[p + "gn2.bias"], groups), st)
+    out = conv(out, p + "conv2.weight", 1, 1)
     if (p + "downsample.2.weight") in sd:
-        res = gn_relu(x, sd[p + "downsample.0.weight"], sd[p + "downsample.0.bias"])
-        res = ws_conv3d(res, sd[p + "downsample.2.weight"], stride, 0)
+        res = stored(gn_relu(x, sd[p + "downsample.0.weight"], sd[p + "downsample.0.bias"], groups), st)
+        res = stored(conv(res, p + "downsample.2.weight", stride, 0), st)
     else:
         res = x
-    return out + res
+    return stored(out + res, st)
 
 
 def upsample2x_add(x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
@@ -171,21 +213,33 @@ def upsample2x_add(x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
     return F.interpolate(x, scale_factor=2, mode="trilinear") + skip
 
 
-def unet3d_forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, base: int = 32, feats: Optional[dict] = None
-                   ) -> torch.Tensor:
+def unet3d_forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, base: int = 32, feats: Optional[dict] = None,
+                   store_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """unet3D_baseline.forward (unet3D.py:663-718), returning the logits [B, num_classes, D, H, W].  When ``feats``
-    is a dict, the stage outputs are stored in it (debugging aid for gradient localisation)."""
+    is a dict, the stage outputs are stored in it (debugging aid for gradient localisation).
+    ``store_dtype=torch.bfloat16`` emulates the storage precision of the B200 bf16 path (see ``stored``); the default
+    is the reference's fp32 arithmetic."""
     spec = {p: (cin, cout, s) for p, cin, cout, s in backbone_spec(base)}
+    st = store_dtype
 
     def blk(x, p):
-        return no_bottleneck(x, sd, p, spec[p][2])
+        return no_bottleneck(x, sd, p, spec[p][2], st)
+
+    def conv(x, w, stride, padding):           # Conv3d.forward; the tensor cores read a bf16 copy of the weight
+        return stored(F.conv3d(x, stored(ws_weight(w), st, round_grad=False), None, stride, padding, 1, 1), st)
+
+    def act(x, gamma, beta):
+        return stored(gn_relu(x, gamma, beta), st)
+
+    def up(x, skip):
+        return stored(upsample2x_add(x, skip), st)
 
     def keep(name, t):
         if feats is not None:
             feats[name] = t
         return t
 
-    x = keep("stem", ws_conv3d(image, sd["conv1.weight"], 1, 1))                      # :666
+    x = keep("stem", conv(image, sd["conv1.weight"], 1, 1))                            # :666
     x = keep("layer0", blk(x, "layer0.0."))
     skip0 = x                                                                         # :667-668
     x = keep("layer1", blk(blk(x, "layer1.0."), "layer1.1."))
@@ -195,14 +249,13 @@ def unet3d_forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, base: int =
     x = keep("layer3", blk(blk(x, "layer3.0."), "layer3.1."))
     skip3 = x
     x = keep("layer4", blk(blk(x, "layer4.0."), "layer4.1."))                         # :679
-    x = keep("fusion", ws_conv3d(gn_relu(x, sd["fusionConv.0.weight"], sd["fusionConv.0.bias"]),
-                                 sd["fusionConv.2.weight"], 1, 0))
-    x = keep("x8", blk(keep("up8", upsample2x_add(x, skip3)), "x8_resb.0."))          # :686-688
-    x = keep("x4", blk(keep("up4", upsample2x_add(x, skip2)), "x4_resb.0."))
-    x = keep("x2", blk(keep("up2", upsample2x_add(x, skip1)), "x2_resb.0."))
-    x = keep("x1", blk(keep("up1", upsample2x_add(x, skip0)), "x1_resb.0."))          # :707-709
-    x = gn_relu(x, sd["precls_conv.0.weight"], sd["precls_conv.0.bias"])
-    return F.conv3d(x, sd["precls_conv.2.weight"], sd["precls_conv.2.bias"])         # :629-633, :713
+    x = keep("fusion", conv(act(x, sd["fusionConv.0.weight"], sd["fusionConv.0.bias"]), sd["fusionConv.2.weight"], 1, 0))
+    x = keep("x8", blk(keep("up8", up(x, skip3)), "x8_resb.0."))                      # :686-688
+    x = keep("x4", blk(keep("up4", up(x, skip2)), "x4_resb.0."))
+    x = keep("x2", blk(keep("up2", up(x, skip1)), "x2_resb.0."))
+    x = keep("x1", blk(keep("up1", up(x, skip0)), "x1_resb.0."))                      # :707-709
+    x = act(x, sd["precls_conv.0.weight"], sd["precls_conv.0.bias"])
+    return F.conv3d(x, sd["precls_conv.2.weight"], sd["precls_conv.2.bias"])         # :629-633, :713 (fp32 logits)
 
 
 def eam_attention_logits(sd: Dict[str, torch.Tensor], p: str, x_tokens: torch.Tensor, class_token: torch.Tensor,
@@ -436,9 +489,13 @@ def tile_grid(image_size: Sequence[int], tile: Sequence[int]) -> List[Tuple[int,
     return [(d, y, x) for d in ds for y in ys for x in xs]
 
 
-def predict_sliding(net, image: np.ndarray, tile: Sequence[int], classes: int) -> torch.Tensor:
-    """predict_sliding without TTA (evaluate_amos.py:211-279): Gaussian-weighted logit accumulation in float64,
-    normalised by the accumulated weights.  ``net(img)`` maps a [B,1,d,h,w] fp32 tensor to logits."""
+_TTA_FLIPS = ([2], [3], [4], [2, 3], [2, 4], [3, 4], [2, 3, 4])
+
+
+def predict_sliding(net, image: np.ndarray, tile: Sequence[int], classes: int, tta: bool = False) -> torch.Tensor:
+    """predict_sliding (evaluate_amos.py:211-279): Gaussian-weighted logit accumulation in float64, normalised by
+    the accumulated weights.  ``net(img)`` maps a [B,1,d,h,w] fp32 tensor to logits.  ``tta``: mean over the identity
+    and the seven axis-flip combinations, each prediction flipped back (:247-255)."""
     g = torch.from_numpy(gaussian_importance(tile))
     B, _, D, H, W = image.shape
     full = torch.zeros((B, classes, D, H, W), dtype=torch.float64)
@@ -447,6 +504,10 @@ def predict_sliding(net, image: np.ndarray, tile: Sequence[int], classes: int) -
         d2, y2, x2 = d1 + tile[0], y1 + tile[1], x1 + tile[2]
         img = torch.from_numpy(image[:, :, d1:d2, y1:y2, x1:x2])
         pred = net(img).float().cpu()
+        if tta:
+            for dims in _TTA_FLIPS:
+                pred = pred + torch.flip(net(torch.flip(img, dims)).float().cpu(), dims)
+            pred = pred / 8.
         pred = pred * g
         count[:, :, d1:d2, y1:y2, x1:x2] += g
         full[:, :, d1:d2, y1:y2, x1:x2] += pred

@@ -13,6 +13,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a); run with -m gpu on the GPU box")
+    config.addinivalue_line("markers", "slow: full-extent parity run (tens of seconds of CPU oracle time)")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -181,6 +181,22 @@ def test_gn_backward_reduction_fused_into_dgrad_epilogue(mm, cin, cout, k, strid
 
     gx_f, gp_f, n_f = run(True)
     gx_u, gp_u, n_u = run(False)
+    # ---- the oracle (bf16-storage emulation, oracle/mmpl_oracle.py::stored): the fused epilogue is what bench.py times,
+    # so it is held to the reference arithmetic itself, not only to the unfused kernels
+    st = torch.bfloat16
+    xr = x.clone().requires_grad_(True)
+    pr = [t.clone().requires_grad_(True) for t in (g1, b1, g2, b2)]
+    a1r = O.stored(O.gn_relu(xr, pr[0], pr[1]), st)
+    yr = F.conv3d(a1r, O.stored(O.ws_weight(w1), st, round_grad=False), None, stride, k // 2)
+    if dual:
+        a2r = O.stored(O.gn_relu(xr, pr[2], pr[3]), st)
+        yr = yr + F.conv3d(a2r, O.stored(O.ws_weight(w2), st, round_grad=False), None, stride, 0)
+    yr.backward(_rand(tuple(yr.shape), 8).bfloat16().float())
+    gx_o = O.stored(xr.grad, st)
+    assert rel(gx_f, gx_o) < 5e-2 and rel(gx_u, gx_o) < 5e-2, (rel(gx_f, gx_o), rel(gx_u, gx_o))
+    for i, (a, b) in enumerate(zip(gp_f, pr)):
+        c = (a.double().flatten() @ b.grad.double().flatten() / (a.double().norm() * b.grad.double().norm())).item()
+        assert rel(a, b.grad) < 5e-2 and c > 0.999, (i, rel(a, b.grad), c)
     assert n_f == n_u - 1, (n_f, n_u)          # exactly the reduction launch disappeared
     assert rel(gx_f, gx_u) < 2e-3               # dx is stored in bf16 (rounding of ~identical fp32 values)
     # the fused sums see xhat through a = relu(gn(x)) as stored in bf16 (relative rounding 2^-9 per element, random):

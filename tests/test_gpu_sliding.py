@@ -104,3 +104,37 @@ def test_unet_sliding_window_fp32_argmax_identical():
     finally:
         mm.set_conv_algo("auto")
         mm.set_compute_dtype(torch.bfloat16)
+
+
+def test_tta_eight_flip_average_matches_oracle_and_graphed_equals_eager():
+    """predict_sliding(tta=True) (reference evaluate_amos.py:247-255): mean over the identity and the seven axis-flip
+    combinations.  fp32 exact kernels vs the CPU oracle (rel-L2 <= 1e-5), and the CUDA-graph network
+    (engine.GraphedInference hands out ONE static output buffer that every replay overwrites) must give the same volume
+    as the eager network -- the un-flipped prediction has to be copied before the next replay."""
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.engine import GraphedInference
+    from multimodal_pl_b200.evaluate import predict_sliding
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    mm.set_compute_dtype(torch.float32)
+    mm.set_conv_algo("direct")
+    try:
+        sd = O.synth_state_dict(32, 16, 3)
+        model = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True).cuda().eval()
+        model.load_state_dict(sd)
+        vol = O.synth_patch((1, 1, 24, 40, 32), 31, "mri")
+        tile = (16, 32, 32)
+        with torch.no_grad():
+            ref = O.predict_sliding(lambda im: O.unet3d_forward(sd, im), vol.numpy(), tile, 16, tta=True)
+            plain = O.predict_sliding(lambda im: O.unet3d_forward(sd, im), vol.numpy(), tile, 16, tta=False)
+        eager = predict_sliding(None, [lambda im, tid: model(im)], vol.numpy(), tile, 16, None, tta=True)
+        err = ((eager.cpu() - ref).norm() / ref.norm()).item()
+        assert err < 1e-5, err
+        assert ((plain - ref).norm() / ref.norm()).item() > 1e-3      # the network is not flip-equivariant: TTA matters
+        net = GraphedInference(model, vol[:, :, :16, :32, :32].cuda().contiguous())
+        graphed = predict_sliding(None, [net], vol.numpy(), tile, 16, None, tta=True)
+        # identical kernels; only the order of the fp64 statistics atomics may differ between a replay and an eager run
+        assert ((graphed - eager).norm() / eager.norm()).item() < 1e-6
+    finally:
+        mm.set_conv_algo("auto")
+        mm.set_compute_dtype(torch.bfloat16)

@@ -185,3 +185,50 @@ def test_get_loss_refine_oracle_matches_reference_fixture(golden_dir, tag):
     for name, t in zip(["output", "attn0", "attn1", "attn2", "refine"], leaves):
         ref = torch.from_numpy(g[tag + ":grad:" + name])
         assert (t.grad - ref).abs().max().item() < 1e-6 * max(1.0, ref.abs().max().item()) + 1e-9, name
+
+
+def test_bf16_storage_emulation_and_its_noise_floor(golden_dir):
+    """``store_dtype=torch.bfloat16`` (the storage precision of the B200 production path, emulated on the CPU):
+    (1) with ``store_dtype=None`` the oracle still reproduces the reference fixture exactly;
+    (2) the bf16-storage logits stay within the 2e-2 bf16 tolerance of the reference's fp32 logits;
+    (3) the noise floor the GPU parity tests are calibrated on: the SAME bf16-storage oracle with its convolutions
+        accumulated in fp64 instead of fp32 (a different but equally valid summation order) already differs by more than
+        1e-3 in the logits and by more than 5e-2 in the deepest gradient tensors, while the tensors next to the loss agree
+        to 1e-3 -- i.e. whole-network per-tensor gradient agreement at 5e-2 is not a property ANY two bf16-storage
+        implementations have at random initialisation; tests/test_gpu_parity_strict.py therefore demands 5e-2 / cosine
+        0.999 per residual block (teacher-forced) and "3 x this floor" for the whole network."""
+    import torch.nn.functional as F
+
+    g = _load(golden_dir, "unet_b1.npz")
+    shape, seed = tuple(int(v) for v in g["shape"]), int(g["seed"])
+    x = O.synth_patch(shape, 1000 + seed, "ct")
+    lab = O.synth_labels((shape[0],) + shape[2:], 2000 + seed, 16, 32)
+    w16 = g["w16"].tolist()
+    cm = O.remap_unsupervised(lab, w16).squeeze(1)
+
+    def run(store, fp64_convs=False):
+        sd = {k: v.clone().requires_grad_(True) for k, v in O.synth_state_dict(32, 16, seed).items()}
+        orig = F.conv3d
+        if fp64_convs:
+            F.conv3d = lambda i, w, b=None, *a, **k: orig(i.double(), w.double(), None if b is None else b.double(), *a,
+                                                         **k).to(i.dtype)
+        try:
+            lg = O.unet3d_forward(sd, x, store_dtype=store)
+            O.partial_label_loss(lg, cm, w16).backward()
+        finally:
+            F.conv3d = orig
+        return lg.detach(), {k: v.grad for k, v in sd.items()}
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+    ref = torch.from_numpy(g["logits"])
+    l32, _ = run(None)
+    assert torch.equal(l32, ref)
+    lb, gb = run(torch.bfloat16)
+    assert 1e-3 < rel(lb, ref) < 2e-2
+    lt, gt = run(torch.bfloat16, fp64_convs=True)
+    assert rel(lt, lb) > 1e-3
+    floors = {k: rel(gt[k], gb[k]) for k in gb}
+    assert max(floors.values()) > 5e-2, max(floors.values())
+    assert floors["precls_conv.2.weight"] < 1e-3 and floors["precls_conv.2.bias"] < 1e-3
