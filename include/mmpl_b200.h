@@ -160,21 +160,29 @@ int mmpl_upsample2x_bwd(const void* dy, void* dx_lo, int n, int d, int h, int w,
                         mmpl_stream_t stream);
 
 /* ---- partial-label loss: EDiceLoss_partial.forward + DiceLoss.forward, loss_partial.py:38-57, :71-99 ----------
- * logits [N,C,S] fp32, target [N,S] fp32 class ids, class_weight [C] fp32 (= mask[0]); lut (may be NULL) is the
- * 16-entry cmask remap of train_amos_atlas_final.py:252-255 applied to the target on the fly.
- * sums: double [4][C] = I, Z, Y, E (zeroed by the call); loss: one fp32.  classes <= 32. */
-int mmpl_partial_loss_fwd(const float* logits, const float* target, const float* class_weight, const float* lut,
-                          double* sums, float* loss, int n, int64_t spatial, int classes, int uce,
-                          mmpl_stream_t stream);
-int mmpl_partial_loss_bwd(const float* logits, const float* target, const float* class_weight, const float* lut,
-                          const double* sums, const float* grad_out /*device scalar*/, float* dlogits, int n,
-                          int64_t spatial, int classes, int uce, mmpl_stream_t stream);
+ * logits [N,C,S] fp32; target [N,S] class ids, fp32 like the reference's label tensors (target_is_u8 = 0) or uint8
+ * (target_is_u8 = 1; a quarter of the bytes over PCIe and HBM).
+ * per_sample = 0 (the reference): Dice sums pooled over batch and voxels, class_weight [C] = mask[0] (:87, :92); lut
+ *   (may be NULL) [C] is the cmask remap of train_amos_atlas_final.py:252-255 applied to the target on the fly.
+ * per_sample = 1 (mixed CT/MRI batches): class_weight [N][C] and lut [N][C]; the reference formula is
+ *   evaluated per sample with that sample's weights (= the reference called once per sample) and averaged over N.
+ * sums: double [G][4][C] = I, Z, Y, E per group (G = N when per_sample else 1) followed by ONE more double the forward
+ * uses as its last-block ticket, i.e. a workspace of G*4*C+1 doubles (zeroed by the call; per call, so launches on
+ * different streams / devices never share state and nothing is allocated by the library); loss: one fp32.
+ * classes <= 32.  16-byte loads (4 voxels per thread and class plane) when S % 4 == 0 and the planes are aligned. */
+int mmpl_partial_loss_fwd(const float* logits, const void* target, int target_is_u8, const float* class_weight,
+                          const float* lut, int per_sample, double* sums, float* loss, int n, int64_t spatial,
+                          int classes, int uce, mmpl_stream_t stream);
+int mmpl_partial_loss_bwd(const float* logits, const void* target, int target_is_u8, const float* class_weight,
+                          const float* lut, int per_sample, const double* sums,
+                          const float* grad_out /*device scalar*/, float* dlogits, int n, int64_t spatial, int classes,
+                          int uce, mmpl_stream_t stream);
 
 /* ---- binary Dice over a voxel gate (+ BCE-with-logits): DiceLoss._dice_loss / EDiceLoss_full2.forward,
  * loss_partial.py:24-36, :150-170 (the pseudo-label terms of get_loss, losses.py:165-176) --------------------------
  * x, target, gate: fp32 [voxels]; gate may be NULL (= all voxels) and is a 0/1 mask otherwise.  sigmoid = 1: the score
- * is sigmoid(x), else x itself.  uce = 1 adds mean BCE-with-logits over ALL voxels.  sums: double[4] = {I, Y, Z, E},
- * written by fwd and read by bwd.  dtarget may be NULL. */
+ * is sigmoid(x), else x itself.  uce = 1 adds mean BCE-with-logits over ALL voxels.  sums: double[5] = {I, Y, Z, E,
+ * last-block ticket}, written by fwd and read by bwd.  dtarget may be NULL. */
 int mmpl_masked_dice_fwd(const float* x, const float* target, const float* gate, double* sums, float* loss,
                          int64_t voxels, int sigmoid, int uce, mmpl_stream_t stream);
 int mmpl_masked_dice_bwd(const float* x, const float* target, const float* gate, const double* sums,
@@ -188,14 +196,26 @@ int mmpl_sgd_step(float* p, const float* grad, float* buf, int64_t count, const 
                   float weight_decay, float grad_scale, int first_step, mmpl_stream_t stream);
 
 /* ---- sliding-window blend + argmax/Dice: predict_sliding evaluate_amos.py:261-279, get_dice :128-141 ----------
- * acc [C][D][H][W] and wsum [D][H][W] in `acc_dtype` bytes per element (4 = fp32, 8 = fp64 like the reference). */
+ * acc and wsum [D][H][W] in `acc_bytes` per element (4 = fp32, 8 = fp64 like the reference).  acc is class-major
+ * [C][D][H][W] (d_outer = 0, the layout predict_sliding returns) or depth-major [D][C][H][W] (d_outer = 1: a depth slab is
+ * one contiguous block, which the multi-GPU path reduce-scatters along D).  wsum may be NULL (not accumulated). */
 int mmpl_sw_blend(void* acc, void* wsum, const float* tile_logits /*[C][td][th][tw]*/, const float* gauss, int c,
-                  int d, int h, int w, int td, int th, int tw, int d0, int h0, int w0, int acc_bytes,
+                  int d, int h, int w, int td, int th, int tw, int d0, int h0, int w0, int acc_bytes, int d_outer,
                   mmpl_stream_t stream);
-/* wsum may be NULL (acc already normalised).  out_logits (may be NULL) [C][D][H][W] fp32 = acc/wsum; argmax uint8 [D][H][W]; counts int64 [3][C] = |P&T|,|P|,|T|
- * (zeroed by the call) against label fp32 [D][H][W] (may be NULL). */
-int mmpl_sw_finalize(const void* acc, const void* wsum, const float* label, float* out_logits, uint8_t* argmax,
-                     long long* counts, int c, int64_t voxels, int acc_bytes, mmpl_stream_t stream);
+/* Classifier + blend in one kernel (bf16 activations a [td*th*tw][cin], cin 32/64, fp32 acc): acc += gauss * (a W^T + b)
+ * at the tile origin read from DEVICE memory (origin_dev = {d0, h0, w0}), so one captured CUDA graph serves every tile.
+ * Replaces mmpl_cls_fwd + mmpl_sw_blend on the inference path (no fp32 logits tile in HBM). */
+int mmpl_cls_blend(const void* a, const float* wc /*[C][cin]*/, const float* bias, const float* gauss, float* acc,
+                   float* wsum /*may be NULL*/, const int* origin_dev, int classes, int d, int h, int w, int td, int th,
+                   int tw, int cin, int d_outer, mmpl_stream_t stream);
+/* normalise -> argmax -> Dice counts over `voxels` = Dl*plane voxels.  plane = 0: acc is class-major [C][voxels];
+ * plane = H*W: acc is depth-major [Dl][C][plane] (any depth slab).  wsum may be NULL (acc already normalised; the fp32
+ * fast path never divides -- the argmax does not depend on a positive normaliser).  label fp32 or uint8 class ids.
+ * out_logits (may be NULL) [C][voxels] fp32 = acc/wsum; argmax uint8 [voxels]; counts int64 [3][C] = |P&T|,|P|,|T|
+ * (zeroed by the call; pass NULL with label NULL to skip the metrics). */
+int mmpl_sw_finalize(const void* acc, const void* wsum, const void* label, int label_is_u8, float* out_logits,
+                     uint8_t* argmax, long long* counts, int c, int64_t voxels, int64_t plane, int acc_bytes,
+                     mmpl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -42,13 +42,15 @@ _SIGNATURES = {
     "mmpl_gn_relu_bwd": [_ptr] * 15 + [_c_int, _c_int, _c_i64, _c_int, _c_int, _c_f32, _c_int, _ptr],
     "mmpl_upsample2x_add_fwd": [_ptr, _ptr, _ptr] + [_c_int] * 6 + [_ptr, _ptr],
     "mmpl_upsample2x_bwd": [_ptr, _ptr] + [_c_int] * 6 + [_ptr],
-    "mmpl_partial_loss_fwd": [_ptr] * 6 + [_c_int, _c_i64, _c_int, _c_int, _ptr],
-    "mmpl_partial_loss_bwd": [_ptr] * 7 + [_c_int, _c_i64, _c_int, _c_int, _ptr],
+    "mmpl_partial_loss_fwd": [_ptr, _ptr, _c_int, _ptr, _ptr, _c_int, _ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _ptr],
+    "mmpl_partial_loss_bwd": [_ptr, _ptr, _c_int, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _c_i64, _c_int, _c_int,
+                              _ptr],
     "mmpl_masked_dice_fwd": [_ptr] * 5 + [_c_i64, _c_int, _c_int, _ptr],
     "mmpl_masked_dice_bwd": [_ptr] * 7 + [_c_i64, _c_int, _c_int, _ptr],
     "mmpl_sgd_step": [_ptr, _ptr, _ptr, _c_i64, _ptr, _c_f32, _c_f32, _c_f32, _c_int, _ptr],
-    "mmpl_sw_blend": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 11 + [_ptr],
-    "mmpl_sw_finalize": [_ptr] * 6 + [_c_int, _c_i64, _c_int, _ptr],
+    "mmpl_sw_blend": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 12 + [_ptr],
+    "mmpl_cls_blend": [_ptr] * 7 + [_c_int] * 10 + [_ptr],
+    "mmpl_sw_finalize": [_ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _c_i64, _c_i64, _c_int, _ptr],
 }
 _RESTYPES = {"mmpl_last_error": ctypes.c_char_p, "mmpl_launch_count": ctypes.c_uint64,
              "mmpl_conv3d_wgrad_workspace": ctypes.c_size_t, "mmpl_stem_conv_wgrad_workspace": ctypes.c_size_t}

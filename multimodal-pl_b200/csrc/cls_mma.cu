@@ -108,6 +108,104 @@ cls_fwd_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward + blend
+// Sliding-window inference (predict_sliding, evaluate_amos.py:244-276): the classifier of a tile is immediately
+// weighted with the Gaussian importance map and accumulated into the volume accumulator -- acc[c][voxel] += g * logit --
+// instead of writing a 151 MB fp32 logits tile that a blend kernel reads back.  Same MMA mainloop as cls_fwd; the
+// epilogue is a read-modify-write of the fp32 accumulator (each element is touched by exactly one thread per launch and
+// launches of one volume are stream-ordered, so no atomics).  The tile origin lives in DEVICE memory so that one captured
+// CUDA graph serves every tile of the volume.
+struct BlendGeo {
+  float* acc;            // [C][D][H][W], or [D][C][H][W] when d_outer
+  float* wsum;           // [D][H][W] or NULL (argmax / Dice do not need the normaliser)
+  const float* gauss;    // [td][th][tw]
+  const int* origin;     // device: d0, h0, w0
+  int D, H, W, td, th, tw, d_outer;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(256)
+cls_blend_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ wc, const float* __restrict__ bias,
+                     BlendGeo q, int classes) {
+  constexpr int KS = CIN / 16;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  uint32_t bh[KS][2][2], bl[KS][2][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = nt * 8 + g, k = ks * 16 + h * 8 + 2 * t;
+        const float w0 = c < classes ? wc[c * CIN + k] : 0.f, w1 = c < classes ? wc[c * CIN + k + 1] : 0.f;
+        split2(w0, w1, bh[ks][nt][h], bl[ks][nt][h]);
+      }
+  float bia[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) bia[nt][j] = (nt * 8 + 2 * t + j) < classes ? bias[nt * 8 + 2 * t + j] : 0.f;
+  const int d0 = __ldg(q.origin), h0 = __ldg(q.origin + 1), w0 = __ldg(q.origin + 2);
+  const int S = q.td * q.th * q.tw;
+  const int64_t plane = static_cast<int64_t>(q.H) * q.W;
+  const int nchunks = (S + 31) / 32;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warps) {
+    const int s0 = chunk * 32;
+    float acc[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+        acc[mt][nt][0] = acc[mt][nt][2] = bia[nt][0], acc[mt][nt][1] = acc[mt][nt][3] = bia[nt][1];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r0 = s0 + mt * 16 + g, r1 = r0 + 8;
+      const bool ok0 = r0 < S, ok1 = r1 < S;
+      uint32_t af[KS][4];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int k = ks * 16 + 2 * t;
+        af[ks][0] = ok0 ? *reinterpret_cast<const uint32_t*>(a + static_cast<int64_t>(r0) * CIN + k) : 0u;
+        af[ks][1] = ok1 ? *reinterpret_cast<const uint32_t*>(a + static_cast<int64_t>(r1) * CIN + k) : 0u;
+        af[ks][2] = ok0 ? *reinterpret_cast<const uint32_t*>(a + static_cast<int64_t>(r0) * CIN + k + 8) : 0u;
+        af[ks][3] = ok1 ? *reinterpret_cast<const uint32_t*>(a + static_cast<int64_t>(r1) * CIN + k + 8) : 0u;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          mma_bf16(acc[mt][nt], af[ks][0], af[ks][1], af[ks][2], af[ks][3], bh[ks][nt][0], bh[ks][nt][1]);
+          mma_bf16(acc[mt][nt], af[ks][0], af[ks][1], af[ks][2], af[ks][3], bl[ks][nt][0], bl[ks][nt][1]);
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = s0 + mt * 16 + g + half * 8;
+        if (r >= S) continue;
+        const int x = r % q.tw, yz = r / q.tw, y = yz % q.th, z = yz / q.th;
+        const int vd = d0 + z, vh = h0 + y, vw = w0 + x;
+        if (vd >= q.D || vh >= q.H || vw >= q.W || vd < 0 || vh < 0 || vw < 0) continue;    // memory safety only
+        const float gv = __ldg(q.gauss + r);
+        const int64_t o = static_cast<int64_t>(vh) * q.W + vw;
+        if (q.wsum != nullptr && t == 0) q.wsum[vd * plane + o] += gv;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c = nt * 8 + 2 * t + j;
+            if (c < classes) {
+              float* dst = q.acc + (q.d_outer ? (static_cast<int64_t>(vd) * classes + c) * plane + o
+                                              : (static_cast<int64_t>(c) * q.D + vd) * plane + o);
+              *dst += gv * acc[mt][nt][half * 2 + j];
+            }
+          }
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ backward
 // One pass over dlogits and a per 16-voxel tile (one tile per warp iteration):
 //   dA[v][k]  = sum_c dl[c][v] W[c][k]       M = voxels, N = CIN, K = 16 classes   (dl hi/lo x W hi/lo, 3 MMAs)
@@ -304,6 +402,34 @@ int cls_fwd_mma(const void* a, const float* wc, const float* bias, float* logits
     cls_fwd_mma_kernel<64><<<blocks, 256, 0, s>>>(ap, wc, bias, logits, n, spatial, classes);
   return MMPL_OK;
 }
+
+}  // namespace mmpl
+
+extern "C" int mmpl_cls_blend(const void* a, const float* wc, const float* bias, const float* gauss, float* acc,
+                              float* wsum, const int* origin_dev, int classes, int d, int h, int w, int td, int th,
+                              int tw, int cin, int d_outer, mmpl_stream_t stream) {
+  using namespace mmpl;
+  MMPL_REQUIRE(cin == 32 || cin == 64, MMPL_E_UNSUPPORTED, "cls_blend: cin=%d (32 or 64)", cin);
+  MMPL_REQUIRE(classes >= 1 && classes <= 16, MMPL_E_SHAPE, "cls_blend: classes=%d (1..16)", classes);
+  MMPL_REQUIRE(td > 0 && th > 0 && tw > 0 && td <= d && th <= h && tw <= w, MMPL_E_SHAPE,
+               "cls_blend: tile (%d,%d,%d) vs volume (%d,%d,%d)", td, th, tw, d, h, w);
+  MMPL_REQUIRE(a && wc && bias && gauss && acc && origin_dev, MMPL_E_SHAPE, "cls_blend: null argument");
+  const int64_t S = static_cast<int64_t>(td) * th * tw;
+  MMPL_REQUIRE(S < (1ll << 31), MMPL_E_SHAPE, "cls_blend: tile too large");
+  BlendGeo q{acc, wsum, gauss, origin_dev, d, h, w, td, th, tw, d_outer};
+  const int64_t chunks = (S + 31) / 32;
+  const int blocks = static_cast<int>(std::min<int64_t>((chunks + 7) / 8, static_cast<int64_t>(num_sms()) * 8));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(a);
+  if (cin == 32)
+    cls_blend_mma_kernel<32><<<blocks, 256, 0, s>>>(ap, wc, bias, q, classes);
+  else
+    cls_blend_mma_kernel<64><<<blocks, 256, 0, s>>>(ap, wc, bias, q, classes);
+  MMPL_CHECK_LAUNCH("cls_blend");
+  return MMPL_OK;
+}
+
+namespace mmpl {
 
 // dwc / dbias must be zero on entry
 int cls_bwd_mma(const void* a, const float* wc, const float* dlogits, void* da, float* dwc, float* dbias,

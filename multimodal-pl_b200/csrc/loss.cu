@@ -19,6 +19,7 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// a label value -> class id in [0, C) or -1 (not a class id); `lut` is the per-sample cmask remap
 __device__ __forceinline__ int class_of(float tv, const float* lut, int C) {
   int ti = static_cast<int>(tv);
   if (static_cast<float>(ti) != tv || ti < 0 || ti >= C) return -1;
@@ -36,17 +37,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// softmax over the class axis, in registers.  exp(z - mx) as one FMA + one MUFU: 2^(z*log2(e) - mx*log2(e)),
+// ex2.approx (max rel. error 2^-22; the arguments are <= 0 so flush-to-zero only affects probabilities below 1e-38).
 template <int MAXC>
-__device__ __forceinline__ void softmax_regs(const float* __restrict__ logits, int64_t base, int64_t S, int C,
-                                             float (&p)[MAXC]) {
+__device__ __forceinline__ void softmax_inplace(float (&p)[MAXC], int C) {
   float mx = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < MAXC; ++c) {
-    p[c] = c < C ? logits[base + c * S] : -INFINITY;
-    mx = fmaxf(mx, p[c]);
-  }
-  // exp(z - mx) as one FMA + one MUFU: 2^(z*log2(e) - mx*log2(e)), ex2.approx (max rel. error 2^-22; the arguments are
-  // <= 0 so flush-to-zero only affects probabilities below 1e-38).  The kernels are instruction-issue bound.
+  for (int c = 0; c < MAXC; ++c) mx = fmaxf(mx, c < C ? p[c] : -INFINITY);
   constexpr float kLog2e = 1.4426950408889634f;
   const float mxs = mx * kLog2e;
   float sum = 0.f;
@@ -60,11 +57,55 @@ __device__ __forceinline__ void softmax_regs(const float* __restrict__ logits, i
   for (int c = 0; c < MAXC; ++c) p[c] *= inv;
 }
 
-template <int MAXC, int NTHR>
-__global__ void __launch_bounds__(NTHR, MAXC <= 16 ? 3 : 1)
-partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+// VEC consecutive voxels of one class plane / of the label volume.  VEC = 4 needs S % 4 == 0 and 16-byte aligned
+// planes (checked by the host); the loads are then 16 bytes per thread and class plane -- four times the bytes in flight
+// of the scalar form, which is what an HBM-bound kernel with a 16-deep dependent softmax needs to cover the latency.
+template <int VEC>
+struct VoxVec {
+  float v[VEC];
+  __device__ __forceinline__ void load(const float* p) {
+    if (VEC == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+      v[0] = t.x, v[1 % VEC] = t.y, v[2 % VEC] = t.z, v[3 % VEC] = t.w;
+    } else {
+      v[0] = __ldg(p);
+    }
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    if (VEC == 4)
+      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+    else
+      *p = v[0];
+  }
+};
+
+// labels: fp32 class ids like the reference's label tensors (train_amos_atlas_final.py:214) or uint8 class ids
+template <int VEC, bool TU8>
+__device__ __forceinline__ void load_labels(const void* target, int64_t idx, float (&t)[VEC]) {
+  if (TU8) {
+    const uint8_t* p = static_cast<const uint8_t*>(target) + idx;
+    if (VEC == 4) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) t[i] = static_cast<float>((w >> (8 * i)) & 0xFFu);
+    } else {
+      t[0] = static_cast<float>(__ldg(p));
+    }
+  } else {
+    VoxVec<VEC> tv;
+    tv.load(static_cast<const float*>(target) + idx);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) t[i] = tv.v[i];
+  }
+}
+
+// Sums layout: double [G][4][C] (G = N in per-sample mode, else 1) followed by the ticket slot.
+template <int MAXC, int NTHR, int VEC, bool TU8>
+__global__ void __launch_bounds__(NTHR, (MAXC <= 16 && VEC == 1) ? 2 : 1)
+partial_loss_fwd_kernel(const float* __restrict__ logits, const void* __restrict__ target,
                         const float* __restrict__ cw, const float* __restrict__ lut, double* __restrict__ sums,
-                        float* __restrict__ loss, unsigned int* __restrict__ ticket, int N, int64_t S, int C, int uce) {
+                        float* __restrict__ loss, unsigned int* __restrict__ ticket, int N, int64_t S, int C, int uce,
+                        int per_sample) {
   __shared__ float s_lut[MAXC];
   __shared__ float s_part[NTHR / 32][4 * MAXC];
   __shared__ bool s_last;
@@ -73,11 +114,15 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
   // conflict-free) take a dynamic class index, which registers cannot; Z_c and E_c stay in registers.  One slot more
   // than MAXC collects voxels whose label is not a class id.
   __shared__ float s_I[MAXC + 1][NTHR], s_Y[MAXC + 1][NTHR];
-  if (threadIdx.x < MAXC) s_lut[threadIdx.x] = (lut && threadIdx.x < C) ? lut[threadIdx.x] : static_cast<float>(threadIdx.x);
+  const int64_t n = blockIdx.y;                  // grid = (blocks per sample, N): no 64-bit division per voxel
+  const int grp = per_sample ? static_cast<int>(n) : 0;
+  const float* cw_g = cw + static_cast<int64_t>(grp) * C;
+  const float* lut_g = lut ? lut + static_cast<int64_t>(grp) * C : nullptr;
+  if (threadIdx.x < MAXC) s_lut[threadIdx.x] = (lut_g && threadIdx.x < C) ? lut_g[threadIdx.x] : static_cast<float>(threadIdx.x);
   if (threadIdx.x == 0) {
     unsigned int m = 0;
     for (int c = 0; c < C; ++c)
-      if (uce && cw[c] != 0.f) m |= 1u << c;
+      if (uce && cw_g[c] != 0.f) m |= 1u << c;
     s_ce_mask = m;
   }
 #pragma unroll
@@ -87,31 +132,42 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
   float aZ[MAXC], aE[MAXC];
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) aZ[c] = aE[c] = 0.f;
-  const int64_t total = static_cast<int64_t>(N) * S;
-  // grid = (blocks per sample, N): no 64-bit division per voxel
-  const int64_t n = blockIdx.y;
-  for (int64_t s = blockIdx.x * static_cast<int64_t>(NTHR) + threadIdx.x; s < S;
-       s += static_cast<int64_t>(gridDim.x) * NTHR) {
-    float p[MAXC];
-    softmax_regs<MAXC>(logits, n * C * S + s, S, C, p);
-    const int tc = class_of(target[n * S + s], lut ? s_lut : nullptr, C);
-    float ptc = 0.f;
+  const float* zb = logits + n * C * S;
+  const int64_t SV = S / VEC;
+  for (int64_t sv = blockIdx.x * static_cast<int64_t>(NTHR) + threadIdx.x; sv < SV;
+       sv += static_cast<int64_t>(gridDim.x) * NTHR) {
+    const int64_t s = sv * VEC;
+    VoxVec<VEC> z[MAXC];
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      if (c < C) {
-        const bool t = (c == tc);
-        ptc = t ? p[c] : ptc;
-        aZ[c] = fmaf(p[c], p[c], aZ[c]);
-        if (ce_mask & (1u << c)) {
-          // nn.BCELoss semantics: log() of the fp32 probability, clamped at -100
-          const float l = t ? logf(p[c]) : logf(1.0f - p[c]);
-          aE[c] -= fmaxf(l, -100.f);
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) z[c].load(zb + c * S + s);
+    float tv[VEC];
+    load_labels<VEC, TU8>(target, n * S + s, tv);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float p[MAXC];
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) p[c] = c < C ? z[c].v[i] : 0.f;
+      softmax_inplace<MAXC>(p, C);
+      const int tc = class_of(tv[i], lut_g ? s_lut : nullptr, C);
+      float ptc = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+          const bool t = (c == tc);
+          ptc = t ? p[c] : ptc;
+          aZ[c] = fmaf(p[c], p[c], aZ[c]);
+          if (ce_mask & (1u << c)) {
+            // nn.BCELoss semantics: log() of the fp32 probability, clamped at -100
+            const float l = t ? logf(p[c]) : logf(1.0f - p[c]);
+            aE[c] -= fmaxf(l, -100.f);
+          }
         }
       }
+      const int slot = tc >= 0 ? tc : MAXC;
+      s_I[slot][threadIdx.x] += ptc;
+      s_Y[slot][threadIdx.x] += 1.f;
     }
-    const int slot = tc >= 0 ? tc : MAXC;
-    s_I[slot][threadIdx.x] += ptc;
-    s_Y[slot][threadIdx.x] += 1.f;
   }
   float aI[MAXC], aY[MAXC];
 #pragma unroll
@@ -128,12 +184,13 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
     }
   }
   __syncthreads();
+  double* sums_g = sums + static_cast<int64_t>(grp) * 4 * C;
   if (threadIdx.x < 4 * MAXC) {
     const int k = threadIdx.x / MAXC, c = threadIdx.x % MAXC;
     if (c < C) {
       double t = 0;
       for (int w = 0; w < NTHR / 32; ++w) t += static_cast<double>(s_part[w][threadIdx.x]);
-      atomicAdd(&sums[k * C + c], t);
+      atomicAdd(&sums_g[k * C + c], t);
     }
   }
   __threadfence();
@@ -142,71 +199,105 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const float* __restric
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     __threadfence();
-    const double sm = 1e-5, nv = static_cast<double>(total);
-    double dice = 0, ce = 0;
-    for (int c = 0; c < C; ++c) {
-      const volatile double* vs = sums;
-      const double I = vs[c], Z = vs[C + c], Y = vs[2 * C + c], E = vs[3 * C + c], w = cw[c];
-      dice += w * (1.0 - (2.0 * I + sm) / (Z + Y + sm));
-      ce += w * (E / nv);
+    // pooled (reference, loss_partial.py:87,92): one group over batch and voxels, class weights = mask[0].
+    // per-sample: the reference formula evaluated per sample with that sample's weights, averaged over the batch.
+    const int G = per_sample ? N : 1;
+    const double sm = 1e-5, nv = static_cast<double>(per_sample ? S : static_cast<int64_t>(N) * S);
+    double total = 0;
+    for (int g = 0; g < G; ++g) {
+      const volatile double* vs = sums + static_cast<int64_t>(g) * 4 * C;
+      double dice = 0, ce = 0;
+      for (int c = 0; c < C; ++c) {
+        const double I = vs[c], Z = vs[C + c], Y = vs[2 * C + c], E = vs[3 * C + c], w = cw[g * C + c];
+        dice += w * (1.0 - (2.0 * I + sm) / (Z + Y + sm));
+        ce += w * (E / nv);
+      }
+      total += dice / C + (uce ? ce : 0.0);
     }
-    *loss = static_cast<float>(dice / C + (uce ? ce : 0.0));
-    *ticket = 0;
+    *loss = static_cast<float>(total / G);
   }
 }
 
-template <int MAXC>
-__global__ void __launch_bounds__(kThreads, MAXC <= 16 ? 2 : 1)
-partial_loss_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+template <int MAXC, int VEC, bool TU8>
+__global__ void __launch_bounds__(kThreads, (MAXC <= 16 && VEC == 1) ? 2 : 1)
+partial_loss_bwd_kernel(const float* __restrict__ logits, const void* __restrict__ target,
                         const float* __restrict__ cw, const float* __restrict__ lut, const double* __restrict__ sums,
                         const float* __restrict__ grad_out, float* __restrict__ dlogits, int N, int64_t S, int C,
-                        int uce) {
+                        int uce, int per_sample) {
   __shared__ float s_lut[MAXC], s_a[MAXC], s_b[MAXC], s_e[MAXC];
-  const int64_t total = static_cast<int64_t>(N) * S;   // voxels in the BCE mean
+  const int64_t n = blockIdx.y;
+  const int grp = per_sample ? static_cast<int>(n) : 0;
+  const float* lut_g = lut ? lut + static_cast<int64_t>(grp) * C : nullptr;
   if (threadIdx.x < MAXC) {
     const int c = threadIdx.x;
-    s_lut[c] = (lut && c < C) ? lut[c] : static_cast<float>(c);
+    s_lut[c] = (lut_g && c < C) ? lut_g[c] : static_cast<float>(c);
     if (c < C) {
-      const double sm = 1e-5, I = sums[c], Z = sums[C + c], Y = sums[2 * C + c], w = cw[c], go = *grad_out;
+      const double* sg = sums + static_cast<int64_t>(grp) * 4 * C;
+      const double sm = 1e-5, I = sg[c], Z = sg[C + c], Y = sg[2 * C + c], w = cw[grp * C + c];
+      const double go = static_cast<double>(*grad_out) / (per_sample ? N : 1);
+      const double nv = static_cast<double>(per_sample ? S : static_cast<int64_t>(N) * S);   // voxels in the BCE mean
       const double Dc = Z + Y + sm;
       s_a[c] = static_cast<float>(go * (w / C) * (-2.0 / Dc));
       s_b[c] = static_cast<float>(go * (w / C) * 2.0 * (2.0 * I + sm) / (Dc * Dc));
-      s_e[c] = uce ? static_cast<float>(go * w / static_cast<double>(total)) : 0.f;
+      s_e[c] = uce ? static_cast<float>(go * w / nv) : 0.f;
     } else {
       s_a[c] = s_b[c] = s_e[c] = 0.f;
     }
   }
   __syncthreads();
-  const int64_t n = blockIdx.y;
-  for (int64_t s = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; s < S;
-       s += static_cast<int64_t>(gridDim.x) * kThreads) {
-    float p[MAXC];
-    softmax_regs<MAXC>(logits, n * C * S + s, S, C, p);
-    const int tc = class_of(target[n * S + s], lut ? s_lut : nullptr, C);
-    // g_c is cheap: evaluate it twice (once for the dot product, once for the output) instead of keeping 16 more
-    // registers live -- the kernel is bound by loads in flight, i.e. by occupancy
-    auto gfun = [&](int c) {
-      const float t = (c == tc) ? 1.f : 0.f;
-      float gc = t * s_a[c] + p[c] * s_b[c];
-      if (s_e[c] != 0.f) gc += s_e[c] * (p[c] - t) / fmaxf(p[c] * (1.0f - p[c]), 1e-12f);   // warp-uniform branch
-      return gc;
-    };
-    float dot = 0.f;
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c) dot = fmaf(gfun(c), p[c], dot);
+  const float* zb = logits + n * C * S;
+  float* db = dlogits + n * C * S;
+  const int64_t SV = S / VEC;
+  for (int64_t sv = blockIdx.x * static_cast<int64_t>(kThreads) + threadIdx.x; sv < SV;
+       sv += static_cast<int64_t>(gridDim.x) * kThreads) {
+    const int64_t s = sv * VEC;
+    VoxVec<VEC> z[MAXC];
 #pragma unroll
     for (int c = 0; c < MAXC; ++c)
-      if (c < C) dlogits[n * C * S + c * S + s] = p[c] * (gfun(c) - dot);
+      if (c < C) z[c].load(zb + c * S + s);
+    float tv[VEC];
+    load_labels<VEC, TU8>(target, n * S + s, tv);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float p[MAXC];
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) p[c] = c < C ? z[c].v[i] : 0.f;
+      softmax_inplace<MAXC>(p, C);
+      const int tc = class_of(tv[i], lut_g ? s_lut : nullptr, C);
+      // g_c is cheap: evaluate it twice (once for the dot product, once for the output) instead of keeping 16 more
+      // registers live
+      auto gfun = [&](int c) {
+        const float t = (c == tc) ? 1.f : 0.f;
+        float gc = t * s_a[c] + p[c] * s_b[c];
+        if (s_e[c] != 0.f) gc += s_e[c] * (p[c] - t) / fmaxf(p[c] * (1.0f - p[c]), 1e-12f);   // warp-uniform branch
+        return gc;
+      };
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) dot = fmaf(gfun(c), p[c], dot);
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) z[c].v[i] = c < C ? p[c] * (gfun(c) - dot) : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) z[c].store(db + c * S + s);
   }
 }
 
-unsigned int* ticket_buffer() {
-  static unsigned int* t = nullptr;
-  if (!t) {
-    if (cudaMalloc(&t, sizeof(unsigned int)) != cudaSuccess) return nullptr;
-    cudaMemset(t, 0, sizeof(unsigned int));
-  }
-  return t;
+template <int MAXC, int NTHR, int VEC, bool TU8>
+void launch_fwd(const float* logits, const void* target, const float* cw, const float* lut, double* sums, float* loss,
+                unsigned int* ticket, int n, int64_t S, int C, int uce, int per_sample, int blocks_per_sm, cudaStream_t s) {
+  const int bx = static_cast<int>(std::min<int64_t>((S / VEC + NTHR - 1) / NTHR, std::max(1, num_sms() * blocks_per_sm / n)));
+  partial_loss_fwd_kernel<MAXC, NTHR, VEC, TU8><<<dim3(bx, n), NTHR, 0, s>>>(logits, target, cw, lut, sums, loss, ticket, n,
+                                                                            S, C, uce, per_sample);
+}
+
+template <int MAXC, int VEC, bool TU8>
+void launch_bwd(const float* logits, const void* target, const float* cw, const float* lut, const double* sums,
+                const float* grad_out, float* dlogits, int n, int64_t S, int C, int uce, int per_sample, cudaStream_t s) {
+  const int bx = static_cast<int>(std::min<int64_t>((S / VEC + kThreads - 1) / kThreads, std::max(1, num_sms() * (VEC == 4 ? 1 : 8) / n)));
+  partial_loss_bwd_kernel<MAXC, VEC, TU8><<<dim3(bx, n), kThreads, 0, s>>>(logits, target, cw, lut, sums, grad_out, dlogits,
+                                                                          n, S, C, uce, per_sample);
 }
 
 }  // namespace
@@ -214,47 +305,61 @@ unsigned int* ticket_buffer() {
 
 using namespace mmpl;
 
-extern "C" int mmpl_partial_loss_fwd(const float* logits, const float* target, const float* class_weight,
-                                     const float* lut, double* sums, float* loss, int n, int64_t spatial, int classes,
-                                     int uce, mmpl_stream_t stream) {
+static bool vec4_ok(const void* logits, const void* target, const void* dlogits, int64_t S, int u8) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits);
+  return S % 4 == 0 && a % 16 == 0 && reinterpret_cast<uintptr_t>(target) % (u8 ? 4 : 16) == 0;
+}
+
+extern "C" int mmpl_partial_loss_fwd(const float* logits, const void* target, int target_is_u8,
+                                     const float* class_weight, const float* lut, int per_sample, double* sums,
+                                     float* loss, int n, int64_t spatial, int classes, int uce, mmpl_stream_t stream) {
   MMPL_REQUIRE(classes >= 1 && classes <= 32, MMPL_E_SHAPE, "partial_loss: classes=%d (1..32 supported)", classes);
   MMPL_REQUIRE(n > 0 && spatial > 0, MMPL_E_SHAPE, "partial_loss: empty input");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  unsigned int* ticket = ticket_buffer();
-  MMPL_REQUIRE(ticket != nullptr, MMPL_E_CUDA, "partial_loss: ticket allocation failed");
-  MMPL_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * classes, s));
-  const int64_t total = static_cast<int64_t>(n) * spatial;
   MMPL_REQUIRE(n <= 65535, MMPL_E_SHAPE, "partial_loss: batch %d exceeds the grid limit", n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // the last-block ticket is the trailing slot of the caller's workspace: nothing is shared between calls in flight on
+  // different streams or devices, and nothing is allocated here (a first call may sit inside a CUDA-graph capture)
+  const int groups = per_sample ? n : 1;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + static_cast<int64_t>(groups) * 4 * classes);
+  MMPL_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (static_cast<int64_t>(groups) * 4 * classes + 1), s));
+  const bool v4 = vec4_ok(logits, target, nullptr, spatial, target_is_u8);
+#define MMPL_LOSS_FWD(MAXC, NTHR, VEC, TU8, BPS) \
+  launch_fwd<MAXC, NTHR, VEC, TU8>(logits, target, class_weight, lut, sums, loss, ticket, n, spatial, classes, uce, per_sample, BPS, s)
   if (classes <= 16) {
-    const int bx = static_cast<int>(std::min<int64_t>((spatial + 255) / 256, std::max(1, num_sms() * 6 / n)));
-    const dim3 blocks(bx, n);
-    partial_loss_fwd_kernel<16, 256><<<blocks, 256, 0, s>>>(logits, target, class_weight, lut, sums, loss, ticket, n,
-                                                           spatial, classes, uce);
+    if (v4 && target_is_u8) MMPL_LOSS_FWD(16, 256, 4, true, 1);
+    else if (v4) MMPL_LOSS_FWD(16, 256, 4, false, 1);
+    else if (target_is_u8) MMPL_LOSS_FWD(16, 256, 1, true, 6);
+    else MMPL_LOSS_FWD(16, 256, 1, false, 6);
   } else {
-    const int bx = static_cast<int>(std::min<int64_t>((spatial + 127) / 128, std::max(1, num_sms() * 8 / n)));
-    const dim3 blocks(bx, n);
-    partial_loss_fwd_kernel<32, 128><<<blocks, 128, 0, s>>>(logits, target, class_weight, lut, sums, loss, ticket, n,
-                                                           spatial, classes, uce);
+    if (target_is_u8) MMPL_LOSS_FWD(32, 128, 1, true, 8);
+    else MMPL_LOSS_FWD(32, 128, 1, false, 8);
   }
+#undef MMPL_LOSS_FWD
   MMPL_CHECK_LAUNCH("partial_loss_fwd");
   return MMPL_OK;
 }
 
-extern "C" int mmpl_partial_loss_bwd(const float* logits, const float* target, const float* class_weight,
-                                     const float* lut, const double* sums, const float* grad_out, float* dlogits, int n,
-                                     int64_t spatial, int classes, int uce, mmpl_stream_t stream) {
+extern "C" int mmpl_partial_loss_bwd(const float* logits, const void* target, int target_is_u8,
+                                     const float* class_weight, const float* lut, int per_sample, const double* sums,
+                                     const float* grad_out, float* dlogits, int n, int64_t spatial, int classes, int uce,
+                                     mmpl_stream_t stream) {
   MMPL_REQUIRE(classes >= 1 && classes <= 32, MMPL_E_SHAPE, "partial_loss: classes=%d (1..32 supported)", classes);
   MMPL_REQUIRE(n > 0 && spatial > 0, MMPL_E_SHAPE, "partial_loss: empty input");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   MMPL_REQUIRE(n <= 65535, MMPL_E_SHAPE, "partial_loss: batch %d exceeds the grid limit", n);
-  const int bx = static_cast<int>(std::min<int64_t>((spatial + kThreads - 1) / kThreads, std::max(1, num_sms() * 8 / n)));
-  const dim3 blocks(bx, n);
-  if (classes <= 16)
-    partial_loss_bwd_kernel<16><<<blocks, kThreads, 0, s>>>(logits, target, class_weight, lut, sums, grad_out, dlogits, n,
-                                                           spatial, classes, uce);
-  else
-    partial_loss_bwd_kernel<32><<<blocks, kThreads, 0, s>>>(logits, target, class_weight, lut, sums, grad_out, dlogits, n,
-                                                           spatial, classes, uce);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool v4 = vec4_ok(logits, target, dlogits, spatial, target_is_u8);
+#define MMPL_LOSS_BWD(MAXC, VEC, TU8) \
+  launch_bwd<MAXC, VEC, TU8>(logits, target, class_weight, lut, sums, grad_out, dlogits, n, spatial, classes, uce, per_sample, s)
+  if (classes <= 16) {
+    if (v4 && target_is_u8) MMPL_LOSS_BWD(16, 4, true);
+    else if (v4) MMPL_LOSS_BWD(16, 4, false);
+    else if (target_is_u8) MMPL_LOSS_BWD(16, 1, true);
+    else MMPL_LOSS_BWD(16, 1, false);
+  } else {
+    if (target_is_u8) MMPL_LOSS_BWD(32, 1, true);
+    else MMPL_LOSS_BWD(32, 1, false);
+  }
+#undef MMPL_LOSS_BWD
   MMPL_CHECK_LAUNCH("partial_loss_bwd");
   return MMPL_OK;
 }

@@ -58,7 +58,6 @@ masked_dice_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
     const volatile double* vs = sums;
     const double sm = 1e-5, I = vs[0], Y = vs[1], Z = vs[2], E = vs[3];
     *loss = static_cast<float>(1.0 - (2.0 * I + sm) / (Z + Y + sm) + (uce ? E / static_cast<double>(V) : 0.0));
-    *ticket = 0;
   }
 }
 
@@ -83,15 +82,6 @@ masked_dice_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
   }
 }
 
-unsigned int* dice_ticket() {
-  static unsigned int* t = nullptr;
-  if (!t) {
-    if (cudaMalloc(&t, sizeof(unsigned int)) != cudaSuccess) return nullptr;
-    cudaMemset(t, 0, sizeof(unsigned int));
-  }
-  return t;
-}
-
 }  // namespace
 }  // namespace mmpl
 
@@ -101,9 +91,8 @@ extern "C" int mmpl_masked_dice_fwd(const float* x, const float* target, const f
                                     int64_t voxels, int sigmoid, int uce, mmpl_stream_t stream) {
   MMPL_REQUIRE(voxels > 0 && x && target && sums && loss, MMPL_E_SHAPE, "masked_dice: empty input");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  unsigned int* ticket = dice_ticket();
-  MMPL_REQUIRE(ticket != nullptr, MMPL_E_CUDA, "masked_dice: ticket allocation failed");
-  MMPL_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 4, s));
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + 4);   // trailing slot of the caller's workspace
+  MMPL_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 5, s));
   const int blocks = static_cast<int>(std::min<int64_t>((voxels + kThreads - 1) / kThreads, static_cast<int64_t>(num_sms()) * 8));
   masked_dice_fwd_kernel<<<blocks, kThreads, 0, s>>>(x, target, gate, sums, loss, ticket, voxels, sigmoid, uce);
   MMPL_CHECK_LAUNCH("masked_dice_fwd");

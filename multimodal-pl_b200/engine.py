@@ -30,9 +30,17 @@ def _env_int(name, default):
 
 class DataParallelModel(torch.nn.Module):
     """Wraps a module for bucketed, overlapped gradient averaging.  ``.module`` is the wrapped model (the train loop
-    uses ``model.module.renew_token``, train_amos_atlas_final.py:391)."""
+    uses ``model.module.renew_token``, train_amos_atlas_final.py:391).
 
-    def __init__(self, module: torch.nn.Module, world_size: int, bucket_mb: float = 16.0, average: bool = True):
+    Gradients live in ONE flat fp32 buffer (the backward kernels write into it directly, ``ops._grad_dst``), cut into
+    buckets in reverse registration order = the order in which backward produces them.  As soon as the last gradient of
+    a bucket exists its NCCL all-reduce is issued asynchronously (``_on_grad``), so the exchange of the big low-resolution
+    layers runs underneath the long full-resolution tail of the backward pass; only the last, small bucket (stem,
+    layer0..2) is exposed.  ``bucket_step`` (set by ``GraphedTrainStep`` / callers that own the optimizer) is applied to
+    each bucket right after its all-reduce has landed, so the optimizer step of bucket i overlaps the exchange of i+1.
+    All of it is stream-ordered and capturable: inside a CUDA graph the collectives become graph nodes."""
+
+    def __init__(self, module: torch.nn.Module, world_size: int, bucket_mb: float = 8.0, average: bool = True):
         super().__init__()
         self.module = module
         self.world_size = world_size
@@ -51,7 +59,7 @@ class DataParallelModel(torch.nn.Module):
         self._buckets: List[dict] = []
         limit = int(bucket_mb * 1024 * 1024 / 4)
         off = total
-        cur = {"hi": total, "lo": total, "pending": 0, "count": 0}
+        cur = {"hi": total, "lo": total, "pending": 0, "count": 0, "handle": None}
         for p in reversed(params):
             off -= p.numel()
             # the backward kernels write parameter gradients straight into this slot (ops._grad_dst); gradients that
@@ -63,12 +71,12 @@ class DataParallelModel(torch.nn.Module):
             cur["count"] += 1
             if cur["hi"] - cur["lo"] >= limit:
                 self._buckets.append(cur)
-                cur = {"hi": off, "lo": off, "pending": 0, "count": 0}
+                cur = {"hi": off, "lo": off, "pending": 0, "count": 0, "handle": None}
         if cur["count"]:
             self._buckets.append(cur)
-        self._handles = []
         self._callback_queued = False
-        self.sync_in_backward = True      # False: the caller reduces flat_grad itself (CUDA-graph replay path)
+        self.sync_in_backward = True      # False: the caller reduces flat_grad itself (all_reduce_flat)
+        self.bucket_step = None           # callable(lo, hi): optimizer step on flat range [lo, hi) once it is reduced
         if world_size > 1:
             for p in params:
                 p.register_post_accumulate_grad_hook(self._on_grad)
@@ -77,11 +85,12 @@ class DataParallelModel(torch.nn.Module):
     def _reset(self):
         for b in self._buckets:
             b["pending"] = b["count"]
-        self._handles = []
+            b["handle"] = None
         self._callback_queued = False
 
     def all_reduce_flat(self):
-        """One blocking all-reduce of the whole flat gradient buffer (used after a CUDA-graph replay)."""
+        """One blocking all-reduce of the whole flat gradient buffer (the un-overlapped fallback)."""
+        ops.join_side_stream()          # weight gradients are finished on a side stream (ops._ws_bwd_launch)
         for p in self._params:
             _adopt_grad(p)
         if self.world_size > 1:
@@ -101,17 +110,22 @@ class DataParallelModel(torch.nn.Module):
         if b["pending"] == 0:
             ops.join_side_stream()      # weight gradients are finished on a side stream (ops._ws_bwd_launch)
             view = self.flat_grad[b["lo"]:b["hi"]]
-            self._handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True))
+            b["handle"] = dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=True)
 
     def _finish(self):
-        for h in self._handles:
-            h.wait()
-        # buckets whose parameters received no gradient this step still have to take part in the collective
+        # buckets that never completed (a parameter without gradient, e.g. eam*.proj of unet3D_with_feam3) are reduced
+        # here without having passed through _on_grad's join: order the side-stream writes before any collective
+        ops.join_side_stream()
         for b in self._buckets:
-            if b["pending"] > 0:
-                dist.all_reduce(self.flat_grad[b["lo"]:b["hi"]], op=dist.ReduceOp.SUM)
-        if self.average:
-            self.flat_grad.mul_(1.0 / self.world_size)
+            view = self.flat_grad[b["lo"]:b["hi"]]
+            if b["handle"] is not None:
+                b["handle"].wait()
+            else:
+                dist.all_reduce(view, op=dist.ReduceOp.SUM)
+            if self.average:
+                view.mul_(1.0 / self.world_size)
+            if self.bucket_step is not None:
+                self.bucket_step(b["lo"], b["hi"])
         self._reset()
 
     def zero_grad(self, set_to_none: bool = True):
@@ -187,37 +201,82 @@ class FusedSGD(torch.optim.Optimizer):
             self._lr_host = g["lr"]
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale: float = 1.0):
+    def step(self, closure=None, grad_scale: float = 1.0, flat_range=None, last: bool = True):
+        """``flat_range=(lo, hi)`` restricts the step to that range of the flat buffers (one reduced gradient bucket);
+        ``last=False`` marks a partial step that further ranges of the same optimisation step will follow."""
         g = self.param_groups[0]
         if not torch.cuda.is_current_stream_capturing():
             self._sync_lr()
         for p in self._params:      # gradients that did not land in the flat buffer by themselves
             _adopt_grad(p)
         _lib.require_device()
-        _lib.check(_lib.lib().mmpl_sgd_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(),
-                                            self.momentum_buf.data_ptr(), self.flat_param.numel(),
-                                            self._lr_dev.data_ptr(), float(g["momentum"]), float(g["weight_decay"]),
-                                            float(grad_scale), int(self._steps == 0), _lib.stream_ptr()), "sgd_step")
-        self._steps += 1
+        # torch.optim.SGD skips parameters whose .grad is None (no weight decay, no momentum update): e.g. eam*.proj of
+        # unet3D_with_feam3 never receives a gradient.  One launch per maximal run of parameters that have one -- a
+        # single launch for the backbone.  Under CUDA-graph capture the runs are those of the captured step.
+        first = int(self._steps == 0)
+        for lo, hi in self._active_ranges():
+            if flat_range is not None:
+                lo, hi = max(lo, flat_range[0]), min(hi, flat_range[1])
+                if lo >= hi:
+                    continue
+            _lib.check(_lib.lib().mmpl_sgd_step(self.flat_param.data_ptr() + 4 * lo, self.flat_grad.data_ptr() + 4 * lo,
+                                                self.momentum_buf.data_ptr() + 4 * lo, hi - lo,
+                                                self._lr_dev.data_ptr(), float(g["momentum"]), float(g["weight_decay"]),
+                                                float(grad_scale), first, _lib.stream_ptr()), "sgd_step")
+        if last:
+            self._steps += 1
+        ops.bump_weights_epoch()       # weights changed behind autograd's back: see ops._check_ws_stamp
+
+    def _active_ranges(self):
+        """[lo, hi) element ranges of the flat buffers covering exactly the parameters with a gradient this step."""
+        out, off, start = [], 0, None
+        for p in self._params:
+            n = p.numel()
+            if p.grad is not None:
+                if start is None:
+                    start = off
+            elif start is not None:
+                out.append((start, off))
+                start = None
+            off += n
+        if start is not None:
+            out.append((start, off))
+        return out
 
 
 class GraphedTrainStep:
-    """One train step (zero_grad -> forward -> loss -> backward [-> fused SGD]) captured ONCE into a CUDA graph and
-    replayed per batch: ~500 kernel launches per step cost one graph launch on the host, so the GPU never waits for
-    Python.  The reference drives every op from the Python loop (train_amos_atlas_final.py:258-378).
+    """One train step (zero_grad -> forward -> loss -> backward -> gradient exchange -> fused SGD) captured ONCE into a
+    CUDA graph and replayed per batch: ~250 kernel launches per step cost one graph launch on the host, so the GPU
+    never waits for Python.  The reference drives every op from the Python loop (train_amos_atlas_final.py:258-378).
 
-    ``loss_fn(logits, labels) -> scalar``.  With world_size > 1 the graph ends after backward; the flat gradient is
-    all-reduced with one NCCL call after the replay and the SGD step follows (3 launches outside the graph).
-    The constructor runs ``warmup`` real optimisation steps on the example batch (CUDA-graph capture needs warmed-up
-    allocators and lazily initialised kernels); inputs are copied into static buffers before each replay."""
+    ``loss_fn(logits, labels) -> scalar``.  With world_size > 1 the NCCL exchange is INSIDE the graph: the bucketed
+    asynchronous all-reduces of ``DataParallelModel`` are captured on NCCL's stream as parallel branches that overlap the
+    rest of the backward pass, and the SGD step of each bucket is captured right behind its all-reduce.
+    (``comm_in_graph=False`` / MMPL_GRAPH_NCCL=0 keeps the exchange outside: one all-reduce of the flat buffer after the
+    replay.)  The constructor runs ``warmup`` real optimisation steps on the example batch (capture needs warmed-up
+    allocators, lazily initialised kernels and an initialised NCCL communicator).
 
-    def __init__(self, dp_model: "DataParallelModel", loss_fn, optimizer: "FusedSGD", image, label, warmup: int = 3):
+    Inputs: ``step(image, label)`` copies them into the graph's static buffers.  Host batches go through a staging
+    buffer filled on a copy stream: ``step.stage(next_image, next_label)`` may be called while the previous step still
+    runs, so the PCIe transfer of batch i+1 overlaps the compute of batch i; ``step.run_staged()`` then costs one
+    device-to-device copy.  Labels may be uint8 (a quarter of the fp32 bytes)."""
+
+    def __init__(self, dp_model: "DataParallelModel", loss_fn, optimizer: "FusedSGD", image, label, warmup: int = 3,
+                 comm_in_graph: Optional[bool] = None):
         self.dp, self.loss_fn, self.opt = dp_model, loss_fn, optimizer
         self.world = dp_model.world_size
-        self.static_image = image.clone()
-        self.static_label = label.clone()
-        prev = dp_model.sync_in_backward
-        dp_model.sync_in_backward = False
+        if comm_in_graph is None:
+            comm_in_graph = os.environ.get("MMPL_GRAPH_NCCL", "1") != "0"
+        self.comm_in_graph = bool(comm_in_graph) and self.world > 1
+        dev = dp_model.flat_grad.device
+        self.static_image = image.to(dev, copy=True)
+        self.static_label = label.to(dev, copy=True)
+        self._stage_img = torch.empty_like(self.static_image)
+        self._stage_lab = torch.empty_like(self.static_label)
+        self._copy_stream = torch.cuda.Stream()
+        self._stage_ready, self._stage_free = torch.cuda.Event(), torch.cuda.Event()
+        self._stage_free.record()
+        self._prev_sync = dp_model.sync_in_backward
         self.opt._sync_lr()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -230,6 +289,17 @@ class GraphedTrainStep:
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         except AttributeError:
             pass
+        try:
+            self._capture()
+        except Exception:
+            if not self.comm_in_graph:
+                raise
+            # NCCL refused to be captured (old NCCL, a watchdog interfering, ...): exchange outside the graph instead
+            self.comm_in_graph = False
+            torch.cuda.synchronize()
+            self._capture()
+
+    def _capture(self):
         self.graph = torch.cuda.CUDAGraph()
         # capture on a HIGH-priority stream: the critical path (forward, dgrad, GroupNorm backward) then wins the SMs
         # over the weight-gradient branch that ops forks onto its default-priority side stream
@@ -237,32 +307,69 @@ class GraphedTrainStep:
         if os.environ.get("MMPL_GRAPH_PRIORITY", "1") != "0":
             lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
             hp = torch.cuda.Stream(priority=hi)
-        with torch.cuda.graph(self.graph, stream=hp):
+        # thread_local: NCCL's watchdog thread polls events while we capture; only OUR thread's calls are policed
+        with torch.cuda.graph(self.graph, stream=hp, capture_error_mode="thread_local"):
             self.static_loss = self._body(in_graph=True)
-        self._prev_sync = prev
+
+    def _bucket_step(self, lo, hi):
+        self.opt.step(grad_scale=1.0 if self.dp.average else 1.0 / self.world, flat_range=(lo, hi), last=False)
 
     def _body(self, in_graph: bool):
-        self.opt.zero_grad()
-        logits = self.dp(self.static_image, self.static_label)
-        logits = logits[0] if isinstance(logits, (tuple, list)) else logits
-        loss = self.loss_fn(logits, self.static_label)
-        loss.backward()
-        if self.world == 1:
+        overlapped = self.world > 1 and self.comm_in_graph
+        self.dp.sync_in_backward = overlapped
+        self.dp.bucket_step = self._bucket_step if overlapped else None
+        try:
+            self.opt.zero_grad()
+            logits = self.dp(self.static_image, self.static_label)
+            logits = logits[0] if isinstance(logits, (tuple, list)) else logits
+            loss = self.loss_fn(logits, self.static_label)
+            loss.backward()      # overlapped: bucket all-reduces + per-bucket SGD are issued from the autograd hooks
+        finally:
+            self.dp.bucket_step = None
+            self.dp.sync_in_backward = self._prev_sync
+        if overlapped:
+            self.opt._steps += 1
+        elif self.world == 1:
             self.opt.step()
         elif not in_graph:
-            self.dp.all_reduce_flat()
-            self.opt.step(grad_scale=1.0 if self.dp.average else 1.0 / self.world)
+            self._exchange_outside()
         return loss
 
-    def __call__(self, image, label):
-        self.static_image.copy_(image, non_blocking=True)
-        self.static_label.copy_(label, non_blocking=True)
+    def _exchange_outside(self):
+        self.dp.all_reduce_flat()
+        self.opt.step(grad_scale=1.0 if self.dp.average else 1.0 / self.world)
+
+    def stage(self, image, label):
+        """Start copying the next batch (pinned host or device tensors) into the staging buffers on the copy stream."""
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free)          # the previous batch has left the staging buffers
+        with torch.cuda.stream(cs):
+            self._stage_img.copy_(image, non_blocking=True)
+            self._stage_lab.copy_(label, non_blocking=True)
+            self._stage_ready.record(cs)
+
+    def run_staged(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._stage_ready)
+        self.static_image.copy_(self._stage_img, non_blocking=True)
+        self.static_label.copy_(self._stage_lab, non_blocking=True)
+        self._stage_free.record(cur)
+        return self._replay()
+
+    def _replay(self):
         self.opt._sync_lr()
         self.graph.replay()
-        if self.world > 1:
-            self.dp.all_reduce_flat()
-            self.opt.step(grad_scale=1.0 if self.dp.average else 1.0 / self.world)
+        if self.world > 1 and not self.comm_in_graph:
+            self._exchange_outside()
         return self.static_loss
+
+    def __call__(self, image, label):
+        if image.is_cuda and label.is_cuda:
+            self.static_image.copy_(image, non_blocking=True)
+            self.static_label.copy_(label, non_blocking=True)
+            return self._replay()
+        self.stage(image, label)
+        return self.run_staged()
 
 
 class GraphedInference:
@@ -301,6 +408,56 @@ class GraphedInference:
         self.static_in.copy_(img, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+
+class GraphedSlidingWindow:
+    """One sliding-window step -- eval-mode forward of a tile, classifier, Gaussian weighting and accumulation into the
+    volume accumulator (``model.blend_tile(tile, sink)``) -- captured ONCE into a CUDA graph and replayed per tile; the tile
+    origin is a device scalar triple the graph reads, so the same graph serves all 96 tiles of a 300x512x512 volume.
+    Owns the fp32 accumulator ``acc`` [1, Dpad, C, H, W] (depth-major; Dpad = D rounded up to a multiple of
+    ``world_size`` so that depth slabs reduce-scatter evenly).  Used by ``evaluate.predict_sliding_dice``.  The weights are
+    treated as frozen (``ops.frozen_weights``): build a new object after they change."""
+
+    def __init__(self, model: torch.nn.Module, volume_dhw, tile, classes: int, world_size: int = 1, warmup: int = 2,
+                 device=None):
+        from .evaluate import _gaussian_device
+
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.model, self.tile, self.classes = model, tuple(int(t) for t in tile), int(classes)
+        self.volume_dhw = tuple(int(v) for v in volume_dhw)
+        D, H, W = self.volume_dhw
+        self.world = max(int(world_size), 1)
+        self.dpad = (D + self.world - 1) // self.world * self.world
+        self.acc = torch.zeros((1, self.dpad, classes, H, W), dtype=torch.float32, device=dev)
+        self.origin_dev = torch.zeros(3, dtype=torch.int32, device=dev)
+        self.static_in = torch.zeros((1, 1) + self.tile, dtype=torch.float32, device=dev)
+        self.sink = ops.BlendSink(self.acc, _gaussian_device(self.tile, dev), self.origin_dev, self.tile, d_outer=True)
+        was_training = model.training
+        model.eval()
+        if not model.blend_supported():
+            raise RuntimeError("GraphedSlidingWindow needs the bf16 compute dtype and a 32/64-channel classifier")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad(), ops.frozen_weights():
+            for _ in range(max(warmup, 1)):
+                model.blend_tile(self.static_in, self.sink)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad(), ops.frozen_weights():
+            model.blend_tile(self.static_in, self.sink)
+        self.acc.zero_()
+        if was_training:
+            model.train()
+
+    def reset(self):
+        self.acc.zero_()
+
+    def blend_tile(self, img, origin_dev_row):
+        """``img`` [1,1,td,th,tw] on the device; ``origin_dev_row`` a device int32[3] = (d0, h0, w0) of the tile."""
+        self.static_in.copy_(img, non_blocking=True)
+        self.origin_dev.copy_(origin_dev_row, non_blocking=True)
+        self.graph.replay()
 
 
 def extant_file(x):

@@ -6,7 +6,8 @@ What changes underneath: the reference copies every tile to the GPU and its logi
 float64 numpy (:242, :259-276).  Here the volume stays on the device: tiles are sliced on the GPU, the Gaussian-weighted
 accumulation is one fused kernel per tile (mmpl_sw_blend, fp64 accumulators by default like the reference), and
 normalise + argmax + per-class counting is one more (mmpl_sw_finalize).  With ``world_size > 1`` tiles are dealt
-round-robin to the ranks and the accumulators are summed with one all-reduce (``predict_sliding_sharded``).
+to the ranks in contiguous runs; the production path reduce-scatters the accumulator along depth, finalises each
+slab where it lands and all-gathers the uint8 mask (``_sliding_blend``).
 """
 from math import ceil
 
@@ -20,17 +21,18 @@ from ._lib import p as _p
 
 
 def _get_gaussian(patch_size, sigma_scale=1. / 8) -> np.ndarray:
-    """Reference evaluate_amos.py:184-197 (scipy on the host; computed once per tile size)."""
+    """Importance map of a tile (reference evaluate_amos.py:184-197): a unit impulse at the tile centre smoothed by
+    scipy's ``gaussian_filter`` with sigma = size * sigma_scale per axis (zero boundary), scaled to a maximum of 1, cast to
+    fp32, exact zeros lifted to the smallest positive value.  Host-side, once per tile size; the scipy call and the order
+    of the casts are what make the map bit-identical to the reference's."""
     from scipy.ndimage import gaussian_filter
 
-    tmp = np.zeros(patch_size)
-    center_coords = [i // 2 for i in patch_size]
-    sigmas = [i * sigma_scale for i in patch_size]
-    tmp[tuple(center_coords)] = 1
-    g = gaussian_filter(tmp, sigmas, 0, mode='constant', cval=0)
-    g = (g / np.max(g) * 1).astype(np.float32)
-    g[g == 0] = np.min(g[g != 0])
-    return g
+    impulse = np.zeros(patch_size)
+    impulse[tuple(n // 2 for n in patch_size)] = 1
+    blurred = gaussian_filter(impulse, [n * sigma_scale for n in patch_size], 0, mode='constant', cval=0)
+    weight = (blurred / np.max(blurred) * 1).astype(np.float32)
+    weight[weight == 0] = np.min(weight[weight != 0])
+    return weight
 
 
 _gauss_cache = {}
@@ -53,25 +55,22 @@ def multi_net(net_list, img, task_id):
     return pred
 
 
+def _axis_starts(extent, window, step):
+    """Window starts along one axis: ceil((extent - window) / step) + 1 windows at multiples of ``step``, each pulled
+    back so that it ends inside the volume (reference :218-239)."""
+    count = int(ceil((extent - window) / step) + 1)
+    return [max(min(i * step + window, extent) - window, 0) for i in range(count)]
+
+
 def tile_origins(image_size, tile_size):
-    """(d1, y1, x1) of every window in the reference's dep -> row -> col order (:215-239); the H/W stride is derived
-    from tile_size[1] only, as in the reference (:217)."""
-    overlap = 1 / 4
-    strideHW = ceil(tile_size[1] * (1 - overlap))
-    strideD = ceil(tile_size[0] * (1 - overlap))
-    tile_deps = int(ceil((image_size[2] - tile_size[0]) / strideD) + 1)
-    tile_rows = int(ceil((image_size[3] - tile_size[1]) / strideHW) + 1)
-    tile_cols = int(ceil((image_size[4] - tile_size[2]) / strideHW) + 1)
-    out = []
-    for dep in range(tile_deps):
-        for row in range(tile_rows):
-            for col in range(tile_cols):
-                d1, x1, y1 = int(dep * strideD), int(col * strideHW), int(row * strideHW)
-                d2 = min(d1 + tile_size[0], image_size[2])
-                x2 = min(x1 + tile_size[2], image_size[4])
-                y2 = min(y1 + tile_size[1], image_size[3])
-                out.append((max(int(d2 - tile_size[0]), 0), max(int(y2 - tile_size[1]), 0), max(int(x2 - tile_size[2]), 0)))
-    return out
+    """(d, y, x) origin of every window in the reference's depth -> row -> column order (:215-239), 25 % overlap; the
+    in-plane step is derived from tile_size[1] alone, as in the reference (:217)."""
+    step_hw = int(ceil(tile_size[1] * 0.75))
+    step_d = int(ceil(tile_size[0] * 0.75))
+    return [(d, y, x)
+            for d in _axis_starts(image_size[2], tile_size[0], step_d)
+            for y in _axis_starts(image_size[3], tile_size[1], step_hw)
+            for x in _axis_starts(image_size[4], tile_size[2], step_hw)]
 
 
 def _tile_logits(net_list, img, task_id, tta):
@@ -86,7 +85,15 @@ def _tile_logits(net_list, img, task_id, tta):
     return pred
 
 
+def _my_tiles(tiles, rank, world):
+    """Contiguous run of the tile list for ``rank``: neighbouring tiles share depth levels, so a rank needs (and uploads)
+    only the depth range of the volume its run covers."""
+    per = (len(tiles) + world - 1) // world
+    return tiles[rank * per:(rank + 1) * per]
+
+
 def _accumulate(net_list, image, tile_size, classes, task_id, tta, acc_dtype, rank=0, world=1):
+    """Generic path (any callable networks, TTA, fp64 or fp32 class-major accumulators like the reference)."""
     _lib.require_device()
     L = _lib.lib()
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -99,16 +106,14 @@ def _accumulate(net_list, image, tile_size, classes, task_id, tta, acc_dtype, ra
     wsum = torch.zeros((B, D, H, W), dtype=acc_dtype, device=dev)
     nbytes = acc.element_size()
     td, th, tw = (int(t) for t in tile_size)
-    for i, (d1, y1, x1) in enumerate(tile_origins(image.shape, tile_size)):
-        if i % world != rank:
-            continue
+    for d1, y1, x1 in _my_tiles(tile_origins(image.shape, tile_size), rank, world):
         img = image[:, :, d1:d1 + td, y1:y1 + th, x1:x1 + tw].contiguous()
         with torch.no_grad():
             pred = _tile_logits(net_list, img, task_id, tta).float().contiguous()
         assert tuple(pred.shape) == (B, classes, td, th, tw), f"network returned {tuple(pred.shape)}"
         for b in range(B):
             _lib.check(L.mmpl_sw_blend(_p(acc[b]), _p(wsum[b]), _p(pred[b]), _p(g), classes, D, H, W, td, th, tw,
-                                       d1, y1, x1, nbytes, _lib.stream_ptr()), "sw_blend")
+                                       d1, y1, x1, nbytes, 0, _lib.stream_ptr()), "sw_blend")
     return acc, wsum
 
 
@@ -119,18 +124,138 @@ def predict_sliding(args, net_list, image, tile_size, classes, task_id, tta=Fals
     return acc / wsum.unsqueeze(1)
 
 
+def _blender_for(net_list, volume_dhw, tile_size, classes, world):
+    """The fused tile-blend engine for ``net_list`` if it has one: an ``engine.GraphedSlidingWindow`` of matching
+    geometry, or a bare model with ``blend_tile`` (eager launches)."""
+    if len(net_list) != 1:
+        return None
+    net = net_list[0]
+    if hasattr(net, "blend_tile") and hasattr(net, "acc"):
+        ok = (net.volume_dhw == tuple(volume_dhw) and net.tile == tuple(int(t) for t in tile_size)
+              and net.classes == classes and net.world == world)
+        return net if ok else None
+    if isinstance(net, torch.nn.Module) and hasattr(net, "blend_supported") and not net.training and net.blend_supported():
+        return _EagerBlender(net, volume_dhw, tile_size, classes, world)
+    return None
+
+
+class _EagerBlender:
+    """Same contract as engine.GraphedSlidingWindow with per-kernel launches (any volume shape, no capture cost)."""
+
+    def __init__(self, model, volume_dhw, tile, classes, world):
+        from . import ops
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        D, H, W = volume_dhw
+        self.model, self.world = model, world
+        self.dpad = (D + world - 1) // world * world
+        self.acc = torch.zeros((1, self.dpad, classes, H, W), dtype=torch.float32, device=dev)
+        self.origin_dev = torch.zeros(3, dtype=torch.int32, device=dev)
+        self.sink = ops.BlendSink(self.acc, _gaussian_device(tile, dev), self.origin_dev, tile, d_outer=True)
+
+    def reset(self):
+        self.acc.zero_()
+
+    def blend_tile(self, img, origin_dev_row):
+        self.origin_dev.copy_(origin_dev_row, non_blocking=True)
+        with torch.no_grad():
+            self.model.blend_tile(img, self.sink)
+
+
+def _sliding_blend(blender, image, tile_size, classes, label, num_class, rank, world):
+    """Production path of predict_sliding_dice.  Every rank: upload the depth range its tiles need, run
+    forward + classifier + Gaussian accumulation per tile into a depth-major fp32 accumulator; then ONE reduce-scatter
+    along depth (each rank receives the summed slab it owns), local argmax + Dice counts on the slab, all-gather of the
+    uint8 mask and all-reduce of 3 x C counters.  The weight sum is never formed: argmax and Dice do not depend on a
+    positive per-voxel normaliser."""
+    L = _lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if isinstance(image, np.ndarray):
+        image = torch.from_numpy(image)
+    B, _, D, H, W = image.shape
+    assert B == 1, "the fused sliding-window path handles one volume per call"
+    td, th, tw = (int(t) for t in tile_size)
+    mine = _my_tiles(tile_origins(image.shape, tile_size), rank, world)
+    blender.reset()
+    if mine:
+        dlo, dhi = min(t[0] for t in mine), max(t[0] for t in mine) + td
+        part = image[:, :, dlo:dhi].to(dev, torch.float32, non_blocking=True)       # contiguous depth range (B = 1)
+        origins = torch.tensor(mine, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+        for i, (d1, y1, x1) in enumerate(mine):
+            tile = part[:, :, d1 - dlo:d1 - dlo + td, y1:y1 + th, x1:x1 + tw]
+            blender.blend_tile(tile, origins[i])
+    acc = blender.acc[0]                                   # [Dpad, C, H, W]
+    dpad = acc.shape[0]
+    slab = dpad // world
+    if world > 1:
+        mine_acc = torch.empty((slab, classes, H, W), dtype=torch.float32, device=dev)
+        dist.reduce_scatter_tensor(mine_acc, acc, op=dist.ReduceOp.SUM)
+    else:
+        mine_acc = acc
+    z0 = rank * slab
+    amax_slab = torch.empty((slab, H, W), dtype=torch.uint8, device=dev)
+    counts = torch.zeros((3, classes), dtype=torch.int64, device=dev)
+    lab = None
+    if label is not None:
+        if isinstance(label, np.ndarray):
+            label = torch.from_numpy(label)
+        lab_full = label.reshape(D, H, W)
+        lab = lab_full[z0:min(z0 + slab, D)].to(dev, non_blocking=True)
+        lab = lab.contiguous() if lab.dtype == torch.uint8 else lab.float().contiguous()
+    valid = max(min(z0 + slab, D) - z0, 0)                 # planes of this slab inside the volume (the rest is padding)
+    if valid > 0:
+        _lib.check(L.mmpl_sw_finalize(_p(mine_acc), None, None if lab is None else _p(lab),
+                                      int(lab is not None and lab.dtype == torch.uint8), None, _p(amax_slab),
+                                      _p(counts) if lab is not None else None, classes, valid * H * W, H * W, 4,
+                                      _lib.stream_ptr()), "sw_finalize")
+    if valid < slab:
+        amax_slab[valid:].zero_()
+    if world > 1:
+        amax = torch.empty((dpad, H, W), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(amax, amax_slab)
+        if lab is not None:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        amax = amax[:D]
+    else:
+        amax = amax_slab[:D]
+    amax = amax.unsqueeze(0)
+    if label is None:
+        return None, None, None, amax
+    return _scores(counts.unsqueeze(0), num_class) + (amax,)
+
+
 def predict_sliding_dice(args, net_list, image, tile_size, classes, task_id, label=None, tta=False,
                          acc_dtype=torch.float64, num_class=None, sharded=False):
     """Fused variant: blend, normalise, argmax and per-class Dice counts without materialising the normalised logit
-    volume.  Returns (dices, senc, spec, argmax uint8 [B,D,H,W]).  ``sharded=True`` deals tiles round-robin over the
-    ranks of the default process group and sums the accumulators with one all-reduce."""
+    volume.  Returns (dices, senc, spec, argmax uint8 [B,D,H,W]).
+
+    ``acc_dtype=torch.float32`` with a single bf16 network that supports it (a ``unet3D_baseline`` in eval mode, or an
+    ``engine.GraphedSlidingWindow``) takes the production path: classifier + Gaussian accumulation in one kernel, and with
+    ``sharded=True`` a contiguous run of tiles per rank, reduce-scatter along depth, local argmax/Dice, all-gather of the
+    uint8 mask (``_sliding_blend``).  Otherwise the generic path (fp64 accumulators like the reference, TTA, several
+    networks); sharded: tiles split over the ranks, accumulators summed with all-reduce."""
     world = dist.get_world_size() if (sharded and dist.is_initialized()) else 1
     rank = dist.get_rank() if world > 1 else 0
+    num_class = num_class if num_class is not None else classes - 1
+    shape = image.shape
+    if acc_dtype == torch.float32 and not tta and shape[0] == 1:
+        blender = _blender_for(net_list, tuple(int(v) for v in shape[2:]), tile_size, classes, world)
+        if blender is not None:
+            return _sliding_blend(blender, image, tile_size, classes, label, num_class, rank, world)
     acc, wsum = _accumulate(net_list, image, tile_size, classes, task_id, tta, acc_dtype, rank, world)
     if world > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
         dist.all_reduce(wsum, op=dist.ReduceOp.SUM)
-    return _finalize(acc, wsum, label, classes, num_class if num_class is not None else classes - 1)
+    return _finalize(acc, wsum, label, classes, num_class)
+
+
+def _scores(counts, num_class):
+    """counts int64 [B][3][C] = |P & T|, |P|, |T| -> per-class lists (dice_score / senc_score / spec_score, :92-126)."""
+    inter, npred, ntgt = counts[:, 0].double(), counts[:, 1].double(), counts[:, 2].double()
+    dices = [(2 * inter[:, l] / (npred[:, l] + ntgt[:, l] + 1)).mean() for l in range(1, num_class + 1)]
+    senc = [(inter[:, l] / (ntgt[:, l] + 1)).mean() for l in range(1, num_class + 1)]
+    spec = [(inter[:, l] / (npred[:, l] + 1)).mean() for l in range(1, num_class + 1)]
+    return dices, senc, spec
 
 
 def _finalize(acc, wsum, label, classes, num_class):
@@ -144,18 +269,16 @@ def _finalize(acc, wsum, label, classes, num_class):
     if label is not None:
         if isinstance(label, np.ndarray):
             label = torch.from_numpy(label)
-        lab = label.to(dev, torch.float32).reshape(B, -1).contiguous()
+        lab = label.to(dev).reshape(B, -1)
+        lab = lab.contiguous() if lab.dtype == torch.uint8 else lab.float().contiguous()
+    u8 = int(lab is not None and lab.dtype == torch.uint8)
     for b in range(B):
         _lib.check(L.mmpl_sw_finalize(_p(acc[b]), None if wsum is None else _p(wsum[b]), None if lab is None else _p(lab[b]),
-                                      None, _p(amax[b]), _p(counts[b]) if lab is not None else None, classes, vox,
+                                      u8, None, _p(amax[b]), _p(counts[b]) if lab is not None else None, classes, vox, 0,
                                       acc.element_size(), _lib.stream_ptr()), "sw_finalize")
     if lab is None:
         return None, None, None, amax
-    inter, npred, ntgt = counts[:, 0].double(), counts[:, 1].double(), counts[:, 2].double()
-    dices = [(2 * inter[:, l] / (npred[:, l] + ntgt[:, l] + 1)).mean() for l in range(1, num_class + 1)]
-    senc = [(inter[:, l] / (ntgt[:, l] + 1)).mean() for l in range(1, num_class + 1)]
-    spec = [(inter[:, l] / (npred[:, l] + 1)).mean() for l in range(1, num_class + 1)]
-    return dices, senc, spec, amax
+    return _scores(counts, num_class) + (amax,)
 
 
 def dice_score(preds, labels):

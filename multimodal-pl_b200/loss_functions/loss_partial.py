@@ -16,24 +16,26 @@ from .. import ops
 _weight_cache = {}
 
 
-def _class_weight(mask, n_classes, device):
+def _class_weight(mask, n_classes, device, per_sample=False):
     """``mask[0]`` of the reference (loss_partial.py:87,92): the first sample's class-weight vector, as a device
-    tensor.  Host vectors are uploaded once per distinct value (a pageable H2D copy per step would serialise the host
-    with the GPU stream)."""
+    tensor -- or, with ``per_sample``, all of them stacked [B, C].  Host vectors are uploaded once per distinct value
+    (a pageable H2D copy per step would serialise the host with the GPU stream)."""
     if mask is None:
+        assert not per_sample, "per-sample class weights need one weight vector per sample"
         key = ("ones", n_classes, str(device))
         if key not in _weight_cache:
             _weight_cache[key] = torch.ones(n_classes, dtype=torch.float32, device=device)
         return _weight_cache[key]
-    w = mask[0]
-    if torch.is_tensor(w) and w.device == torch.device(device) and w.dtype == torch.float32:
-        return w
-    vals = tuple(float(v) for v in (w.tolist() if torch.is_tensor(w) else w))
+    rows = list(mask) if per_sample else [mask[0]]
+    if len(rows) == 1 and torch.is_tensor(rows[0]) and rows[0].device == torch.device(device) and rows[0].dtype == torch.float32:
+        return rows[0]
+    vals = tuple(tuple(float(v) for v in (w.tolist() if torch.is_tensor(w) else w)) for w in rows)
     key = (vals, str(device))
     if key not in _weight_cache:
         if len(_weight_cache) > 4096:
             _weight_cache.clear()
-        _weight_cache[key] = torch.tensor(vals, dtype=torch.float32, device=device)
+        t = torch.tensor(vals, dtype=torch.float32, device=device)
+        _weight_cache[key] = t if per_sample else t[0]
     return _weight_cache[key]
 
 
@@ -91,13 +93,17 @@ class EDiceLoss_partial(nn.Module):
         self.diceloss = DiceLoss(n_classes=n_classes)
         self.bce = nn.BCELoss()
 
-    def forward(self, inputs, target, mask=None, soft_max=True, uce=True, lut=None):
-        """inputs [B,C,D,H,W] logits, target [B,D,H,W] float class ids, mask = list of per-sample weight vectors
-        (only mask[0] is used, as in the reference).  ``lut`` optionally folds the cmask remap of
-        train_amos_atlas_final.py:252-255 into the kernel (not part of the reference signature)."""
-        w = _class_weight(mask, inputs.shape[1], inputs.device)
+    def forward(self, inputs, target, mask=None, soft_max=True, uce=True, lut=None, per_sample=False):
+        """inputs [B,C,D,H,W] logits, target [B,D,H,W] class ids (float like the reference, or uint8), mask = list of
+        per-sample weight vectors.  As in the reference only mask[0] is used and the Dice sums pool over the batch
+        (loss_partial.py:87,92) -- unless ``per_sample=True`` (not part of the reference signature): then
+        sample b is scored with mask[b] exactly as the reference would score it alone, and the batch is averaged, which
+        is what a mixed CT/MRI partial-label batch needs.  ``lut`` ([C], or [B,C] with per_sample) optionally folds the
+        cmask remap of train_amos_atlas_final.py:252-255 into the kernel."""
+        w = _class_weight(mask, inputs.shape[1], inputs.device, per_sample and soft_max)
         if soft_max:
-            return ops.partial_label_loss(inputs, target, w, lut=lut, uce=uce)
+            return ops.partial_label_loss(inputs, target, w, lut=lut, uce=uce, per_sample=per_sample)
+        assert not per_sample, "per_sample is implemented for the soft_max=True training form"
         # sigmoid variant (not used by the train loop): same formula on independent sigmoids
         p = torch.sigmoid(inputs)
         dice = self.diceloss(p, target, softmax=False, weight=w)

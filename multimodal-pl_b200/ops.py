@@ -246,7 +246,23 @@ _WS_TABLES = {}
 
 
 class _WsEntry:
-    __slots__ = ("w_hat", "inv_std", "pf", "pd", "key", "shape_key", "on_side")
+    __slots__ = ("w_hat", "inv_std", "pf", "pd", "key", "shape_key", "on_side", "stamp")
+
+
+# The per-weight buffers are rewritten in place by the next refresh, behind autograd's version counters.  Each refresh
+# stamps the entry with (optimizer epoch, weight._version); a convolution remembers the stamp it ran with and its backward
+# refuses to run on buffers that were meanwhile refreshed from CHANGED weights (stock PyTorch raises "modified by an
+# inplace operation" in that situation).  A refresh from unchanged weights rewrites the same values and is harmless.
+_WEIGHTS_EPOCH = [0]
+
+
+def bump_weights_epoch():
+    """Called by optimizers that update weights through raw pointers (engine.FusedSGD)."""
+    _WEIGHTS_EPOCH[0] += 1
+
+
+def _ws_stamp(weight):
+    return (_WEIGHTS_EPOCH[0], weight._version)
 
 
 def _ws_key(weight, dt, standardise, stem_kch):
@@ -273,6 +289,7 @@ def _ws_entry(weight, dt, stem_kch=0, packed=True):
             e.pf = e.pd = None
         e.key = None
         e.on_side = False
+        e.stamp = None
         e.shape_key = shape_key
         weight._mmpl_ws = e
     return e
@@ -397,9 +414,10 @@ def prepare_ws(convs):
         _lib.check(L.mmpl_ws_weight_fwd_batched(_p(tab[0]), tab[1], tab[2], code, _lib.stream_ptr()),
                    "ws_weight_fwd_batched")
         side_ids = set()
-    for (_, _, _, e), key in zip(items, keys):
+    for (w_, _, _, e), key in zip(items, keys):
         e.key = key
         e.on_side = id(e) in side_ids
+        e.stamp = _ws_stamp(w_)
 
 
 _WS_SIDE = {"stream": None, "pending": False}
@@ -411,6 +429,7 @@ def _ws_get(weight, dt, standardise, stem_kch=0, packed=True):
         e = _ws_entry(weight, dt, stem_kch, packed)
         if e.key != _ws_key(weight, dt, standardise, stem_kch):
             _ws_refresh_one(weight, e, dt, standardise, stem_kch)
+            e.stamp = _ws_stamp(weight)
         elif e.on_side and _WS_SIDE["pending"]:
             torch.cuda.current_stream().wait_stream(_WS_SIDE["stream"])      # join the side-stream refresh once
             _WS_SIDE["pending"] = False
@@ -422,6 +441,7 @@ def _ws_get(weight, dt, standardise, stem_kch=0, packed=True):
     w32 = weight.detach().float().contiguous()
     e = _ws_entry(w32, dt, stem_kch, packed)
     _ws_refresh_one(w32, e, dt, standardise, stem_kch)
+    e.stamp = _ws_stamp(w32)
     return e
 
 
@@ -469,6 +489,7 @@ class WSConv3dFn(torch.autograd.Function):
         # stride-2 3x3x3 on tensor cores: the parity-split copy is what wgrad reads, so keep it instead of x
         keep = src if (algo == _lib.ALGO_TCGEN05_PSPLIT and _tc_wgrad_supported(dt, k, stride, cin, cout)) else x
         ctx.save_for_backward(keep, w_hat, inv_std, pd)
+        ctx.ws_entry, ctx.ws_stamp = ws, ws.stamp
         ctx.x_is_psplit = keep is not x
         ctx.meta = (n, d, h, w, cin, cout, k, stride, int(standardise), residual is not None, weight.dtype)
         ctx.weight = weight
@@ -485,6 +506,7 @@ class WSConv3dFn(torch.autograd.Function):
     def backward(ctx, dy, _dstats=None):
         L = _lib.lib()
         x, w_hat, inv_std, pd = ctx.saved_tensors
+        _check_ws_stamp(ctx)
         n, d, h, w, cin, cout, k, stride, standardise, has_res, wdtype = ctx.meta
         dt = pd.dtype
         code = _lib.dtype_code(dt)
@@ -550,6 +572,13 @@ class WSConv3dFn(torch.autograd.Function):
         if has_res and ctx.needs_input_grad[2]:
             dres = dy
         return dx, dw, dres, None, None, None
+
+
+def _check_ws_stamp(ctx):
+    if ctx.ws_entry.stamp != ctx.ws_stamp:
+        raise RuntimeError("the weights of this convolution were changed and re-standardised between its forward and "
+                           "its backward (optimizer step or in-place update followed by another forward): the saved "
+                           "standardised weights no longer exist -- run backward before updating the weights")
 
 
 _TC_WGRAD = {"enabled": os.environ.get("MMPL_TC_WGRAD", "1") != "0"}
@@ -625,6 +654,7 @@ class StemConvFn(torch.autograd.Function):
             _lib.check(L.mmpl_stem_conv_fwd(_p(img), _p(w_hat), _p(y), n, d, h, w, cout, _lib.dtype_code(dt), st),
                        "stem_conv_fwd")
             ctx.save_for_backward(img, w_hat, inv_std)
+        ctx.ws_entry, ctx.ws_stamp = ws, ws.stamp
         ctx.meta = (n, d, h, w, cout, int(standardise), weight.dtype, use_tc, tc_fwd, kch)
         ctx.weight = weight
         if not tc_fwd or stats is None:
@@ -636,6 +666,7 @@ class StemConvFn(torch.autograd.Function):
     def backward(ctx, dy, _dstats=None):
         L = _lib.lib()
         src, w_hat, inv_std = ctx.saved_tensors
+        _check_ws_stamp(ctx)
         n, d, h, w, cout, standardise, wdtype, use_tc, tc_fwd, kch = ctx.meta
         dy = to_cl(dy)
         st = _lib.stream_ptr()
@@ -899,46 +930,92 @@ def classifier(a, weight, bias):
     return ClassifierFn.apply(a, weight, bias)
 
 
+class BlendSink:
+    """Where the sliding-window classifier accumulates (predict_sliding, evaluate_amos.py:261-276): fp32 accumulator
+    ``acc`` [B, D, C, H, W] (depth-major, ``d_outer``) or [B, C, D, H, W], optional weight sum ``wsum`` [B, D, H, W], the
+    Gaussian importance map of the tile and the tile origin as a DEVICE int32[3] (so a captured graph serves all tiles)."""
+
+    def __init__(self, acc, gauss, origin_dev, tile, d_outer=True, wsum=None):
+        assert acc.dtype == torch.float32 and acc.is_contiguous() and gauss.dtype == torch.float32
+        assert origin_dev.dtype == torch.int32 and origin_dev.numel() == 3 and origin_dev.is_cuda
+        self.acc, self.gauss, self.origin_dev, self.wsum = acc, gauss.contiguous(), origin_dev, wsum
+        self.tile = tuple(int(t) for t in tile)
+        self.d_outer = bool(d_outer)
+        if d_outer:
+            self.B, self.D, self.C, self.H, self.W = acc.shape
+        else:
+            self.B, self.C, self.D, self.H, self.W = acc.shape
+
+
+def classifier_blend_supported(a_channels, classes, dtype) -> bool:
+    return dtype == torch.bfloat16 and a_channels in (32, 64) and classes <= 16
+
+
+@torch.no_grad()
+def classifier_blend(a, weight, bias, sink: BlendSink):
+    """acc += gauss * (classifier(a)) at the sink's tile origin: nn.Conv3d(base, classes, 1) (unet3D.py:632) fused with
+    the Gaussian-weighted accumulation of predict_sliding -- no fp32 logits tile is written.  bf16 activations only."""
+    _lib.require_device()
+    L = _lib.lib()
+    a = to_cl(a, torch.bfloat16)
+    n, cin, d, h, w = a.shape
+    classes = weight.shape[0]
+    assert (d, h, w) == sink.tile and n == sink.B and classes == sink.C, "tile / batch / classes do not match the sink"
+    wc = weight.detach().float().reshape(classes, cin).contiguous()
+    b = bias.detach().float().contiguous()
+    a_rows = a.permute(0, 2, 3, 4, 1)      # the NDHWC storage
+    for i in range(n):
+        _lib.check(L.mmpl_cls_blend(_p(a_rows[i]), _p(wc), _p(b), _p(sink.gauss), _p(sink.acc[i]),
+                                    None if sink.wsum is None else _p(sink.wsum[i]), _p(sink.origin_dev), classes,
+                                    sink.D, sink.H, sink.W, d, h, w, cin, int(sink.d_outer), _lib.stream_ptr()), "cls_blend")
+
+
 # --------------------------------------------------------------------------------------------------------------
 class PartialLossFn(torch.autograd.Function):
     """EDiceLoss_partial.forward with soft_max=True (loss_partial.py:71-99): one fused forward pass, one fused
-    backward pass, no host synchronisation."""
+    backward pass, no host synchronisation.  ``target`` may be float class ids (the reference) or uint8.
+    ``class_weight`` [C] (= mask[0], pooled over the batch like the reference) or [N, C] with ``per_sample`` (the
+    reference formula per sample with that sample's weights, averaged over the batch); ``lut`` likewise."""
 
     @staticmethod
-    def forward(ctx, logits, target, class_weight, lut, uce):
+    def forward(ctx, logits, target, class_weight, lut, uce, per_sample):
         _lib.require_device()
         L = _lib.lib()
         z = logits.detach().float().contiguous()
         n, c = z.shape[0], z.shape[1]
         spatial = z[0, 0].numel()
-        t = target.detach().float().contiguous()
+        t = target.detach()
+        u8 = t.dtype == torch.uint8
+        t = t.contiguous() if u8 else t.float().contiguous()
         assert t.numel() == n * spatial, f"target {tuple(target.shape)} does not match logits {tuple(logits.shape)}"
         dev = z.device
+        groups = n if per_sample else 1
         cw = class_weight.detach().to(device=dev, dtype=torch.float32).contiguous()
-        assert cw.numel() == c
+        assert cw.numel() == groups * c, f"class weights {tuple(class_weight.shape)} for {groups} group(s) of {c} classes"
         lt = None if lut is None else lut.detach().to(device=dev, dtype=torch.float32).contiguous()
-        sums = torch.empty(4 * c, dtype=torch.float64, device=dev)
+        assert lt is None or lt.numel() == groups * c
+        sums = torch.empty(groups * 4 * c + 1, dtype=torch.float64, device=dev)   # [G][4][C] sums + the ticket slot
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        _lib.check(L.mmpl_partial_loss_fwd(_p(z), _p(t), _p(cw), _p(lt), _p(sums), _p(loss), n, spatial, c, int(uce),
-                                           _lib.stream_ptr()), "partial_loss_fwd")
+        _lib.check(L.mmpl_partial_loss_fwd(_p(z), _p(t), int(u8), _p(cw), _p(lt), int(per_sample), _p(sums), _p(loss), n,
+                                           spatial, c, int(uce), _lib.stream_ptr()), "partial_loss_fwd")
         ctx.save_for_backward(z, t, cw, lt, sums)
-        ctx.meta = (n, spatial, c, int(uce), logits.dtype)
+        ctx.meta = (n, spatial, c, int(uce), logits.dtype, int(u8), int(per_sample))
         return loss
 
     @staticmethod
     def backward(ctx, gout):
         L = _lib.lib()
         z, t, cw, lt, sums = ctx.saved_tensors
-        n, spatial, c, uce, ldtype = ctx.meta
+        n, spatial, c, uce, ldtype, u8, per_sample = ctx.meta
         g = gout.detach().float().contiguous()
         dz = torch.empty_like(z)
-        _lib.check(L.mmpl_partial_loss_bwd(_p(z), _p(t), _p(cw), _p(lt), _p(sums), _p(g), _p(dz), n, spatial, c, uce,
-                                           _lib.stream_ptr()), "partial_loss_bwd")
-        return dz.to(ldtype), None, None, None, None
+        _lib.check(L.mmpl_partial_loss_bwd(_p(z), _p(t), u8, _p(cw), _p(lt), per_sample, _p(sums), _p(g), _p(dz), n,
+                                           spatial, c, uce, _lib.stream_ptr()), "partial_loss_bwd")
+        return dz.to(ldtype), None, None, None, None, None
 
 
-def partial_label_loss(logits, target, class_weight, lut=None, uce=True):
-    return PartialLossFn.apply(logits, target, class_weight, lut, bool(uce))
+def partial_label_loss(logits, target, class_weight, lut=None, uce=True, per_sample=False):
+    return PartialLossFn.apply(logits, target, class_weight, lut, bool(uce), bool(per_sample))
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -959,7 +1036,7 @@ class MaskedDiceFn(torch.autograd.Function):
             gf = gate.detach().to(torch.float32).contiguous()
             assert gf.numel() == v, f"masked dice: gate {tuple(gate.shape)} vs score {tuple(x.shape)}"
         dev = xf.device
-        sums = torch.empty(4, dtype=torch.float64, device=dev)
+        sums = torch.empty(5, dtype=torch.float64, device=dev)             # I, Y, Z, E + the kernel's ticket slot
         loss = torch.empty((), dtype=torch.float32, device=dev)
         _lib.check(L.mmpl_masked_dice_fwd(_p(xf), _p(tf), _p(gf), _p(sums), _p(loss), v, int(sigmoid), int(uce),
                                           _lib.stream_ptr()), "masked_dice_fwd")

@@ -79,9 +79,12 @@ class GNReLUClassifier(nn.Sequential):
     """precls_conv = Sequential(GroupNorm(16, base), ReLU, nn.Conv3d(base, classes, 1)) (:629-633): plain 1x1x1
     convolution WITH bias and without weight standardisation, emitting fp32 NCDHW logits."""
 
-    def forward(self, x):
+    def forward(self, x, blend=None):
         gn, conv = self[0], self[2]
         a = ops.gn_relu(x, gn.weight, gn.bias, gn.num_groups, gn.eps)
+        if blend is not None:       # sliding-window inference: accumulate g * logits straight into the volume
+            ops.classifier_blend(a, conv.weight, conv.bias, blend)
+            return None
         if conv.in_channels in (32, 64) and conv.out_channels <= 16:
             return ops.classifier(a, conv.weight, conv.bias)
         # deepout1 of unet3D_with_feam3 (128 channels, 1/8 resolution, 9 216 voxels per sample at cfg2): outside the
@@ -222,7 +225,13 @@ class unet3D_baseline(nn.Module):
             object.__setattr__(self, "_ws_conv_list", convs)
         return [(m.weight, m._standardise, m.in_channels == 1) for m in convs]
 
-    def forward(self, input, mask=None):
+    def blend_supported(self):
+        """True if ``blend_tile`` can run (bf16 compute dtype, classifier width the fused kernel covers)."""
+        conv = self.precls_conv[2]
+        return ops.classifier_blend_supported(conv.in_channels, conv.out_channels, ops.get_compute_dtype())
+
+    def _features(self, input):
+        """Everything up to (not including) precls_conv: reference :666-709."""
         # one launch standardises + packs the weights of every convolution (the reference does it per Conv3d.forward,
         # unet3D.py:22-26); one zero-fill serves all GroupNorm statistics accumulators
         ops.prepare_ws(self._ws_convs())
@@ -237,11 +246,20 @@ class unet3D_baseline(nn.Module):
         x = self.x8_resb(self.upsamplex2(x, skip3))
         x = self.x4_resb(self.upsamplex2(x, skip2))
         x = self.x2_resb(self.upsamplex2(x, skip1))
-        x = self.x1_resb(self.upsamplex2(x, skip0))
-        logits = self.precls_conv(x)
+        return self.x1_resb(self.upsamplex2(x, skip0))
+
+    def forward(self, input, mask=None):
+        logits = self.precls_conv(self._features(input))
         if self.training:
             return logits, [], []
         return logits
+
+    @torch.no_grad()
+    def blend_tile(self, input, sink):
+        """One sliding-window step (not part of the reference surface; used by evaluate.predict_sliding_dice): the
+        logits of the tile are not returned but Gaussian-weighted and accumulated into the volume accumulator of
+        ``sink`` (an ``ops.BlendSink``) by the classifier kernel itself (predict_sliding, evaluate_amos.py:244-276)."""
+        self.precls_conv(self._features(input), blend=sink)
 
 
 class EAM(nn.Module):

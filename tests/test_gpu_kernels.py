@@ -366,6 +366,48 @@ def test_partial_loss_lut_and_mask0(mm):
     assert abs(a.item() - ref.item()) < 2e-6 * max(1.0, ref.item())
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 4, 6, 8), (3, 16, 3, 5, 7), (2, 5, 4, 4, 4), (1, 20, 2, 4, 6)])
+def test_partial_loss_uint8_labels_and_per_sample_weights(mm, shape):
+    """uint8 labels give the same loss and gradient as the reference's float labels (vectorised 16-byte path when the
+    plane size is a multiple of 4, scalar path otherwise).  per_sample=True (mixed CT/MRI batches) equals the
+    reference loss evaluated sample by sample with that sample's weights and cmask, averaged over the batch."""
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+
+    B, C = shape[0], shape[1]
+    z0 = _rand(shape, 11, 2.0)
+    lab = torch.randint(0, C, (B,) + shape[2:], generator=torch.Generator().manual_seed(12)).float()
+    ws = []
+    for b in range(B):                      # CT-like rows: background + one organ; the last one MRI-like (bg only)
+        w = [1.0] + [0.0] * (C - 1)
+        if b < B - 1 or B == 1:
+            w[1 + (3 * b) % (C - 1)] = 1.0
+        ws.append(w)
+    crit = EDiceLoss_partial(C)
+    # (a) uint8 == float, pooled
+    zf = z0.cuda().requires_grad_(True)
+    zu = z0.cuda().requires_grad_(True)
+    lf = crit(zf, lab.cuda(), mask=[torch.tensor(ws[0])] * B)
+    lu = crit(zu, lab.cuda().to(torch.uint8), mask=[torch.tensor(ws[0])] * B)
+    lf.backward()
+    lu.backward()
+    assert lf.item() == lu.item() and torch.equal(zf.grad, zu.grad)
+    zr = z0.clone().requires_grad_(True)
+    ref = O.partial_label_loss(zr, lab, ws[0])
+    ref.backward()
+    assert abs(lf.item() - ref.item()) < 2e-6 * max(1.0, ref.item())
+    assert rel(zf.grad, zr.grad) < 1e-5
+    # (b) per-sample weights + per-sample cmask LUT
+    luts = torch.tensor([[float(l) if (l == 0 or w[l]) else 0.0 for l in range(C)] for w in ws])
+    zp = z0.cuda().requires_grad_(True)
+    lp = crit(zp, lab.cuda().to(torch.uint8), mask=[torch.tensor(w) for w in ws], lut=luts, per_sample=True)
+    lp.backward()
+    zr = z0.clone().requires_grad_(True)
+    ref = sum(O.partial_label_loss(zr[b:b + 1], O.remap_unsupervised(lab[b:b + 1], ws[b]), ws[b]) for b in range(B)) / B
+    ref.backward()
+    assert abs(lp.item() - ref.item()) < 2e-6 * max(1.0, ref.item()), (lp.item(), ref.item())
+    assert rel(zp.grad, zr.grad) < 1e-5
+
+
 def test_sgd_step(mm):
     from multimodal_pl_b200 import _lib
 

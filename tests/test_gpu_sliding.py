@@ -138,3 +138,42 @@ def test_tta_eight_flip_average_matches_oracle_and_graphed_equals_eager():
     finally:
         mm.set_conv_algo("auto")
         mm.set_compute_dtype(torch.bfloat16)
+
+
+def test_fused_classifier_blend_path_equals_generic_path():
+    """predict_sliding_dice(acc_dtype=float32) with a bf16 unet3D_baseline takes the production path: classifier + Gaussian
+    accumulation in ONE kernel into a depth-major accumulator (mmpl_cls_blend), vectorised argmax/Dice (mmpl_sw_finalize).
+    Same MMA sequence and same tile order as classifier -> fp32 logits tile -> mmpl_sw_blend, so the argmax volume and
+    the Dice counts must be identical; the CUDA-graph engine (one graph for all tiles, origin in device memory) likewise.
+    Also: uint8 labels == float labels."""
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.engine import GraphedSlidingWindow
+    from multimodal_pl_b200.evaluate import predict_sliding_dice
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    mm.set_compute_dtype(torch.bfloat16)
+    sd = O.synth_state_dict(32, 16, 2)
+    model = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True).cuda().eval()
+    model.load_state_dict(sd)
+    vol = O.synth_patch((1, 1, 40, 72, 88), 41, "ct")
+    lab = O.synth_labels((1, 40, 72, 88), 42, 16, 32)
+    tile = (16, 32, 32)
+    generic = predict_sliding_dice(None, [lambda im, tid: model(im)], vol, tile, 16, None, label=lab,
+                                   acc_dtype=torch.float32, num_class=15)
+    fused = predict_sliding_dice(None, [model], vol.numpy(), tile, 16, None, label=lab, acc_dtype=torch.float32,
+                                 num_class=15)
+    assert fused[3].shape == generic[3].shape and fused[3].dtype == torch.uint8
+    assert torch.equal(fused[3], generic[3])
+    assert [float(a) for a in fused[0]] == [float(a) for a in generic[0]]
+    eng = GraphedSlidingWindow(model, (40, 72, 88), tile, 16)
+    for _ in range(2):          # second volume: the accumulator is reset between volumes
+        graphed = predict_sliding_dice(None, [eng], vol, tile, 16, None, label=lab.to(torch.uint8),
+                                       acc_dtype=torch.float32, num_class=15)
+        assert torch.equal(graphed[3], generic[3])
+        assert [float(a) for a in graphed[0]] == [float(a) for a in generic[0]]
+    # against the fp32 CPU oracle: bf16 logits flip only near-ties of the blended volume
+    with torch.no_grad():
+        ref = O.predict_sliding(lambda im: O.unet3d_forward(sd, im), vol.numpy(), tile, 16)
+    top2 = ref.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 5e-2 * top2[:, 0].abs().clamp_min(1.0)
+    assert (fused[3].cpu().long() != ref.argmax(1))[decided].float().mean().item() < 2e-3

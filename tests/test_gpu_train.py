@@ -49,6 +49,54 @@ def test_fused_sgd_matches_torch_sgd_on_model():
         mm.set_compute_dtype(torch.bfloat16)
 
 
+def test_fused_sgd_skips_parameters_without_gradient_like_torch_sgd():
+    """torch.optim.SGD leaves a parameter whose .grad is None untouched (no weight decay, no momentum): in
+    unet3D_with_feam3 the eam*.proj parameters never receive a gradient.  FusedSGD steps only the runs of the flat buffer
+    that have one, including a run that starts off a 16-byte boundary (the 14-element bias)."""
+    from multimodal_pl_b200.engine import FusedSGD
+
+    torch.manual_seed(0)
+    shapes = [(6,), (14,), (3, 5), (9,), (32,)]           # element offsets 0, 6, 20, 35, 44
+    pa = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    opt_a = torch.optim.SGD(pa, lr=0.05, momentum=0.9, weight_decay=1e-2)
+    opt_b = FusedSGD(pb, lr=0.05, momentum=0.9, weight_decay=1e-2)
+    for step in range(3):
+        opt_a.zero_grad(set_to_none=True)
+        opt_b.zero_grad()
+        live = [0, 1, 3] if step < 2 else [1, 3, 4]        # parameter 2 never gets a gradient, 4 only at the end
+        for i in live:
+            g = torch.randn(shapes[i], device="cuda", generator=torch.Generator("cuda").manual_seed(10 * step + i))
+            pa[i].grad = g.clone()
+            pb[i].grad = g.clone()
+        opt_a.step()
+        opt_b.step()
+    for i, (a, b) in enumerate(zip(pa, pb)):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), i
+
+
+def test_backward_refuses_standardised_weights_refreshed_from_changed_weights():
+    """The standardised-weight buffers a convolution saved for backward are per-parameter and rewritten in place by the
+    next forward.  Unchanged weights -> same values -> a second forward before the backward is fine (GAN-style loops do
+    that); weights changed in between -> backward must raise like stock PyTorch, not silently use the new weights."""
+    import multimodal_pl_b200 as mm
+    from multimodal_pl_b200.unet3D import Conv3d
+
+    mm.set_compute_dtype(torch.bfloat16)
+    conv = Conv3d(32, 32, 3, padding=1).cuda()
+    x = torch.randn(1, 32, 4, 8, 8, device="cuda").requires_grad_(True)
+    y1 = conv(x)
+    y2 = conv(x)                       # same weights: harmless refresh
+    (y1.float().sum() + y2.float().sum()).backward()
+    assert torch.isfinite(conv.weight.grad).all()
+    y1 = conv(x)
+    with torch.no_grad():
+        conv.weight.mul_(1.5)          # an optimizer step between forward and backward ...
+    conv(x)                            # ... and a forward that re-standardises into the same buffers
+    with pytest.raises(RuntimeError, match="between its forward and its backward"):
+        y1.float().sum().backward()
+
+
 def test_parameter_gradients_land_in_the_flat_buffer_without_copies():
     """Backward kernels write every parameter gradient straight into its slot of the flat buffer and autograd adopts
     the view (no per-parameter add/copy launches); a second backward before zero_grad accumulates (p.grad += new)."""
