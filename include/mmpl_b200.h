@@ -114,6 +114,16 @@ size_t mmpl_conv3d_wgrad_workspace(int n, int d, int h, int w, int cin, int cout
 /* ---- stem (Cin = 1) and classifier (1x1x1 with bias, NCDHW fp32 logits): unet3D.py:594, :629-633 -------------- */
 int mmpl_stem_conv_fwd(const float* image, const float* w_hat /*[Cout][27]*/, void* y, int n, int d, int h, int w,
                        int cout, int dtype, mmpl_stream_t stream);
+/* ---- stem conv3x3x3(1 -> base) on tcgen05 with the 27-tap (hi/lo bf16) operand tile built in shared memory from an
+ * fp32 image halo: no expanded image tensor in HBM (self.conv1, unet3D.py:594, :666).  image [N,1,D,H,W] fp32;
+ * w_packed = the stem packing [cout][64] bf16 written by mmpl_ws_weight_fwd_batched (stem_kch = 64); y [N,D,H,W,cout]
+ * bf16; gn_stats_out (may be NULL) zero-initialised double [N][16][2], receives the GroupNorm(16) raw sums of y.
+ * wgrad: dy [N,D,H,W,cout] bf16 -> dw_tapmajor fp32 [27][cout] (zeroed by the call).  cout 32 or 64. */
+int mmpl_stem_tc_fwd(const float* image, const void* w_packed, void* y, double* gn_stats_out, int n, int d, int h,
+                     int w, int cout, mmpl_stream_t stream);
+int mmpl_stem_tc_wgrad(const float* image, const void* dy, float* dw_tapmajor, int n, int d, int h, int w, int cout,
+                       mmpl_stream_t stream);
+
 /* bf16 path: x27 [N,D,H,W,channels] bf16 = the 27 shifted copies of the image; the stem is then a channels -> Cout
  * 1x1x1 convolution for mmpl_conv3d_fprop / mmpl_conv3d_wgrad (tcgen05).  channels = 32: taps in 0..26, zeros in
  * 27..31.  channels = 64: hi bf16 part in 0..26 and the lo part (x - hi) in 32..58, i.e. the image keeps 16 mantissa

@@ -32,6 +32,8 @@ _SIGNATURES = {
     "mmpl_conv3d_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 10 + [_ptr, _c_size, _ptr],
     "mmpl_conv3d_wgrad_workspace": [_c_int] * 9,
     "mmpl_stem_im2col": [_ptr, _ptr] + [_c_int] * 5 + [_ptr],
+    "mmpl_stem_tc_fwd": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 5 + [_ptr],
+    "mmpl_stem_tc_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 5 + [_ptr],
     "mmpl_stem_conv_fwd": [_ptr, _ptr, _ptr] + [_c_int] * 6 + [_ptr],
     "mmpl_stem_conv_wgrad": [_ptr, _ptr, _ptr] + [_c_int] * 6 + [_ptr, _c_size, _ptr],
     "mmpl_stem_conv_wgrad_workspace": [_c_int] * 4,
@@ -49,7 +51,7 @@ _SIGNATURES = {
     "mmpl_masked_dice_bwd": [_ptr] * 7 + [_c_i64, _c_int, _c_int, _ptr],
     "mmpl_sgd_step": [_ptr, _ptr, _ptr, _c_i64, _ptr, _c_f32, _c_f32, _c_f32, _c_int, _ptr],
     "mmpl_sw_blend": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 12 + [_ptr],
-    "mmpl_cls_blend": [_ptr] * 7 + [_c_int] * 10 + [_ptr],
+    "mmpl_cls_blend": [_ptr] * 7 + [_c_int] * 9 + [_ptr],
     "mmpl_sw_finalize": [_ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _c_i64, _c_i64, _c_int, _ptr],
 }
 _RESTYPES = {"mmpl_last_error": ctypes.c_char_p, "mmpl_launch_count": ctypes.c_uint64,

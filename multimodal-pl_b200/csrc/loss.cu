@@ -10,6 +10,8 @@
 //   dz_c = p_c (g_c - sum_k g_k p_k) * grad_out
 // No one-hot tensor, no host synchronisation (the reference does 16 .item() syncs, loss_partial.py:55).
 // Algorithmic HBM bytes per voxel (fp32 logits, fp32 labels): fwd 4C+4, bwd 8C+4.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -305,9 +307,13 @@ void launch_bwd(const float* logits, const void* target, const float* cw, const 
 
 using namespace mmpl;
 
+// Measured on B200 (cfg2, profiles/r02_bench_kernels.txt): the 4-voxel form needs ~220 registers, i.e. 8 resident warps
+// per SM, and its long compute phases between load batches then expose the HBM latency (fwd 211 us vs 140 us scalar at 24
+// warps per SM).  The scalar form stays the default; MMPL_LOSS_VEC4=1 selects the vector form for experiments.
 static bool vec4_ok(const void* logits, const void* target, const void* dlogits, int64_t S, int u8) {
+  static const bool enabled = [] { const char* e = getenv("MMPL_LOSS_VEC4"); return e && e[0] == '1'; }();
   const uintptr_t a = reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits);
-  return S % 4 == 0 && a % 16 == 0 && reinterpret_cast<uintptr_t>(target) % (u8 ? 4 : 16) == 0;
+  return enabled && S % 4 == 0 && a % 16 == 0 && reinterpret_cast<uintptr_t>(target) % (u8 ? 4 : 16) == 0;
 }
 
 extern "C" int mmpl_partial_loss_fwd(const float* logits, const void* target, int target_is_u8,

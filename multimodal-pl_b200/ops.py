@@ -345,7 +345,7 @@ def _ws_table(items, dt):
 def _stem_plan(dt, cout):
     """-> (use_tc, tc_fwd, kch) for the Cin = 1 stem under the current dtype / algo / stem mode."""
     mode = _STEM["mode"]
-    kch = 64 if mode == "split" else 32
+    kch = 64 if mode in ("split", "fused") else 32
     use_tc = (mode != "direct" and _algo(dt, kch, cout) == _lib.ALGO_TCGEN05
               and _tc_wgrad_supported(dt, 1, 1, kch, cout))
     return use_tc, use_tc and mode != "fp32fwd", kch
@@ -606,13 +606,15 @@ def ws_conv3d(x, weight, stride=1, standardise=True, residual=None, want_stats=F
 
 
 # --------------------------------------------------------------------------------------------------------------
-_STEM = {"mode": os.environ.get("MMPL_STEM", "split")}
+_STEM = {"mode": os.environ.get("MMPL_STEM", "fused")}
 
 
 def set_stem_mode(mode: str):
-    """bf16 stem: 'split' (tcgen05, image carried as hi+lo bf16 parts, K = 64), 'tc32' (tcgen05, image rounded to bf16,
-    K = 32), 'fp32fwd' (CUDA-core fp32 forward, tcgen05 weight gradient) or 'direct' (CUDA cores only)."""
-    assert mode in ("split", "tc32", "fp32fwd", "direct")
+    """bf16 stem: 'fused' (default: tcgen05, the 27-tap hi+lo bf16 operand tile is built in shared memory from the fp32
+    image, nothing is expanded in HBM), 'split' (tcgen05 on an expanded [N,D,H,W,64] hi+lo copy of the image), 'tc32'
+    (expanded, image rounded to bf16, K = 32), 'fp32fwd' (CUDA-core fp32 forward, tcgen05 weight gradient) or 'direct'
+    (CUDA cores only)."""
+    assert mode in ("fused", "split", "tc32", "fp32fwd", "direct")
     _STEM["mode"] = mode
 
 
@@ -639,7 +641,15 @@ class StemConvFn(torch.autograd.Function):
         use_tc, tc_fwd, kch = _stem_plan(dt, cout)
         ws = _ws_get(weight, dt, standardise, kch if tc_fwd else 0, packed=False)
         w_hat, inv_std, pf = ws.w_hat, ws.inv_std, ws.pf
-        if tc_fwd:
+        fused = tc_fwd and _STEM["mode"] == "fused" and cout in (32, 64)
+        if fused:
+            # the K = 64 operand tile is built in shared memory inside the kernel (csrc/stem_tc.cu)
+            stats = _zero_stats(n * 16 * 2, dev) if cout % 16 == 0 else None
+            flops = 2 * n * d * h * w * cout * 27          # algorithmic (the tensor core multiplies K = 64: hi + lo + padding)
+            with _timed(_lib.ALGO_TCGEN05, flops, ("stem_tc", 1, cout, 3, 1, n * d * h * w, "fprop")):
+                _lib.check(L.mmpl_stem_tc_fwd(_p(img), _p(pf), _p(y), _p(stats), n, d, h, w, cout, st), "stem_tc_fwd")
+            ctx.save_for_backward(img, w_hat, inv_std)
+        elif tc_fwd:
             x27 = torch.empty((n, d, h, w, kch), dtype=dt, device=dev)
             _lib.check(L.mmpl_stem_im2col(_p(img), _p(x27), n, d, h, w, kch, st), "stem_im2col")
             code = _lib.dtype_code(dt)
@@ -655,7 +665,7 @@ class StemConvFn(torch.autograd.Function):
                        "stem_conv_fwd")
             ctx.save_for_backward(img, w_hat, inv_std)
         ctx.ws_entry, ctx.ws_stamp = ws, ws.stamp
-        ctx.meta = (n, d, h, w, cout, int(standardise), weight.dtype, use_tc, tc_fwd, kch)
+        ctx.meta = (n, d, h, w, cout, int(standardise), weight.dtype, use_tc, tc_fwd, kch, fused)
         ctx.weight = weight
         if not tc_fwd or stats is None:
             stats = torch.empty(0, dtype=torch.float64, device=dev)
@@ -667,11 +677,16 @@ class StemConvFn(torch.autograd.Function):
         L = _lib.lib()
         src, w_hat, inv_std = ctx.saved_tensors
         _check_ws_stamp(ctx)
-        n, d, h, w, cout, standardise, wdtype, use_tc, tc_fwd, kch = ctx.meta
+        n, d, h, w, cout, standardise, wdtype, use_tc, tc_fwd, kch, fused = ctx.meta
         dy = to_cl(dy)
         st = _lib.stream_ptr()
         dev = src.device
-        if use_tc:
+        if fused:
+            g_hat = torch.empty(27 * cout, dtype=torch.float32, device=dev)             # tap-major [27][cout]
+            flops = 2 * n * d * h * w * cout * 27
+            with _timed(_lib.ALGO_TCGEN05, flops, ("stem_tc", 1, cout, 3, 1, n * d * h * w, "wgrad")):
+                _lib.check(L.mmpl_stem_tc_wgrad(_p(src), _p(dy), _p(g_hat), n, d, h, w, cout, st), "stem_tc_wgrad")
+        elif use_tc:
             if not tc_fwd:      # forward ran on the fp32 image: expand it now (bf16 rounding is fine for dW)
                 x27 = torch.empty((n, d, h, w, kch), dtype=dy.dtype, device=dev)
                 _lib.check(L.mmpl_stem_im2col(_p(src), _p(x27), n, d, h, w, kch, st), "stem_im2col")

@@ -289,6 +289,39 @@ def test_ws_conv3d(mm, cin, cout, k, stride, sp, dtype, algo, tol_f, tol_b):
         mm.set_conv_algo("auto")
 
 
+@pytest.mark.parametrize("mode", ["fused", "split"])
+@pytest.mark.parametrize("shape,cout", [((2, 1, 5, 7, 9), 32), ((1, 1, 9, 33, 17), 32), ((2, 1, 4, 16, 8), 64),
+                                        ((1, 1, 16, 48, 40), 32)])
+def test_stem_tcgen05_modes(mm, mode, shape, cout):
+    """conv3x3x3(1 -> base) on the bf16 path: 'fused' builds the K = 64 hi/lo operand tile in shared memory inside the
+    kernel (csrc/stem_tc.cu), 'split' is the round-1 path through an expanded image.  Forward (<= 1e-2 vs the fp32 oracle;
+    hi + lo carries 16 mantissa bits of the image so the error is the bf16 weights and output), the GroupNorm(16)
+    statistics the epilogue emits, and the weight gradient (ragged edges, partial tiles, both output widths)."""
+    mm.set_compute_dtype(torch.bfloat16)
+    mm.set_stem_mode(mode)
+    try:
+        img = O.synth_patch(shape, 3)
+        w = _rand((cout, 1, 3, 3, 3), 1)
+        wr = w.clone().requires_grad_(True)
+        yr = O.ws_conv3d(img, wr, 1, 1)
+        dy = _rand(tuple(yr.shape), 2).bfloat16().float()
+        (yr * dy).sum().backward()
+        wd = w.cuda().requires_grad_(True)
+        mm.ops.begin_forward(torch.device("cuda"))
+        y = mm.ops.stem_conv(img.cuda(), wd, True)
+        assert rel(y.float(), yr) < 1e-2
+        st = getattr(y, "_mmpl_gn_stats", None)
+        assert st is not None and st[1] == 16
+        yf = y.detach().float().cpu()
+        grp = yf.reshape(shape[0], 16, -1).double()
+        ref_stats = torch.stack([grp.sum(-1), (grp * grp).sum(-1)], dim=-1).reshape(-1)
+        assert rel(st[0].cpu(), ref_stats) < 1e-5
+        y.backward(dy.cuda().to(y.dtype))
+        assert rel(wd.grad, wr.grad) < 1e-2
+    finally:
+        mm.set_stem_mode("fused")
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
 def test_stem_and_classifier(mm, dtype, tol):
     mm.set_compute_dtype(dtype)
