@@ -161,6 +161,21 @@ int mmpl_gn_relu_bwd(const void* x, const double* stats, const float* gamma, con
                      float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, double* workspace, int reduced, int n,
                      int64_t spatial, int c, int groups, float eps, int dtype, mmpl_stream_t stream);
 
+/* ---- class-token attention maps + token EMA of unet3D_with_feam3 (unet3D.py:142-212, :1051-1068, :1127-1175) --------
+ * mmpl_ln_rows_*: LayerNorm over the channel axis of `rows` NDHWC voxel rows without affine (biased variance, eps under
+ * the square root); fwd writes y = xhat and rstd [rows]; bwd: dx = rstd (g - mean(g) - xhat mean(g xhat)).  The attention
+ * map itself is mmpl_cls_fwd on xhat with the folded 15 x C matrix (csrc/eam.cu explains the algebra).
+ * mmpl_token_stats: sums [ntok][C], counts [ntok] (zeroed by the call) of the feature rows whose nearest-neighbour
+ * down-sampled label (mask [N][dm][hm][wm], fp32 or uint8 class ids) is l + 1; mmpl_token_ema: token[l] <- (1-alpha)
+ * token[l] + alpha sums[l]/counts[l] where counts[l] > 0 (renew_token without host synchronisation). */
+int mmpl_ln_rows_fwd(const void* x, void* y, float* rstd, int64_t rows, int c, float eps, int dtype, mmpl_stream_t stream);
+int mmpl_ln_rows_bwd(const void* xhat, const float* rstd, const void* g, void* dx, int64_t rows, int c, int dtype,
+                     mmpl_stream_t stream);
+int mmpl_token_stats(const void* x, const void* mask, int mask_is_u8, float* sums, float* counts, int n, int d, int h,
+                     int w, int c, int dm, int hm, int wm, int ntok, int dtype, mmpl_stream_t stream);
+int mmpl_token_ema(float* token, const float* sums, const float* counts, int ntok, int c, float alpha,
+                   mmpl_stream_t stream);
+
 /* ---- trilinear x2 upsample (align_corners=False) + skip add: unet3D.py:608, :686-687 -------------------------- */
 /* gn_stats (optional, may be NULL): double [N][16][2], zeroed by the caller; receives the GroupNorm(16) raw sums
  * (sum, sum of squares per group) of y, i.e. the statistics of the next block's gn1 / downsample.0 (unet3D.py:59, :645). */

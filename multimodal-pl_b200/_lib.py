@@ -39,6 +39,10 @@ _SIGNATURES = {
     "mmpl_stem_conv_wgrad_workspace": [_c_int] * 4,
     "mmpl_cls_fwd": [_ptr, _ptr, _ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_cls_bwd": [_ptr] * 8 + [_c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
+    "mmpl_ln_rows_fwd": [_ptr, _ptr, _ptr, _c_i64, _c_int, _c_f32, _c_int, _ptr],
+    "mmpl_ln_rows_bwd": [_ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _ptr],
+    "mmpl_token_stats": [_ptr, _ptr, _c_int, _ptr, _ptr] + [_c_int] * 10 + [_ptr],
+    "mmpl_token_ema": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_f32, _ptr],
     "mmpl_gn_stats": [_ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_gn_relu_fwd": [_ptr] * 8 + [_c_int, _c_i64, _c_int, _c_int, _c_f32, _c_int, _ptr],
     "mmpl_gn_relu_bwd": [_ptr] * 15 + [_c_int, _c_int, _c_i64, _c_int, _c_int, _c_f32, _c_int, _ptr],

@@ -484,6 +484,8 @@ void launch_cls_bwd(int cin, int blocks, cudaStream_t s, const T* a, const float
 
 namespace mmpl {
 int cls_fwd_mma(const void*, const float*, const float*, float*, int, int64_t, int, int, cudaStream_t);
+int cls_fwd_generic(const void*, const float*, const float*, float*, int, int64_t, int, int, int, cudaStream_t);
+int cls_bwd_generic(const void*, const float*, const float*, void*, float*, float*, int, int64_t, int, int, int, cudaStream_t);
 int cls_bwd_mma(const void*, const float*, const float*, void*, float*, float*, const float*, double*, int, int64_t, int,
                 int, cudaStream_t);
 }  // namespace mmpl
@@ -554,11 +556,16 @@ extern "C" int mmpl_stem_conv_wgrad(const float* image, const void* dy, float* d
 
 extern "C" int mmpl_cls_fwd(const void* a, const float* wc, const float* bias, float* logits, int n, int64_t spatial,
                             int cin, int classes, int dtype, mmpl_stream_t stream) {
-  MMPL_REQUIRE((cin == 32 || cin == 64) && classes >= 1 && classes <= 16, MMPL_E_SHAPE,
-               "cls: cin=%d classes=%d (cin 32|64, classes<=16)", cin, classes);
+  MMPL_REQUIRE(cin >= 8 && cin % 8 == 0 && classes >= 1 && classes <= 16, MMPL_E_SHAPE,
+               "cls: cin=%d classes=%d (cin a multiple of 8, classes<=16)", cin, classes);
   const int64_t total = static_cast<int64_t>(n) * spatial;
   const int blocks = static_cast<int>((total + 511) / 512);   // 256 threads x 2 voxels
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cin != 32 && cin != 64) {   // widths outside the tuned kernels (128 at 1/8 resolution): generic kernel, eam.cu
+    if (int e = cls_fwd_generic(a, wc, bias, logits, n, spatial, cin, classes, dtype, s)) return e;
+    MMPL_CHECK_LAUNCH("cls_fwd");
+    return MMPL_OK;
+  }
   if (dtype == MMPL_BF16) {   // warp-MMA kernel (cls_mma.cu); the CUDA-core kernel below is the fp32 exact path
     if (int e = cls_fwd_mma(a, wc, bias, logits, n, spatial, cin, classes, s)) return e;
     MMPL_CHECK_LAUNCH("cls_fwd");
@@ -578,11 +585,17 @@ extern "C" int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits
                             const float* gn_beta, double* gn_ws, int n, int64_t spatial, int cin, int classes, int dtype,
                             mmpl_stream_t stream) {
   MMPL_REQUIRE((gn_beta == nullptr) == (gn_ws == nullptr), MMPL_E_SHAPE, "cls_bwd: gn_beta and gn_ws go together");
-  MMPL_REQUIRE((cin == 32 || cin == 64) && classes >= 1 && classes <= 16, MMPL_E_SHAPE,
-               "cls: cin=%d classes=%d (cin 32|64, classes<=16)", cin, classes);
+  MMPL_REQUIRE(cin >= 8 && cin % 8 == 0 && classes >= 1 && classes <= 16, MMPL_E_SHAPE,
+               "cls: cin=%d classes=%d (cin a multiple of 8, classes<=16)", cin, classes);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   MMPL_CUDA(cudaMemsetAsync(dwc, 0, sizeof(float) * classes * cin, s));
   MMPL_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * classes, s));
+  if (cin != 32 && cin != 64) {
+    MMPL_REQUIRE(gn_ws == nullptr, MMPL_E_UNSUPPORTED, "cls_bwd: the fused GroupNorm-backward reduction needs cin 32 or 64");
+    if (int e = cls_bwd_generic(a, wc, dlogits, da, dwc, dbias, n, spatial, cin, classes, dtype, s)) return e;
+    MMPL_CHECK_LAUNCH("cls_bwd");
+    return MMPL_OK;
+  }
   if (dtype == MMPL_BF16) {   // warp-MMA kernel (cls_mma.cu)
     if (int e = cls_bwd_mma(a, wc, dlogits, da, dwc, dbias, gn_beta, gn_ws, n, spatial, cin, classes, s)) return e;
     MMPL_CHECK_LAUNCH("cls_bwd");

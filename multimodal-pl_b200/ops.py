@@ -932,7 +932,7 @@ class ClassifierFn(torch.autograd.Function):
         # The backward reduction of precls_conv.0/1 rides on the bf16 warp-MMA kernel (8 extra loads + 12 FMAs per 16x8
         # fragment); the fp32 CUDA-core kernel is issue-bound, there the stand-alone reduction pass is cheaper.
         fuse_cls = _cfg["fuse_gn_bwd_cls"] if _cfg["fuse_gn_bwd_cls"] is not None else a.dtype == torch.bfloat16
-        if fuse_cls and ctx.gn_bwd is not None and ctx.gn_bwd[2] == 0:
+        if fuse_cls and ctx.gn_bwd is not None and ctx.gn_bwd[2] == 0 and cin in (32, 64):
             gb, gws, _ = ctx.gn_bwd
         _lib.check(L.mmpl_cls_bwd(_p(a), _p(wc), _p(dl), _p(da), _p(dwc), _p(db), _p(gb), _p(gws), n, d * h * w, cin,
                                   classes, _lib.dtype_code(a.dtype), _lib.stream_ptr()), "cls_bwd")
@@ -943,6 +943,69 @@ class ClassifierFn(torch.autograd.Function):
 
 def classifier(a, weight, bias):
     return ClassifierFn.apply(a, weight, bias)
+
+
+class LayerNormRowsFn(torch.autograd.Function):
+    """LayerNorm over the channel axis of a channels-last volume, WITHOUT affine: xhat = (x - mean_c) * rstd_c per voxel.
+    The per-voxel rows of ``EAM.norm2`` (unet3D.py:197); its affine is folded into the attention matrix (csrc/eam.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        _lib.require_device()
+        L = _lib.lib()
+        dt = _cfg["dtype"]
+        x = to_cl(x, dt)
+        n, c, d, h, w = x.shape
+        rows = n * d * h * w
+        y = empty_cl(n, c, d, h, w, dt, x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        _lib.check(L.mmpl_ln_rows_fwd(_p(x), _p(y), _p(rstd), rows, c, float(eps), _lib.dtype_code(dt), _lib.stream_ptr()),
+                   "ln_rows_fwd")
+        ctx.save_for_backward(y, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        y, rstd = ctx.saved_tensors
+        g = to_cl(g, y.dtype)
+        dx = torch.empty_like(y)
+        _lib.check(L.mmpl_ln_rows_bwd(_p(y), _p(rstd), _p(g), _p(dx), rstd.numel(), y.shape[1], _lib.dtype_code(y.dtype),
+                                      _lib.stream_ptr()), "ln_rows_bwd")
+        return dx, None
+
+
+def layer_norm_rows(x, eps=1e-5):
+    return LayerNormRowsFn.apply(x, float(eps))
+
+
+@torch.no_grad()
+def renew_tokens(token, feature, mask, alpha):
+    """In-place EMA of the class tokens (unet3D_with_feam3.renew_token, unet3D.py:1051-1068) for ONE feature level:
+    token [ntok, C] fp32 on the device; feature [N, C, D, H, W]; mask [N, 1, Dm, Hm, Wm] class ids (float or uint8) at
+    any resolution (nearest-neighbour sampled at the feature resolution like F.interpolate(mode='nearest')).  Two
+    launches, no host synchronisation; classes absent from the (down-sampled) mask keep their token."""
+    _lib.require_device()
+    L = _lib.lib()
+    x = feature.detach()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = to_cl(x, x.dtype)
+    n, c, d, h, w = x.shape
+    m = mask.detach()
+    u8 = m.dtype == torch.uint8
+    m = m.contiguous() if u8 else m.float().contiguous()
+    dm, hm, wm = m.shape[-3:]
+    assert m.numel() == n * dm * hm * wm, f"mask {tuple(mask.shape)} vs features {tuple(feature.shape)}"
+    assert token.dtype == torch.float32 and token.is_contiguous() and token.shape[1] == c
+    ntok = token.shape[0]
+    sums = torch.empty(ntok * c, dtype=torch.float32, device=x.device)
+    cnt = torch.empty(ntok, dtype=torch.float32, device=x.device)
+    st = _lib.stream_ptr()
+    _lib.check(L.mmpl_token_stats(_p(x), _p(m), int(u8), _p(sums), _p(cnt), n, d, h, w, c, dm, hm, wm, ntok,
+                                  _lib.dtype_code(x.dtype), st), "token_stats")
+    _lib.check(L.mmpl_token_ema(_p(token), _p(sums), _p(cnt), ntok, c, float(alpha), st), "token_ema")
+    return token
 
 
 class BlendSink:

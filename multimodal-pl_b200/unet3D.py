@@ -77,7 +77,8 @@ class GNReLUConv(nn.Sequential):
 
 class GNReLUClassifier(nn.Sequential):
     """precls_conv = Sequential(GroupNorm(16, base), ReLU, nn.Conv3d(base, classes, 1)) (:629-633): plain 1x1x1
-    convolution WITH bias and without weight standardisation, emitting fp32 NCDHW logits."""
+    convolution WITH bias and without weight standardisation, emitting fp32 NCDHW logits.  Also the deep-supervision
+    heads deepout1..3 of unet3D_with_feam3 (:969-993; 128 / 64 / 32 channels)."""
 
     def forward(self, x, blend=None):
         gn, conv = self[0], self[2]
@@ -85,15 +86,7 @@ class GNReLUClassifier(nn.Sequential):
         if blend is not None:       # sliding-window inference: accumulate g * logits straight into the volume
             ops.classifier_blend(a, conv.weight, conv.bias, blend)
             return None
-        if conv.in_channels in (32, 64) and conv.out_channels <= 16:
-            return ops.classifier(a, conv.weight, conv.bias)
-        # deepout1 of unet3D_with_feam3 (128 channels, 1/8 resolution, 9 216 voxels per sample at cfg2): outside the
-        # width the classifier kernels are built for; a plain fp32 library GEMM on this tiny tensor (a matmul, not a
-        # cuDNN convolution: those default to TF32)
-        n, c = a.shape[0], a.shape[1]
-        rows = a.permute(0, 2, 3, 4, 1).reshape(n, -1, c).float()                 # view of the NDHWC storage
-        out = rows @ conv.weight.view(conv.out_channels, c).t().float() + conv.bias.float()
-        return out.permute(0, 2, 1).reshape((n, conv.out_channels) + tuple(a.shape[2:])).contiguous()
+        return ops.classifier(a, conv.weight, conv.bias)
 
 
 class NoBottleneck(nn.Module):
@@ -263,10 +256,14 @@ class unet3D_baseline(nn.Module):
 
 
 class EAM(nn.Module):
-    """Class-token cross attention of the reference (unet3D.py:142-212), same constructor, parameters and outputs:
-    ``forward(x [B,N,C], modality_token [B,Nt,C]) -> (x_out [B,Nt,C], attn [B,heads,Nt,N])`` with ``attn`` the UNSCALED
-    q.k^T logits (the model averages them over the heads into its attention maps, :1133-1137).  Tiny next to the
-    backbone (<= 2.4 GFLOP per call at cfg2): LayerNorm + library GEMMs in fp32."""
+    """Class-token cross attention (reference unet3D.py:142-212): same constructor, parameters (``kv``, ``q``, ``proj``,
+    ``norm2``, ``norm3``) and ``forward(x, modality_token) -> (tokens_out, attn)`` contract, ``attn`` being the UNSCALED
+    per-head q.k^T logits [B, heads, Nt, N].
+
+    The model only consumes ``attn.mean(1)`` (:1133-1137).  ``attention_map`` computes exactly that on the device kernels
+    without ever forming keys, values or per-head logits: the head mean of per-head dot products is one dot product over
+    all channels, so with M = q(norm3(token)) @ Wk the map is a 15-row "classifier" (M * gamma2 / heads, bias M beta2 /
+    heads) over the LayerNorm-ed voxel rows -- ``ops.layer_norm_rows`` + ``ops.classifier`` (csrc/eam.cu)."""
 
     def __init__(self, dim, input_resolution, num_heads, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop=0.,
                  attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, upsample=None, use_checkpoint=False):
@@ -275,8 +272,7 @@ class EAM(nn.Module):
         self.input_resolution = input_resolution
         self.use_checkpoint = use_checkpoint
         self.num_heads = num_heads
-        head_dim = dim // num_heads
-        self.scale = qk_scale or head_dim ** -0.5
+        self.scale = qk_scale or (dim // num_heads) ** -0.5
         self.kv = nn.Linear(dim, dim * 2, bias=False)
         self.q = nn.Linear(dim, dim, bias=False)
         self.softmax = nn.Softmax(dim=-1)
@@ -284,19 +280,29 @@ class EAM(nn.Module):
         self.norm2 = norm_layer(dim)
         self.norm3 = norm_layer(dim)
 
+    def _folded(self, token):
+        """-> (W [Nt, C], b [Nt]) with  attn.mean(1)[t, v] = W[t] . xhat[v] + b[t],  xhat = LayerNorm2 without affine."""
+        qt = self.q(self.norm3(token.float()))                         # [Nt, C]
+        m = qt @ self.kv.weight[: self.dim].float()                    # keys are the first C rows of kv (:198-199)
+        return m * self.norm2.weight.float() / self.num_heads, (m @ self.norm2.bias.float()) / self.num_heads
+
+    def attention_map(self, x, token):
+        """x [B, C, D, H, W] feature volume, token [Nt, C] -> head-mean attention logits [B, Nt, D, H, W] (fp32)."""
+        w, b = self._folded(token)
+        xhat = ops.layer_norm_rows(x, self.norm2.eps)
+        return ops.classifier(xhat, w.reshape(w.shape[0], w.shape[1], 1, 1, 1), b)
+
     def forward(self, x, modality_token):
-        B_, N, C = x.shape
-        B_, Nt, ct = modality_token.shape
-        x = self.norm2(x.float())
-        modality_token = self.norm3(modality_token.float())
-        kv = self.kv(x).reshape(B_, N, 2, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
-        k, v = kv[0], kv[1]
-        q = self.q(modality_token).reshape(B_, Nt, self.num_heads, C // self.num_heads).permute(0, 2, 1, 3)
-        attn = (q @ k.transpose(-2, -1))
-        attnf = self.softmax(attn * self.scale)
-        x = (attnf @ v).transpose(1, 2).reshape(B_, Nt, C)
-        x = self.proj(self.norm2(x)) + x
-        return x, attn
+        """The reference's full contract, for callers that want the updated tokens or per-head logits; plain tensor
+        algebra (the model's hot path is ``attention_map``)."""
+        batch, n_vox, c = x.shape
+        n_tok, heads, hd = modality_token.shape[1], self.num_heads, c // self.num_heads
+        feats = self.norm2(x.float())
+        keys, values = self.kv(feats).view(batch, n_vox, 2, heads, hd).unbind(2)           # each [B, N, heads, hd]
+        queries = self.q(self.norm3(modality_token.float())).view(-1, n_tok, heads, hd)    # token batch is 1 in the model
+        attn = torch.einsum("bthd,bnhd->bhtn", queries.expand(batch, -1, -1, -1), keys)
+        mixed = torch.einsum("bhtn,bnhd->bthd", self.softmax(attn * self.scale), values).reshape(batch, n_tok, c)
+        return self.proj(self.norm2(mixed)) + mixed, attn
 
 
 class unet3D_with_feam3(unet3D_baseline):
@@ -329,10 +335,7 @@ class unet3D_with_feam3(unet3D_baseline):
 
     def _attend(self, eam, token, x, up):
         """attention map of one decoder scale (:1131-1137): mean over heads of the q.k^T logits, as a volume"""
-        n, c = x.shape[0], x.shape[1]
-        x_t = x.permute(0, 2, 3, 4, 1).reshape(n, -1, c)          # [B, voxels, C]: a view of the NDHWC storage
-        _, cattn = eam(x_t, token.view(1, self.num_classes - 1, c).detach())
-        amap = cattn.mean(1).reshape((n, self.num_classes - 1) + tuple(x.shape[2:]))
+        amap = eam.attention_map(x, token.detach())
         return up(amap) if self.deep_up else amap
 
     def forward(self, input, mask=None):
@@ -367,22 +370,13 @@ class unet3D_with_feam3(unet3D_baseline):
 
     @torch.no_grad()
     def renew_token(self, features, mask):
-        """EMA of the per-class mean feature into the class tokens (:1051-1068), without the reference's host
-        synchronisations: classes absent from ``mask`` (or from its nearest-neighbour down-sampling) keep their token.
-        Per-channel means pool over the batch (the reference's reshape is only meaningful for batch 1)."""
-        tokens = [self.class_token1, self.class_token2, self.class_token3]
+        """EMA of the per-class mean feature into the class tokens (:1051-1068) on the device (ops.renew_tokens: one
+        segmented-sum launch + one update launch per level, no host synchronisation): classes absent from ``mask`` (or
+        from its nearest-neighbour down-sampling) keep their token.  Per-channel means pool over the batch (the
+        reference's reshape is only meaningful for batch 1)."""
+        names = ["class_token1", "class_token2", "class_token3"]
         for index, x in enumerate(features):
-            tok = tokens[min(index, 2)].to(x.device)
-            xf = x.float()
-            for l in range(self.num_classes - 1):
-                cm = torch.nn.functional.interpolate((mask == (l + 1)).float(), xf.shape[2:], mode="nearest")
-                cnt = cm.sum()
-                mean = (xf * cm).sum(dim=(0, 2, 3, 4)) / cnt.clamp_min(1.0)
-                upd = tok[l] * (1 - self.alpha) + mean * self.alpha
-                tok[l] = torch.where(cnt > 0, upd, tok[l])
-            if index == 0:
-                self.class_token1 = tok
-            elif index == 1:
-                self.class_token2 = tok
-            else:
-                self.class_token3 = tok
+            name = names[min(index, 2)]
+            tok = getattr(self, name).to(x.device, torch.float32).contiguous()
+            ops.renew_tokens(tok, x, mask, self.alpha)
+            setattr(self, name, tok)

@@ -253,6 +253,10 @@ def test_unet3d_with_feam3_bf16_train_step_runs():
     logits, attn, deep, feats = model(x, lab)
     ref = torch.from_numpy(g["logits"])
     assert ((logits.float().cpu() - ref).norm() / ref.norm()).item() < 2e-2
+    for i in range(3):      # attention maps (LayerNorm rows + folded 15-row classifier) and deep-supervision heads, bf16
+        for name, got, tol in (("attn", attn[i], 3e-2), ("deep", deep[i], 2e-2), ("feat", feats[i], 2e-2)):
+            r = torch.from_numpy(g[f"{name}{i}"])
+            assert ((got.float().cpu() - r).norm() / r.norm()).item() < tol, (name, i)
     loss, _ = get_loss(logits, 0, deep, lab, [torch.ones(16)])
     (loss + sum(a.float().mean() for a in attn) + sum(d.float().mean() for d in deep)).backward()
     for k, p in model.named_parameters():
