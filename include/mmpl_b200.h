@@ -176,6 +176,28 @@ int mmpl_token_stats(const void* x, const void* mask, int mask_is_u8, float* sum
 int mmpl_token_ema(float* token, const float* sums, const float* counts, int ntok, int c, float alpha,
                    mmpl_stream_t stream);
 
+/* ---- device-side input pipeline: AMOSDataSet_newatlas.__getitem__, MOTSDataset.py:299-395, and the
+ * intensity augmentations of get_train_transform, :33-52.  Volumes are [h][w][d] (d fastest) as the reference holds them,
+ * src_dtype 0 = fp32, 1 = int16, 2 = uint8; outputs are [crop_d][crop_h][crop_w].
+ * mmpl_volume_moments: moments[2] = {sum, sum of squares} in fp64 (zeroed by the call) for the MRI z-score.
+ * mmpl_prepare_patch: zero-pad to crop + 5 (:370-372), scale (mode 0: CT clip +-325 HU / 325; mode 1: MRI (x - mean) / std
+ *   over the padded volume, `moments` from mmpl_volume_moments; mode 2: copy, for labels; :171-186), crop at (b, c, a)
+ *   (:377-383), transpose (:389-391).  Integer sources are scaled in fp64 and rounded once, like numpy promotes them.
+ * mmpl_atlas_patch: nearest-neighbour resize of atlas [k][ha][wa][da] to (h, w, d) (:357), then pad / crop / transpose.
+ * mmpl_augment_patch (in place): x += N(0, noise_std) from a counter-based generator (seed), x = x * mult + add,
+ *   x = clip((x - mean) * contrast + mean, min, max) with stats = {sum, min, max} from mmpl_patch_stats (double[4]);
+ *   neutral parameters (0, 1, 0, 1) skip a step.  mmpl_blur_axis: one axis of scipy.ndimage.gaussian_filter ('reflect'). */
+int mmpl_volume_moments(const void* volume, int src_dtype, int64_t count, double* moments, mmpl_stream_t stream);
+int mmpl_prepare_patch(const void* volume, int src_dtype, void* out, int out_is_u8, int h, int w, int d, int b, int c, int a,
+                       int crop_h, int crop_w, int crop_d, int mode, const double* moments, mmpl_stream_t stream);
+int mmpl_atlas_patch(const float* atlas, float* out, int k, int ha, int wa, int da, int h, int w, int d, int b, int c, int a,
+                     int crop_h, int crop_w, int crop_d, mmpl_stream_t stream);
+int mmpl_patch_stats(const float* x, int64_t n, double* stats /*[4]*/, mmpl_stream_t stream);
+int mmpl_augment_patch(float* x, int64_t n, float noise_std, uint64_t seed, float mult, float add, float contrast,
+                       const double* stats, mmpl_stream_t stream);
+int mmpl_blur_axis(const float* src, float* dst, int d, int h, int w, int axis, const float* taps_dev, int radius,
+                   mmpl_stream_t stream);
+
 /* ---- trilinear x2 upsample (align_corners=False) + skip add: unet3D.py:608, :686-687 -------------------------- */
 /* gn_stats (optional, may be NULL): double [N][16][2], zeroed by the caller; receives the GroupNorm(16) raw sums
  * (sum, sum of squares per group) of y, i.e. the statistics of the next block's gn1 / downsample.0 (unet3D.py:59, :645). */

@@ -43,6 +43,12 @@ _SIGNATURES = {
     "mmpl_ln_rows_bwd": [_ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_int, _ptr],
     "mmpl_token_stats": [_ptr, _ptr, _c_int, _ptr, _ptr] + [_c_int] * 10 + [_ptr],
     "mmpl_token_ema": [_ptr, _ptr, _ptr, _c_int, _c_int, _c_f32, _ptr],
+    "mmpl_volume_moments": [_ptr, _c_int, _c_i64, _ptr, _ptr],
+    "mmpl_prepare_patch": [_ptr, _c_int, _ptr, _c_int] + [_c_int] * 10 + [_ptr, _ptr],
+    "mmpl_atlas_patch": [_ptr, _ptr] + [_c_int] * 13 + [_ptr],
+    "mmpl_patch_stats": [_ptr, _c_i64, _ptr, _ptr],
+    "mmpl_augment_patch": [_ptr, _c_i64, _c_f32, ctypes.c_uint64, _c_f32, _c_f32, _c_f32, _ptr, _ptr],
+    "mmpl_blur_axis": [_ptr, _ptr] + [_c_int] * 4 + [_ptr, _c_int, _ptr],
     "mmpl_gn_stats": [_ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_gn_relu_fwd": [_ptr] * 8 + [_c_int, _c_i64, _c_int, _c_int, _c_f32, _c_int, _ptr],
     "mmpl_gn_relu_bwd": [_ptr] * 15 + [_c_int, _c_int, _c_i64, _c_int, _c_int, _c_f32, _c_int, _ptr],

@@ -582,3 +582,80 @@ def synth_labels(shape: Sequence[int], seed: int, num_classes: int = 16, n_seeds
             lab[m] = c
         out[b] = lab
     return torch.from_numpy(out).unsqueeze(1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Input pipeline                                             MOTSDataset.py:33-52, :171-186, :269-297, :299-395
+# ----------------------------------------------------------------------------------------------------------------
+# The reference's dataset needs SimpleITK, nibabel and batchgenerators (none installed here), so these are
+# restatements: numpy statements copied in meaning from __getitem__ for the deterministic part, and the PUBLISHED algorithms
+# of batchgenerators' transforms (MIC-DKFZ/batchgenerators, the version the reference imports is unpinned -- no
+# requirements file) for the augmentations, anchored on the call site get_train_transform (:33-52).  "parity unpinned" for
+# the augmentations: the reference holds no fixture for them.
+
+
+def pad_image_ref(img: np.ndarray, target) -> np.ndarray:
+    """pad_image (MOTSDataset.py:269-282): zero-pad at the end of each axis up to ``target``."""
+    miss = [max(int(math.ceil(t - s)), 0) for t, s in zip(target, img.shape[-3:])]
+    pad = [(0, 0)] * (img.ndim - 3) + [(0, m) for m in miss]
+    return np.pad(img, pad, "constant")
+
+
+def truncate_ref(ct: np.ndarray, is_ct: bool) -> np.ndarray:
+    """truncate (MOTSDataset.py:171-186): CT clipped to [-325, 325] HU and divided by 325; MRI z-scored."""
+    ct = ct.copy()
+    if is_ct:
+        ct[np.where(ct <= -325)] = -325
+        ct[np.where(ct >= 325)] = 325
+        return (ct - 0) / 325.
+    ct = ct - np.mean(ct)
+    return ct / np.std(ct)
+
+
+def prepare_patch_ref(image: np.ndarray, label: np.ndarray, atlas: Optional[np.ndarray], is_ct: bool, crop, origin):
+    """AMOSDataSet_newatlas.__getitem__ from the atlas resize to the final cast (MOTSDataset.py:357-394) with the crop
+    origin (b, c, a) given instead of drawn.  image / label [h, w, d]; -> image [1,D,H,W] f32, label [1,D,H,W] f32,
+    catlas [K,D,H,W] f32 (or None)."""
+    ch, cw, cd = crop
+    b, c, a = origin
+    catlas = None
+    if atlas is not None:
+        catlas = F.interpolate(torch.tensor(atlas).unsqueeze(0), image.shape).numpy()[0]                  # :357
+    if image.shape != label.shape:                                                                       # :360-368
+        fs = [min(image.shape[i], label.shape[i]) for i in range(3)]
+        image, label = image[:fs[0], :fs[1], :fs[2]], label[:fs[0], :fs[1], :fs[2]]
+    tgt = [ch + 5, cw + 5, cd + 5]
+    image, label = pad_image_ref(image, tgt), pad_image_ref(label, tgt)                                   # :370-371
+    if catlas is not None:
+        catlas = pad_image_ref(catlas, tgt)                                                               # :372
+    image = truncate_ref(image, is_ct)                                                                   # :374
+    image = image[b:b + ch, c:c + cw, a:a + cd]                                                           # :381-383
+    label = label[b:b + ch, c:c + cw, a:a + cd]
+    image = image[np.newaxis].transpose((0, 3, 1, 2)).astype(np.float32)                                  # :386-392
+    label = label[np.newaxis].transpose((0, 3, 1, 2)).astype(np.float32)
+    if catlas is not None:
+        catlas = catlas[:, b:b + ch, c:c + cw, a:a + cd].transpose((0, 3, 1, 2)).astype(np.float32)
+    return image, label, catlas
+
+
+def augment_ref(img: np.ndarray, params: dict, noise: Optional[np.ndarray] = None) -> np.ndarray:
+    """get_train_transform (MOTSDataset.py:33-52) with the draws given: GaussianNoise (``noise`` = the unit normal field to
+    scale by noise_std), GaussianBlur (scipy gaussian_filter, order 0), multiplicative and additive brightness, contrast
+    with preserve_range.  img [1, D, H, W] float32."""
+    from scipy.ndimage import gaussian_filter
+
+    x = img.astype(np.float32).copy()
+    if params.get("noise_std") and noise is not None:
+        x = x + np.float32(params["noise_std"]) * noise.astype(np.float32)
+    if params.get("blur_sigma"):
+        x[0] = gaussian_filter(x[0], params["blur_sigma"], order=0)
+    if params.get("mult") is not None:
+        x = x * np.float32(params["mult"])
+    if params.get("add") is not None:
+        x = x + np.float32(params["add"])
+    if params.get("contrast") is not None:
+        mn, lo, hi = x.mean(), x.min(), x.max()
+        x = (x - mn) * np.float32(params["contrast"]) + mn
+        x[x < lo] = lo
+        x[x > hi] = hi
+    return x.astype(np.float32)
