@@ -475,9 +475,11 @@ def run_train(args):
     # ---- BASELINE configs[3] in the same record: sliding-window inference (all ranks take part) ----------------------
     infer = None
     comm_in_graph = bool(use_graph and getattr(step, "comm_in_graph", False))
+    if use_graph:
+        step.close()        # the graph pins NCCL kernels: release it before the process group is destroyed
+    del step
+    torch.cuda.empty_cache()
     if args.workload == "cfg2" and not args.no_infer:
-        del step
-        torch.cuda.empty_cache()
         try:
             # the ranks hold identical weights (same reduced gradients, same SGD): reuse the trained model
             infer = infer_record(model, dev, rank, world, steps=2, warmup=1, eager=args.eager)

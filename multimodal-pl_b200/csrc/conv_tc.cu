@@ -701,7 +701,11 @@ int dispatch_tc(const TcProblem& q, cudaStream_t s) {
     // irrelevant at this size.
     const int64_t sp = static_cast<int64_t>(q.N) * ceil_div(q.H, TC_TH) * ceil_div(q.W, TC_TW);
     const int64_t items_default = sp * ceil_div(q.D, nt == 128 ? 2 : 1) * (nout / nt);
-    if (items_default * 2 <= num_sms()) return launch_tc<64, 64, 1, MODE, false, 1>(q, s);
+    // two activation stages here (139 KB + 8 weight stages): with one plane per item the MMAs of a 64-channel chunk take
+    // about as long as the TMA round trip of the next chunk, so a single stage leaves the tensor core idle half the time
+    static const bool small_na2 = [] { const char* e = getenv("MMPL_TC_SMALL_NA2"); return !(e && e[0] == '0'); }();
+    if (items_default * 2 <= num_sms())
+      return small_na2 ? launch_tc<64, 64, 1, MODE, false, 2>(q, s) : launch_tc<64, 64, 1, MODE, false, 1>(q, s);
   }
   if (deep_b && MODE == MODE_S1K3) {
     if (nt == 32) return launch_tc<64, 32, 4, MODE, false, 1>(q, s);

@@ -311,6 +311,15 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph, stream=hp, capture_error_mode="thread_local"):
             self.static_loss = self._body(in_graph=True)
 
+    def close(self):
+        """Release the captured graph.  With world_size > 1 the graph holds NCCL kernels: call this (or drop the last
+        reference to the object) BEFORE ``dist.destroy_process_group()``, which otherwise waits on the communicator the
+        graph still pins."""
+        torch.cuda.synchronize()
+        graph, self.graph = getattr(self, "graph", None), None
+        if graph is not None:
+            graph.reset()
+
     def _bucket_step(self, lo, hi):
         self.opt.step(grad_scale=1.0 if self.dp.average else 1.0 / self.world, flat_range=(lo, hi), last=False)
 
