@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace mmpl {
 namespace {
@@ -286,6 +287,237 @@ partial_loss_bwd_kernel(const float* __restrict__ logits, const void* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------ staged kernels
+// A producer warp streams [C planes x V voxels] + labels into shared memory with 1-D bulk-async copies (TMA engine,
+// mbarrier completion) three stages ahead, and eight consumer warps read their voxels from shared memory: the loads no
+// longer occupy registers, issue slots or the load/store unit of the warps that do the arithmetic.  Requirements:
+// S % 16 == 0 and 16-byte aligned planes (else the register kernels run).  See the dispatch for which direction uses it.
+constexpr int LS_V = 512;                 // voxels per stage
+constexpr int LS_NS = 3;                  // stages
+constexpr int LS_CONSUMERS = 256;         // 8 consumer warps; warp 8 is the producer
+constexpr int LS_THREADS = LS_CONSUMERS + 32;
+
+template <int MAXC>
+struct LossStage {
+  float z[MAXC][LS_V];
+  float t[LS_V];                          // fp32 labels, or LS_V bytes of uint8 labels in the first quarter
+};
+
+template <int MAXC>
+__device__ __forceinline__ void loss_produce(LossStage<MAXC>* stages, uint64_t* full, uint64_t* empty, const float* zb,
+                                             const void* tb, bool tu8, int64_t S, int C, int chunk0, int chunk_step,
+                                             int nchunks) {
+  uint32_t it = 0;
+  for (int ch = chunk0; ch < nchunks; ch += chunk_step, ++it) {
+    const uint32_t s = it % LS_NS, ph = (it / LS_NS) & 1;
+    ptx::mbar_wait(&empty[s], ph ^ 1);
+    const int64_t s0 = static_cast<int64_t>(ch) * LS_V;
+    const uint32_t nv = static_cast<uint32_t>(min(static_cast<int64_t>(LS_V), S - s0));
+    const uint32_t lab_bytes = tu8 ? nv : nv * 4u;
+    ptx::mbar_expect_tx(&full[s], nv * 4u * C + lab_bytes);
+    for (int c = 0; c < C; ++c) ptx::bulk_load_1d(stages[s].z[c], zb + c * S + s0, nv * 4u, &full[s]);
+    if (tu8)
+      ptx::bulk_load_1d(stages[s].t, static_cast<const uint8_t*>(tb) + s0, lab_bytes, &full[s]);
+    else
+      ptx::bulk_load_1d(stages[s].t, static_cast<const float*>(tb) + s0, lab_bytes, &full[s]);
+  }
+}
+
+template <int MAXC, bool TU8>
+__global__ void __launch_bounds__(LS_THREADS, 2)
+partial_loss_fwd_staged_kernel(const float* __restrict__ logits, const void* __restrict__ target,
+                               const float* __restrict__ cw, const float* __restrict__ lut, double* __restrict__ sums,
+                               float* __restrict__ loss, unsigned int* __restrict__ ticket, int N, int64_t S, int C, int uce,
+                               int per_sample) {
+  extern __shared__ uint8_t smem_raw[];
+  // aligned by pointer arithmetic on the shared array, so that the accesses below stay LDS (see stem_tc.cu)
+  LossStage<MAXC>* stages = reinterpret_cast<LossStage<MAXC>*>(smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u));
+  __shared__ uint64_t full[LS_NS], empty[LS_NS];
+  __shared__ float s_lut[MAXC];
+  __shared__ float s_part[LS_CONSUMERS / 32][4 * MAXC];
+  __shared__ bool s_last;
+  __shared__ unsigned int s_ce_mask;
+  const int64_t n = blockIdx.y;
+  const int grp = per_sample ? static_cast<int>(n) : 0;
+  const float* cw_g = cw + static_cast<int64_t>(grp) * C;
+  const float* lut_g = lut ? lut + static_cast<int64_t>(grp) * C : nullptr;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < LS_NS; ++i) ptx::mbar_init(&full[i], 1), ptx::mbar_init(&empty[i], LS_CONSUMERS / 32);
+    ptx::fence_barrier_init();
+    unsigned int m = 0;
+    for (int c = 0; c < C; ++c)
+      if (uce && cw_g[c] != 0.f) m |= 1u << c;
+    s_ce_mask = m;
+  }
+  if (threadIdx.x < MAXC) s_lut[threadIdx.x] = (lut_g && threadIdx.x < C) ? lut_g[threadIdx.x] : static_cast<float>(threadIdx.x);
+  __syncthreads();
+  const int nchunks = static_cast<int>((S + LS_V - 1) / LS_V);
+  const float* zb = logits + n * C * S;
+  const uint8_t* tb = static_cast<const uint8_t*>(target) + n * S * (TU8 ? 1 : 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float aI[MAXC], aZ[MAXC], aY[MAXC], aE[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) aI[c] = aZ[c] = aY[c] = aE[c] = 0.f;
+  if (warp == LS_CONSUMERS / 32) {
+    if (lane == 0) loss_produce<MAXC>(stages, full, empty, zb, tb, TU8, S, C, blockIdx.x, gridDim.x, nchunks);
+  } else {
+    const unsigned int ce_mask = s_ce_mask;
+    uint32_t it = 0;
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
+      const uint32_t s = it % LS_NS, ph = (it / LS_NS) & 1;
+      ptx::mbar_wait(&full[s], ph);
+      const int nv = static_cast<int>(min(static_cast<int64_t>(LS_V), S - static_cast<int64_t>(ch) * LS_V));
+#pragma unroll
+      for (int j = 0; j < LS_V / LS_CONSUMERS; ++j) {
+        const int v = threadIdx.x + j * LS_CONSUMERS;
+        if (v < nv) {
+          float p[MAXC];
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) p[c] = c < C ? stages[s].z[c][v] : 0.f;
+          softmax_inplace<MAXC>(p, C);
+          const float tv = TU8 ? static_cast<float>(reinterpret_cast<const uint8_t*>(stages[s].t)[v]) : stages[s].t[v];
+          const int tc = class_of(tv, lut_g ? s_lut : nullptr, C);
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) {
+            if (c < C) {
+              const bool t = (c == tc);
+              aZ[c] = fmaf(p[c], p[c], aZ[c]);
+              aI[c] += t ? p[c] : 0.f;
+              aY[c] += t ? 1.f : 0.f;
+              if (ce_mask & (1u << c)) {
+                const float l = t ? logf(p[c]) : logf(1.0f - p[c]);     // nn.BCELoss: log of the fp32 probability, clamp -100
+                aE[c] -= fmaxf(l, -100.f);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty[s]);
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const float a = warp_sum(aI[c]), b = warp_sum(aZ[c]), d = warp_sum(aY[c]), e = warp_sum(aE[c]);
+      if (lane == 0) {
+        s_part[warp][c] = a;
+        s_part[warp][MAXC + c] = b;
+        s_part[warp][2 * MAXC + c] = d;
+        s_part[warp][3 * MAXC + c] = e;
+      }
+    }
+  }
+  __syncthreads();
+  double* sums_g = sums + static_cast<int64_t>(grp) * 4 * C;
+  if (threadIdx.x < 4 * MAXC) {
+    const int k = threadIdx.x / MAXC, c = threadIdx.x % MAXC;
+    if (c < C) {
+      double t = 0;
+      for (int w = 0; w < LS_CONSUMERS / 32; ++w) t += static_cast<double>(s_part[w][threadIdx.x]);
+      atomicAdd(&sums_g[k * C + c], t);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    const int G = per_sample ? N : 1;
+    const double sm = 1e-5, nv = static_cast<double>(per_sample ? S : static_cast<int64_t>(N) * S);
+    double total = 0;
+    for (int g = 0; g < G; ++g) {
+      const volatile double* vs = sums + static_cast<int64_t>(g) * 4 * C;
+      double dice = 0, ce = 0;
+      for (int c = 0; c < C; ++c) {
+        const double I = vs[c], Z = vs[C + c], Y = vs[2 * C + c], E = vs[3 * C + c], w = cw[g * C + c];
+        dice += w * (1.0 - (2.0 * I + sm) / (Z + Y + sm));
+        ce += w * (E / nv);
+      }
+      total += dice / C + (uce ? ce : 0.0);
+    }
+    *loss = static_cast<float>(total / G);
+  }
+}
+
+template <int MAXC, bool TU8>
+__global__ void __launch_bounds__(LS_THREADS, 2)
+partial_loss_bwd_staged_kernel(const float* __restrict__ logits, const void* __restrict__ target,
+                               const float* __restrict__ cw, const float* __restrict__ lut, const double* __restrict__ sums,
+                               const float* __restrict__ grad_out, float* __restrict__ dlogits, int N, int64_t S, int C,
+                               int uce, int per_sample) {
+  extern __shared__ uint8_t smem_raw[];
+  // aligned by pointer arithmetic on the shared array, so that the accesses below stay LDS (see stem_tc.cu)
+  LossStage<MAXC>* stages = reinterpret_cast<LossStage<MAXC>*>(smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u));
+  __shared__ uint64_t full[LS_NS], empty[LS_NS];
+  __shared__ float s_lut[MAXC], s_a[MAXC], s_b[MAXC], s_e[MAXC];
+  const int64_t n = blockIdx.y;
+  const int grp = per_sample ? static_cast<int>(n) : 0;
+  const float* lut_g = lut ? lut + static_cast<int64_t>(grp) * C : nullptr;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < LS_NS; ++i) ptx::mbar_init(&full[i], 1), ptx::mbar_init(&empty[i], LS_CONSUMERS / 32);
+    ptx::fence_barrier_init();
+  }
+  if (threadIdx.x < MAXC) {
+    const int c = threadIdx.x;
+    s_lut[c] = (lut_g && c < C) ? lut_g[c] : static_cast<float>(c);
+    if (c < C) {
+      const double* sg = sums + static_cast<int64_t>(grp) * 4 * C;
+      const double sm = 1e-5, I = sg[c], Z = sg[C + c], Y = sg[2 * C + c], w = cw[grp * C + c];
+      const double go = static_cast<double>(*grad_out) / (per_sample ? N : 1);
+      const double nv = static_cast<double>(per_sample ? S : static_cast<int64_t>(N) * S);
+      const double Dc = Z + Y + sm;
+      s_a[c] = static_cast<float>(go * (w / C) * (-2.0 / Dc));
+      s_b[c] = static_cast<float>(go * (w / C) * 2.0 * (2.0 * I + sm) / (Dc * Dc));
+      s_e[c] = uce ? static_cast<float>(go * w / nv) : 0.f;
+    } else {
+      s_a[c] = s_b[c] = s_e[c] = 0.f;
+    }
+  }
+  __syncthreads();
+  const int nchunks = static_cast<int>((S + LS_V - 1) / LS_V);
+  const float* zb = logits + n * C * S;
+  float* db = dlogits + n * C * S;
+  const uint8_t* tb = static_cast<const uint8_t*>(target) + n * S * (TU8 ? 1 : 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == LS_CONSUMERS / 32) {
+    if (lane == 0) loss_produce<MAXC>(stages, full, empty, zb, tb, TU8, S, C, blockIdx.x, gridDim.x, nchunks);
+    return;
+  }
+  uint32_t it = 0;
+  for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
+    const uint32_t s = it % LS_NS, ph = (it / LS_NS) & 1;
+    ptx::mbar_wait(&full[s], ph);
+    const int64_t s0 = static_cast<int64_t>(ch) * LS_V;
+    const int nv = static_cast<int>(min(static_cast<int64_t>(LS_V), S - s0));
+#pragma unroll
+    for (int j = 0; j < LS_V / LS_CONSUMERS; ++j) {
+      const int v = threadIdx.x + j * LS_CONSUMERS;
+      if (v < nv) {
+        float p[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) p[c] = c < C ? stages[s].z[c][v] : 0.f;
+        softmax_inplace<MAXC>(p, C);
+        const float tv = TU8 ? static_cast<float>(reinterpret_cast<const uint8_t*>(stages[s].t)[v]) : stages[s].t[v];
+        const int tc = class_of(tv, lut_g ? s_lut : nullptr, C);
+        auto gfun = [&](int c) {
+          const float t = (c == tc) ? 1.f : 0.f;
+          float gc = t * s_a[c] + p[c] * s_b[c];
+          if (s_e[c] != 0.f) gc += s_e[c] * (p[c] - t) / fmaxf(p[c] * (1.0f - p[c]), 1e-12f);   // warp-uniform branch
+          return gc;
+        };
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) dot = fmaf(gfun(c), p[c], dot);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+          if (c < C) db[c * S + s0 + v] = p[c] * (gfun(c) - dot);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[s]);
+  }
+}
+
 template <int MAXC, int NTHR, int VEC, bool TU8>
 void launch_fwd(const float* logits, const void* target, const float* cw, const float* lut, double* sums, float* loss,
                 unsigned int* ticket, int n, int64_t S, int C, int uce, int per_sample, int blocks_per_sm, cudaStream_t s) {
@@ -316,6 +548,14 @@ static bool vec4_ok(const void* logits, const void* target, const void* dlogits,
   return enabled && S % 4 == 0 && a % 16 == 0 && reinterpret_cast<uintptr_t>(target) % (u8 ? 4 : 16) == 0;
 }
 
+// staged (bulk-async) kernels: <= 16 classes, plane size a multiple of 16 voxels (every chunk then starts 16-byte aligned
+// for fp32 planes and uint8 labels alike and has a size that is a multiple of 16 bytes), 16-byte aligned bases
+static bool staged_ok(const void* logits, const void* target, const void* dlogits, int64_t S, int classes) {
+  static const bool enabled = [] { const char* e = getenv("MMPL_LOSS_STAGED"); return !(e && e[0] == '0'); }();
+  const uintptr_t a = reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits) | reinterpret_cast<uintptr_t>(target);
+  return enabled && classes <= 16 && S % 16 == 0 && a % 16 == 0;
+}
+
 extern "C" int mmpl_partial_loss_fwd(const float* logits, const void* target, int target_is_u8,
                                      const float* class_weight, const float* lut, int per_sample, double* sums,
                                      float* loss, int n, int64_t spatial, int classes, int uce, mmpl_stream_t stream) {
@@ -328,6 +568,27 @@ extern "C" int mmpl_partial_loss_fwd(const float* logits, const void* target, in
   const int groups = per_sample ? n : 1;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(sums + static_cast<int64_t>(groups) * 4 * classes);
   MMPL_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (static_cast<int64_t>(groups) * 4 * classes + 1), s));
+  // forward: ncu shows both forms issue ~78 M warp instructions (about 540 per voxel: the kernel is instruction-issue bound,
+  // not bandwidth bound), and the register form keeps 24 warps per SM busy against 16 for the staged one -- 167 us vs
+  // 272 us at cfg2.  The staged forward is kept behind MMPL_LOSS_STAGED_FWD=1; the staged BACKWARD is the default (230 us
+  // vs 255 us: its stores no longer compete with the loads for the load/store unit).
+  static const bool staged_fwd = [] { const char* e = getenv("MMPL_LOSS_STAGED_FWD"); return e && e[0] == '1'; }();
+  if (staged_fwd && staged_ok(logits, target, nullptr, spatial, classes)) {
+    const size_t smem = sizeof(LossStage<16>) * LS_NS + 128;
+    const int nchunks = static_cast<int>((spatial + LS_V - 1) / LS_V);
+    const dim3 grid(std::min(nchunks, std::max(1, num_sms() * 2 / n)), n);
+    if (target_is_u8) {
+      MMPL_CUDA(cudaFuncSetAttribute(partial_loss_fwd_staged_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      partial_loss_fwd_staged_kernel<16, true><<<grid, LS_THREADS, smem, s>>>(logits, target, class_weight, lut, sums, loss, ticket,
+                                                                           n, spatial, classes, uce, per_sample);
+    } else {
+      MMPL_CUDA(cudaFuncSetAttribute(partial_loss_fwd_staged_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      partial_loss_fwd_staged_kernel<16, false><<<grid, LS_THREADS, smem, s>>>(logits, target, class_weight, lut, sums, loss, ticket,
+                                                                            n, spatial, classes, uce, per_sample);
+    }
+    MMPL_CHECK_LAUNCH("partial_loss_fwd");
+    return MMPL_OK;
+  }
   const bool v4 = vec4_ok(logits, target, nullptr, spatial, target_is_u8);
 #define MMPL_LOSS_FWD(MAXC, NTHR, VEC, TU8, BPS) \
   launch_fwd<MAXC, NTHR, VEC, TU8>(logits, target, class_weight, lut, sums, loss, ticket, n, spatial, classes, uce, per_sample, BPS, s)
@@ -353,6 +614,22 @@ extern "C" int mmpl_partial_loss_bwd(const float* logits, const void* target, in
   MMPL_REQUIRE(n > 0 && spatial > 0, MMPL_E_SHAPE, "partial_loss: empty input");
   MMPL_REQUIRE(n <= 65535, MMPL_E_SHAPE, "partial_loss: batch %d exceeds the grid limit", n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (staged_ok(logits, target, dlogits, spatial, classes)) {
+    const size_t smem = sizeof(LossStage<16>) * LS_NS + 128;
+    const int nchunks = static_cast<int>((spatial + LS_V - 1) / LS_V);
+    const dim3 grid(std::min(nchunks, std::max(1, num_sms() * 2 / n)), n);
+    if (target_is_u8) {
+      MMPL_CUDA(cudaFuncSetAttribute(partial_loss_bwd_staged_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      partial_loss_bwd_staged_kernel<16, true><<<grid, LS_THREADS, smem, s>>>(logits, target, class_weight, lut, sums, grad_out,
+                                                                           dlogits, n, spatial, classes, uce, per_sample);
+    } else {
+      MMPL_CUDA(cudaFuncSetAttribute(partial_loss_bwd_staged_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      partial_loss_bwd_staged_kernel<16, false><<<grid, LS_THREADS, smem, s>>>(logits, target, class_weight, lut, sums, grad_out,
+                                                                            dlogits, n, spatial, classes, uce, per_sample);
+    }
+    MMPL_CHECK_LAUNCH("partial_loss_bwd");
+    return MMPL_OK;
+  }
   const bool v4 = vec4_ok(logits, target, dlogits, spatial, target_is_u8);
 #define MMPL_LOSS_BWD(MAXC, VEC, TU8) \
   launch_bwd<MAXC, VEC, TU8>(logits, target, class_weight, lut, sums, grad_out, dlogits, n, spatial, classes, uce, per_sample, s)

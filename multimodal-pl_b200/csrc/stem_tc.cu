@@ -102,13 +102,17 @@ struct StemFwdCfg {
   static constexpr int TMEM_COLS = SF_TD * NT <= 128 ? 128 : 256;
 };
 
+// three CTAs per SM (74 KB of shared memory, 128 TMEM columns and <= 85 registers each): the kernel is instruction-issue
+// bound (ncu: 72 M warp instructions, issue slots 31 % busy at 16 resident warps), so resident warps are what buys time
 template <int NT>
-__global__ void __launch_bounds__(SF_THREADS, 2)
+__global__ void __launch_bounds__(SF_THREADS, NT == 32 ? 3 : 2)
 stem_tc_fwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ wpk, __nv_bfloat16* __restrict__ y,
                    double* __restrict__ stats, int N, int D, int H, int W, int DT, int HT, int WT, int total_items) {
   using Cfg = StemFwdCfg<NT>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER arithmetic on the shared array (an integer round trip would hide the address space from
+  // the compiler and turn every halo / tile access below into a generic LD / ST instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_tiles = smem;
   uint8_t* b_tile = smem + Cfg::A_BYTES;
   float* halo = reinterpret_cast<float*>(b_tile + Cfg::B_BYTES);
@@ -233,10 +237,15 @@ stem_tc_fwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restric
               // statistics of the value as stored (bf16-rounded)
               const float x0 = __uint_as_float(o[k] << 16), x1 = __uint_as_float(o[k] & 0xFFFF0000u);
               const int g0 = (c0 + v * 8 + 2 * k) / CPG, g1 = (c0 + v * 8 + 2 * k + 1) / CPG;
-              gsum[g0] += x0;
-              gsq[g0] = fmaf(x0, x0, gsq[g0]);
-              gsum[g1] += x1;
-              gsq[g1] = fmaf(x1, x1, gsq[g1]);
+              if (g0 == g1) {                 // compile-time: both channels of the pair belong to one group
+                gsum[g0] += x0 + x1;
+                gsq[g0] = fmaf(x0, x0, fmaf(x1, x1, gsq[g0]));
+              } else {
+                gsum[g0] += x0;
+                gsq[g0] = fmaf(x0, x0, gsq[g0]);
+                gsum[g1] += x1;
+                gsq[g1] = fmaf(x1, x1, gsq[g1]);
+              }
             }
             *reinterpret_cast<uint4*>(dst + c0 + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
           }
@@ -280,11 +289,13 @@ struct StemWgParams {
 };
 
 template <int NCO>
-__global__ void __launch_bounds__(SW_THREADS, 1)
+__global__ void __launch_bounds__(SW_THREADS, 2)
 stem_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ StemWgParams p) {
   using Cfg = StemWgCfg<NCO>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER arithmetic on the shared array (an integer round trip would hide the address space from
+  // the compiler and turn every halo / tile access below into a generic LD / ST instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* x_stage = smem;
   uint8_t* y_stage = smem + SW_NS * Cfg::X_STAGE;
   float* halo = reinterpret_cast<float*>(y_stage + SW_NS * Cfg::Y_STAGE);
@@ -442,7 +453,7 @@ int launch_stem_fwd(const float* img, const void* wpk, void* y, double* stats, i
   const int64_t items = static_cast<int64_t>(n) * DT * HT * WT;
   MMPL_REQUIRE(items < (1ll << 31), MMPL_E_SHAPE, "stem_tc_fwd: too many work items");
   MMPL_CUDA(cudaFuncSetAttribute(stem_tc_fwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const int grid = static_cast<int>(std::min<int64_t>(items, static_cast<int64_t>(num_sms()) * 2));
+  const int grid = static_cast<int>(std::min<int64_t>(items, static_cast<int64_t>(num_sms()) * (NT == 32 ? 3 : 2)));
   stem_tc_fwd_kernel<NT><<<grid, SF_THREADS, Cfg::SMEM_BYTES, s>>>(img, static_cast<const __nv_bfloat16*>(wpk),
                                                                  static_cast<__nv_bfloat16*>(y), stats, n, d, h, w, DT, HT, WT,
                                                                  static_cast<int>(items));
@@ -470,7 +481,7 @@ int launch_stem_wgrad(const float* img, const void* dy, float* dw, int n, int d,
   MMPL_REQUIRE(blocks < (1ll << 31), MMPL_E_SHAPE, "stem_tc_wgrad: too many voxel blocks");
   p.total_blocks = static_cast<int>(blocks);
   p.n_co = cout / NCO;
-  int ks = num_sms() / p.n_co;
+  int ks = 2 * num_sms() / p.n_co;          // two CTAs per SM: twice the builder warps per SM
   if (ks < 1) ks = 1;
   if (ks > p.total_blocks) ks = p.total_blocks;
   p.ksplit = ks;
