@@ -661,7 +661,11 @@ int launch_tc(const TcProblem& q, cudaStream_t s) {
   const int64_t items = static_cast<int64_t>(p.NTILES) * p.NPAR * q.N * p.DT * p.HT * p.WT;
   MMPL_REQUIRE(items < (1ll << 31), MMPL_E_SHAPE, "conv_tc: too many work items");
   p.total_items = static_cast<int>(items);
-  static bool attr_set = false;
+  // the attribute is per device: one flag per device ordinal for every instantiation
+  static bool attr_set_dev[64] = {};
+  int dev_ord = 0;
+  cudaGetDevice(&dev_ord);
+  bool& attr_set = attr_set_dev[dev_ord & 63];
   if (!attr_set) {
     MMPL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, NT, TD, MODE, WRES, NA_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::SMEM_BYTES));

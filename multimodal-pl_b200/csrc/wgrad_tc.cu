@@ -288,7 +288,11 @@ int launch_wg(const WgSource& src, const void* dy, WgParams p, int taps, cudaStr
   if (ks < 1) ks = 1;
   if (ks > p.total_blocks) ks = p.total_blocks;
   p.ksplit = ks;
-  static bool attr_set = false;
+  // the attribute is per device: one flag per device ordinal for every instantiation
+  static bool attr_set_dev[64] = {};
+  int dev_ord = 0;
+  cudaGetDevice(&dev_ord);
+  bool& attr_set = attr_set_dev[dev_ord & 63];
   if (!attr_set) {
     MMPL_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KC, NCO, TD, HALO, XB, PDE, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::SMEM_BYTES));

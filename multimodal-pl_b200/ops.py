@@ -168,7 +168,10 @@ _STATS_POOL = {"buf": None, "off": 0}
 
 
 # dX tensors whose producer (conv dgrad / classifier backward) already accumulated the GroupNorm-backward sums:
-# data_ptr -> (workspace data_ptr, head).  Consumed by GNReLUFn.backward.
+# data_ptr -> (workspace data_ptr, head).  Consumed (popped) by the GNReLUFn.backward that autograd runs next and cleared
+# by every begin_forward.  A hand-off that is lost or does not match (autograd summed two gradients into a new tensor, a
+# second model ran a forward in between) only costs the fusion: GNReLUFn.backward then zeroes the workspace and runs its
+# own reduction pass (mmpl_gn_relu_bwd, reduced = 0), so interleaving several networks in one loop is safe.
 _GN_REDUCED = {}
 
 
@@ -219,6 +222,9 @@ def _tc_supported(dtype, kred, nout) -> bool:
     return ok_in and ok_out
 
 
+_FALLBACK_WARNED = set()
+
+
 def _algo(dtype, kred, nout) -> int:
     mode = _cfg["conv_algo"]
     if mode == "direct":
@@ -227,6 +233,14 @@ def _algo(dtype, kred, nout) -> int:
         return _lib.ALGO_TCGEN05
     if mode == "tcgen05":
         raise RuntimeError(f"tcgen05 conv path does not cover dtype={dtype} {kred}->{nout}")
+    if dtype == torch.bfloat16 and (kred, nout) not in _FALLBACK_WARNED:
+        # a 10-100x performance cliff must not be silent (e.g. the refiner's 24/48/96-channel layers)
+        _FALLBACK_WARNED.add((kred, nout))
+        import warnings
+
+        warnings.warn(f"multimodal-pl_b200: no tcgen05 kernel for a bf16 {kred}->{nout} channel convolution (reduction "
+                      "channels 32 or a multiple of 64, outputs 32/64/128/256 or a multiple of 256); it runs on the "
+                      "CUDA-core direct kernel, 10-100x slower", RuntimeWarning, stacklevel=3)
     return _lib.ALGO_DIRECT
 
 
