@@ -146,10 +146,14 @@ int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits, void* da,
 int mmpl_gn_stats(const void* x, double* stats, int n, int64_t spatial, int c, int groups, int dtype,
                   mmpl_stream_t stream);
 /* y = relu(gn(x; gamma,beta)); if gamma2 != NULL also y2 = relu(gn(x; gamma2,beta2)) from the same read of x
- * (gn1 and downsample.0 share their input, unet3D.py:59 and :69). */
+ * (gn1 and downsample.0 share their input, unet3D.py:59 and :69).
+ * real_cpg (0 = all): how many of the C/groups channels of every group carry data.  Networks whose widths the tensor-core
+ * kernels do not cover (the refiner unet3D_g: 24/48/96/192 channels in groups of 6/12/24/48, unet3D.py:1507-1559) run
+ * zero-padded to 32/64/128/256 channels with every group padded in place; the zero channels add nothing to the raw sums
+ * and real_cpg makes mean / variance (and the group means of the backward) divide by the real element count. */
 int mmpl_gn_relu_fwd(const void* x, const double* stats, const float* gamma, const float* beta, void* y,
                      const float* gamma2, const float* beta2, void* y2, int n, int64_t spatial, int c, int groups,
-                     float eps, int dtype, mmpl_stream_t stream);
+                     int real_cpg, float eps, int dtype, mmpl_stream_t stream);
 /* dx = d/dx of the one or two GN+ReLU heads (+ addend if non-NULL); dgamma/dbeta per head (fp32 [C]).
  * workspace: N*C*6 + 1 doubles: [N][C][6] = per head {S1 = sum g, Q = gamma * sum g*xhat} (g = dy*[relu gate]) in columns 0..3 and
  * scratch in 4..5.  reduced = 0: the call zeroes it and runs the reduction pass over (x, dy[, dy2]); reduced = 1: the
@@ -159,7 +163,7 @@ int mmpl_gn_relu_fwd(const void* x, const double* stats, const float* gamma, con
 int mmpl_gn_relu_bwd(const void* x, const double* stats, const float* gamma, const float* beta, const void* dy,
                      const float* gamma2, const float* beta2, const void* dy2, const void* addend, void* dx,
                      float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, double* workspace, int reduced, int n,
-                     int64_t spatial, int c, int groups, float eps, int dtype, mmpl_stream_t stream);
+                     int64_t spatial, int c, int groups, int real_cpg, float eps, int dtype, mmpl_stream_t stream);
 
 /* ---- class-token attention maps + token EMA of unet3D_with_feam3 (unet3D.py:142-212, :1051-1068, :1127-1175) --------
  * mmpl_ln_rows_*: LayerNorm over the channel axis of `rows` NDHWC voxel rows without affine (biased variance, eps under

@@ -88,14 +88,14 @@ template <typename T, bool DUAL>
 __global__ void __launch_bounds__(kThreads)
 gn_relu_fwd_kernel(const T* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                    const float* __restrict__ beta, T* __restrict__ y, const float* __restrict__ gamma2,
-                   const float* __restrict__ beta2, T* __restrict__ y2, int64_t spatial, int C, int groups, float eps,
-                   int64_t vox_per_block) {
+                   const float* __restrict__ beta2, T* __restrict__ y2, int64_t spatial, int C, int groups, int cnt_cpg,
+                   float eps, int64_t vox_per_block) {
   constexpr int VN = Vec<T>::N;
   const int vpv = C / VN;
   const int cv = threadIdx.x % vpv, vl = threadIdx.x / vpv, vstep = kThreads / vpv;
   const int n = blockIdx.y;
   const int cpg = C / groups;
-  const double m = static_cast<double>(cpg) * static_cast<double>(spatial);
+  const double m = static_cast<double>(cnt_cpg) * static_cast<double>(spatial);   // elements that count per group
   float sc[VN], sh[VN], sc2[VN], sh2[VN];
 #pragma unroll
   for (int i = 0; i < VN; ++i) {
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kThreads)
 gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                           const float* __restrict__ beta, const T* __restrict__ dy, const float* __restrict__ gamma2,
                           const float* __restrict__ beta2, const T* __restrict__ dy2, double* __restrict__ ws,
-                          int64_t spatial, int C, int groups, float eps, int64_t vox_per_block) {
+                          int64_t spatial, int C, int groups, int cnt_cpg, float eps, int64_t vox_per_block) {
   using V = VecH<T>;   // 8-byte vectors: half the per-thread channel state -> higher occupancy
   constexpr int VN = V::N;
   constexpr int NH = DUAL ? 2 : 1;
@@ -147,7 +147,7 @@ gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ st
   const int cv = threadIdx.x % vpv, vl = threadIdx.x / vpv, vstep = kThreads / vpv;
   const int n = blockIdx.y;
   const int cpg = C / groups;
-  const double m = static_cast<double>(cpg) * static_cast<double>(spatial);
+  const double m = static_cast<double>(cnt_cpg) * static_cast<double>(spatial);   // elements that count per group
   float mu[VN], rs[VN], ga[NH][VN], be[NH][VN];
 #pragma unroll
   for (int i = 0; i < VN; ++i) {
@@ -222,7 +222,7 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
                          const float* __restrict__ beta2, const T* __restrict__ dy2, const T* __restrict__ addend,
                          T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                          float* __restrict__ dgamma2, float* __restrict__ dbeta2, double* __restrict__ ws,
-                         int N, int64_t spatial, int C, int groups, float eps, int64_t vox_per_block) {
+                         int N, int64_t spatial, int C, int groups, int cnt_cpg, float eps, int64_t vox_per_block) {
   using V = VecH<T>;
   constexpr int VN = V::N;
   constexpr int NH = DUAL ? 2 : 1;
@@ -230,7 +230,7 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
   const int cv = threadIdx.x % vpv, vl = threadIdx.x / vpv, vstep = kThreads / vpv;
   const int n = blockIdx.y;
   const int cpg = C / groups;
-  const double m = static_cast<double>(cpg) * static_cast<double>(spatial);
+  const double m = static_cast<double>(cnt_cpg) * static_cast<double>(spatial);   // elements that count per group
   __shared__ float gm[32][4];  // per group: m1,m2 per head (already divided by m)
   __shared__ bool s_last;
   if (threadIdx.x < groups * NH) {
@@ -370,7 +370,7 @@ template <typename T>
 int launch_gn_bwd(const void* x, const double* stats, const float* gamma, const float* beta, const void* dy,
                   const float* gamma2, const float* beta2, const void* dy2, const void* addend, void* dx,
                   float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, double* workspace, int reduced, int n,
-                  int64_t spatial, int c, int groups, float eps, int bx, int64_t vpb, cudaStream_t s) {
+                  int64_t spatial, int c, int groups, int cnt_cpg, float eps, int bx, int64_t vpb, cudaStream_t s) {
   const bool dual = gamma2 != nullptr;
   const bool add = addend != nullptr;
   const T* xx = static_cast<const T*>(x);
@@ -382,24 +382,24 @@ int launch_gn_bwd(const void* x, const double* stats, const float* gamma, const 
   if (!reduced) {
     if (dual)
       gn_relu_bwd_reduce_kernel<T, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
-                                                                  workspace, spatial, c, groups, eps, vpb);
+                                                                  workspace, spatial, c, groups, cnt_cpg, eps, vpb);
     else
       gn_relu_bwd_reduce_kernel<T, false><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, nullptr, nullptr,
-                                                                   nullptr, workspace, spatial, c, groups, eps, vpb);
+                                                                   nullptr, workspace, spatial, c, groups, cnt_cpg, eps, vpb);
     MMPL_CHECK_LAUNCH("gn_relu_bwd_reduce");
   }
   if (dual && add)
     gn_relu_bwd_apply_kernel<T, true, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
-        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, eps, vpb);
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb);
   else if (dual)
     gn_relu_bwd_apply_kernel<T, true, false><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
-        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, eps, vpb);
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb);
   else if (add)
     gn_relu_bwd_apply_kernel<T, false, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
-        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, eps, vpb);
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb);
   else
     gn_relu_bwd_apply_kernel<T, false, false><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
-        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, eps, vpb);
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb);
   return MMPL_OK;
 }
 
@@ -423,8 +423,10 @@ extern "C" int mmpl_gn_stats(const void* x, double* stats, int n, int64_t spatia
 
 extern "C" int mmpl_gn_relu_fwd(const void* x, const double* stats, const float* gamma, const float* beta, void* y,
                                 const float* gamma2, const float* beta2, void* y2, int n, int64_t spatial, int c,
-                                int groups, float eps, int dtype, mmpl_stream_t stream) {
+                                int groups, int real_cpg, float eps, int dtype, mmpl_stream_t stream) {
   if (int e = check_shape(c, groups, dtype)) return e;
+  MMPL_REQUIRE(real_cpg >= 0 && real_cpg <= c / groups, MMPL_E_SHAPE, "GroupNorm: real_cpg=%d of %d", real_cpg, c / groups);
+  const int cnt_cpg = real_cpg > 0 ? real_cpg : c / groups;
   int bx;
   int64_t vpb;
   plan(n, spatial, c, dtype, bx, vpb);
@@ -434,11 +436,11 @@ extern "C" int mmpl_gn_relu_fwd(const void* x, const double* stats, const float*
     if (dual)
       gn_relu_fwd_kernel<T, true><<<dim3(bx, n), kThreads, 0, s>>>(static_cast<const T*>(x), stats, gamma, beta,
                                                                   static_cast<T*>(y), gamma2, beta2,
-                                                                  static_cast<T*>(y2), spatial, c, groups, eps, vpb);
+                                                                  static_cast<T*>(y2), spatial, c, groups, cnt_cpg, eps, vpb);
     else
       gn_relu_fwd_kernel<T, false><<<dim3(bx, n), kThreads, 0, s>>>(static_cast<const T*>(x), stats, gamma, beta,
                                                                    static_cast<T*>(y), nullptr, nullptr, nullptr,
-                                                                   spatial, c, groups, eps, vpb);
+                                                                   spatial, c, groups, cnt_cpg, eps, vpb);
   });
   MMPL_CHECK_LAUNCH("gn_relu_fwd");
   return MMPL_OK;
@@ -448,8 +450,10 @@ extern "C" int mmpl_gn_relu_bwd(const void* x, const double* stats, const float*
                                 const void* dy, const float* gamma2, const float* beta2, const void* dy2,
                                 const void* addend, void* dx, float* dgamma, float* dbeta, float* dgamma2,
                                 float* dbeta2, double* workspace, int reduced, int n, int64_t spatial, int c, int groups,
-                                float eps, int dtype, mmpl_stream_t stream) {
+                                int real_cpg, float eps, int dtype, mmpl_stream_t stream) {
   if (int e = check_shape(c, groups, dtype, true)) return e;
+  MMPL_REQUIRE(real_cpg >= 0 && real_cpg <= c / groups, MMPL_E_SHAPE, "GroupNorm: real_cpg=%d of %d", real_cpg, c / groups);
+  const int cnt_cpg = real_cpg > 0 ? real_cpg : c / groups;
   int bx;
   int64_t vpb;
   plan(n, spatial, c, dtype, bx, vpb, true);
@@ -459,7 +463,7 @@ extern "C" int mmpl_gn_relu_bwd(const void* x, const double* stats, const float*
   int rc = MMPL_OK;
   MMPL_DISPATCH_DTYPE(dtype, T, rc = (launch_gn_bwd<T>(x, stats, gamma, beta, dy, gamma2, beta2, dy2, addend, dx, dgamma,
                                                      dbeta, dgamma2, dbeta2, workspace, reduced, n, spatial, c, groups,
-                                                     eps, bx, vpb, s)));
+                                                     cnt_cpg, eps, bx, vpb, s)));
   if (rc) return rc;
   MMPL_CHECK_LAUNCH("gn_relu_bwd_apply");
   // leave the workspace clean: producers of a later backward through the same node accumulate into it again

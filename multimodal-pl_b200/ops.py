@@ -743,7 +743,7 @@ class GNReLUFn(torch.autograd.Function):
     gradient arrives here and is added inside the backward kernel instead of by a separate elementwise add."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps, stats_in=None, alias=False, ws=None):
+    def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps, stats_in=None, alias=False, ws=None, real_cpg=0):
         _lib.require_device()
         L = _lib.lib()
         dt = _cfg["dtype"]
@@ -764,8 +764,9 @@ class GNReLUFn(torch.autograd.Function):
         y = empty_cl(n, c, d, h, w, dt, dev)
         y2 = empty_cl(n, c, d, h, w, dt, dev) if dual else None
         _lib.check(L.mmpl_gn_relu_fwd(_p(x), _p(stats), _p(g1), _p(b1), _p(y), _p(g2), _p(b2), _p(y2), n, spatial, c,
-                                      groups, eps, code, st), "gn_relu_fwd")
+                                      groups, int(real_cpg), eps, code, st), "gn_relu_fwd")
         ctx.save_for_backward(x, stats, g1, b1, g2, b2)
+        ctx.real_cpg = int(real_cpg)
         ctx.meta = (n, c, spatial, groups, eps, dual, gamma.dtype, bool(alias))
         ctx.params = (gamma, beta, gamma2, beta2)
         ctx.ws = ws
@@ -819,10 +820,10 @@ class GNReLUFn(torch.autograd.Function):
             ws = torch.empty(n * c * 6 + 2, dtype=torch.float64, device=dev)
         _lib.check(L.mmpl_gn_relu_bwd(_p(x), _p(stats), _p(g1), _p(b1), _p(dy), _p(g2), _p(b2), _p(dy2) if dual else None,
                                       _p(dres), _p(dx), _p(dg1), _p(db1), _p(dg2), _p(db2), _p(ws), reduced, n, spatial, c,
-                                      groups, eps, code, st), "gn_relu_bwd")
+                                      groups, ctx.real_cpg, eps, code, st), "gn_relu_bwd")
         if dual:
-            return dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype), None, None, None, None, None
-        return dx, dg1.to(pdtype), db1.to(pdtype), None, None, None, None, None, None, None
+            return dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype), None, None, None, None, None, None
+        return dx, dg1.to(pdtype), db1.to(pdtype), None, None, None, None, None, None, None, None
 
 
 def _attached_stats(x, groups):
@@ -849,17 +850,17 @@ def _tag_gn_outputs(outs, n_heads):
     return outs
 
 
-def gn_relu(x, gamma, beta, groups=16, eps=1e-5, alias=False):
-    """-> y, or (y, x_alias) with alias=True."""
+def gn_relu(x, gamma, beta, groups=16, eps=1e-5, alias=False, real_cpg=0):
+    """-> y, or (y, x_alias) with alias=True.  ``real_cpg``: channels per group that carry data (zero-padded layouts)."""
     outs = GNReLUFn.apply(x, gamma, beta, None, None, int(groups), float(eps), _attached_stats(x, groups), bool(alias),
-                          _gn_bwd_ws(x))
+                          _gn_bwd_ws(x), int(real_cpg))
     return _tag_gn_outputs(outs, 1)
 
 
-def gn_relu_dual(x, gamma, beta, gamma2, beta2, groups=16, eps=1e-5, alias=False):
+def gn_relu_dual(x, gamma, beta, gamma2, beta2, groups=16, eps=1e-5, alias=False, real_cpg=0):
     """-> (y, y2), or (y, y2, x_alias) with alias=True."""
     outs = GNReLUFn.apply(x, gamma, beta, gamma2, beta2, int(groups), float(eps), _attached_stats(x, groups),
-                          bool(alias), _gn_bwd_ws(x))
+                          bool(alias), _gn_bwd_ws(x), int(real_cpg))
     return _tag_gn_outputs(outs, 2)
 
 
