@@ -202,6 +202,23 @@ int mmpl_augment_patch(float* x, int64_t n, float noise_std, uint64_t seed, floa
 int mmpl_blur_axis(const float* src, float* dst, int d, int h, int w, int axis, const float* taps_dev, int radius,
                    mmpl_stream_t stream);
 
+/* ---- helpers for the refiner unet3D_g and the discriminator norm_style_discriminator_output (SURVEY 8f-f3;
+ * unet3D.py:1507-1623, :1907-1947; csrc/aux_nets.cu explains how their convolutions map onto the tcgen05 kernels).
+ * mmpl_space_to_depth2: [N,D,H,W,C] (bf16 or fp32) -> [N,D/2,H/2,W/2,cp], channel (pd*4+ph*2+pw)*C + c, zero beyond 8*C
+ *   (inverse = 1: the transpose, x is the s2d tensor and y the full-resolution one; used as the backward).
+ * mmpl_bias_lrelu_*: y = leaky_relu(x + bias[c], slope) over `rows` NDHWC rows; bwd reads the gate from y (slope > 0),
+ *   writes dx and dbias [C] (zeroed by the call).
+ * mmpl_upsample2x_ncdhw_*: nn.Upsample(scale_factor=2, mode='trilinear') (align_corners=False) of `planes` fp32
+ *   [d][h][w] volumes (the refiner's final up-sampling of its logits, unet3D.py:1621) and its transpose. */
+int mmpl_space_to_depth2(const void* x, void* y, int n, int d, int h, int w, int c, int cp, int inverse, int dtype,
+                         mmpl_stream_t stream);
+int mmpl_bias_lrelu_fwd(const void* x, const float* bias, void* y, int64_t rows, int c, float slope, int dtype,
+                        mmpl_stream_t stream);
+int mmpl_bias_lrelu_bwd(const void* y, const void* dy, void* dx, float* dbias, int64_t rows, int c, float slope, int dtype,
+                        mmpl_stream_t stream);
+int mmpl_upsample2x_ncdhw_fwd(const float* x, float* y, int64_t planes, int d, int h, int w, mmpl_stream_t stream);
+int mmpl_upsample2x_ncdhw_bwd(const float* dy, float* dx, int64_t planes, int d, int h, int w, mmpl_stream_t stream);
+
 /* ---- trilinear x2 upsample (align_corners=False) + skip add: unet3D.py:608, :686-687 -------------------------- */
 /* gn_stats (optional, may be NULL): double [N][16][2], zeroed by the caller; receives the GroupNorm(16) raw sums
  * (sum, sum of squares per group) of y, i.e. the statistics of the next block's gn1 / downsample.0 (unet3D.py:59, :645). */

@@ -49,6 +49,11 @@ _SIGNATURES = {
     "mmpl_patch_stats": [_ptr, _c_i64, _ptr, _ptr],
     "mmpl_augment_patch": [_ptr, _c_i64, _c_f32, ctypes.c_uint64, _c_f32, _c_f32, _c_f32, _ptr, _ptr],
     "mmpl_blur_axis": [_ptr, _ptr] + [_c_int] * 4 + [_ptr, _c_int, _ptr],
+    "mmpl_space_to_depth2": [_ptr, _ptr] + [_c_int] * 8 + [_ptr],
+    "mmpl_bias_lrelu_fwd": [_ptr, _ptr, _ptr, _c_i64, _c_int, _c_f32, _c_int, _ptr],
+    "mmpl_bias_lrelu_bwd": [_ptr, _ptr, _ptr, _ptr, _c_i64, _c_int, _c_f32, _c_int, _ptr],
+    "mmpl_upsample2x_ncdhw_fwd": [_ptr, _ptr, _c_i64, _c_int, _c_int, _c_int, _ptr],
+    "mmpl_upsample2x_ncdhw_bwd": [_ptr, _ptr, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_gn_stats": [_ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_gn_relu_fwd": [_ptr] * 8 + [_c_int, _c_i64, _c_int, _c_int, _c_int, _c_f32, _c_int, _ptr],
     "mmpl_gn_relu_bwd": [_ptr] * 15 + [_c_int, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_f32, _c_int, _ptr],

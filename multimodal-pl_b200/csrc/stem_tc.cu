@@ -102,10 +102,11 @@ struct StemFwdCfg {
   static constexpr int TMEM_COLS = SF_TD * NT <= 128 ? 128 : 256;
 };
 
-// three CTAs per SM (74 KB of shared memory, 128 TMEM columns and <= 85 registers each): the kernel is instruction-issue
-// bound (ncu: 72 M warp instructions, issue slots 31 % busy at 16 resident warps), so resident warps are what buys time
+// Two CTAs per SM.  The kernel is instruction-issue bound (ncu, profiles/r02_ncu_stem.md: 72 M warp instructions, issue
+// slots 31 % busy at 16 resident warps); a third CTA per SM (80 registers, 3 x 74 KB of shared memory) measured SLOWER
+// (324 us vs 268 us): the register cap spills the 27-tap expansion.
 template <int NT>
-__global__ void __launch_bounds__(SF_THREADS, NT == 32 ? 3 : 2)
+__global__ void __launch_bounds__(SF_THREADS, 2)
 stem_tc_fwd_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ wpk, __nv_bfloat16* __restrict__ y,
                    double* __restrict__ stats, int N, int D, int H, int W, int DT, int HT, int WT, int total_items) {
   using Cfg = StemFwdCfg<NT>;
@@ -453,7 +454,7 @@ int launch_stem_fwd(const float* img, const void* wpk, void* y, double* stats, i
   const int64_t items = static_cast<int64_t>(n) * DT * HT * WT;
   MMPL_REQUIRE(items < (1ll << 31), MMPL_E_SHAPE, "stem_tc_fwd: too many work items");
   MMPL_CUDA(cudaFuncSetAttribute(stem_tc_fwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const int grid = static_cast<int>(std::min<int64_t>(items, static_cast<int64_t>(num_sms()) * (NT == 32 ? 3 : 2)));
+  const int grid = static_cast<int>(std::min<int64_t>(items, static_cast<int64_t>(num_sms()) * 2));
   stem_tc_fwd_kernel<NT><<<grid, SF_THREADS, Cfg::SMEM_BYTES, s>>>(img, static_cast<const __nv_bfloat16*>(wpk),
                                                                  static_cast<__nv_bfloat16*>(y), stats, n, d, h, w, DT, HT, WT,
                                                                  static_cast<int>(items));

@@ -1023,6 +1023,96 @@ def renew_tokens(token, feature, mask, alpha):
     return token
 
 
+class SpaceToDepth2Fn(torch.autograd.Function):
+    """[N,C,D,H,W] -> [N,cp,D/2,H/2,W/2] with channel (pd*4+ph*2+pw)*C + c (zero beyond 8C): the input side of the
+    4x4x4 stride-2 -> 3x3x3 stride-1 rewrite of the discriminator's convolutions (csrc/aux_nets.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, cp):
+        _lib.require_device()
+        dt = _cfg["dtype"]
+        x = to_cl(x, dt)
+        n, c, d, h, w = x.shape
+        y = empty_cl(n, cp, d // 2, h // 2, w // 2, dt, x.device)
+        _lib.check(_lib.lib().mmpl_space_to_depth2(_p(x), _p(y), n, d, h, w, c, cp, 0, _lib.dtype_code(dt), _lib.stream_ptr()),
+                   "space_to_depth2")
+        ctx.meta = (n, c, d, h, w, cp, dt)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, d, h, w, cp, dt = ctx.meta
+        g = to_cl(g, dt)
+        dx = empty_cl(n, c, d, h, w, dt, g.device)
+        _lib.check(_lib.lib().mmpl_space_to_depth2(_p(g), _p(dx), n, d, h, w, c, cp, 1, _lib.dtype_code(dt), _lib.stream_ptr()),
+                   "depth_to_space2")
+        return dx, None
+
+
+def space_to_depth2(x, cp):
+    return SpaceToDepth2Fn.apply(x, int(cp))
+
+
+class BiasLeakyReLUFn(torch.autograd.Function):
+    """leaky_relu(x + bias[c], slope) on a channels-last activation: nn.Conv3d bias + nn.LeakyReLU(0.2) of the
+    discriminator blocks (unet3D.py:1912-1936), one pass forward, one backward (dx and dbias)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, slope):
+        _lib.require_device()
+        dt = _cfg["dtype"]
+        x = to_cl(x, dt)
+        n, c, d, h, w = x.shape
+        b = bias.detach().float().contiguous()
+        y = torch.empty_like(x)
+        _lib.check(_lib.lib().mmpl_bias_lrelu_fwd(_p(x), _p(b), _p(y), n * d * h * w, c, float(slope), _lib.dtype_code(dt),
+                                                  _lib.stream_ptr()), "bias_lrelu_fwd")
+        ctx.save_for_backward(y)
+        ctx.meta = (n * d * h * w, c, float(slope), bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        rows, c, slope, bdtype = ctx.meta
+        g = to_cl(g, y.dtype)
+        dx = torch.empty_like(y)
+        db = torch.empty(c, dtype=torch.float32, device=y.device)
+        _lib.check(_lib.lib().mmpl_bias_lrelu_bwd(_p(y), _p(g), _p(dx), _p(db), rows, c, slope, _lib.dtype_code(y.dtype),
+                                                  _lib.stream_ptr()), "bias_lrelu_bwd")
+        return dx, db.to(bdtype), None
+
+
+def bias_leaky_relu(x, bias, slope=0.2):
+    return BiasLeakyReLUFn.apply(x, bias, float(slope))
+
+
+class Upsample2xNCDHWFn(torch.autograd.Function):
+    """nn.Upsample(scale_factor=2, mode='trilinear') of an fp32 NCDHW tensor (the refiner's logits, unet3D.py:1621)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _lib.require_device()
+        x = x.float().contiguous()
+        n, c, d, h, w = x.shape
+        y = torch.empty((n, c, 2 * d, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().mmpl_upsample2x_ncdhw_fwd(_p(x), _p(y), n * c, d, h, w, _lib.stream_ptr()), "upsample2x_ncdhw_fwd")
+        ctx.meta = (n, c, d, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, d, h, w = ctx.meta
+        g = g.float().contiguous()
+        dx = torch.empty((n, c, d, h, w), dtype=torch.float32, device=g.device)
+        _lib.check(_lib.lib().mmpl_upsample2x_ncdhw_bwd(_p(g), _p(dx), n * c, d, h, w, _lib.stream_ptr()), "upsample2x_ncdhw_bwd")
+        return dx
+
+
+def upsample2x_ncdhw(x):
+    return Upsample2xNCDHWFn.apply(x)
+
+
 class BlendSink:
     """Where the sliding-window classifier accumulates (predict_sliding, evaluate_amos.py:261-276): fp32 accumulator
     ``acc`` [B, D, C, H, W] (depth-major, ``d_outer``) or [B, C, D, H, W], optional weight sum ``wsum`` [B, D, H, W], the

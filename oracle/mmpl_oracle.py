@@ -659,3 +659,20 @@ def augment_ref(img: np.ndarray, params: dict, noise: Optional[np.ndarray] = Non
         x[x < lo] = lo
         x[x > hi] = hi
     return x.astype(np.float32)
+
+
+def synth_named_state(shapes: Dict[str, Tuple[int, ...]], seed: int) -> Dict[str, torch.Tensor]:
+    """Deterministic weights for ANY module, keyed by state_dict name (so the unmodified reference module and the B200
+    module get identical values): 1-D "...weight" tensors (norm scales) ~ 1 + 0.1 N(0,1), biases ~ 0.1 N(0,1),
+    everything else ~ N(0,1) / sqrt(fan_in)."""
+    out = {}
+    for i, (k, shp) in enumerate(sorted(shapes.items())):
+        g = torch.Generator().manual_seed(seed * 100003 + 9000 + i)
+        if len(shp) == 1 and k.endswith("weight"):
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif k.endswith("bias"):
+            t = 0.1 * torch.randn(shp, generator=g)
+        else:
+            t = torch.randn(shp, generator=g) / math.sqrt(int(np.prod(shp[1:])))
+        out[k] = t.float()
+    return out

@@ -114,6 +114,24 @@ def test_feam3_contract_eam_and_tokens_on_cpu(golden_dir):
     # (renew_token runs on the device: tests/test_gpu_more.py checks it against the tokens the reference produced)
 
 
+def test_aux_nets_state_dict_contract():
+    """unet3D_g / norm_style_discriminator_output: the reference's state_dict keys and shapes, recorded in
+    tests/golden/aux_nets.npz by oracle/make_golden_aux.py (one gradient-norm entry per reference parameter)."""
+    from multimodal_pl_b200.aux_nets import norm_style_discriminator_output, unet3D_g
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aux_nets.npz"))
+    ref_keys = {k.split("norm:")[1] for k in g.files if k.startswith("refiner/norm:")}
+    net = unet3D_g([1, 1, 1, 1, 1], num_classes=2, weight_std=True, init_filter=24, in_channel=2)
+    assert {k for k, _ in net.named_parameters()} == ref_keys
+    assert tuple(net.conv0.weight.shape) == (24, 2, 3, 3, 3) and net.fusionConv[0].num_groups == 12
+    assert net.layer1[0].gn1.num_groups == 4 and net.precls_conv[0].num_groups == 6
+    assert list(inspect.signature(unet3D_g.__init__).parameters)[1:] == \
+        ["layers", "num_classes", "weight_std", "in_channel", "init_filter"]
+    dis = norm_style_discriminator_output(num_classes=2)
+    assert {k for k, _ in dis.named_parameters()} == {k.split("norm:")[1] for k in g.files if k.startswith("disc/norm:")}
+    assert tuple(dis.block1[0].weight.shape) == (32, 2, 4, 4, 4) and tuple(dis.block4[8].weight.shape) == (2, 256)
+
+
 def test_flat_gradient_adoption_on_cpu():
     """engine.DataParallelModel keeps gradients in one flat buffer: gradients that autograd produced elsewhere are
     folded into their slots (engine._adopt_grad), zero_grad drops the views and clears the buffer."""
