@@ -628,6 +628,7 @@ def infer_record(model, dev, rank, world, steps, warmup, eager=False):
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
+    r0 = 0 if eager else nets[0].tiles_replayed
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -635,7 +636,9 @@ def infer_record(model, dev, rank, world, steps, warmup, eager=False):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - l0
+    launches = _lib.launch_count() - l0      # C-ABI calls made directly (finalize, ...) in the timed region
+    if not eager:                           # + the kernels executed by this rank's graph replays
+        launches += (nets[0].tiles_replayed - r0) * nets[0].launches_per_tile
     clocks = sampler.stop() if rank == 0 else None
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()

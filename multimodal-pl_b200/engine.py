@@ -453,8 +453,11 @@ class GraphedSlidingWindow:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        launches0 = _lib.launch_count()
         with torch.cuda.graph(self.graph), torch.no_grad(), ops.frozen_weights():
             model.blend_tile(self.static_in, self.sink)
+        self.launches_per_tile = _lib.launch_count() - launches0     # library kernels one replay executes
+        self.tiles_replayed = 0
         self.acc.zero_()
         if was_training:
             model.train()
@@ -467,6 +470,7 @@ class GraphedSlidingWindow:
         self.static_in.copy_(img, non_blocking=True)
         self.origin_dev.copy_(origin_dev_row, non_blocking=True)
         self.graph.replay()
+        self.tiles_replayed += 1
 
 
 def extant_file(x):
