@@ -384,10 +384,20 @@ def run_train(args):
     def loss_fn(logits, lab):
         return crit(logits, lab.squeeze(1), mask=wts, soft_max=True, lut=luts, per_sample=True)
 
+    # default: the head of the step is unet3D_baseline.forward_partial_loss -- classifier + EDiceLoss_partial in one
+    # forward and one backward launch, no logits tensor (csrc/cls_loss.cu); --two-step-head runs model(x) -> crit(logits)
+    fused_head = not args.two_step_head
+
+    def fused_loss(module, img, lab):
+        return module.forward_partial_loss(img, lab, wts, lut=luts, per_sample=True)
+
     def eager_step(img, lab):
         opt.zero_grad()
-        logits, _, _ = dp(img, lab)
-        loss = loss_fn(logits, lab)
+        if fused_head:
+            loss = fused_loss(dp.module, img, lab)
+        else:
+            logits, _, _ = dp(img, lab)
+            loss = loss_fn(logits, lab)
         loss.backward()
         opt.step(grad_scale=1.0 / world)
         return loss
@@ -401,7 +411,8 @@ def run_train(args):
     warm = max(args.warmup, 3)
     if use_graph:
         # the public API for a launch-overhead-free step: capture once, replay per batch (engine.GraphedTrainStep)
-        step = GraphedTrainStep(dp, loss_fn, opt, image_d, label_d, warmup=warm)
+        step = GraphedTrainStep(dp, loss_fn, opt, image_d, label_d, warmup=warm,
+                                fused_loss=fused_loss if fused_head else None)
     else:
         step = eager_step
     for _ in range(warm):
@@ -546,6 +557,8 @@ def run_train(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": train_config(args.workload, world), "launch": launch,
         "batch": "per GPU: CT and MRI samples alternate, uint8 Voronoi labels, per-sample class weights + cmask LUT",
+        "head": ("unet3D_baseline.forward_partial_loss: classifier + EDiceLoss_partial fused, no logits tensor (mmpl_cls_loss_fwd/_bwd)"
+                 if fused_head else "model(x) -> EDiceLoss_partial(logits) (mmpl_cls_fwd, mmpl_partial_loss_fwd/_bwd, mmpl_cls_bwd)"),
         "clocks": clocks,
         "e2e": {"value": patches / (ms_e2e / 1e3), "unit": "patches/s",
                 "h2d_bytes_per_step": image_h.numel() * image_h.element_size() + label_h.numel() * label_h.element_size(),
@@ -571,7 +584,7 @@ def run_train(args):
 def infer_record(model, dev, rank, world, steps, warmup, eager=False):
     """BASELINE configs[3]: sliding-window inference of one synthetic 300x512x512 CT volume, tile 64x192x192 -> 96 tiles.
     Forward + classifier + Gaussian blending per tile in ONE CUDA graph replayed per tile, argmax + Dice on the device
-    (evaluate.predict_sliding_dice); N > 1: contiguous runs of tiles per rank, reduce-scatter of the fp32 accumulator along
+    (evaluate.predict_sliding_dice); N > 1: contiguous runs of tiles per rank, exchange of the touched fp32 accumulator planes along
     depth, local argmax/Dice per slab, all-gather of the uint8 mask.  A step = one volume; value = tiles (3-D patches) per
     second over the whole job with the volume resident in HBM; e2e = the same call fed from pinned host memory (each rank
     uploads only the depth range it needs) with the uint8 mask and the Dice values read back.  Fixed total work: strong."""
@@ -607,7 +620,7 @@ def infer_record(model, dev, rank, world, steps, warmup, eager=False):
         dist.all_reduce(mism, op=dist.ReduceOp.MAX)
         sw_par = {"argmax_mismatches": int(mism.item()), "voxels": int(one[3].numel()),
                   "max_dice_diff": max(abs(float(a) - float(b)) for a, b in zip(one[0], two[0])),
-                  "what": "sharded (reduce-scatter along depth) vs single-rank sliding window on a 40x72x88 volume; fp32 sums "
+                  "what": "sharded (per-slab plane exchange along depth) vs single-rank sliding window on a 40x72x88 volume; fp32 sums "
                           "of <= 8 tile contributions in a different order, only exact near-ties may flip"}
         assert sw_par["argmax_mismatches"] <= 5 and sw_par["max_dice_diff"] < 1e-4, sw_par
     nets = [model] if eager else [GraphedSlidingWindow(model, vol_shape[2:], tile, classes, world_size=world)]
@@ -640,12 +653,18 @@ def infer_record(model, dev, rank, world, steps, warmup, eager=False):
     if not eager:                           # + the kernels executed by this rank's graph replays
         launches += (nets[0].tiles_replayed - r0) * nets[0].launches_per_tile
     clocks = sampler.stop() if rank == 0 else None
+    # end to end: the volume and its labels start in pinned host memory (each rank uploads the depth range / label slab it
+    # needs); the result -- the uint8 segmentation mask and the Dice values -- is read back into host memory on rank 0,
+    # the process that would write the prediction (evaluate_amos.py:333-349); the other ranks read back the Dice values
+    mask_h = torch.empty((1,) + tuple(vol_shape[2:]), dtype=torch.uint8).pin_memory() if rank == 0 else None
+    barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(steps):
-        dices, _, _, amax = volume(vol_h, lab_h)           # host volume: each rank uploads the depth range it needs
-        mask_h = amax.cpu()
-        dice_h = [float(d) for d in dices]
+        dices, _, _, amax = volume(vol_h, lab_h)
+        if rank == 0:
+            mask_h.copy_(amax, non_blocking=True)
+        dice_h = torch.stack([d.reshape(()) for d in dices]).tolist()      # one D2H, synchronises the step
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -662,14 +681,14 @@ def infer_record(model, dev, rank, world, steps, warmup, eager=False):
         "scaling": "strong", "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "cfg4", "volume": list(vol_shape[2:]), "tile": list(tile), "tiles": ntiles, "base": base,
                    "classes": classes,
-                   "parallelism": f"contiguous tile runs over {world} rank(s)" + (", reduce-scatter along depth + all-gather of the uint8 mask" if world > 1 else ""),
+                   "parallelism": f"contiguous tile runs over {world} rank(s)" + (", touched accumulator planes sent to their depth-slab owner (grouped NCCL send/recv) + all-gather of the uint8 mask" if world > 1 else ""),
                    "blend": "classifier + Gaussian accumulation fused (mmpl_cls_blend), fp32 depth-major accumulator",
                    "launch": "eager" if eager else "one cuda graph per tile shape, replayed per tile (engine.GraphedSlidingWindow)",
                    "l2": "volume + accumulators >> 126 MB L2, no flush needed"},
         "clocks": clocks,
         "e2e": {"value": ntiles * steps / (ms_e2e / 1e3), "unit": "patches/s",
                 "h2d_bytes_per_step": vol_h.numel() * 4 + lab_h.numel(),
-                "d2h_bytes_per_step": mask_h.numel() + 8 * len(dice_h), "ms_per_step": ms_e2e / steps,
+                "d2h_bytes_per_step": vol_shape[2] * vol_shape[3] * vol_shape[4] + 8 * len(dice_h), "ms_per_step": ms_e2e / steps,
                 "mean_dice": sum(dice_h) / max(len(dice_h), 1)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "all conv kernels of the forward pass (whole-volume average)",
@@ -734,6 +753,8 @@ def main():
     ap.add_argument("--no-infer", action="store_true", help="skip the cfg4 inference record of the default run")
     ap.add_argument("--conv-table", action="store_true", help="print per-kernel-key tcgen05 conv timings to stderr")
     ap.add_argument("--eager", action="store_true", help="drive every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--two-step-head", action="store_true",
+                    help="model(x) -> EDiceLoss_partial(logits) instead of the fused classifier + loss kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

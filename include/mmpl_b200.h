@@ -140,6 +140,18 @@ int mmpl_cls_fwd(const void* a, const float* wc /*[C][Cin]*/, const float* bias,
 int mmpl_cls_bwd(const void* a, const float* wc, const float* dlogits, void* da, float* dwc, float* dbias,
                  const float* gn_beta, double* gn_ws, int n, int64_t spatial, int cin, int classes, int dtype,
                  mmpl_stream_t stream);
+/* Training head fused: precls_conv.2 (unet3D.py:632) + EDiceLoss_partial.forward (loss_partial.py:71-99) without the
+ * fp32 logits / dlogits tensors ever reaching memory.  a: [n][spatial][cin] bf16 (cin 32 or 64), classes <= 16; target,
+ * class_weight, lut, per_sample, sums, loss, uce as in mmpl_partial_loss_fwd / _bwd.  The backward recomputes the logits,
+ * writes da (bf16), dwc [classes][cin] and dbias [classes] and, with gn_beta / gn_ws, adds the first
+ * pass of the GroupNorm+ReLU backward of `a` exactly like mmpl_cls_bwd. */
+int mmpl_cls_loss_fwd(const void* a, const float* wc, const float* bias, const void* target, int target_is_u8,
+                      const float* class_weight, const float* lut, int per_sample, double* sums, float* loss, int n,
+                      int64_t spatial, int cin, int classes, int uce, mmpl_stream_t stream);
+int mmpl_cls_loss_bwd(const void* a, const float* wc, const float* bias, const void* target, int target_is_u8,
+                      const float* class_weight, const float* lut, int per_sample, const double* sums,
+                      const float* grad_out, void* da, float* dwc, float* dbias, const float* gn_beta, double* gn_ws,
+                      int n, int64_t spatial, int cin, int classes, int uce, mmpl_stream_t stream);
 
 /* ---- GroupNorm(16)+ReLU: NoBottleneck.forward, unet3D.py:59-60,64-65 and downsample.0/1, :645-646 -------------
  * stats: double [N][G][2], must be zero before mmpl_gn_stats accumulates into it. */
@@ -284,6 +296,9 @@ int mmpl_cls_blend(const void* a, const float* wc /*[C][cin]*/, const float* bia
 int mmpl_sw_finalize(const void* acc, const void* wsum, const void* label, int label_is_u8, float* out_logits,
                      uint8_t* argmax, long long* counts, int c, int64_t voxels, int64_t plane, int acc_bytes,
                      mmpl_stream_t stream);
+/* dst[i] += src[i], fp32: the slab owner of the sharded sliding window adds the partial accumulator planes
+ * its peers send (evaluate._sliding_blend; the reference sums full_probs on one device, evaluate_amos.py:268-272). */
+int mmpl_accumulate_f32(float* dst, const float* src, int64_t n, mmpl_stream_t stream);
 
 #ifdef __cplusplus
 }

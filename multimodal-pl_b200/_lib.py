@@ -67,6 +67,9 @@ _SIGNATURES = {
     "mmpl_sgd_step": [_ptr, _ptr, _ptr, _c_i64, _ptr, _c_f32, _c_f32, _c_f32, _c_int, _ptr],
     "mmpl_sw_blend": [_ptr, _ptr, _ptr, _ptr] + [_c_int] * 12 + [_ptr],
     "mmpl_cls_blend": [_ptr] * 7 + [_c_int] * 9 + [_ptr],
+    "mmpl_accumulate_f32": [_ptr, _ptr, _c_i64, _ptr],
+    "mmpl_cls_loss_fwd": [_ptr] * 4 + [_c_int] + [_ptr] * 2 + [_c_int] + [_ptr] * 2 + [_c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
+    "mmpl_cls_loss_bwd": [_ptr] * 4 + [_c_int] + [_ptr] * 2 + [_c_int] + [_ptr] * 7 + [_c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_sw_finalize": [_ptr, _ptr, _ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _c_i64, _c_i64, _c_int, _ptr],
 }
 _RESTYPES = {"mmpl_last_error": ctypes.c_char_p, "mmpl_launch_count": ctypes.c_uint64,

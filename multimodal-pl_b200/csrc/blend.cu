@@ -140,6 +140,20 @@ sw_finalize_f32x4_kernel(const float* __restrict__ acc, const void* __restrict__
   }
 }
 
+// dst += src over n floats: the partial accumulator slabs other ranks send to the slab owner (sharded sliding window)
+__global__ void __launch_bounds__(256) accumulate_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n4,
+                                                             int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t i0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  for (int64_t q = i0; q < n4; q += stride) {
+    float4 d = reinterpret_cast<float4*>(dst)[q];
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
+    d.x += v.x, d.y += v.y, d.z += v.z, d.w += v.w;
+    reinterpret_cast<float4*>(dst)[q] = d;
+  }
+  for (int64_t i = n4 * 4 + i0; i < n; i += stride) dst[i] += src[i];
+}
+
 }  // namespace
 }  // namespace mmpl
 
@@ -197,5 +211,16 @@ extern "C" int mmpl_sw_finalize(const void* acc, const void* wsum, const void* l
     sw_finalize_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(acc), static_cast<const float*>(wsum), lab,
                                                     label_is_u8, out_logits, argmax, cnt, c, voxels, pl, d_outer);
   MMPL_CHECK_LAUNCH("sw_finalize");
+  return MMPL_OK;
+}
+
+extern "C" int mmpl_accumulate_f32(float* dst, const float* src, int64_t n, mmpl_stream_t stream) {
+  MMPL_REQUIRE(n >= 0, MMPL_E_SHAPE, "accumulate_f32: n=%lld", (long long)n);
+  if (n == 0) return MMPL_OK;
+  const bool vec = (reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) % 16 == 0;
+  const int64_t n4 = vec ? n / 4 : 0;
+  const int blocks = static_cast<int>(std::min<int64_t>((std::max<int64_t>(n4, 1) + 255) / 256, static_cast<int64_t>(num_sms()) * 8));
+  accumulate_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, src, n4, n);
+  MMPL_CHECK_LAUNCH("accumulate_f32");
   return MMPL_OK;
 }

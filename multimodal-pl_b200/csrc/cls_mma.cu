@@ -12,28 +12,10 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "mma.cuh"
 
 namespace mmpl {
 namespace {
-
-__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                         uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-// (x, y) -> bf16x2 with x in the low half; hi = round-to-nearest part, lo = what is left of the fp32 values
-__device__ __forceinline__ uint32_t pack_hi(float x, float y) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  hi = pack_hi(x, y);
-  const float xh = __uint_as_float(hi << 16), yh = __uint_as_float(hi & 0xFFFF0000u);
-  lo = pack_hi(x - xh, y - yh);
-}
 
 // ------------------------------------------------------------------------------------------------ forward
 // logits[n][c][s] = bias[c] + sum_k a[n][s][k] W[c][k].  A warp owns chunks of 32 voxels of one sample (2 m16 tiles);

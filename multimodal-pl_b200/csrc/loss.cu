@@ -15,30 +15,13 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "loss_math.cuh"
 #include "ptx.cuh"
 
 namespace mmpl {
 namespace {
 
 constexpr int kThreads = 256;
-
-// a label value -> class id in [0, C) or -1 (not a class id); `lut` is the per-sample cmask remap
-__device__ __forceinline__ int class_of(float tv, const float* lut, int C) {
-  int ti = static_cast<int>(tv);
-  if (static_cast<float>(ti) != tv || ti < 0 || ti >= C) return -1;
-  if (lut) {
-    tv = lut[ti];
-    ti = static_cast<int>(tv);
-    if (static_cast<float>(ti) != tv || ti < 0 || ti >= C) return -1;
-  }
-  return ti;
-}
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 // softmax over the class axis, in registers.  exp(z - mx) as one FMA + one MUFU: 2^(z*log2(e) - mx*log2(e)),
 // ex2.approx (max rel. error 2^-22; the arguments are <= 0 so flush-to-zero only affects probabilities below 1e-38).
@@ -202,22 +185,7 @@ partial_loss_fwd_kernel(const float* __restrict__ logits, const void* __restrict
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     __threadfence();
-    // pooled (reference, loss_partial.py:87,92): one group over batch and voxels, class weights = mask[0].
-    // per-sample: the reference formula evaluated per sample with that sample's weights, averaged over the batch.
-    const int G = per_sample ? N : 1;
-    const double sm = 1e-5, nv = static_cast<double>(per_sample ? S : static_cast<int64_t>(N) * S);
-    double total = 0;
-    for (int g = 0; g < G; ++g) {
-      const volatile double* vs = sums + static_cast<int64_t>(g) * 4 * C;
-      double dice = 0, ce = 0;
-      for (int c = 0; c < C; ++c) {
-        const double I = vs[c], Z = vs[C + c], Y = vs[2 * C + c], E = vs[3 * C + c], w = cw[g * C + c];
-        dice += w * (1.0 - (2.0 * I + sm) / (Z + Y + sm));
-        ce += w * (E / nv);
-      }
-      total += dice / C + (uce ? ce : 0.0);
-    }
-    *loss = static_cast<float>(total / G);
+    partial_loss_finalize(sums, cw, N, S, C, uce, per_sample, loss);
   }
 }
 
@@ -422,20 +390,7 @@ partial_loss_fwd_staged_kernel(const float* __restrict__ logits, const void* __r
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     __threadfence();
-    const int G = per_sample ? N : 1;
-    const double sm = 1e-5, nv = static_cast<double>(per_sample ? S : static_cast<int64_t>(N) * S);
-    double total = 0;
-    for (int g = 0; g < G; ++g) {
-      const volatile double* vs = sums + static_cast<int64_t>(g) * 4 * C;
-      double dice = 0, ce = 0;
-      for (int c = 0; c < C; ++c) {
-        const double I = vs[c], Z = vs[C + c], Y = vs[2 * C + c], E = vs[3 * C + c], w = cw[g * C + c];
-        dice += w * (1.0 - (2.0 * I + sm) / (Z + Y + sm));
-        ce += w * (E / nv);
-      }
-      total += dice / C + (uce ? ce : 0.0);
-    }
-    *loss = static_cast<float>(total / G);
+    partial_loss_finalize(sums, cw, N, S, C, uce, per_sample, loss);
   }
 }
 

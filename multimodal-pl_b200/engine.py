@@ -259,11 +259,17 @@ class GraphedTrainStep:
     Inputs: ``step(image, label)`` copies them into the graph's static buffers.  Host batches go through a staging
     buffer filled on a copy stream: ``step.stage(next_image, next_label)`` may be called while the previous step still
     runs, so the PCIe transfer of batch i+1 overlaps the compute of batch i; ``step.run_staged()`` then costs one
-    device-to-device copy.  Labels may be uint8 (a quarter of the fp32 bytes)."""
+    device-to-device copy.  Labels may be uint8 (a quarter of the fp32 bytes).
+
+    ``fused_loss(module, image, label) -> loss`` (optional) replaces ``loss_fn(module(image)[0], label)``; with
+    ``unet3D_baseline.forward_partial_loss`` the step never materialises logits."""
 
     def __init__(self, dp_model: "DataParallelModel", loss_fn, optimizer: "FusedSGD", image, label, warmup: int = 3,
-                 comm_in_graph: Optional[bool] = None):
+                 comm_in_graph: Optional[bool] = None, fused_loss=None):
         self.dp, self.loss_fn, self.opt = dp_model, loss_fn, optimizer
+        # fused_loss(module, image, label) -> loss replaces  loss_fn(module(image)[0], label): e.g.
+        # lambda m, x, y: m.forward_partial_loss(x, y, masks, lut=luts, per_sample=True)  (no logits tensor at all)
+        self.fused_loss = fused_loss
         self.world = dp_model.world_size
         if comm_in_graph is None:
             comm_in_graph = os.environ.get("MMPL_GRAPH_NCCL", "1") != "0"
@@ -329,9 +335,12 @@ class GraphedTrainStep:
         self.dp.bucket_step = self._bucket_step if overlapped else None
         try:
             self.opt.zero_grad()
-            logits = self.dp(self.static_image, self.static_label)
-            logits = logits[0] if isinstance(logits, (tuple, list)) else logits
-            loss = self.loss_fn(logits, self.static_label)
+            if self.fused_loss is not None:
+                loss = self.fused_loss(self.dp.module, self.static_image, self.static_label)
+            else:
+                logits = self.dp(self.static_image, self.static_label)
+                logits = logits[0] if isinstance(logits, (tuple, list)) else logits
+                loss = self.loss_fn(logits, self.static_label)
             loss.backward()      # overlapped: bucket all-reduces + per-bucket SGD are issued from the autograd hooks
         finally:
             self.dp.bucket_step = None
@@ -424,7 +433,7 @@ class GraphedSlidingWindow:
     volume accumulator (``model.blend_tile(tile, sink)``) -- captured ONCE into a CUDA graph and replayed per tile; the tile
     origin is a device scalar triple the graph reads, so the same graph serves all 96 tiles of a 300x512x512 volume.
     Owns the fp32 accumulator ``acc`` [1, Dpad, C, H, W] (depth-major; Dpad = D rounded up to a multiple of
-    ``world_size`` so that depth slabs reduce-scatter evenly).  Used by ``evaluate.predict_sliding_dice``.  The weights are
+    ``world_size`` so that every rank owns a depth slab of the same size).  Used by ``evaluate.predict_sliding_dice``.  The weights are
     treated as frozen (``ops.frozen_weights``): build a new object after they change."""
 
     def __init__(self, model: torch.nn.Module, volume_dhw, tile, classes: int, world_size: int = 1, warmup: int = 2,
@@ -462,8 +471,9 @@ class GraphedSlidingWindow:
         if was_training:
             model.train()
 
-    def reset(self):
-        self.acc.zero_()
+    def reset(self, lo=0, hi=None):
+        """Zero the accumulator planes [lo, hi) (default: all) before a volume."""
+        self.acc[0, lo:hi].zero_()
 
     def blend_tile(self, img, origin_dev_row):
         """``img`` [1,1,td,th,tw] on the device; ``origin_dev_row`` a device int32[3] = (d0, h0, w0) of the tile."""

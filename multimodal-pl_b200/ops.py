@@ -1201,6 +1201,77 @@ def partial_label_loss(logits, target, class_weight, lut=None, uce=True, per_sam
     return PartialLossFn.apply(logits, target, class_weight, lut, bool(uce), bool(per_sample))
 
 
+class ClassifierPartialLossFn(torch.autograd.Function):
+    """``partial_label_loss(classifier(a, weight, bias), target, ...)`` as two launches (csrc/cls_loss.cu): the fp32 logits
+    and their gradient only ever exist in the registers of the warp MMAs.  Forward: a + labels -> per-class sums -> loss.
+    Backward: logits recomputed from ``a``, dA / dW / db and the GroupNorm-backward reduction of the node that produced
+    ``a`` -- everything ClassifierFn.backward does."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias, target, class_weight, lut, uce, per_sample):
+        _lib.require_device()
+        L = _lib.lib()
+        ctx.gn_bwd = getattr(a, "_mmpl_gn_bwd", None)
+        a = to_cl(a, torch.bfloat16)
+        n, cin, d, h, w = a.shape
+        classes = weight.shape[0]
+        spatial = d * h * w
+        dev = a.device
+        wc = weight.detach().float().reshape(classes, cin).contiguous()
+        b = bias.detach().float().contiguous()
+        t = target.detach()
+        u8 = t.dtype == torch.uint8
+        t = t.contiguous() if u8 else t.float().contiguous()
+        assert t.numel() == n * spatial, f"target {tuple(target.shape)} does not match activations {tuple(a.shape)}"
+        groups = n if per_sample else 1
+        cw = class_weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+        assert cw.numel() == groups * classes, \
+            f"class weights {tuple(class_weight.shape)} for {groups} group(s) of {classes} classes"
+        lt = None if lut is None else lut.detach().to(device=dev, dtype=torch.float32).contiguous()
+        assert lt is None or lt.numel() == groups * classes
+        sums = torch.empty(groups * 4 * classes + 1, dtype=torch.float64, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        _lib.check(L.mmpl_cls_loss_fwd(_p(a), _p(wc), _p(b), _p(t), int(u8), _p(cw), _p(lt), int(per_sample), _p(sums),
+                                       _p(loss), n, spatial, cin, classes, int(uce), _lib.stream_ptr()), "cls_loss_fwd")
+        ctx.save_for_backward(a, wc, b, t, cw, lt, sums)
+        ctx.meta = (n, cin, d, h, w, classes, weight.dtype, tuple(weight.shape), int(u8), int(uce), int(per_sample))
+        ctx.params = (weight, bias)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        L = _lib.lib()
+        a, wc, b, t, cw, lt, sums = ctx.saved_tensors
+        n, cin, d, h, w, classes, wdtype, wshape, u8, uce, per_sample = ctx.meta
+        g = gout.detach().float().contiguous()
+        da = torch.empty_like(a)
+        dwc = _grad_dst(ctx.params[0], wshape)
+        db = _grad_dst(ctx.params[1], (classes,))
+        gb = gws = None
+        fuse_cls = _cfg["fuse_gn_bwd_cls"] if _cfg["fuse_gn_bwd_cls"] is not None else True
+        if fuse_cls and ctx.gn_bwd is not None and ctx.gn_bwd[2] == 0:
+            gb, gws, _ = ctx.gn_bwd
+        _lib.check(L.mmpl_cls_loss_bwd(_p(a), _p(wc), _p(b), _p(t), u8, _p(cw), _p(lt), per_sample, _p(sums), _p(g), _p(da),
+                                       _p(dwc), _p(db), _p(gb), _p(gws), n, d * h * w, cin, classes, uce,
+                                       _lib.stream_ptr()), "cls_loss_bwd")
+        if gws is not None:
+            _GN_REDUCED[da.data_ptr()] = (gws.data_ptr(), 0)
+        return da, dwc.to(wdtype), db.to(wdtype), None, None, None, None, None
+
+
+def classifier_partial_loss_supported(cin: int, classes: int, dtype=None) -> bool:
+    dtype = _cfg["dtype"] if dtype is None else dtype
+    return dtype == torch.bfloat16 and cin in (32, 64) and 1 <= classes <= 16
+
+
+def classifier_partial_loss(a, weight, bias, target, class_weight, lut=None, uce=True, per_sample=False):
+    """Loss of the classifier applied to ``a`` without materialising the logits when the fused kernels cover the shape
+    (bf16 activations, 32/64 channels, <= 16 classes); the two-step composition otherwise -- same value, same gradients."""
+    if classifier_partial_loss_supported(weight.shape[1], weight.shape[0]):
+        return ClassifierPartialLossFn.apply(a, weight, bias, target, class_weight, lut, bool(uce), bool(per_sample))
+    return partial_label_loss(classifier(a, weight, bias), target, class_weight, lut, uce, per_sample)
+
+
 # --------------------------------------------------------------------------------------------------------------
 class MaskedDiceFn(torch.autograd.Function):
     """DiceLoss._dice_loss over a voxel gate, optionally on sigmoid(x) and with the BCE-with-logits term of

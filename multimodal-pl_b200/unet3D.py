@@ -88,6 +88,13 @@ class GNReLUClassifier(nn.Sequential):
             return None
         return ops.classifier(a, conv.weight, conv.bias)
 
+    def partial_loss(self, x, target, class_weight, lut=None, uce=True, per_sample=False):
+        """EDiceLoss_partial of this head's logits (loss_partial.py:71-99) without writing them: GroupNorm+ReLU, then the
+        fused classifier + loss kernels (ops.classifier_partial_loss)."""
+        gn, conv = self[0], self[2]
+        a = ops.gn_relu(x, gn.weight, gn.bias, gn.num_groups, gn.eps)
+        return ops.classifier_partial_loss(a, conv.weight, conv.bias, target, class_weight, lut, uce, per_sample)
+
 
 class NoBottleneck(nn.Module):
     """Pre-activation residual block (reference unet3D.py:40-73):
@@ -246,6 +253,17 @@ class unet3D_baseline(nn.Module):
         if self.training:
             return logits, [], []
         return logits
+
+    def forward_partial_loss(self, input, target, mask=None, lut=None, per_sample=False, uce=True):
+        """``EDiceLoss_partial(C)(self(input)[0], target, mask, lut=..., per_sample=...)`` in one call (not part of the
+        reference surface): the training step of train_amos_atlas_final.py:226-262 when only the loss of the main head
+        is needed.  The fp32 logits and their gradient (2 x 64 B/voxel, four passes over them) are never written: the
+        classifier runs inside the loss kernels, forward and backward.  Same value and gradients as the two-step form."""
+        from .loss_functions.loss_partial import _class_weight
+
+        conv = self.precls_conv[2]
+        w = _class_weight(mask, conv.out_channels, input.device, per_sample)
+        return self.precls_conv.partial_loss(self._features(input), target, w, lut, uce, per_sample)
 
     @torch.no_grad()
     def blend_tile(self, input, sink):

@@ -1,6 +1,7 @@
 """torchrun worker (tests/test_gpu_train.py::test_sharded_sliding_window): the sharded sliding window must give the same
 argmax / Dice as a single rank -- generic path (tiles split over the ranks, fp64 accumulators all-reduced) and production
-path (bf16 unet3D_baseline, fused classifier+blend, reduce-scatter along depth, local finalize, all-gather of the mask)."""
+path (bf16 unet3D_baseline, fused classifier+blend, exchange of the touched accumulator planes along depth, local
+finalize, all-gather of the mask)."""
 import os
 import sys
 
@@ -31,7 +32,7 @@ d_1, _, _, am_1 = predict_sliding_dice(None, f, vol, (16, 32, 32), 6, None, labe
 mism = (am_sh != am_1).sum().item()
 assert mism <= 2, mism
 assert max(abs(float(a) - float(b)) for a, b in zip(d_sh, d_1)) < 1e-5
-# ---- production path: reduce-scatter along depth (40 planes / 2 ranks; 41 planes exercises the padded slab)
+# ---- production path: plane exchange along depth (40 planes / 2 ranks; 41 planes exercises the padded slab)
 import multimodal_pl_b200 as mm  # noqa: E402
 from multimodal_pl_b200.engine import GraphedSlidingWindow  # noqa: E402
 from multimodal_pl_b200.unet3D import unet3D_baseline  # noqa: E402
@@ -47,6 +48,11 @@ for depth in (40, 41):
     two = predict_sliding_dice(None, [model], vol, (16, 32, 32), 16, None, sharded=True, **kw)
     eng = GraphedSlidingWindow(model, (depth, 72, 88), (16, 32, 32), 16, world_size=world)
     thr = predict_sliding_dice(None, [eng], vol, (16, 32, 32), 16, None, sharded=True, **kw)
+    # a second volume through the same object: only the planes a rank writes or owns are re-zeroed between volumes
+    vol2 = O.synth_patch((1, 1, depth, 72, 88), 43, "ct")
+    predict_sliding_dice(None, [eng], vol2, (16, 32, 32), 16, None, sharded=True, **kw)
+    again = predict_sliding_dice(None, [eng], vol, (16, 32, 32), 16, None, sharded=True, **kw)
+    assert torch.equal(again[3], thr[3])
     for got in (two, thr):
         # fp32 sums of <= 8 tile contributions in a different order: only exact near-ties may flip
         bad = (got[3] != one[3]).sum().item()

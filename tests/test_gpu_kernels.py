@@ -441,6 +441,102 @@ def test_partial_loss_uint8_labels_and_per_sample_weights(mm, shape):
     assert rel(zp.grad, zr.grad) < 1e-5
 
 
+@pytest.mark.parametrize("cin,classes,dhw", [(32, 16, (4, 6, 8)), (32, 16, (3, 5, 7)), (64, 16, (4, 4, 6)), (32, 5, (3, 5, 5)),
+                                            (64, 13, (2, 7, 9))])
+def test_fused_classifier_loss_vs_oracle_and_two_step_form(mm, cin, classes, dhw):
+    """mmpl_cls_loss_fwd/_bwd (classifier inside the loss kernels, no logits tensor) against (a) the CPU oracle -- 1x1x1
+    convolution with bias on the same bf16 activations, then the reference loss -- and (b) the two-launch-pair form it
+    replaces.  Ragged voxel counts (tails of the 16/32-voxel tiles), fewer than 16 classes, float and uint8 labels,
+    pooled (reference) and per-sample weights with the cmask LUT."""
+    import multimodal_pl_b200 as mmp
+    from multimodal_pl_b200 import ops
+
+    mmp.set_compute_dtype(torch.bfloat16)
+    try:
+        B = 2
+        a0 = _rand((B, cin) + dhw, 21, 1.0).relu().to(torch.bfloat16)            # the head's input is a ReLU output
+        wt = _rand((classes, cin, 1, 1, 1), 22, 0.3)
+        bs = _rand((classes,), 23, 0.2)
+        lab = torch.randint(0, classes, (B,) + dhw, generator=torch.Generator().manual_seed(24)).float()
+        ws = [[1.0] + [0.0] * (classes - 1) for _ in range(B)]
+        ws[0][1 + 2 % (classes - 1)] = 1.0                                   # CT-like row; the second sample: background only
+        luts = torch.tensor([[float(l) if (l == 0 or w[l]) else 0.0 for l in range(classes)] for w in ws])
+        for per_sample, u8 in ((False, False), (False, True), (True, True)):
+            cw = torch.tensor(ws if per_sample else ws[0])
+            lut = luts if per_sample else None
+            tgt = lab.cuda().to(torch.uint8) if u8 else lab.cuda()
+
+            def run(fused):
+                a = a0.cuda().requires_grad_(True)
+                w_ = wt.cuda().requires_grad_(True)
+                b_ = bs.cuda().requires_grad_(True)
+                if fused:
+                    assert ops.classifier_partial_loss_supported(cin, classes)
+                    L = ops.classifier_partial_loss(a, w_, b_, tgt, cw.cuda(), lut, True, per_sample)
+                else:
+                    L = ops.partial_label_loss(ops.classifier(a, w_, b_), tgt, cw.cuda(), lut, True, per_sample)
+                L.backward()
+                return L.item(), a.grad.float().cpu(), w_.grad.cpu(), b_.grad.cpu()
+
+            lf, daf, dwf, dbf = run(True)
+            l2, da2, dw2, db2 = run(False)
+            tag = f"per_sample={per_sample} u8={u8}"
+            # (b) same arithmetic, different summation order
+            assert abs(lf - l2) < 1e-6 * max(1.0, abs(l2)), tag
+            assert rel(daf, da2) < 4e-3 and rel(dwf, dw2) < 1e-4 and rel(dbf, db2) < 1e-4, tag
+            # (a) oracle: fp32 conv on the same bf16 activations, reference loss per group
+            ar = a0.float().requires_grad_(True)
+            wr, br = wt.clone().requires_grad_(True), bs.clone().requires_grad_(True)
+            z = torch.nn.functional.conv3d(ar, wr, br)
+            if per_sample:
+                ref = sum(O.partial_label_loss(z[b:b + 1], O.remap_unsupervised(lab[b:b + 1], ws[b]), ws[b]) for b in range(B)) / B
+            else:
+                ref = O.partial_label_loss(z, lab, ws[0])
+            ref.backward()
+            assert abs(lf - ref.item()) < 2e-6 * max(1.0, ref.item()), (tag, lf, ref.item())
+            assert rel(daf, ar.grad) < 6e-3, tag                              # dA is stored as bf16
+            assert rel(dwf, wr.grad) < 1e-4 and rel(dbf, br.grad) < 1e-4, tag
+    finally:
+        mmp.set_compute_dtype(torch.float32)
+
+
+def test_unet_forward_partial_loss_equals_two_step_training_step(mm):
+    """unet3D_baseline.forward_partial_loss == EDiceLoss_partial(model(x)[0], ...) in value and in every parameter
+    gradient (bf16 tcgen05 path; the GroupNorm-backward reduction of precls_conv rides on the fused backward)."""
+    import multimodal_pl_b200 as mmp
+    from multimodal_pl_b200 import synth
+    from multimodal_pl_b200.loss_functions.loss_partial import EDiceLoss_partial
+    from multimodal_pl_b200.unet3D import unet3D_baseline
+
+    mmp.set_compute_dtype(torch.bfloat16)
+    try:
+        torch.manual_seed(0)
+        model = unet3D_baseline([1, 2, 2, 2, 2], num_classes=16, weight_std=True).cuda().train()
+        x = synth.synth_patch((2, 1, 16, 32, 32), 5, "ct").cuda()
+        lab = synth.synth_labels((2, 16, 32, 32), 6, 16, 12, dtype=torch.uint8).cuda()
+        masks = [torch.tensor([1.0, 0, 0, 1.0] + [0.0] * 12), torch.tensor([1.0] + [0.0] * 15)]
+        luts = torch.stack([torch.tensor([float(l) if (l == 0 or m[l]) else 0.0 for l in range(16)]) for m in masks])
+        grads = []
+        losses = []
+        for fused in (False, True):
+            model.zero_grad(set_to_none=True)
+            if fused:
+                L = model.forward_partial_loss(x, lab, masks, lut=luts, per_sample=True)
+            else:
+                L = EDiceLoss_partial(16)(model(x)[0], lab, mask=masks, lut=luts, per_sample=True)
+            L.backward()
+            torch.cuda.synchronize()
+            losses.append(L.item())
+            grads.append({k: p.grad.detach().float().clone() for k, p in model.named_parameters()})
+        assert abs(losses[0] - losses[1]) < 1e-5 * max(1.0, abs(losses[0])), losses
+        worst = max((rel(grads[1][k], grads[0][k]), k) for k in grads[0] if grads[0][k].abs().max() > 0)
+        # dA differs by bf16 rounding of a different fp32 summation order only at the head; everything upstream sees the
+        # same arithmetic on nearly identical inputs
+        assert worst[0] < 2e-2, worst
+    finally:
+        mmp.set_compute_dtype(torch.float32)
+
+
 def test_sgd_step(mm):
     from multimodal_pl_b200 import _lib
 

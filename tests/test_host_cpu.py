@@ -245,3 +245,42 @@ def test_engine_surface():
                 assert callable(getattr(e, name))
     finally:
         sys.argv = argv
+
+
+@pytest.mark.parametrize("volume,tile,world", [((300, 512, 512), (64, 192, 192), 8), ((300, 512, 512), (64, 192, 192), 4),
+                                               ((40, 72, 88), (16, 32, 32), 2), ((41, 72, 88), (16, 32, 32), 3),
+                                               ((64, 192, 192), (64, 192, 192), 8)])
+def test_sliding_window_plane_exchange_plan_sums_every_contribution_once(volume, tile, world):
+    """The sharded sliding window exchanges only the accumulator planes a rank touched (evaluate._exchange_plan).  Simulated
+    on the host with one number per (rank, plane): after the exchange the owner of every plane holds the sum over all
+    ranks that touched it, every send has a matching receive of the same extent, and far fewer planes move than a
+    reduce-scatter of the whole accumulator would move."""
+    from multimodal_pl_b200 import evaluate as E
+
+    D = volume[0]
+    tiles = E.tile_origins((1, 1) + tuple(volume), tile)
+    runs = [E._my_tiles(tiles, r, world) for r in range(world)]
+    assert sorted(t for m in runs for t in m) == sorted(tiles)
+    ranges = [E._depth_range(m, tile[0]) for m in runs]
+    dpad = (D + world - 1) // world * world
+    slab = dpad // world
+    rng = np.random.RandomState(0)
+    acc = np.zeros((world, dpad))
+    for r, (lo, hi) in enumerate(ranges):
+        acc[r, lo:hi] = rng.rand(hi - lo) + 1.0
+    plans = [E._exchange_plan(ranges, r, slab, world) for r in range(world)]
+    out = acc.copy()
+    moved = 0
+    for r in range(world):
+        for peer, lo, hi in plans[r][1]:
+            assert (r, lo, hi) in plans[peer][0], "a receive without the matching send"
+            assert r * slab <= lo < hi <= (r + 1) * slab
+            out[r, lo:hi] += acc[peer, lo:hi]
+            moved += hi - lo
+        for peer, lo, hi in plans[r][0]:
+            assert (r, lo, hi) in plans[peer][1], "a send without the matching receive"
+    total = acc.sum(0)
+    for r in range(world):
+        np.testing.assert_allclose(out[r, r * slab:(r + 1) * slab], total[r * slab:(r + 1) * slab], rtol=1e-12)
+    if world >= 4 and len(tiles) >= 4 * world:
+        assert moved < 0.5 * (world - 1) * dpad, (moved, (world - 1) * dpad)

@@ -87,6 +87,20 @@ loss1 = ops.partial_label_loss(z, tgt, cw1)
 timeit("partial_loss fwd (all classes)", lambda: ops.partial_label_loss(z, tgt, cw1), V * 68)
 timeit("partial_loss bwd (all classes)", lambda: torch.autograd.grad(loss1, z, retain_graph=True), V * 132)
 
+# classifier + loss fused (csrc/cls_loss.cu): per-sample CT/MRI weights + LUT and uint8 labels like bench.py
+tgt8 = tgt.to(torch.uint8)
+cw2 = torch.tensor([[1.0, 0, 0, 0, 1.0] + [0.0] * 11, [1.0] + [0.0] * 15], device=dev)
+lut2 = torch.stack([torch.tensor([float(l) if (l == 0 or w[l]) else 0.0 for l in range(16)]) for w in cw2.tolist()]).to(dev)
+lossf = ops.classifier_partial_loss(a, wc, bc, tgt8, cw2, lut2, True, True)
+timeit("head fused fwd (cls+loss)", lambda: ops.classifier_partial_loss(a, wc, bc, tgt8, cw2, lut2, True, True), V * (32 * A + 1))
+timeit("head fused bwd (cls+loss)", lambda: torch.autograd.grad(lossf, a, retain_graph=True), V * (64 * A + 1))
+loss2 = ops.partial_label_loss(ops.classifier(a, wc, bc), tgt8, cw2, lut2, True, True)
+timeit("head two-step fwd (cls, loss)", lambda: ops.partial_label_loss(ops.classifier(a, wc, bc), tgt8, cw2, lut2, True, True), V * (32 * A + 1))
+timeit("head two-step bwd (loss, cls)", lambda: torch.autograd.grad(loss2, a, retain_graph=True), V * (64 * A + 1))
+lossa = ops.classifier_partial_loss(a, wc, bc, tgt8, torch.ones(2, 16, device=dev), None, True, True)
+timeit("head fused fwd (all classes)", lambda: ops.classifier_partial_loss(a, wc, bc, tgt8, torch.ones(2, 16, device=dev), None, True, True), V * (32 * A + 1))
+timeit("head fused bwd (all classes)", lambda: torch.autograd.grad(lossa, a, retain_graph=True), V * (64 * A + 1))
+
 # stem
 img = torch.randn(N, 1, D, H, W, device=dev)
 ws = torch.randn(32, 1, 3, 3, 3, device=dev, requires_grad=True)
