@@ -364,7 +364,7 @@ def run_train(args):
     torch.manual_seed(0)
     model = unet3D_baseline([1, 2, 2, 2, 2], num_classes=classes, weight_std=True, base=base).to(dev)
     model.train()
-    dp = DataParallelModel(model, world, average=False)
+    dp = DataParallelModel(model, world, bucket_mb=args.bucket_mb, average=False)
     opt = FusedSGD(dp.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4, flat_grad=dp.flat_grad)
     crit = EDiceLoss_partial(classes)
 
@@ -492,8 +492,11 @@ def run_train(args):
     torch.cuda.empty_cache()
     if args.workload == "cfg2" and not args.no_infer:
         try:
-            # the ranks hold identical weights (same reduced gradients, same SGD): reuse the trained model
-            infer = infer_record(model, dev, rank, world, steps=2, warmup=1, eager=args.eager)
+            # a freshly initialised network (seed 0, broadcast from rank 0): 30 SGD steps on noise labels would leave one that
+            # predicts background everywhere
+            del model, dp, opt
+            torch.cuda.empty_cache()
+            infer = infer_record(None, dev, rank, world, steps=2, warmup=1, eager=args.eager)
         except Exception as e:  # noqa: BLE001
             infer = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
@@ -753,6 +756,7 @@ def main():
     ap.add_argument("--no-infer", action="store_true", help="skip the cfg4 inference record of the default run")
     ap.add_argument("--conv-table", action="store_true", help="print per-kernel-key tcgen05 conv timings to stderr")
     ap.add_argument("--eager", action="store_true", help="drive every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--bucket-mb", type=float, default=8.0, help="gradient bucket size of the in-graph NCCL all-reduces")
     ap.add_argument("--two-step-head", action="store_true",
                     help="model(x) -> EDiceLoss_partial(logits) instead of the fused classifier + loss kernels")
     args = ap.parse_args()
