@@ -496,7 +496,7 @@ def run_train(args):
             # predicts background everywhere
             del model, dp, opt
             torch.cuda.empty_cache()
-            infer = infer_record(None, dev, rank, world, steps=2, warmup=1, eager=args.eager)
+            infer = infer_record(None, dev, rank, world, steps=3, warmup=2, eager=args.eager)
         except Exception as e:  # noqa: BLE001
             infer = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
@@ -519,6 +519,7 @@ def run_train(args):
     achieved = dom_flops / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else 0.0
     tc_ms, tc_flops = prof["ms"], prof["flops"]
     tc_tf = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+    k3_tf = prof["k3"]["flops"] / (prof["k3"]["ms"] / 1e3) / 1e12 if prof["k3"]["ms"] > 0 else 0.0
     dom_name = "wgrad_tc_kernel (tcgen05 weight gradient) " if dom["key"] and dom["key"][0] == "wgrad_tc" else \
         "conv_tc_kernel (tcgen05 implicit-GEMM conv: fprop, fprop+residual, dgrad, dgrad+GN-backward launches) "
     dom_vox = dom["key"][5] if dom["key"] else 0
@@ -537,6 +538,10 @@ def run_train(args):
                                       "launches": prof["launches"], "ms_per_step": tc_ms / prof_steps,
                                       "share_of_step": (tc_ms / prof_steps) / ms_step,
                                       "note": "north_star target: >= 0.5 of the dense bf16 roofline over all conv launches"},
+                "tensor_bound_convs": {"achieved": k3_tf, "frac": k3_tf / peak_tf, "unit": "TFLOP/s",
+                                       "launches": prof["k3"]["launches"], "ms_per_step": prof["k3"]["ms"] / prof_steps,
+                                       "note": "the 3x3x3 convolutions with >= 32 input channels only: the Cin=1 stem and the "
+                                               "1x1x1 convolutions are HBM / issue bound (SURVEY 8d) and dilute the aggregate above"},
                 "whole_step": {"achieved": TRAIN_TFLOP_PER_PATCH[args.workload] * value / world,
                                "frac": TRAIN_TFLOP_PER_PATCH[args.workload] * value / world / peak_tf, "unit": "TFLOP/s per GPU",
                                "note": "algorithmic conv FLOPs of the step / step time (includes every non-conv kernel)"}}

@@ -77,7 +77,11 @@ def collect_conv_profile():
         e[1] += v[1]
         e[2] += v[2]
     dom = max(inst.items(), key=lambda kv: kv[1][0]) if inst else (None, [0.0, 0.0, 0])
+    # roofline classes: the 3x3x3 convolutions with >= 32 input channels are tensor bound; the Cin = 1 stem
+    # and the 1x1x1 convolutions (<= 43 FLOP per byte at 64 -> 128 channels) sit far below the ridge: HBM / issue bound
+    k3 = [v for k, v in per.items() if k[3] == 3 and not str(k[0]).startswith("stem")]
     return {"ms": tot_ms, "launches": len(_PROF["events"]), "flops": float(tot_fl),
+            "k3": {"ms": sum(v[0] for v in k3), "flops": float(sum(v[1] for v in k3)), "launches": sum(v[2] for v in k3)},
             "per_key": {str(k): {"ms": v[0], "flops": float(v[1]), "launches": v[2]} for k, v in per.items()},
             "dominant": {"key": dom[0], "ms": dom[1][0], "flops": float(dom[1][1]), "launches": dom[1][2]}}
 
