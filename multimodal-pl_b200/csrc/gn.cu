@@ -84,12 +84,36 @@ __device__ __forceinline__ bool relu_gate(float x, float mean, float rstd, float
   return fmaf(x, sc, sh) > 0.f;
 }
 
+// Second head on the even voxels only (the 1x1x1 stride-2 downsample of NoBottleneck, unet3D.py:645-651, reads nothing
+// else): its tensor is stored compact, [N][ceil(D/2)][ceil(H/2)][ceil(W/2)][C].  Walks (d, h, w) of a strided voxel run.
+struct EvenWalk {
+  int d, h, w, H, W, Hc, Wc;
+  int64_t sp2;     // voxels of the compact tensor per sample
+  __device__ __forceinline__ void init(int64_t v, int D_, int H_, int W_) {
+    H = H_, W = W_, Hc = (H_ + 1) >> 1, Wc = (W_ + 1) >> 1;
+    sp2 = static_cast<int64_t>((D_ + 1) >> 1) * Hc * Wc;
+    const int64_t hw = static_cast<int64_t>(H_) * W_;
+    d = static_cast<int>(v / hw);
+    const int r = static_cast<int>(v - d * hw);
+    h = r / W_, w = r - h * W_;
+  }
+  __device__ __forceinline__ void step(int n) {
+    w += n;
+    while (w >= W) {
+      w -= W;
+      if (++h == H) h = 0, ++d;
+    }
+  }
+  __device__ __forceinline__ bool even() const { return ((d | h | w) & 1) == 0; }
+  __device__ __forceinline__ int64_t index() const { return (static_cast<int64_t>(d >> 1) * Hc + (h >> 1)) * Wc + (w >> 1); }
+};
+
 template <typename T, bool DUAL>
 __global__ void __launch_bounds__(kThreads)
 gn_relu_fwd_kernel(const T* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                    const float* __restrict__ beta, T* __restrict__ y, const float* __restrict__ gamma2,
                    const float* __restrict__ beta2, T* __restrict__ y2, int64_t spatial, int C, int groups, int cnt_cpg,
-                   float eps, int64_t vox_per_block) {
+                   float eps, int64_t vox_per_block, int cd, int ch, int cw) {
   constexpr int VN = Vec<T>::N;
   const int vpv = C / VN;
   const int cv = threadIdx.x % vpv, vl = threadIdx.x / vpv, vstep = kThreads / vpv;
@@ -112,6 +136,9 @@ gn_relu_fwd_kernel(const T* __restrict__ x, const double* __restrict__ stats, co
   const int64_t v0 = static_cast<int64_t>(blockIdx.x) * vox_per_block;
   const int64_t v1 = min(v0 + vox_per_block, spatial);
   const int64_t off = (static_cast<int64_t>(n) * spatial) * C + cv * VN;
+  const bool compact = DUAL && cw > 0;
+  EvenWalk ew;
+  if (compact) ew.init(v0 + vl, cd, ch, cw);
   for (int64_t v = v0 + vl; v < v1; v += vstep) {
     Vec<T> a, o;
     a.load(x + off + v * C);
@@ -119,9 +146,12 @@ gn_relu_fwd_kernel(const T* __restrict__ x, const double* __restrict__ stats, co
     for (int i = 0; i < VN; ++i) o.v[i] = fmaxf(fmaf(a.v[i], sc[i], sh[i]), 0.f);
     o.store(y + off + v * C);
     if (DUAL) {
+      if (!compact || ew.even()) {
 #pragma unroll
-      for (int i = 0; i < VN; ++i) o.v[i] = fmaxf(fmaf(a.v[i], sc2[i], sh2[i]), 0.f);
-      o.store(y2 + off + v * C);
+        for (int i = 0; i < VN; ++i) o.v[i] = fmaxf(fmaf(a.v[i], sc2[i], sh2[i]), 0.f);
+        o.store(compact ? y2 + (n * ew.sp2 + ew.index()) * C + cv * VN : y2 + off + v * C);
+      }
+      if (compact) ew.step(vstep);
     }
   }
 }
@@ -139,7 +169,8 @@ __global__ void __launch_bounds__(kThreads)
 gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                           const float* __restrict__ beta, const T* __restrict__ dy, const float* __restrict__ gamma2,
                           const float* __restrict__ beta2, const T* __restrict__ dy2, double* __restrict__ ws,
-                          int64_t spatial, int C, int groups, int cnt_cpg, float eps, int64_t vox_per_block) {
+                          int64_t spatial, int C, int groups, int cnt_cpg, float eps, int64_t vox_per_block, int cd, int ch,
+                          int cw) {
   using V = VecH<T>;   // 8-byte vectors: half the per-thread channel state -> higher occupancy
   constexpr int VN = V::N;
   constexpr int NH = DUAL ? 2 : 1;
@@ -164,6 +195,9 @@ gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ st
   for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
     for (int i = 0; i < VN; ++i) d1[hh][i] = d2[hh][i] = 0.f;
+  const bool compact = DUAL && cw > 0;
+  EvenWalk ew;
+  if (compact) ew.init(v0 + vl, cd, ch, cw);
 #pragma unroll 2
   for (int64_t v = v0 + vl; v < v1; v += vstep) {
     V a, g;
@@ -177,14 +211,17 @@ gn_relu_bwd_reduce_kernel(const T* __restrict__ x, const double* __restrict__ st
       d2[0][i] = fmaf(gg, xh, d2[0][i]);
     }
     if (DUAL) {
-      g.load(dy2 + off + v * C);
+      if (!compact || ew.even()) {
+        g.load(compact ? dy2 + (n * ew.sp2 + ew.index()) * C + cv * VN : dy2 + off + v * C);
 #pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        const float xh = (a.v[i] - mu[i]) * rs[i];
-        const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[NH - 1][i], be[NH - 1][i]) ? g.v[i] : 0.f;
-        d1[NH - 1][i] += gg;
-        d2[NH - 1][i] = fmaf(gg, xh, d2[NH - 1][i]);
+        for (int i = 0; i < VN; ++i) {
+          const float xh = (a.v[i] - mu[i]) * rs[i];
+          const float gg = relu_gate(a.v[i], mu[i], rs[i], ga[NH - 1][i], be[NH - 1][i]) ? g.v[i] : 0.f;
+          d1[NH - 1][i] += gg;
+          d2[NH - 1][i] = fmaf(gg, xh, d2[NH - 1][i]);
+        }
       }
+      if (compact) ew.step(vstep);
     }
   }
   __shared__ double sc[kMaxC][4];
@@ -222,7 +259,8 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
                          const float* __restrict__ beta2, const T* __restrict__ dy2, const T* __restrict__ addend,
                          T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                          float* __restrict__ dgamma2, float* __restrict__ dbeta2, double* __restrict__ ws,
-                         int N, int64_t spatial, int C, int groups, int cnt_cpg, float eps, int64_t vox_per_block) {
+                         int N, int64_t spatial, int C, int groups, int cnt_cpg, float eps, int64_t vox_per_block, int cd,
+                         int ch, int cw) {
   using V = VecH<T>;
   constexpr int VN = V::N;
   constexpr int NH = DUAL ? 2 : 1;
@@ -281,12 +319,29 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
     for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
       for (int i = 0; i < VN; ++i) ex[hh][i] = 0.f;
+    const bool compact = DUAL && cw > 0;
+    EvenWalk ew;
+    if (compact) ew.init(v0 + vl, cd, ch, cw);
 #pragma unroll 2
     for (int64_t v = v0 + vl; v < v1; v += vstep) {
       V a, g, g2, ad, o;
       a.load(x + off + v * C);
       g.load(dy + off + v * C);
-      if (DUAL) g2.load(dy2 + off + v * C);
+      if (DUAL) {
+        if (!compact) {
+          g2.load(dy2 + off + v * C);
+        } else {
+          // the gradient of the compact head exists on the even voxels only; the m1 / m2 terms of that head still reach
+          // every voxel (its statistics are those of the whole tensor)
+          if (ew.even()) {
+            g2.load(dy2 + (n * ew.sp2 + ew.index()) * C + cv * VN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < VN; ++i) g2.v[i] = 0.f;
+          }
+          ew.step(vstep);
+        }
+      }
       if (ADD) ad.load(addend + off + v * C);
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
@@ -370,7 +425,8 @@ template <typename T>
 int launch_gn_bwd(const void* x, const double* stats, const float* gamma, const float* beta, const void* dy,
                   const float* gamma2, const float* beta2, const void* dy2, const void* addend, void* dx,
                   float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, double* workspace, int reduced, int n,
-                  int64_t spatial, int c, int groups, int cnt_cpg, float eps, int bx, int64_t vpb, cudaStream_t s) {
+                  int64_t spatial, int c, int groups, int cnt_cpg, float eps, int bx, int64_t vpb, int cd, int ch, int cw,
+                  cudaStream_t s) {
   const bool dual = gamma2 != nullptr;
   const bool add = addend != nullptr;
   const T* xx = static_cast<const T*>(x);
@@ -382,24 +438,24 @@ int launch_gn_bwd(const void* x, const double* stats, const float* gamma, const 
   if (!reduced) {
     if (dual)
       gn_relu_bwd_reduce_kernel<T, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
-                                                                  workspace, spatial, c, groups, cnt_cpg, eps, vpb);
+                                                                  workspace, spatial, c, groups, cnt_cpg, eps, vpb, cd, ch, cw);
     else
       gn_relu_bwd_reduce_kernel<T, false><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, nullptr, nullptr,
-                                                                   nullptr, workspace, spatial, c, groups, cnt_cpg, eps, vpb);
+                                                                   nullptr, workspace, spatial, c, groups, cnt_cpg, eps, vpb, 0, 0, 0);
     MMPL_CHECK_LAUNCH("gn_relu_bwd_reduce");
   }
   if (dual && add)
     gn_relu_bwd_apply_kernel<T, true, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
-        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb);
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb, cd, ch, cw);
   else if (dual)
     gn_relu_bwd_apply_kernel<T, true, false><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
-        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb);
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb, cd, ch, cw);
   else if (add)
     gn_relu_bwd_apply_kernel<T, false, true><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
-        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb);
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb, cd, ch, cw);
   else
     gn_relu_bwd_apply_kernel<T, false, false><<<grid, kThreads, 0, s>>>(xx, stats, gamma, beta, g1, gamma2, beta2, g2,
-        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb);
+        ad, out, dgamma, dbeta, dgamma2, dbeta2, workspace, n, spatial, c, groups, cnt_cpg, eps, vpb, cd, ch, cw);
   return MMPL_OK;
 }
 
@@ -423,8 +479,12 @@ extern "C" int mmpl_gn_stats(const void* x, double* stats, int n, int64_t spatia
 
 extern "C" int mmpl_gn_relu_fwd(const void* x, const double* stats, const float* gamma, const float* beta, void* y,
                                 const float* gamma2, const float* beta2, void* y2, int n, int64_t spatial, int c,
-                                int groups, int real_cpg, float eps, int dtype, mmpl_stream_t stream) {
+                                int groups, int real_cpg, int y2_d, int y2_h, int y2_w, float eps, int dtype,
+                                mmpl_stream_t stream) {
   if (int e = check_shape(c, groups, dtype)) return e;
+  MMPL_REQUIRE((y2_d | y2_h | y2_w) == 0 || (y2 != nullptr && static_cast<int64_t>(y2_d) * y2_h * y2_w == spatial), MMPL_E_SHAPE,
+               "GroupNorm: compact second head needs the volume extents (%d,%d,%d) of the %lld voxels", y2_d, y2_h, y2_w,
+               (long long)spatial);
   MMPL_REQUIRE(real_cpg >= 0 && real_cpg <= c / groups, MMPL_E_SHAPE, "GroupNorm: real_cpg=%d of %d", real_cpg, c / groups);
   const int cnt_cpg = real_cpg > 0 ? real_cpg : c / groups;
   int bx;
@@ -436,11 +496,12 @@ extern "C" int mmpl_gn_relu_fwd(const void* x, const double* stats, const float*
     if (dual)
       gn_relu_fwd_kernel<T, true><<<dim3(bx, n), kThreads, 0, s>>>(static_cast<const T*>(x), stats, gamma, beta,
                                                                   static_cast<T*>(y), gamma2, beta2,
-                                                                  static_cast<T*>(y2), spatial, c, groups, cnt_cpg, eps, vpb);
+                                                                  static_cast<T*>(y2), spatial, c, groups, cnt_cpg, eps, vpb,
+                                                                  y2_d, y2_h, y2_w);
     else
       gn_relu_fwd_kernel<T, false><<<dim3(bx, n), kThreads, 0, s>>>(static_cast<const T*>(x), stats, gamma, beta,
                                                                    static_cast<T*>(y), nullptr, nullptr, nullptr,
-                                                                   spatial, c, groups, cnt_cpg, eps, vpb);
+                                                                   spatial, c, groups, cnt_cpg, eps, vpb, 0, 0, 0);
   });
   MMPL_CHECK_LAUNCH("gn_relu_fwd");
   return MMPL_OK;
@@ -450,8 +511,11 @@ extern "C" int mmpl_gn_relu_bwd(const void* x, const double* stats, const float*
                                 const void* dy, const float* gamma2, const float* beta2, const void* dy2,
                                 const void* addend, void* dx, float* dgamma, float* dbeta, float* dgamma2,
                                 float* dbeta2, double* workspace, int reduced, int n, int64_t spatial, int c, int groups,
-                                int real_cpg, float eps, int dtype, mmpl_stream_t stream) {
+                                int real_cpg, int y2_d, int y2_h, int y2_w, float eps, int dtype, mmpl_stream_t stream) {
   if (int e = check_shape(c, groups, dtype, true)) return e;
+  MMPL_REQUIRE((y2_d | y2_h | y2_w) == 0 || (dy2 != nullptr && static_cast<int64_t>(y2_d) * y2_h * y2_w == spatial), MMPL_E_SHAPE,
+               "GroupNorm: compact second head needs the volume extents (%d,%d,%d) of the %lld voxels", y2_d, y2_h, y2_w,
+               (long long)spatial);
   MMPL_REQUIRE(real_cpg >= 0 && real_cpg <= c / groups, MMPL_E_SHAPE, "GroupNorm: real_cpg=%d of %d", real_cpg, c / groups);
   const int cnt_cpg = real_cpg > 0 ? real_cpg : c / groups;
   int bx;
@@ -463,7 +527,7 @@ extern "C" int mmpl_gn_relu_bwd(const void* x, const double* stats, const float*
   int rc = MMPL_OK;
   MMPL_DISPATCH_DTYPE(dtype, T, rc = (launch_gn_bwd<T>(x, stats, gamma, beta, dy, gamma2, beta2, dy2, addend, dx, dgamma,
                                                      dbeta, dgamma2, dbeta2, workspace, reduced, n, spatial, c, groups,
-                                                     cnt_cpg, eps, bx, vpb, s)));
+                                                     cnt_cpg, eps, bx, vpb, y2_d, y2_h, y2_w, s)));
   if (rc) return rc;
   MMPL_CHECK_LAUNCH("gn_relu_bwd_apply");
   // leave the workspace clean: producers of a later backward through the same node accumulate into it again

@@ -747,7 +747,8 @@ class GNReLUFn(torch.autograd.Function):
     gradient arrives here and is added inside the backward kernel instead of by a separate elementwise add."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps, stats_in=None, alias=False, ws=None, real_cpg=0):
+    def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps, stats_in=None, alias=False, ws=None, real_cpg=0,
+                compact2=False):
         _lib.require_device()
         L = _lib.lib()
         dt = _cfg["dtype"]
@@ -766,11 +767,17 @@ class GNReLUFn(torch.autograd.Function):
         if not have_stats:
             _lib.check(L.mmpl_gn_stats(_p(x), _p(stats), n, spatial, c, groups, code, st), "gn_stats")
         y = empty_cl(n, c, d, h, w, dt, dev)
-        y2 = empty_cl(n, c, d, h, w, dt, dev) if dual else None
+        # compact2: the second head lives on the even voxels only (input of a 1x1x1 stride-2 convolution)
+        cdims = (d, h, w) if (dual and compact2) else (0, 0, 0)
+        y2 = None
+        if dual:
+            y2 = empty_cl(n, c, (d + 1) // 2, (h + 1) // 2, (w + 1) // 2, dt, dev) if compact2 else empty_cl(n, c, d, h, w, dt, dev)
         _lib.check(L.mmpl_gn_relu_fwd(_p(x), _p(stats), _p(g1), _p(b1), _p(y), _p(g2), _p(b2), _p(y2), n, spatial, c,
-                                      groups, int(real_cpg), eps, code, st), "gn_relu_fwd")
+                                      groups, int(real_cpg), cdims[0], cdims[1], cdims[2], eps, code, st), "gn_relu_fwd")
         ctx.save_for_backward(x, stats, g1, b1, g2, b2)
         ctx.real_cpg = int(real_cpg)
+        ctx.cdims = cdims
+        ctx.y2_shape = tuple(y2.shape) if dual else None
         ctx.meta = (n, c, spatial, groups, eps, dual, gamma.dtype, bool(alias))
         ctx.params = (gamma, beta, gamma2, beta2)
         ctx.ws = ws
@@ -803,8 +810,9 @@ class GNReLUFn(torch.autograd.Function):
         dy = to_cl(dy, dt)
         if dual:
             if dy2 is None:
-                dy2 = torch.zeros_like(x)
+                dy2 = torch.zeros(ctx.y2_shape, dtype=dt, device=dev)
             dy2 = to_cl(dy2, dt)
+            assert tuple(dy2.shape) == ctx.y2_shape
         if dres is not None:
             dres = to_cl(dres, dt)
         dx = torch.empty_like(x)
@@ -824,10 +832,11 @@ class GNReLUFn(torch.autograd.Function):
             ws = torch.empty(n * c * 6 + 2, dtype=torch.float64, device=dev)
         _lib.check(L.mmpl_gn_relu_bwd(_p(x), _p(stats), _p(g1), _p(b1), _p(dy), _p(g2), _p(b2), _p(dy2) if dual else None,
                                       _p(dres), _p(dx), _p(dg1), _p(db1), _p(dg2), _p(db2), _p(ws), reduced, n, spatial, c,
-                                      groups, ctx.real_cpg, eps, code, st), "gn_relu_bwd")
+                                      groups, ctx.real_cpg, ctx.cdims[0], ctx.cdims[1], ctx.cdims[2], eps, code, st),
+                   "gn_relu_bwd")
         if dual:
-            return dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype), None, None, None, None, None, None
-        return dx, dg1.to(pdtype), db1.to(pdtype), None, None, None, None, None, None, None, None
+            return (dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype)) + (None,) * 7
+        return (dx, dg1.to(pdtype), db1.to(pdtype)) + (None,) * 9
 
 
 def _attached_stats(x, groups):
@@ -861,10 +870,11 @@ def gn_relu(x, gamma, beta, groups=16, eps=1e-5, alias=False, real_cpg=0):
     return _tag_gn_outputs(outs, 1)
 
 
-def gn_relu_dual(x, gamma, beta, gamma2, beta2, groups=16, eps=1e-5, alias=False, real_cpg=0):
-    """-> (y, y2), or (y, y2, x_alias) with alias=True."""
+def gn_relu_dual(x, gamma, beta, gamma2, beta2, groups=16, eps=1e-5, alias=False, real_cpg=0, compact2=False):
+    """-> (y, y2), or (y, y2, x_alias) with alias=True.  ``compact2``: y2 only on the even voxels,
+    [N, C, ceil(D/2), ceil(H/2), ceil(W/2)] == the full y2[:, :, ::2, ::2, ::2] (what a 1x1x1 stride-2 convolution reads)."""
     outs = GNReLUFn.apply(x, gamma, beta, gamma2, beta2, int(groups), float(eps), _attached_stats(x, groups),
-                          bool(alias), _gn_bwd_ws(x), int(real_cpg))
+                          bool(alias), _gn_bwd_ws(x), int(real_cpg), bool(compact2))
     return _tag_gn_outputs(outs, 2)
 
 

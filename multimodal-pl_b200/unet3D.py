@@ -28,6 +28,11 @@ def _triple(v):
     return int(v)
 
 
+import os as _os
+
+_COMPACT_DS = _os.environ.get("MMPL_COMPACT_DS", "1") != "0"     # compact second GroupNorm head for 1x1x1 s2 downsamples
+
+
 class Conv3d(nn.Conv3d):
     """Weight-standardised convolution (reference unet3D.py:16-27).  Supports what the backbone uses: kernel 1 or 3,
     padding k//2, stride 1 or 2, dilation 1, groups 1, no bias."""
@@ -124,12 +129,16 @@ class NoBottleneck(nn.Module):
         x_alias = None
         if fused_ds:
             # gn1 and downsample.0 normalise the same tensor: one statistics pass, one read, two affine heads
+            # a 1x1x1 stride-2 downsample reads the even voxels of its input only: that head is produced compact and the
+            # convolution becomes a stride-1 one on it (same arithmetic, 7/8 of the head's traffic gone, both directions)
+            dconv = ds[2]
+            compact = isinstance(dconv, Conv3d) and dconv._k == 1 and dconv._s == 2 and _COMPACT_DS
             outs = ops.gn_relu_dual(x, self.gn1.weight, self.gn1.bias, ds[0].weight, ds[0].bias,
-                                    self.gn1.num_groups, self.gn1.eps, alias=want_alias)
+                                    self.gn1.num_groups, self.gn1.eps, alias=want_alias, compact2=compact)
             a1, ads = outs[0], outs[1]
             if want_alias:
                 x_alias = outs[2]
-            residual = ds[2](ads)
+            residual = ops.ws_conv3d(ads, dconv.weight, 1, dconv._standardise) if compact else dconv(ads)
         elif ds is None:
             # identity residual: its gradient is folded into gn1's backward through the alias output
             a1, x_alias = ops.gn_relu(x, self.gn1.weight, self.gn1.bias, self.gn1.num_groups, self.gn1.eps, alias=True)

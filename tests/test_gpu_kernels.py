@@ -441,6 +441,51 @@ def test_partial_loss_uint8_labels_and_per_sample_weights(mm, shape):
     assert rel(zp.grad, zr.grad) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 32, 4, 6, 8), (1, 64, 5, 7, 9), (2, 32, 3, 10, 13)])
+def test_gn_dual_compact_second_head_equals_strided_slice(mm, dtype, shape):
+    """gn_relu_dual(compact2=True): the second head exists on the even voxels only (input of the 1x1x1 stride-2
+    downsample, unet3D.py:645-651).  Forward == the full second head sliced [::2, ::2, ::2]; backward == the full kernel fed
+    a gradient that is zero off the even voxels (odd extents included); and both against the oracle's GroupNorm+ReLU."""
+    import multimodal_pl_b200 as mmp
+    from multimodal_pl_b200 import ops
+
+    mmp.set_compute_dtype(dtype)
+    try:
+        n, c, d, h, w = shape
+        x0 = _rand(shape, 31, 1.5).to(dtype)
+        g1, b1, g2, b2 = (_rand((c,), 32 + i, 0.5) + (1.0 if i % 2 == 0 else 0.0) for i in range(4))
+        dy1 = _rand(shape, 40, 1.0).to(dtype)
+        cs = (n, c, (d + 1) // 2, (h + 1) // 2, (w + 1) // 2)
+        dy2c = _rand(cs, 41, 1.0).to(dtype)
+        dy2f = torch.zeros(shape, dtype=dtype)
+        dy2f[:, :, ::2, ::2, ::2] = dy2c
+        res = {}
+        for compact in (False, True):
+            x = x0.cuda().requires_grad_(True)
+            ps = [t.cuda().requires_grad_(True) for t in (g1, b1, g2, b2)]
+            y1, y2 = ops.gn_relu_dual(x, ps[0], ps[1], ps[2], ps[3], 16, 1e-5, compact2=compact)
+            assert tuple(y2.shape) == (cs if compact else shape)
+            torch.autograd.backward([y1, y2], [dy1.cuda(), (dy2c if compact else dy2f).cuda()])
+            y2s = y2 if compact else y2[:, :, ::2, ::2, ::2]
+            res[compact] = [y1.float().cpu(), y2s.float().cpu(), x.grad.float().cpu()] + [p_.grad.cpu() for p_ in ps]
+        for a, b in zip(res[True], res[False]):
+            assert torch.equal(a, b) or rel(a, b) < 1e-6
+        # oracle
+        xr = x0.float().requires_grad_(True)
+        pr = [t.clone().requires_grad_(True) for t in (g1, b1, g2, b2)]
+        r1 = F.relu(F.group_norm(xr, 16, pr[0], pr[1], 1e-5))
+        r2 = F.relu(F.group_norm(xr, 16, pr[2], pr[3], 1e-5))[:, :, ::2, ::2, ::2]
+        torch.autograd.backward([r1, r2], [dy1.float(), dy2c.float()])
+        tol = 1e-5 if dtype == torch.float32 else 1.2e-2
+        assert rel(res[True][1], r2.detach()) < tol
+        assert rel(res[True][2], xr.grad) < (1e-4 if dtype == torch.float32 else 2e-2)
+        for got, want in zip(res[True][3:], pr):
+            assert rel(got, want.grad) < (1e-4 if dtype == torch.float32 else 2e-2)
+    finally:
+        mmp.set_compute_dtype(torch.float32)
+
+
 @pytest.mark.parametrize("cin,classes,dhw", [(32, 16, (4, 6, 8)), (32, 16, (3, 5, 7)), (64, 16, (4, 4, 6)), (32, 5, (3, 5, 5)),
                                             (64, 13, (2, 7, 9))])
 def test_fused_classifier_loss_vs_oracle_and_two_step_form(mm, cin, classes, dhw):
