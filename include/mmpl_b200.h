@@ -163,12 +163,16 @@ int mmpl_gn_stats(const void* x, double* stats, int n, int64_t spatial, int c, i
  * kernels do not cover (the refiner unet3D_g: 24/48/96/192 channels in groups of 6/12/24/48, unet3D.py:1507-1559) run
  * zero-padded to 32/64/128/256 channels with every group padded in place; the zero channels add nothing to the raw sums
  * and real_cpg makes mean / variance (and the group means of the backward) divide by the real element count. */
-/* y2_d/h/w (all 0 = off): the volume extents when the SECOND head is stored on the even voxels only, compact
- * [N][ceil(D/2)][ceil(H/2)][ceil(W/2)][C] -- the 1x1x1 stride-2 downsample (unet3D.py:645-651) reads nothing else, so
- * 7/8 of that head's writes (and of its gradient's reads in the backward) never happen. */
+/* layout (0 = plain NDHWC outputs; otherwise vol_d*vol_h*vol_w == spatial are the volume extents):
+ *   bit 1 (2): the SECOND head is stored on the even voxels only, compact [N][ceil(D/2)][ceil(H/2)][ceil(W/2)][C] -- the
+ *              1x1x1 stride-2 downsample (unet3D.py:645-651) reads nothing else, so 7/8 of that head's writes (and of its
+ *              gradient's reads in the backward) never happen;
+ *   bit 0 (1): the FIRST head is written in the parity-split layout P[pc*N + n][d/2][h/2][w/2][C], pc = (d&1)<<2 | (h&1)<<1 |
+ *              (w&1), that the stride-2 3x3x3 tensor-core convolution reads (even extents only; forward only) -- what
+ *              mmpl_parity_split would otherwise produce in an extra pass. */
 int mmpl_gn_relu_fwd(const void* x, const double* stats, const float* gamma, const float* beta, void* y,
                      const float* gamma2, const float* beta2, void* y2, int n, int64_t spatial, int c, int groups,
-                     int real_cpg, int y2_d, int y2_h, int y2_w, float eps, int dtype, mmpl_stream_t stream);
+                     int real_cpg, int vol_d, int vol_h, int vol_w, int layout, float eps, int dtype, mmpl_stream_t stream);
 /* dx = d/dx of the one or two GN+ReLU heads (+ addend if non-NULL); dgamma/dbeta per head (fp32 [C]).
  * workspace: N*C*6 + 1 doubles: [N][C][6] = per head {S1 = sum g, Q = gamma * sum g*xhat} (g = dy*[relu gate]) in columns 0..3 and
  * scratch in 4..5.  reduced = 0: the call zeroes it and runs the reduction pass over (x, dy[, dy2]); reduced = 1: the
@@ -178,8 +182,8 @@ int mmpl_gn_relu_fwd(const void* x, const double* stats, const float* gamma, con
 int mmpl_gn_relu_bwd(const void* x, const double* stats, const float* gamma, const float* beta, const void* dy,
                      const float* gamma2, const float* beta2, const void* dy2, const void* addend, void* dx,
                      float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, double* workspace, int reduced, int n,
-                     int64_t spatial, int c, int groups, int real_cpg, int y2_d, int y2_h, int y2_w, float eps, int dtype,
-                     mmpl_stream_t stream);
+                     int64_t spatial, int c, int groups, int real_cpg, int vol_d, int vol_h, int vol_w, int layout, float eps,
+                     int dtype, mmpl_stream_t stream);
 
 /* ---- class-token attention maps + token EMA of unet3D_with_feam3 (unet3D.py:142-212, :1051-1068, :1127-1175) --------
  * mmpl_ln_rows_*: LayerNorm over the channel axis of `rows` NDHWC voxel rows without affine (biased variance, eps under

@@ -55,8 +55,8 @@ _SIGNATURES = {
     "mmpl_upsample2x_ncdhw_fwd": [_ptr, _ptr, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_upsample2x_ncdhw_bwd": [_ptr, _ptr, _c_i64, _c_int, _c_int, _c_int, _ptr],
     "mmpl_gn_stats": [_ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _c_int, _ptr],
-    "mmpl_gn_relu_fwd": [_ptr] * 8 + [_c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _ptr],
-    "mmpl_gn_relu_bwd": [_ptr] * 15 + [_c_int, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _ptr],
+    "mmpl_gn_relu_fwd": [_ptr] * 8 + [_c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _ptr],
+    "mmpl_gn_relu_bwd": [_ptr] * 15 + [_c_int, _c_int, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f32, _c_int, _ptr],
     "mmpl_upsample2x_add_fwd": [_ptr, _ptr, _ptr] + [_c_int] * 6 + [_ptr, _ptr],
     "mmpl_upsample2x_bwd": [_ptr, _ptr] + [_c_int] * 6 + [_ptr],
     "mmpl_partial_loss_fwd": [_ptr, _ptr, _c_int, _ptr, _ptr, _c_int, _ptr, _ptr, _c_int, _c_i64, _c_int, _c_int, _ptr],

@@ -41,6 +41,17 @@ extern std::atomic<uint64_t> g_launches;
 
 int num_sms();
 
+// The tensor-map encoders are DRIVER entry points: they need the primary context current on the calling thread, which the
+// runtime only guarantees after the thread's first runtime call.  A backward pass that starts with a convolution runs on
+// an autograd worker thread that may not have made one yet (cuTensorMapEncodeTiled then fails with INVALID_CONTEXT).
+inline void bind_primary_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 static inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------- vector access

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads)
 gn_relu_fwd_kernel(const T* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                    const float* __restrict__ beta, T* __restrict__ y, const float* __restrict__ gamma2,
                    const float* __restrict__ beta2, T* __restrict__ y2, int64_t spatial, int C, int groups, int cnt_cpg,
-                   float eps, int64_t vox_per_block, int cd, int ch, int cw) {
+                   float eps, int64_t vox_per_block, int cd, int ch, int cw, int layout) {
   constexpr int VN = Vec<T>::N;
   const int vpv = C / VN;
   const int cv = threadIdx.x % vpv, vl = threadIdx.x / vpv, vstep = kThreads / vpv;
@@ -136,23 +136,30 @@ gn_relu_fwd_kernel(const T* __restrict__ x, const double* __restrict__ stats, co
   const int64_t v0 = static_cast<int64_t>(blockIdx.x) * vox_per_block;
   const int64_t v1 = min(v0 + vox_per_block, spatial);
   const int64_t off = (static_cast<int64_t>(n) * spatial) * C + cv * VN;
-  const bool compact = DUAL && cw > 0;
+  const bool compact = DUAL && (layout & 2) != 0;   // second head on the even voxels only
+  const bool psplit = (layout & 1) != 0;            // first head in the parity-split layout P[pc*N + n][d/2][h/2][w/2][c]
+  const bool walk = compact || psplit;
   EvenWalk ew;
-  if (compact) ew.init(v0 + vl, cd, ch, cw);
+  if (walk) ew.init(v0 + vl, cd, ch, cw);
   for (int64_t v = v0 + vl; v < v1; v += vstep) {
     Vec<T> a, o;
     a.load(x + off + v * C);
 #pragma unroll
     for (int i = 0; i < VN; ++i) o.v[i] = fmaxf(fmaf(a.v[i], sc[i], sh[i]), 0.f);
-    o.store(y + off + v * C);
+    if (psplit) {
+      const int pc = ((ew.d & 1) << 2) | ((ew.h & 1) << 1) | (ew.w & 1);
+      o.store(y + ((static_cast<int64_t>(pc) * gridDim.y + n) * ew.sp2 + ew.index()) * C + cv * VN);
+    } else {
+      o.store(y + off + v * C);
+    }
     if (DUAL) {
       if (!compact || ew.even()) {
 #pragma unroll
         for (int i = 0; i < VN; ++i) o.v[i] = fmaxf(fmaf(a.v[i], sc2[i], sh2[i]), 0.f);
         o.store(compact ? y2 + (n * ew.sp2 + ew.index()) * C + cv * VN : y2 + off + v * C);
       }
-      if (compact) ew.step(vstep);
     }
+    if (walk) ew.step(vstep);
   }
 }
 
@@ -479,12 +486,16 @@ extern "C" int mmpl_gn_stats(const void* x, double* stats, int n, int64_t spatia
 
 extern "C" int mmpl_gn_relu_fwd(const void* x, const double* stats, const float* gamma, const float* beta, void* y,
                                 const float* gamma2, const float* beta2, void* y2, int n, int64_t spatial, int c,
-                                int groups, int real_cpg, int y2_d, int y2_h, int y2_w, float eps, int dtype,
-                                mmpl_stream_t stream) {
+                                int groups, int real_cpg, int vol_d, int vol_h, int vol_w, int layout, float eps,
+                                int dtype, mmpl_stream_t stream) {
   if (int e = check_shape(c, groups, dtype)) return e;
-  MMPL_REQUIRE((y2_d | y2_h | y2_w) == 0 || (y2 != nullptr && static_cast<int64_t>(y2_d) * y2_h * y2_w == spatial), MMPL_E_SHAPE,
-               "GroupNorm: compact second head needs the volume extents (%d,%d,%d) of the %lld voxels", y2_d, y2_h, y2_w,
+  MMPL_REQUIRE((layout & ~3) == 0, MMPL_E_SHAPE, "GroupNorm: layout=%d", layout);
+  MMPL_REQUIRE(layout == 0 || static_cast<int64_t>(vol_d) * vol_h * vol_w == spatial, MMPL_E_SHAPE,
+               "GroupNorm: layout %d needs the volume extents (%d,%d,%d) of the %lld voxels", layout, vol_d, vol_h, vol_w,
                (long long)spatial);
+  MMPL_REQUIRE(!(layout & 2) || y2 != nullptr, MMPL_E_SHAPE, "GroupNorm: compact second head without a second head");
+  MMPL_REQUIRE(!(layout & 1) || ((vol_d | vol_h | vol_w) & 1) == 0, MMPL_E_SHAPE,
+               "GroupNorm: the parity-split layout needs even extents, got (%d,%d,%d)", vol_d, vol_h, vol_w);
   MMPL_REQUIRE(real_cpg >= 0 && real_cpg <= c / groups, MMPL_E_SHAPE, "GroupNorm: real_cpg=%d of %d", real_cpg, c / groups);
   const int cnt_cpg = real_cpg > 0 ? real_cpg : c / groups;
   int bx;
@@ -497,11 +508,12 @@ extern "C" int mmpl_gn_relu_fwd(const void* x, const double* stats, const float*
       gn_relu_fwd_kernel<T, true><<<dim3(bx, n), kThreads, 0, s>>>(static_cast<const T*>(x), stats, gamma, beta,
                                                                   static_cast<T*>(y), gamma2, beta2,
                                                                   static_cast<T*>(y2), spatial, c, groups, cnt_cpg, eps, vpb,
-                                                                  y2_d, y2_h, y2_w);
+                                                                  vol_d, vol_h, vol_w, layout);
     else
       gn_relu_fwd_kernel<T, false><<<dim3(bx, n), kThreads, 0, s>>>(static_cast<const T*>(x), stats, gamma, beta,
                                                                    static_cast<T*>(y), nullptr, nullptr, nullptr,
-                                                                   spatial, c, groups, cnt_cpg, eps, vpb, 0, 0, 0);
+                                                                   spatial, c, groups, cnt_cpg, eps, vpb, vol_d, vol_h, vol_w,
+                                                                   layout);
   });
   MMPL_CHECK_LAUNCH("gn_relu_fwd");
   return MMPL_OK;
@@ -511,11 +523,14 @@ extern "C" int mmpl_gn_relu_bwd(const void* x, const double* stats, const float*
                                 const void* dy, const float* gamma2, const float* beta2, const void* dy2,
                                 const void* addend, void* dx, float* dgamma, float* dbeta, float* dgamma2,
                                 float* dbeta2, double* workspace, int reduced, int n, int64_t spatial, int c, int groups,
-                                int real_cpg, int y2_d, int y2_h, int y2_w, float eps, int dtype, mmpl_stream_t stream) {
+                                int real_cpg, int vol_d, int vol_h, int vol_w, int layout, float eps, int dtype,
+                                mmpl_stream_t stream) {
   if (int e = check_shape(c, groups, dtype, true)) return e;
-  MMPL_REQUIRE((y2_d | y2_h | y2_w) == 0 || (dy2 != nullptr && static_cast<int64_t>(y2_d) * y2_h * y2_w == spatial), MMPL_E_SHAPE,
-               "GroupNorm: compact second head needs the volume extents (%d,%d,%d) of the %lld voxels", y2_d, y2_h, y2_w,
+  MMPL_REQUIRE((layout & ~2) == 0, MMPL_E_SHAPE, "GroupNorm backward: layout=%d (only the compact second head, 2)", layout);
+  MMPL_REQUIRE(layout == 0 || (dy2 != nullptr && static_cast<int64_t>(vol_d) * vol_h * vol_w == spatial), MMPL_E_SHAPE,
+               "GroupNorm: compact second head needs the volume extents (%d,%d,%d) of the %lld voxels", vol_d, vol_h, vol_w,
                (long long)spatial);
+  const int y2_d = layout ? vol_d : 0, y2_h = layout ? vol_h : 0, y2_w = layout ? vol_w : 0;
   MMPL_REQUIRE(real_cpg >= 0 && real_cpg <= c / groups, MMPL_E_SHAPE, "GroupNorm: real_cpg=%d of %d", real_cpg, c / groups);
   const int cnt_cpg = real_cpg > 0 ? real_cpg : c / groups;
   int bx;

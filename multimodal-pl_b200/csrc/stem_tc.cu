@@ -438,6 +438,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn stem_encode() {
+  bind_primary_context();
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* q = nullptr;

@@ -473,6 +473,7 @@ class WSConv3dFn(torch.autograd.Function):
         L = _lib.lib()
         dt = _cfg["dtype"]
         ctx.gn_bwd = getattr(x, "_mmpl_gn_bwd", None)      # x = relu(gn(.)): its backward reduction rides on our dgrad
+        presplit = bool(getattr(x, "_mmpl_psplit", False))   # x's memory already is the parity-split tensor (gn_relu_dual)
         x = to_cl(x, dt)
         cout, cin, k = weight.shape[0], weight.shape[1], weight.shape[2]
         taps = k * k * k
@@ -491,10 +492,18 @@ class WSConv3dFn(torch.autograd.Function):
             assert res.shape == y.shape
         algo = _algo(dt, cin, cout)
         src = x
+        if presplit and not (algo == _lib.ALGO_TCGEN05 and stride == 2 and k == 3):
+            raise RuntimeError("a parity-split activation (gn_relu_dual(psplit1=True)) can only feed the stride-2 3x3x3 "
+                               "tensor-core convolution")
         if algo == _lib.ALGO_TCGEN05 and stride == 2 and k == 3:
-            # stride-2 3x3x3 on tensor cores reads a parity-split copy of the input (one extra streaming pass)
-            src = torch.empty((8 * n, do, ho, wo, cin), dtype=dt, device=dev)
-            _lib.check(L.mmpl_parity_split(_p(x), _p(src), n, d, h, w, cin, code, st), "parity_split")
+            # stride-2 3x3x3 on tensor cores reads a parity-split copy of the input: written directly by the GroupNorm
+            # kernel that produced x (presplit), else by one extra streaming pass
+            if presplit:
+                src = x.permute(0, 2, 3, 4, 1).reshape(8 * n, do, ho, wo, cin)
+                assert src.data_ptr() == x.data_ptr()
+            else:
+                src = torch.empty((8 * n, do, ho, wo, cin), dtype=dt, device=dev)
+                _lib.check(L.mmpl_parity_split(_p(x), _p(src), n, d, h, w, cin, code, st), "parity_split")
             algo = _lib.ALGO_TCGEN05_PSPLIT
         flops = 2 * n * do * ho * wo * cout * cin * taps
         # fprop and stride-1 dgrad of a Cin==Cout layer are the same kernel instantiation on the same problem size
@@ -610,6 +619,17 @@ def _tc_wgrad_supported(dtype, k, stride, cin, cout) -> bool:
     if cin == 32:
         return cout == 32 or cout % 64 == 0
     return cin % 64 == 0 and (cout == 32 or cout % 64 == 0)
+
+
+def psplit_consumer(cin, cout, k, stride) -> bool:
+    """True if ``ws_conv3d`` with these parameters reads a parity-split input on the current path, i.e. its producer may
+    write that layout directly (``gn_relu_dual(psplit1=True)``)."""
+    dt = _cfg["dtype"]
+    return (k == 3 and stride == 2 and _PSPLIT_DIRECT and _algo(dt, cin, cout) == _lib.ALGO_TCGEN05
+            and _tc_wgrad_supported(dt, k, stride, cin, cout))
+
+
+_PSPLIT_DIRECT = os.environ.get("MMPL_PSPLIT_DIRECT", "1") != "0"
 
 
 def ws_conv3d(x, weight, stride=1, standardise=True, residual=None, want_stats=False):
@@ -748,7 +768,7 @@ class GNReLUFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, gamma2, beta2, groups, eps, stats_in=None, alias=False, ws=None, real_cpg=0,
-                compact2=False):
+                compact2=False, psplit1=False):
         _lib.require_device()
         L = _lib.lib()
         dt = _cfg["dtype"]
@@ -767,13 +787,21 @@ class GNReLUFn(torch.autograd.Function):
         if not have_stats:
             _lib.check(L.mmpl_gn_stats(_p(x), _p(stats), n, spatial, c, groups, code, st), "gn_stats")
         y = empty_cl(n, c, d, h, w, dt, dev)
+        # psplit1: the first head's MEMORY is the parity-split tensor P[pc*N + n][d/2][h/2][w/2][c] the stride-2 3x3x3
+        # tensor-core convolution reads (same element count; the logical NCDHW shape is kept so that the gradient autograd
+        # hands back -- a plain NDHWC tensor -- has the shape it expects).  Only that convolution may consume it.
+        psplit1 = bool(psplit1)
+        assert not psplit1 or (d % 2 == 0 and h % 2 == 0 and w % 2 == 0 and dt == torch.bfloat16)
         # compact2: the second head lives on the even voxels only (input of a 1x1x1 stride-2 convolution)
-        cdims = (d, h, w) if (dual and compact2) else (0, 0, 0)
+        compact2 = bool(dual and compact2)
+        layout = (1 if psplit1 else 0) | (2 if compact2 else 0)
+        cdims = (d, h, w) if compact2 else (0, 0, 0)
         y2 = None
         if dual:
             y2 = empty_cl(n, c, (d + 1) // 2, (h + 1) // 2, (w + 1) // 2, dt, dev) if compact2 else empty_cl(n, c, d, h, w, dt, dev)
         _lib.check(L.mmpl_gn_relu_fwd(_p(x), _p(stats), _p(g1), _p(b1), _p(y), _p(g2), _p(b2), _p(y2), n, spatial, c,
-                                      groups, int(real_cpg), cdims[0], cdims[1], cdims[2], eps, code, st), "gn_relu_fwd")
+                                      groups, int(real_cpg), d if layout else 0, h if layout else 0, w if layout else 0,
+                                      layout, eps, code, st), "gn_relu_fwd")
         ctx.save_for_backward(x, stats, g1, b1, g2, b2)
         ctx.real_cpg = int(real_cpg)
         ctx.cdims = cdims
@@ -832,11 +860,11 @@ class GNReLUFn(torch.autograd.Function):
             ws = torch.empty(n * c * 6 + 2, dtype=torch.float64, device=dev)
         _lib.check(L.mmpl_gn_relu_bwd(_p(x), _p(stats), _p(g1), _p(b1), _p(dy), _p(g2), _p(b2), _p(dy2) if dual else None,
                                       _p(dres), _p(dx), _p(dg1), _p(db1), _p(dg2), _p(db2), _p(ws), reduced, n, spatial, c,
-                                      groups, ctx.real_cpg, ctx.cdims[0], ctx.cdims[1], ctx.cdims[2], eps, code, st),
-                   "gn_relu_bwd")
+                                      groups, ctx.real_cpg, ctx.cdims[0], ctx.cdims[1], ctx.cdims[2],
+                                      2 if ctx.cdims[2] else 0, eps, code, st), "gn_relu_bwd")
         if dual:
-            return (dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype)) + (None,) * 7
-        return (dx, dg1.to(pdtype), db1.to(pdtype)) + (None,) * 9
+            return (dx, dg1.to(pdtype), db1.to(pdtype), dg2.to(pdtype), db2.to(pdtype)) + (None,) * 8
+        return (dx, dg1.to(pdtype), db1.to(pdtype)) + (None,) * 10
 
 
 def _attached_stats(x, groups):
@@ -870,11 +898,18 @@ def gn_relu(x, gamma, beta, groups=16, eps=1e-5, alias=False, real_cpg=0):
     return _tag_gn_outputs(outs, 1)
 
 
-def gn_relu_dual(x, gamma, beta, gamma2, beta2, groups=16, eps=1e-5, alias=False, real_cpg=0, compact2=False):
+def gn_relu_dual(x, gamma, beta, gamma2, beta2, groups=16, eps=1e-5, alias=False, real_cpg=0, compact2=False,
+                 psplit1=False):
     """-> (y, y2), or (y, y2, x_alias) with alias=True.  ``compact2``: y2 only on the even voxels,
-    [N, C, ceil(D/2), ceil(H/2), ceil(W/2)] == the full y2[:, :, ::2, ::2, ::2] (what a 1x1x1 stride-2 convolution reads)."""
+    [N, C, ceil(D/2), ceil(H/2), ceil(W/2)] == the full y2[:, :, ::2, ::2, ::2] (what a 1x1x1 stride-2 convolution reads).
+    ``psplit1``: y is laid out in memory as the parity-split tensor of the stride-2 3x3x3 tensor-core convolution (even
+    extents, bf16 tensor-core path; see ``psplit_consumer``) -- pass it to that convolution and nothing else."""
+    psplit1 = bool(psplit1) and all(int(v) % 2 == 0 for v in x.shape[2:]) and _cfg["dtype"] == torch.bfloat16
     outs = GNReLUFn.apply(x, gamma, beta, gamma2, beta2, int(groups), float(eps), _attached_stats(x, groups),
-                          bool(alias), _gn_bwd_ws(x), int(real_cpg), bool(compact2))
+                          bool(alias), _gn_bwd_ws(x), int(real_cpg), bool(compact2), psplit1)
+    if psplit1:
+        outs[0]._mmpl_psplit = True       # read by WSConv3dFn.forward
+
     return _tag_gn_outputs(outs, 2)
 
 

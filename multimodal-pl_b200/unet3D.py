@@ -133,8 +133,11 @@ class NoBottleneck(nn.Module):
             # convolution becomes a stride-1 one on it (same arithmetic, 7/8 of the head's traffic gone, both directions)
             dconv = ds[2]
             compact = isinstance(dconv, Conv3d) and dconv._k == 1 and dconv._s == 2 and _COMPACT_DS
+            c1 = self.conv1
+            psplit = (isinstance(c1, Conv3d) and x.is_cuda
+                      and ops.psplit_consumer(c1.in_channels, c1.out_channels, c1._k, c1._s))
             outs = ops.gn_relu_dual(x, self.gn1.weight, self.gn1.bias, ds[0].weight, ds[0].bias,
-                                    self.gn1.num_groups, self.gn1.eps, alias=want_alias, compact2=compact)
+                                    self.gn1.num_groups, self.gn1.eps, alias=want_alias, compact2=compact, psplit1=psplit)
             a1, ads = outs[0], outs[1]
             if want_alias:
                 x_alias = outs[2]

@@ -486,6 +486,43 @@ def test_gn_dual_compact_second_head_equals_strided_slice(mm, dtype, shape):
         mmp.set_compute_dtype(torch.float32)
 
 
+def test_gn_first_head_written_as_parity_split_tensor(mm):
+    """gn_relu_dual(psplit1=True) writes its first head straight into the parity-split layout the stride-2 3x3x3 tensor-core
+    convolution reads: bit-identical to mmpl_parity_split of the plain output, and the stride-2 convolution fed with it gives
+    bit-identical results and gradients to the path with the extra split pass."""
+    import multimodal_pl_b200 as mmp
+    from multimodal_pl_b200 import _lib, ops
+
+    mmp.set_compute_dtype(torch.bfloat16)
+    try:
+        n, c, d, h, w = 2, 32, 4, 8, 12
+        x0 = _rand((n, c, d, h, w), 51, 1.5).to(torch.bfloat16)
+        prm = [(_rand((c,), 52 + i, 0.5) + (1.0 if i % 2 == 0 else 0.0)) for i in range(4)]
+        wt = _rand((64, c, 3, 3, 3), 57, 0.2)
+        dy = _rand((n, 64, d // 2, h // 2, w // 2), 58, 1.0).to(torch.bfloat16)
+        out = {}
+        for ps in (False, True):
+            x = x0.cuda().requires_grad_(True)
+            p_ = [t.cuda().requires_grad_(True) for t in prm]
+            wc = wt.cuda().requires_grad_(True)
+            ops.begin_forward(x.device)
+            y1, y2 = ops.gn_relu_dual(x, p_[0], p_[1], p_[2], p_[3], 16, 1e-5, compact2=True, psplit1=ps)
+            assert bool(getattr(y1, "_mmpl_psplit", False)) == ps
+            raw = y1.detach().permute(0, 2, 3, 4, 1).reshape(-1).clone()      # memory order
+            z = ops.ws_conv3d(y1, wc, 2)
+            (z.float() * dy.cuda().float()).sum().backward()
+            out[ps] = (raw, z.detach().float().cpu(), x.grad.float().cpu(), wc.grad.cpu(), y1.detach())
+        plain = out[False][4]
+        P = torch.empty((8 * n, d // 2, h // 2, w // 2, c), dtype=torch.bfloat16, device="cuda")
+        _lib.check(_lib.lib().mmpl_parity_split(plain.data_ptr(), P.data_ptr(), n, d, h, w, c, _lib.dtype_code(torch.bfloat16),
+                                                _lib.stream_ptr()))
+        assert torch.equal(out[True][0], P.reshape(-1))
+        for a, b in zip(out[True][1:4], out[False][1:4]):
+            assert torch.equal(a, b) or rel(a, b) < 1e-6
+    finally:
+        mmp.set_compute_dtype(torch.float32)
+
+
 @pytest.mark.parametrize("cin,classes,dhw", [(32, 16, (4, 6, 8)), (32, 16, (3, 5, 7)), (64, 16, (4, 4, 6)), (32, 5, (3, 5, 5)),
                                             (64, 13, (2, 7, 9))])
 def test_fused_classifier_loss_vs_oracle_and_two_step_form(mm, cin, classes, dhw):
