@@ -10,7 +10,8 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libmmpl_b200.so")
+# MMPL_LIB: an alternative build of the same ABI (kernel experiments); the product library sits next to this file
+_LIB_PATH = os.environ.get("MMPL_LIB") or os.path.join(_HERE, "libmmpl_b200.so")
 
 F32, BF16 = 0, 1
 ALGO_DIRECT, ALGO_TCGEN05, ALGO_TCGEN05_PSPLIT = 0, 1, 2
