@@ -23,6 +23,10 @@
 //    the fused GroupNorm statistics / GroupNorm-backward reduction).  A 12-warp variant with two epilogue warpgroups on
 //    alternate items and a setmaxnreg register re-partition is kept behind MMPL_TC_TWO_GROUPS (see below).
 //  * WRES: for 32->32 layers all 27 weight tiles (55 KB) stay resident in shared memory for the life of the CTA.
+//  * EPI: the epilogue is compiled per variant (conv_tc_problem.cuh) -- plain, forward (statistics / residual), fused
+//    GroupNorm backward -- so that a launch only carries the code it executes: with a single warp per scheduler the
+//    epilogue is latency bound per instruction, and one kernel holding all variants spent most of its stall samples on
+//    instruction fetches.
 #pragma once
 #include <stdlib.h>
 
