@@ -437,6 +437,11 @@ def run_train(args):
 
     # ---- timed region 2: end to end through the public API with pinned-host inputs ------------------------------------
     # every step: H2D of that step's batch (copy stream, overlapping the previous step's compute) and D2H of its loss
+    if use_graph:
+        # warm-up of THIS path too (copy stream, staging buffers, first transfers out of the pinned batch): untimed
+        for _ in range(warm):
+            step.stage(image_h, label_h)
+            step.run_staged()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()

@@ -40,6 +40,8 @@ namespace {
 using namespace ptx;
 
 constexpr int TC_TH = 16, TC_TW = 8;
+// weight handling: one tap tile per ring stage / all 27 tiles resident / the three kd tiles of a (kh, kw) per ring stage
+enum : int { WM_STREAM = 0, WM_RESIDENT = 1, WM_PLANE_MAJOR = 2 };
 // Optional 12-warp layout (MMPL_TC_TWO_GROUPS=1): 0 = activation TMA, 1 = weight TMA, 2 = MMA issuer, 3 = idle, 4..7 and
 // 8..11 = two epilogue warpgroups that take alternate work items (one per TMEM accumulator buffer), so an epilogue has two
 // MMA periods to finish.  The register file is re-partitioned with setmaxnreg: 64 for warps 0..3, 216 for the epilogue
@@ -66,8 +68,9 @@ struct Geo {
   static constexpr bool PARITY_CHUNKS = (MODE == MODE_S2F);
 };
 
-template <int KC, int NT, int TD, int MODE, bool WRES, int NA_>
+template <int KC, int NT, int TD, int MODE, int WM, int NA_>
 struct TcCfg {
+  static constexpr bool WRES = WM == WM_RESIDENT, WPM = WM == WM_PLANE_MAJOR;
   using G = Geo<MODE>;
   static constexpr int RB = KC * 2;
   static constexpr uint32_t SWZ = RB == 128 ? SWZ_128B : SWZ_64B;
@@ -75,18 +78,21 @@ struct TcCfg {
   static constexpr int A_BYTES = PD * G::PH * G::PW * RB;
   static constexpr int A_STAGE = (A_BYTES + 1023) / 1024 * 1024;
   static constexpr int NA = NA_;
-  static constexpr int B_BYTES = NT * RB;
+  static constexpr int B_BYTES = NT * RB;                        // one tap tile
+  static constexpr int B_STAGE = (WPM ? 3 : 1) * B_BYTES;        // plane-major: the three kd tiles of one (kh, kw)
   static constexpr int SMEM_LIMIT = 227 * 1024 - 2048;
-  static constexpr int NB_FIT = (SMEM_LIMIT - NA * A_STAGE) / B_BYTES;
-  static constexpr int NB = WRES ? 27 : (NB_FIT > 8 ? 8 : NB_FIT);
+  static constexpr int NB_FIT = (SMEM_LIMIT - NA * A_STAGE) / B_STAGE;
+  static constexpr int NB_CAP = WPM ? 4 : 8;
+  static constexpr int NB = WRES ? 27 : (NB_FIT > NB_CAP ? NB_CAP : NB_FIT);
   static constexpr int ACC_COLS = TD * NT;
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(B_BYTES % 1024 == 0, "weight stage must keep 1024-byte alignment");
   static_assert(NB >= 2, "need at least two weight stages");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  static_assert(!WRES || (MODE == MODE_S1K3), "resident weights only for the 3x3x3 stride-1 mode");
+  static_assert(WM == WM_STREAM || (MODE == MODE_S1K3), "resident / plane-major weights only for the 3x3x3 stride-1 mode");
+  static_assert(!WPM || (TD >= 2 && NT * (TD >= 3 ? 3 : 2) <= 256), "plane-major issue: N = NT * planes sharing one A view <= 256");
 };
 
 struct TcParams {
@@ -120,16 +126,17 @@ struct TcParams {
 __device__ __forceinline__ int axis_ntaps(int par) { return par ? 2 : 1; }
 __device__ __forceinline__ int axis_tap(int par, int i) { return par ? 2 * i : 1; }
 
-template <int KC, int NT, int TD, int MODE, bool WRES, int NA_, int EPI>
+template <int KC, int NT, int TD, int MODE, int WM, int NA_, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  using Cfg = TcCfg<KC, NT, TD, MODE, WRES, NA_>;
+  using Cfg = TcCfg<KC, NT, TD, MODE, WM, NA_>;
   using G = Geo<MODE>;
+  constexpr bool WRES = Cfg::WRES, WPM = Cfg::WPM;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_stage = smem;
   uint8_t* b_stage = smem + Cfg::NA * Cfg::A_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stage + Cfg::NB * Cfg::B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_stage + Cfg::NB * Cfg::B_STAGE);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + Cfg::NA;
   uint64_t* b_full = a_empty + Cfg::NA;
@@ -206,6 +213,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int kd = tap / 9, khw = tap % 9, slot = khw * 3 + (2 - kd);
           mbar_expect_tx(&b_full[slot], Cfg::B_BYTES);
           tma_load_3d(b_stage + slot * Cfg::B_BYTES, &tmB, &b_full[slot], 0, 0, tap);
+        }
+      } else if (WPM) {
+        // per (chunk, kh, kw): the three kd tiles land in ONE stage, slot order (2 - kd) like the resident layout
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+          int nt, pc, n, d0, h0, w0;
+          item_coords(item, nt, pc, n, d0, h0, w0);
+          for (int c = 0; c < p.nch; ++c)
+            for (int khw = 0; khw < 9; ++khw, ++it) {
+              const uint32_t s = it % Cfg::NB, ph = (it / Cfg::NB) & 1;
+              mbar_wait(&b_empty[s], ph ^ 1);
+              mbar_expect_tx(&b_full[s], Cfg::B_STAGE);
+#pragma unroll
+              for (int kd = 0; kd < 3; ++kd)
+                tma_load_3d(b_stage + s * Cfg::B_STAGE + (2 - kd) * Cfg::B_BYTES, &tmB, &b_full[s], c * KC, nt * NT, kd * 9 + khw);
+            }
         }
       } else {
         uint32_t it = 0;
@@ -295,6 +318,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         ++ita;
+      } else if (WPM) {
+        // ---- plane-major issue with streamed weights: as above, but the weight ring delivers the three kd tiles of one
+        // (kh, kw) per stage, so the (kh, kw) loop is the outer one and runs per reduction chunk
+        for (int c = 0; c < p.nch; ++c, ++ita) {
+          const uint32_t sa = ita % Cfg::NA, pha = (ita / Cfg::NA) & 1;
+          mbar_wait(&a_full[sa], pha);
+          tc_fence_after();
+          const uint32_t a_addr = a_base + sa * Cfg::A_STAGE;
+          for (int khw = 0; khw < 9; ++khw, ++itb) {
+            const uint32_t sb = itb % Cfg::NB;
+            mbar_wait(&b_full[sb], (itb / Cfg::NB) & 1);
+            tc_fence_after();
+            const int kh = khw / 3, kw = khw - 3 * kh;
+            const uint32_t a_tap = a_addr + (kh * G::PW + kw) * Cfg::RB;
+            const uint32_t b_tap = b_base + sb * Cfg::B_STAGE;
+            const bool first_tap = c == 0 && khw == 0;
+            if (elect_one()) {
+#pragma unroll
+              for (int sp = 0; sp < TD + 2; ++sp) {
+                const int kd_hi = sp < 2 ? sp : 2;                       // p_lo = sp - kd_hi
+                const int kd_lo = sp - (TD - 1) > 0 ? sp - (TD - 1) : 0;  // p_hi = sp - kd_lo
+                const int nblk = kd_hi - kd_lo + 1;
+                const uint32_t d_lo = d_tmem + (sp - kd_hi) * NT;
+                const uint32_t a_lo = a_lo_fix | ((a_tap + sp * (G::PH * G::PW * Cfg::RB)) >> 4);
+                const uint32_t b_lo = b_lo_fix | ((b_tap + (2 - kd_hi) * Cfg::B_BYTES) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < KC / 16; ++ks) {
+                  if (sp < TD && ks == 0 && first_tap) {
+                    // first touch of plane sp: older planes accumulate, the fresh one is overwritten
+                    if (nblk > 1)
+                      umma_f16_lohi(d_lo, a_lo, a_hi, b_lo, b_hi, make_idesc_bf16(128, NT * (nblk - 1), 0, 0), 1u);
+                    umma_f16_lohi(d_lo + (nblk - 1) * NT, a_lo, a_hi, b_lo + (((nblk - 1) * Cfg::B_BYTES) >> 4), b_hi,
+                                  make_idesc_bf16(128, NT, 0, 0), 0u);
+                  } else {
+                    umma_f16_lohi(d_lo, a_lo + ((ks * 32) >> 4), a_hi, b_lo + ((ks * 32) >> 4), b_hi,
+                                  make_idesc_bf16(128, NT * nblk, 0, 0), 1u);
+                  }
+                }
+              }
+              umma_commit(&b_empty[sb]);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit(&a_empty[sa]);
+          __syncwarp();
+        }
       } else {
       uint32_t first = 1;
       for (int c = 0; c < chunks_per_item; ++c, ++ita) {
@@ -616,12 +685,12 @@ int make_weight_map(CUtensorMap* m, const void* ptr, int taps, int cout, int cin
   return MMPL_OK;
 }
 
-template <int KC, int NT, int TD, int MODE, bool WRES, int NA_, int EPI>
+template <int KC, int NT, int TD, int MODE, int WM, int NA_, int EPI>
 int launch_tc(const TcProblem& q, cudaStream_t s) {
   static_assert(EPI == EPI_PLAIN || EPI == EPI_FWD || EPI == EPI_GN, "epilogue variant");
   MMPL_REQUIRE((EPI == EPI_GN) == (q.gn != nullptr), MMPL_E_UNSUPPORTED, "conv_tc: epilogue variant %d vs fused GroupNorm backward", EPI);
   MMPL_REQUIRE(EPI == EPI_FWD || q.residual == nullptr, MMPL_E_UNSUPPORTED, "conv_tc: a residual needs the forward epilogue");
-  using Cfg = TcCfg<KC, NT, TD, MODE, WRES, NA_>;
+  using Cfg = TcCfg<KC, NT, TD, MODE, WM, NA_>;
   using G = Geo<MODE>;
   CUtensorMap tmA, tmB;
   if (int e = make_act_map(&tmA, q.a, q.aN, q.aD, q.aH, q.aW, q.kred, KC, Cfg::PD, G::PH, G::PW, MODE == MODE_S2K1F ? 2 : 1)) return e;
@@ -658,16 +727,23 @@ int launch_tc(const TcProblem& q, cudaStream_t s) {
   cudaGetDevice(&dev_ord);
   bool& attr_set = attr_set_dev[dev_ord & 63];
   if (!attr_set) {
-    MMPL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, NT, TD, MODE, WRES, NA_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MMPL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, NT, TD, MODE, WM, NA_, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int grid = static_cast<int>(std::min<int64_t>(items, num_sms()));
-  conv_tc_kernel<KC, NT, TD, MODE, WRES, NA_, EPI><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
+  conv_tc_kernel<KC, NT, TD, MODE, WM, NA_, EPI><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, p);
   MMPL_CHECK_LAUNCH("conv_tc");
   return MMPL_OK;
 }
 
+}  // namespace
+
+namespace {
+inline bool plane_major() {
+  static const bool on = [] { const char* e = getenv("MMPL_TC_PLANE_MAJOR"); return !(e && e[0] == '0'); }();
+  return on;
+}
 }  // namespace
 
 template <int MODE, int EPI>
@@ -681,8 +757,11 @@ int dispatch_tc(const TcProblem& q, cudaStream_t s) {
   }
   MMPL_REQUIRE(nt == 32 || nt == 64 || nt == 128 || nt == 256, MMPL_E_UNSUPPORTED, "conv_tc: output channels %d", nout);
   if (kred == 32) {
-    if (nt == 32) return launch_tc<32, 32, 4, MODE, MODE == MODE_S1K3, 2, EPI>(q, s);
-    if (nt == 64) return launch_tc<32, 64, 4, MODE, false, 2, EPI>(q, s);
+    if (nt == 32) return launch_tc<32, 32, 4, MODE, MODE == MODE_S1K3 ? WM_RESIDENT : WM_STREAM, 2, EPI>(q, s);
+    if constexpr (MODE == MODE_S1K3) {
+      if (nt == 64 && plane_major()) return launch_tc<32, 64, 4, MODE, WM_PLANE_MAJOR, 2, EPI>(q, s);
+    }
+    if (nt == 64) return launch_tc<32, 64, 4, MODE, WM_STREAM, 2, EPI>(q, s);
     MMPL_FAIL(MMPL_E_UNSUPPORTED, "conv_tc: 32 reduction channels with %d output channels", nout);
   }
   if constexpr (MODE == MODE_S1K3) {
@@ -693,25 +772,33 @@ int dispatch_tc(const TcProblem& q, cudaStream_t s) {
       // about as long as the TMA round trip of the next chunk.
       const int64_t sp = static_cast<int64_t>(q.N) * ceil_div(q.H, TC_TH) * ceil_div(q.W, TC_TW);
       const int64_t items_default = sp * ceil_div(q.D, nt == 128 ? 2 : 1) * (nout / nt);
-      if (items_default * 2 <= num_sms()) return launch_tc<64, 64, 1, MODE, false, 2, EPI>(q, s);
+      if (items_default * 2 <= num_sms()) return launch_tc<64, 64, 1, MODE, WM_STREAM, 2, EPI>(q, s);
     }
     // Streamed-weight 64-channel configs: ONE activation stage, more planes per item and a deeper weight ring (the weight
     // tiles, one TMA round trip per tap, are the latency-critical stream).
-    if (nt == 32) return launch_tc<64, 32, 4, MODE, false, 1, EPI>(q, s);
-    if (nt == 64) return launch_tc<64, 64, 4, MODE, false, 1, EPI>(q, s);
-    if (nt == 128) return launch_tc<64, 128, 2, MODE, false, 1, EPI>(q, s);
-    return launch_tc<64, 256, 1, MODE, false, 1, EPI>(q, s);
+    // Plane-major issue (like the resident-weight kernel): one A view per input plane and (kh, kw) feeds the accumulators of
+    // up to three output planes (N = 2-3 x NT), halving the A-operand reads -- the tcgen05 operand fetch from shared memory
+    // (measured ~85 B/clk/SM here) is what bounds these kernels, not the MMA rate.
+    if (plane_major()) {
+      if (nt == 32) return launch_tc<64, 32, 4, MODE, WM_PLANE_MAJOR, 1, EPI>(q, s);
+      if (nt == 64) return launch_tc<64, 64, 4, MODE, WM_PLANE_MAJOR, 1, EPI>(q, s);
+      if (nt == 128) return launch_tc<64, 128, 2, MODE, WM_PLANE_MAJOR, 1, EPI>(q, s);
+    }
+    if (nt == 32) return launch_tc<64, 32, 4, MODE, WM_STREAM, 1, EPI>(q, s);
+    if (nt == 64) return launch_tc<64, 64, 4, MODE, WM_STREAM, 1, EPI>(q, s);
+    if (nt == 128) return launch_tc<64, 128, 2, MODE, WM_STREAM, 1, EPI>(q, s);
+    return launch_tc<64, 256, 1, MODE, WM_STREAM, 1, EPI>(q, s);
   }
   if constexpr (MODE == MODE_S2D) {
     // stride-2 dgrad: every parity class re-reads the dY halo block, so deeper tiles (4 planes, one activation stage)
     // cut the L2->SMEM traffic per output voxel
-    if (nt == 32) return launch_tc<64, 32, 4, MODE, false, 1, EPI>(q, s);
-    if (nt == 64) return launch_tc<64, 64, 4, MODE, false, 1, EPI>(q, s);
+    if (nt == 32) return launch_tc<64, 32, 4, MODE, WM_STREAM, 1, EPI>(q, s);
+    if (nt == 64) return launch_tc<64, 64, 4, MODE, WM_STREAM, 1, EPI>(q, s);
   }
-  if (nt == 32) return launch_tc<64, 32, 2, MODE, false, 2, EPI>(q, s);
-  if (nt == 64) return launch_tc<64, 64, 2, MODE, false, 2, EPI>(q, s);
-  if (nt == 128) return launch_tc<64, 128, 2, MODE, false, 2, EPI>(q, s);
-  return launch_tc<64, 256, 1, MODE, false, 2, EPI>(q, s);
+  if (nt == 32) return launch_tc<64, 32, 2, MODE, WM_STREAM, 2, EPI>(q, s);
+  if (nt == 64) return launch_tc<64, 64, 2, MODE, WM_STREAM, 2, EPI>(q, s);
+  if (nt == 128) return launch_tc<64, 128, 2, MODE, WM_STREAM, 2, EPI>(q, s);
+  return launch_tc<64, 256, 1, MODE, WM_STREAM, 2, EPI>(q, s);
 }
 
 }  // namespace mmpl
