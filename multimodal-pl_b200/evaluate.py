@@ -10,6 +10,7 @@ to the ranks in contiguous runs; the production path sends every touched accumul
 (a reduce-scatter restricted to the non-zero planes), finalises each slab where it lands and all-gathers the uint8 mask
 (``_sliding_blend``).
 """
+import os
 from math import ceil
 
 import numpy as np
@@ -163,6 +164,30 @@ class _EagerBlender:
             self.model.blend_tile(img, self.sink)
 
 
+_SW_TRACE = os.environ.get("MMPL_SW_TRACE", "0") == "1"
+
+
+class _PhaseTrace:
+    """MMPL_SW_TRACE=1: device time of the phases of one sharded sliding-window volume (CUDA events on the current stream),
+    printed per rank to stderr.  Diagnostic only (it synchronises at the end of the volume)."""
+
+    def __init__(self):
+        self.ev = [("start", torch.cuda.Event(enable_timing=True))]
+        self.ev[0][1].record()
+
+    def mark(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.ev.append((name, e))
+
+    def report(self, rank):
+        import sys
+
+        torch.cuda.synchronize()
+        parts = [f"{n} {a.elapsed_time(b):.2f}" for (_, a), (n, b) in zip(self.ev[:-1], self.ev[1:])]
+        sys.stderr.write(f"[sw rank {rank}] ms: " + ", ".join(parts) + "\n")
+
+
 def _depth_range(tiles, td):
     """Depth planes [lo, hi) touched by a run of tiles ((0, 0) for an empty run)."""
     if not tiles:
@@ -204,6 +229,7 @@ def _sliding_blend(blender, image, tile_size, classes, label, num_class, rank, w
     sum is never formed: argmax and Dice do not depend on a positive per-voxel normaliser."""
     L = _lib.lib()
     dev = torch.device("cuda", torch.cuda.current_device())
+    trace = _PhaseTrace() if _SW_TRACE else None
     if isinstance(image, np.ndarray):
         image = torch.from_numpy(image)
     B, _, D, H, W = image.shape
@@ -226,6 +252,8 @@ def _sliding_blend(blender, image, tile_size, classes, label, num_class, rank, w
         for i, (d1, y1, x1) in enumerate(mine):
             tile = part[:, :, d1 - dlo:d1 - dlo + td, y1:y1 + th, x1:x1 + tw]
             blender.blend_tile(tile, origins[i])
+    if trace:
+        trace.mark("tiles")
     if world > 1:
         sends, recvs = _exchange_plan(ranges, rank, slab, world)
         p2p, received = [], []
@@ -238,8 +266,12 @@ def _sliding_blend(blender, image, tile_size, classes, label, num_class, rank, w
         if p2p:
             for req in dist.batch_isend_irecv(p2p):
                 req.wait()
+        if trace:
+            trace.mark("exchange")
         for lo, hi, buf in received:
             _lib.check(L.mmpl_accumulate_f32(_p(acc[lo:hi]), _p(buf), buf.numel(), _lib.stream_ptr()), "accumulate_f32")
+    if trace:
+        trace.mark("accumulate")
     mine_acc = acc[z0:z0 + slab]
     amax_slab = torch.empty((slab, H, W), dtype=torch.uint8, device=dev)
     counts = torch.zeros((3, classes), dtype=torch.int64, device=dev)
@@ -258,6 +290,8 @@ def _sliding_blend(blender, image, tile_size, classes, label, num_class, rank, w
                                       _lib.stream_ptr()), "sw_finalize")
     if valid < slab:
         amax_slab[valid:].zero_()
+    if trace:
+        trace.mark("finalize")
     if world > 1:
         amax = torch.empty((dpad, H, W), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(amax, amax_slab)
@@ -266,6 +300,9 @@ def _sliding_blend(blender, image, tile_size, classes, label, num_class, rank, w
         amax = amax[:D]
     else:
         amax = amax_slab[:D]
+    if trace:
+        trace.mark("gather")
+        trace.report(rank)
     amax = amax.unsqueeze(0)
     if label is None:
         return None, None, None, amax
