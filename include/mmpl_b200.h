@@ -286,7 +286,7 @@ int mmpl_sgd_step(float* p, const float* grad, float* buf, int64_t count, const 
 /* ---- sliding-window blend + argmax/Dice: predict_sliding evaluate_amos.py:261-279, get_dice :128-141 ----------
  * acc and wsum [D][H][W] in `acc_bytes` per element (4 = fp32, 8 = fp64 like the reference).  acc is class-major
  * [C][D][H][W] (d_outer = 0, the layout predict_sliding returns) or depth-major [D][C][H][W] (d_outer = 1: a depth slab is
- * one contiguous block, which the multi-GPU path reduce-scatters along D).  wsum may be NULL (not accumulated). */
+ * one contiguous block, which the multi-GPU path exchanges plane-wise along D).  wsum may be NULL (not accumulated). */
 int mmpl_sw_blend(void* acc, void* wsum, const float* tile_logits /*[C][td][th][tw]*/, const float* gauss, int c,
                   int d, int h, int w, int td, int th, int tw, int d0, int h0, int w0, int acc_bytes, int d_outer,
                   mmpl_stream_t stream);
