@@ -96,8 +96,9 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = sorted(float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit())
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "power_w": pw[len(pw) // 2] if pw else None}
 
 
 def load_peaks():
@@ -236,6 +237,57 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+def _e2e_probe(step, image_h, label_h, steps):
+    """Diagnostic (MMPL_BENCH_E2E_PROBE=1): where does a step of the host-fed path spend its time?  Prints to stderr: the
+    H2D time of one batch alone, then three repetitions of the e2e loop with, per step, the host time of each call and
+    the device time between consecutive step-end events."""
+    import time
+
+    import torch
+
+    cs = step._copy_stream
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    for k in range(3):
+        a.record(cs)
+        step.stage(image_h, label_h)
+        b.record(cs)
+        torch.cuda.synchronize()
+        step._stage_free.record()
+        sys.stderr.write(f"[e2e probe] H2D of one batch alone: {a.elapsed_time(b):.3f} ms\n")
+    loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
+    for rep in range(3):
+        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        host = []
+        torch.cuda.synchronize()
+        ends[0].record()
+        t_begin = time.perf_counter()
+        step.stage(image_h, label_h)
+        for i in range(steps):
+            t0 = time.perf_counter()
+            out = step.run_staged()
+            t1 = time.perf_counter()
+            loss_pin[i % 2:i % 2 + 1].copy_(out.detach().reshape(1), non_blocking=True)
+            loss_ev[i % 2].record()
+            ends[i + 1].record()
+            t2 = time.perf_counter()
+            if i + 1 < steps:
+                step.stage(image_h, label_h)
+            t3 = time.perf_counter()
+            if i > 0:
+                loss_ev[(i - 1) % 2].synchronize()
+            t4 = time.perf_counter()
+            host.append((t1 - t0, t2 - t1, t3 - t2, t4 - t3))
+        torch.cuda.synchronize()
+        total = (time.perf_counter() - t_begin) * 1e3
+        dev = [ends[i].elapsed_time(ends[i + 1]) for i in range(steps)]
+        sys.stderr.write(f"[e2e probe] rep {rep}: {total / steps:.3f} ms/step wall; device ms between step ends: "
+                         + " ".join(f"{d:.2f}" for d in dev) + "\n")
+        sys.stderr.write("[e2e probe]   host ms (run_staged, loss copy+record, stage, wait prev): "
+                         + " | ".join(" ".join(f"{x * 1e3:.2f}" for x in h) for h in host) + "\n")
 
 
 def cpu_baseline(workload, seconds=14.0):
@@ -434,6 +486,7 @@ def run_train(args):
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    time.sleep(0.05)          # let the poller's teardown finish before the host-fed loop starts
 
     # ---- timed region 2: end to end through the public API with pinned-host inputs ------------------------------------
     # every step: H2D of that step's batch (copy stream, overlapping the previous step's compute) and D2H of its loss
@@ -443,6 +496,9 @@ def run_train(args):
             step.stage(image_h, label_h)
             step.run_staged()
     barrier()
+    # no nvidia-smi polling in THIS region: the host feeds it step by step, and a 20 ms NVML poll holds driver locks long
+    # enough to stall that loop (measured on B200: the identical loop 11.8-11.9 ms/step alone, 12.0-16.6 ms/step with the
+    # sampler running; region 1 is immune because all its replays are queued within the first millisecond)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     last = 0.0
@@ -470,6 +526,8 @@ def run_train(args):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    if os.environ.get("MMPL_BENCH_E2E_PROBE") and use_graph and rank == 0:
+        _e2e_probe(step, image_h, label_h, args.steps)
 
     # ---- roofline region: the same step run eagerly with every tcgen05 conv launch bracketed by CUDA events on the
     # launching stream (a graph replay cannot be bracketed per kernel); identical kernels, shapes and data
@@ -666,7 +724,7 @@ def infer_record(model, dev, rank, world, steps, warmup, eager=False):
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
-    r0 = 0 if eager else nets[0].tiles_replayed
+    r0 = 0 if eager else nets[0].launches_replayed
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -676,7 +734,7 @@ def infer_record(model, dev, rank, world, steps, warmup, eager=False):
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - l0      # C-ABI calls made directly (finalize, ...) in the timed region
     if not eager:                           # + the kernels executed by this rank's graph replays
-        launches += (nets[0].tiles_replayed - r0) * nets[0].launches_per_tile
+        launches += nets[0].launches_replayed - r0
     clocks = sampler.stop() if rank == 0 else None
     # end to end: the volume and its labels start in pinned host memory (each rank uploads the depth range / label slab it
     # needs); the result -- the uint8 segmentation mask and the Dice values -- is read back into host memory on rank 0,
@@ -708,7 +766,7 @@ def infer_record(model, dev, rank, world, steps, warmup, eager=False):
                    "classes": classes,
                    "parallelism": f"contiguous tile runs over {world} rank(s)" + (", touched accumulator planes sent to their depth-slab owner (grouped NCCL send/recv) + all-gather of the uint8 mask" if world > 1 else ""),
                    "blend": "classifier + Gaussian accumulation fused (mmpl_cls_blend), fp32 depth-major accumulator",
-                   "launch": "eager" if eager else "one cuda graph per tile shape, replayed per tile (engine.GraphedSlidingWindow)",
+                   "launch": "eager" if eager else f"one cuda graph per batch of {nets[0].tile_batch} tiles, replayed per batch; tiles accumulated in the reference's order (engine.GraphedSlidingWindow)",
                    "l2": "volume + accumulators >> 126 MB L2, no flush needed"},
         "clocks": clocks,
         "e2e": {"value": ntiles * steps / (ms_e2e / 1e3), "unit": "patches/s",

@@ -401,6 +401,11 @@ gn_relu_bwd_apply_kernel(const T* __restrict__ x, const double* __restrict__ sta
       (hh == 0 ? dbeta : dbeta2)[c] = static_cast<float>(a);
       (hh == 0 ? dgamma : dgamma2)[c] = static_cast<float>(b);
     }
+    // Leave the workspace clean (sums and ticket): producers of a later backward through the same node accumulate into
+    // it again.  Every other block has passed its ticket, i.e. is done with the workspace -- no separate memset node.
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < static_cast<int64_t>(N) * C * kWs; i += kThreads) ws[i] = 0.0;
+    if (threadIdx.x == 0) *ticket = 0u;
   }
 }
 
@@ -544,8 +549,6 @@ extern "C" int mmpl_gn_relu_bwd(const void* x, const double* stats, const float*
                                                      dbeta, dgamma2, dbeta2, workspace, reduced, n, spatial, c, groups,
                                                      cnt_cpg, eps, bx, vpb, y2_d, y2_h, y2_w, s)));
   if (rc) return rc;
-  MMPL_CHECK_LAUNCH("gn_relu_bwd_apply");
-  // leave the workspace clean: producers of a later backward through the same node accumulate into it again
-  MMPL_CUDA(cudaMemsetAsync(workspace, 0, ws_bytes, s));
+  MMPL_CHECK_LAUNCH("gn_relu_bwd_apply");      // its last block leaves the workspace zeroed
   return MMPL_OK;
 }

@@ -429,58 +429,110 @@ class GraphedInference:
 
 
 class GraphedSlidingWindow:
-    """One sliding-window step -- eval-mode forward of a tile, classifier, Gaussian weighting and accumulation into the
-    volume accumulator (``model.blend_tile(tile, sink)``) -- captured ONCE into a CUDA graph and replayed per tile; the tile
-    origin is a device scalar triple the graph reads, so the same graph serves all 96 tiles of a 300x512x512 volume.
+    """One sliding-window step -- eval-mode forward of a batch of ``tile_batch`` tiles of the volume, classifier, Gaussian
+    weighting and accumulation into the volume accumulator (``model.blend_tile(tiles, sink)``) -- captured ONCE into a CUDA
+    graph and replayed per tile batch; the tile origins are device int32 rows the graph reads, so the same graph serves all
+    96 tiles of a 300x512x512 volume.  Tiles of a batch are accumulated in order, one ``mmpl_cls_blend`` launch each, so the
+    accumulator sees the reference's tile order (evaluate_amos.py:228-276) whatever the batch size; batching only gives the
+    low-resolution levels of the network (1 152 / 9 216 voxels per tile: fewer work items than SMs) more rows per launch.
+    One more graph serves the remainder of a rank's run in a single replay, and a single-tile graph ``blend_tile``.
     Owns the fp32 accumulator ``acc`` [1, Dpad, C, H, W] (depth-major; Dpad = D rounded up to a multiple of
     ``world_size`` so that every rank owns a depth slab of the same size).  Used by ``evaluate.predict_sliding_dice``.  The weights are
     treated as frozen (``ops.frozen_weights``): build a new object after they change."""
 
-    def __init__(self, model: torch.nn.Module, volume_dhw, tile, classes: int, world_size: int = 1, warmup: int = 2,
-                 device=None):
-        from .evaluate import _gaussian_device
+    class _Captured:
+        __slots__ = ("graph", "static_in", "origin_dev", "sink", "launches")
 
+    def __init__(self, model: torch.nn.Module, volume_dhw, tile, classes: int, world_size: int = 1, warmup: int = 2,
+                 device=None, tile_batch: int = None):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.model, self.tile, self.classes = model, tuple(int(t) for t in tile), int(classes)
         self.volume_dhw = tuple(int(v) for v in volume_dhw)
         D, H, W = self.volume_dhw
         self.world = max(int(world_size), 1)
         self.dpad = (D + self.world - 1) // self.world * self.world
+        from .evaluate import tile_origins
+
+        # tiles per forward: as given, else MMPL_SW_TILE_BATCH, else up to 8 (beyond that the low-resolution levels are
+        # saturated: 370 -> 447 -> 490 -> 511 tiles/s for 1 / 2 / 4 / 8 on one B200).  A rank's run of ``run`` tiles is
+        # served by full batches, then ONE replay of a remainder graph (run % tile_batch tiles), so no tile goes alone.
+        ntiles = len(tile_origins((1, 1) + self.volume_dhw, self.tile))
+        self.run = (ntiles + self.world - 1) // self.world
+        if tile_batch is None:
+            tile_batch = int(os.environ.get("MMPL_SW_TILE_BATCH", "0")) or 8
+        self.tile_batch = max(min(int(tile_batch), self.run), 1)
         self.acc = torch.zeros((1, self.dpad, classes, H, W), dtype=torch.float32, device=dev)
-        self.origin_dev = torch.zeros(3, dtype=torch.int32, device=dev)
-        self.static_in = torch.zeros((1, 1) + self.tile, dtype=torch.float32, device=dev)
-        self.sink = ops.BlendSink(self.acc, _gaussian_device(self.tile, dev), self.origin_dev, self.tile, d_outer=True)
+        self._dev, self._warmup = dev, max(int(warmup), 1)
         was_training = model.training
         model.eval()
         if not model.blend_supported():
             raise RuntimeError("GraphedSlidingWindow needs the bf16 compute dtype and a 32/64-channel classifier")
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side), torch.no_grad(), ops.frozen_weights():
-            for _ in range(max(warmup, 1)):
-                model.blend_tile(self.static_in, self.sink)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        launches0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph), torch.no_grad(), ops.frozen_weights():
-            model.blend_tile(self.static_in, self.sink)
-        self.launches_per_tile = _lib.launch_count() - launches0     # library kernels one replay executes
+        self._graphs = {t: self._capture(t) for t in sorted({1, self.tile_batch, max(self.run % self.tile_batch, 1)})}
+        one = self._graphs[1]
+        self.graph, self.static_in, self.origin_dev, self.sink = one.graph, one.static_in, one.origin_dev, one.sink
+        self.launches_per_tile = one.launches          # library kernels one single-tile replay executes
         self.tiles_replayed = 0
+        self.launches_replayed = 0                     # library kernels executed by all replays so far
         self.acc.zero_()
         if was_training:
             model.train()
+
+    def _capture(self, tiles: int):
+        from .evaluate import _gaussian_device
+
+        c = GraphedSlidingWindow._Captured()
+        c.origin_dev = torch.zeros((tiles, 3), dtype=torch.int32, device=self._dev)
+        c.static_in = torch.zeros((tiles, 1) + self.tile, dtype=torch.float32, device=self._dev)
+        c.sink = ops.BlendSink(self.acc, _gaussian_device(self.tile, self._dev), c.origin_dev, self.tile, d_outer=True)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad(), ops.frozen_weights():
+            for _ in range(self._warmup):
+                self.model.blend_tile(c.static_in, c.sink)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        c.graph = torch.cuda.CUDAGraph()
+        launches0 = _lib.launch_count()
+        with torch.cuda.graph(c.graph), torch.no_grad(), ops.frozen_weights():
+            self.model.blend_tile(c.static_in, c.sink)
+        c.launches = _lib.launch_count() - launches0
+        return c
+
+    def close(self):
+        """Release the captured graphs (before the process group goes away, like GraphedTrainStep.close)."""
+        self._graphs.clear()
+        self.graph = None
 
     def reset(self, lo=0, hi=None):
         """Zero the accumulator planes [lo, hi) (default: all) before a volume."""
         self.acc[0, lo:hi].zero_()
 
+    def _replay(self, c, tiles):
+        c.graph.replay()
+        self.tiles_replayed += tiles
+        self.launches_replayed += c.launches
+
     def blend_tile(self, img, origin_dev_row):
         """``img`` [1,1,td,th,tw] on the device; ``origin_dev_row`` a device int32[3] = (d0, h0, w0) of the tile."""
-        self.static_in.copy_(img, non_blocking=True)
-        self.origin_dev.copy_(origin_dev_row, non_blocking=True)
-        self.graph.replay()
-        self.tiles_replayed += 1
+        c = self._graphs[1]
+        c.static_in.copy_(img, non_blocking=True)
+        c.origin_dev.copy_(origin_dev_row.reshape(1, 3), non_blocking=True)
+        self._replay(c, 1)
+
+    def blend_tiles(self, imgs, origins_dev):
+        """``imgs``: a list of T device views [1,1,td,th,tw]; ``origins_dev`` device int32[T,3].  Full batches go through
+        the ``tile_batch`` graph, whatever is left through the single-tile graph, in list order."""
+        T, i = len(imgs), 0
+        while i < T:
+            tb = min(self.tile_batch, T - i)
+            if tb not in self._graphs:           # a run length this object was not built for: single tiles
+                tb = 1
+            c = self._graphs[tb]
+            for j in range(tb):
+                c.static_in[j:j + 1].copy_(imgs[i + j], non_blocking=True)
+            c.origin_dev.copy_(origins_dev[i:i + tb].reshape(tb, 3), non_blocking=True)
+            self._replay(c, tb)
+            i += tb
 
 
 def extant_file(x):

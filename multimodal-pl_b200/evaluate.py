@@ -249,9 +249,12 @@ def _sliding_blend(blender, image, tile_size, classes, label, num_class, rank, w
     if mine:
         part = image[:, :, dlo:dhi].to(dev, torch.float32, non_blocking=True)       # contiguous depth range (B = 1)
         origins = torch.tensor(mine, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
-        for i, (d1, y1, x1) in enumerate(mine):
-            tile = part[:, :, d1 - dlo:d1 - dlo + td, y1:y1 + th, x1:x1 + tw]
-            blender.blend_tile(tile, origins[i])
+        views = [part[:, :, d1 - dlo:d1 - dlo + td, y1:y1 + th, x1:x1 + tw] for d1, y1, x1 in mine]
+        if hasattr(blender, "blend_tiles"):         # several tiles per forward, accumulated in this order
+            blender.blend_tiles(views, origins)
+        else:
+            for i, tile in enumerate(views):
+                blender.blend_tile(tile, origins[i])
     if trace:
         trace.mark("tiles")
     if world > 1:

@@ -1165,11 +1165,17 @@ def upsample2x_ncdhw(x):
 class BlendSink:
     """Where the sliding-window classifier accumulates (predict_sliding, evaluate_amos.py:261-276): fp32 accumulator
     ``acc`` [B, D, C, H, W] (depth-major, ``d_outer``) or [B, C, D, H, W], optional weight sum ``wsum`` [B, D, H, W], the
-    Gaussian importance map of the tile and the tile origin as a DEVICE int32[3] (so a captured graph serves all tiles)."""
+    Gaussian importance map of the tile and the tile origin as a DEVICE int32[3] (so a captured graph serves all tiles).
+    ``origin_dev`` may also be int32[T, 3] with B = 1: a batch of T tiles of the SAME volume goes through the network in one
+    forward and is accumulated tile by tile, in order, into ``acc[0]`` (stream-ordered launches, so overlapping tiles add in
+    the order the reference visits them)."""
 
     def __init__(self, acc, gauss, origin_dev, tile, d_outer=True, wsum=None):
         assert acc.dtype == torch.float32 and acc.is_contiguous() and gauss.dtype == torch.float32
-        assert origin_dev.dtype == torch.int32 and origin_dev.numel() == 3 and origin_dev.is_cuda
+        assert origin_dev.dtype == torch.int32 and origin_dev.numel() % 3 == 0 and origin_dev.is_cuda
+        assert origin_dev.is_contiguous() and (origin_dev.numel() == 3 or acc.shape[0] == 1), \
+            "a tile batch (origin_dev [T, 3]) accumulates into ONE volume"
+        self.tiles = origin_dev.numel() // 3
         self.acc, self.gauss, self.origin_dev, self.wsum = acc, gauss.contiguous(), origin_dev, wsum
         self.tile = tuple(int(t) for t in tile)
         self.d_outer = bool(d_outer)
@@ -1192,13 +1198,18 @@ def classifier_blend(a, weight, bias, sink: BlendSink):
     a = to_cl(a, torch.bfloat16)
     n, cin, d, h, w = a.shape
     classes = weight.shape[0]
-    assert (d, h, w) == sink.tile and n == sink.B and classes == sink.C, "tile / batch / classes do not match the sink"
+    batch_of_tiles = sink.tiles > 1          # n tiles of one volume: acc[0], origin row i
+    assert (d, h, w) == sink.tile and n == (sink.tiles if batch_of_tiles else sink.B) and classes == sink.C, \
+        "tile / batch / classes do not match the sink"
     wc = weight.detach().float().reshape(classes, cin).contiguous()
     b = bias.detach().float().contiguous()
     a_rows = a.permute(0, 2, 3, 4, 1)      # the NDHWC storage
+    origins = sink.origin_dev.reshape(-1, 3)
     for i in range(n):
-        _lib.check(L.mmpl_cls_blend(_p(a_rows[i]), _p(wc), _p(b), _p(sink.gauss), _p(sink.acc[i]),
-                                    None if sink.wsum is None else _p(sink.wsum[i]), _p(sink.origin_dev), classes,
+        v = 0 if batch_of_tiles else i
+        _lib.check(L.mmpl_cls_blend(_p(a_rows[i]), _p(wc), _p(b), _p(sink.gauss), _p(sink.acc[v]),
+                                    None if sink.wsum is None else _p(sink.wsum[v]),
+                                    _p(origins[i if batch_of_tiles else 0]), classes,
                                     sink.D, sink.H, sink.W, d, h, w, cin, int(sink.d_outer), _lib.stream_ptr()), "cls_blend")
 
 
