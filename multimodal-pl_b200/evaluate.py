@@ -142,26 +142,39 @@ def _blender_for(net_list, volume_dhw, tile_size, classes, world):
 
 
 class _EagerBlender:
-    """Same contract as engine.GraphedSlidingWindow with per-kernel launches (any volume shape, no capture cost)."""
+    """Same contract as engine.GraphedSlidingWindow with per-kernel launches (any volume shape, no capture cost): up to
+    ``tile_batch`` tiles of the volume per forward, accumulated tile by tile in list order."""
 
-    def __init__(self, model, volume_dhw, tile, classes, world):
-        from . import ops
-
+    def __init__(self, model, volume_dhw, tile, classes, world, tile_batch=8):
         dev = torch.device("cuda", torch.cuda.current_device())
         D, H, W = volume_dhw
-        self.model, self.world = model, world
+        self.model, self.world, self.tile, self.tile_batch = model, world, tuple(int(t) for t in tile), int(tile_batch)
         self.dpad = (D + world - 1) // world * world
         self.acc = torch.zeros((1, self.dpad, classes, H, W), dtype=torch.float32, device=dev)
-        self.origin_dev = torch.zeros(3, dtype=torch.int32, device=dev)
-        self.sink = ops.BlendSink(self.acc, _gaussian_device(tile, dev), self.origin_dev, tile, d_outer=True)
+        self._sinks = {}
+
+    def _sink(self, tiles):
+        from . import ops
+
+        if tiles not in self._sinks:
+            origin_dev = torch.zeros((tiles, 3), dtype=torch.int32, device=self.acc.device)
+            self._sinks[tiles] = ops.BlendSink(self.acc, _gaussian_device(self.tile, self.acc.device), origin_dev,
+                                               self.tile, d_outer=True)
+        return self._sinks[tiles]
 
     def reset(self, lo=0, hi=None):
         self.acc[0, lo:hi].zero_()
 
     def blend_tile(self, img, origin_dev_row):
-        self.origin_dev.copy_(origin_dev_row, non_blocking=True)
-        with torch.no_grad():
-            self.model.blend_tile(img, self.sink)
+        self.blend_tiles([img], origin_dev_row.reshape(1, 3))
+
+    def blend_tiles(self, imgs, origins_dev):
+        for i in range(0, len(imgs), self.tile_batch):
+            chunk = imgs[i:i + self.tile_batch]
+            sink = self._sink(len(chunk))
+            sink.origin_dev.copy_(origins_dev[i:i + len(chunk)].reshape(len(chunk), 3), non_blocking=True)
+            with torch.no_grad():
+                self.model.blend_tile(chunk[0] if len(chunk) == 1 else torch.cat(chunk), sink)
 
 
 _SW_TRACE = os.environ.get("MMPL_SW_TRACE", "0") == "1"
