@@ -766,7 +766,7 @@ def infer_record(model, dev, rank, world, steps, warmup, eager=False):
                    "classes": classes,
                    "parallelism": f"contiguous tile runs over {world} rank(s)" + (", touched accumulator planes sent to their depth-slab owner (grouped NCCL send/recv) + all-gather of the uint8 mask" if world > 1 else ""),
                    "blend": "classifier + Gaussian accumulation fused (mmpl_cls_blend), fp32 depth-major accumulator",
-                   "launch": "eager" if eager else f"one cuda graph per batch of {nets[0].tile_batch} tiles, replayed per batch; tiles accumulated in the reference's order (engine.GraphedSlidingWindow)",
+                   "launch": "eager" if eager else f"cuda graphs per batch of {nets[0].tile_batch} tiles, batches alternating between {nets[0].lanes} stream(s); tiles accumulated one launch each in the reference's order (engine.GraphedSlidingWindow)",
                    "l2": "volume + accumulators >> 126 MB L2, no flush needed"},
         "clocks": clocks,
         "e2e": {"value": ntiles * steps / (ms_e2e / 1e3), "unit": "patches/s",

@@ -430,21 +430,28 @@ class GraphedInference:
 
 class GraphedSlidingWindow:
     """One sliding-window step -- eval-mode forward of a batch of ``tile_batch`` tiles of the volume, classifier, Gaussian
-    weighting and accumulation into the volume accumulator (``model.blend_tile(tiles, sink)``) -- captured ONCE into a CUDA
-    graph and replayed per tile batch; the tile origins are device int32 rows the graph reads, so the same graph serves all
-    96 tiles of a 300x512x512 volume.  Tiles of a batch are accumulated in order, one ``mmpl_cls_blend`` launch each, so the
-    accumulator sees the reference's tile order (evaluate_amos.py:228-276) whatever the batch size; batching only gives the
-    low-resolution levels of the network (1 152 / 9 216 voxels per tile: fewer work items than SMs) more rows per launch.
-    One more graph serves the remainder of a rank's run in a single replay, and a single-tile graph ``blend_tile``.
+    weighting and accumulation into the volume accumulator -- captured ONCE into CUDA graphs and replayed per tile batch;
+    the tile origins are device int32 rows the graphs read, so the same graphs serve all 96 tiles of a 300x512x512 volume.
+    Tiles of a batch are accumulated in order, one ``mmpl_cls_blend`` launch each, so the accumulator sees the reference's
+    tile order (evaluate_amos.py:228-276) whatever the batch size; batching only gives the low-resolution levels of the
+    network (1 152 / 9 216 voxels per tile: fewer work items than SMs) more rows per launch.  One more graph pair serves
+    the remainder of a rank's run in a single replay, and a single-tile pair ``blend_tile``.
+
+    ``lanes`` = 2 (default) alternates the tile batches between two streams, each with its own graphs and buffers: the
+    bandwidth-bound kernels of one batch (GroupNorm+ReLU, up-sampling) run under the tensor-bound convolutions of the other.
+    A step is therefore two graphs -- the network up to the classifier's input, and the accumulation launches -- and the
+    accumulation of batch k waits for the accumulation of batch k-1 on the other stream: the order in which overlapping
+    tiles are added stays the reference's.
+
     Owns the fp32 accumulator ``acc`` [1, Dpad, C, H, W] (depth-major; Dpad = D rounded up to a multiple of
     ``world_size`` so that every rank owns a depth slab of the same size).  Used by ``evaluate.predict_sliding_dice``.  The weights are
     treated as frozen (``ops.frozen_weights``): build a new object after they change."""
 
     class _Captured:
-        __slots__ = ("graph", "static_in", "origin_dev", "sink", "launches")
+        __slots__ = ("graph_f", "graph_b", "static_in", "origin_dev", "sink", "feat", "launches", "done")
 
     def __init__(self, model: torch.nn.Module, volume_dhw, tile, classes: int, world_size: int = 1, warmup: int = 2,
-                 device=None, tile_batch: int = None):
+                 device=None, tile_batch: int = None, lanes: int = None):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.model, self.tile, self.classes = model, tuple(int(t) for t in tile), int(classes)
         self.volume_dhw = tuple(int(v) for v in volume_dhw)
@@ -454,22 +461,35 @@ class GraphedSlidingWindow:
         from .evaluate import tile_origins
 
         # tiles per forward: as given, else MMPL_SW_TILE_BATCH, else up to 8 (beyond that the low-resolution levels are
-        # saturated: 370 -> 447 -> 490 -> 511 tiles/s for 1 / 2 / 4 / 8 on one B200).  A rank's run of ``run`` tiles is
-        # served by full batches, then ONE replay of a remainder graph (run % tile_batch tiles), so no tile goes alone.
+        # saturated: 370 -> 447 -> 490 -> 511 tiles/s for 1 / 2 / 4 / 8 on one B200, one lane).  A rank's run of ``run``
+        # tiles is served by full batches, then ONE replay of a remainder graph (run % tile_batch tiles).
         ntiles = len(tile_origins((1, 1) + self.volume_dhw, self.tile))
         self.run = (ntiles + self.world - 1) // self.world
+        if lanes is None:
+            lanes = int(os.environ.get("MMPL_SW_LANES", "0")) or 2
         if tile_batch is None:
-            tile_batch = int(os.environ.get("MMPL_SW_TILE_BATCH", "0")) or 8
+            tile_batch = int(os.environ.get("MMPL_SW_TILE_BATCH", "0")) or None
+        if tile_batch is None:
+            # as few batches of at most 8 tiles as cover the run, their number a multiple of the lanes, equal sizes
+            # (96 tiles: 12 x 8; a rank's 12 tiles of an 8-GPU job: 2 x 6, one batch per lane)
+            nb = (self.run + 7) // 8
+            nb = min((nb + lanes - 1) // lanes * lanes, self.run)
+            tile_batch = (self.run + nb - 1) // nb
         self.tile_batch = max(min(int(tile_batch), self.run), 1)
+        self.lanes = max(min(int(lanes), (self.run + self.tile_batch - 1) // self.tile_batch), 1)
         self.acc = torch.zeros((1, self.dpad, classes, H, W), dtype=torch.float32, device=dev)
         self._dev, self._warmup = dev, max(int(warmup), 1)
         was_training = model.training
         model.eval()
         if not model.blend_supported():
             raise RuntimeError("GraphedSlidingWindow needs the bf16 compute dtype and a 32/64-channel classifier")
-        self._graphs = {t: self._capture(t) for t in sorted({1, self.tile_batch, max(self.run % self.tile_batch, 1)})}
-        one = self._graphs[1]
-        self.graph, self.static_in, self.origin_dev, self.sink = one.graph, one.static_in, one.origin_dev, one.sink
+        sizes = sorted({self.tile_batch, max(self.run % self.tile_batch, 1)})
+        self._graphs = [{t: self._capture(t) for t in sizes} for _ in range(self.lanes)]
+        if 1 not in self._graphs[0]:
+            self._graphs[0][1] = self._capture(1)
+        self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.lanes)] if self.lanes > 1 else []
+        one = self._graphs[0][1]
+        self.static_in, self.origin_dev, self.sink = one.static_in, one.origin_dev, one.sink
         self.launches_per_tile = one.launches          # library kernels one single-tile replay executes
         self.tiles_replayed = 0
         self.launches_replayed = 0                     # library kernels executed by all replays so far
@@ -484,55 +504,82 @@ class GraphedSlidingWindow:
         c.origin_dev = torch.zeros((tiles, 3), dtype=torch.int32, device=self._dev)
         c.static_in = torch.zeros((tiles, 1) + self.tile, dtype=torch.float32, device=self._dev)
         c.sink = ops.BlendSink(self.acc, _gaussian_device(self.tile, self._dev), c.origin_dev, self.tile, d_outer=True)
+        c.done = torch.cuda.Event()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad(), ops.frozen_weights():
             for _ in range(self._warmup):
-                self.model.blend_tile(c.static_in, c.sink)
+                self.model.blend_accumulate(self.model.blend_features(c.static_in), c.sink)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        c.graph = torch.cuda.CUDAGraph()
+        c.graph_f, c.graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         launches0 = _lib.launch_count()
-        with torch.cuda.graph(c.graph), torch.no_grad(), ops.frozen_weights():
-            self.model.blend_tile(c.static_in, c.sink)
+        with torch.cuda.graph(c.graph_f), torch.no_grad(), ops.frozen_weights():
+            c.feat = self.model.blend_features(c.static_in)
+        with torch.cuda.graph(c.graph_b), torch.no_grad():
+            self.model.blend_accumulate(c.feat, c.sink)
         c.launches = _lib.launch_count() - launches0
         return c
 
     def close(self):
         """Release the captured graphs (before the process group goes away, like GraphedTrainStep.close)."""
-        self._graphs.clear()
-        self.graph = None
+        self._graphs = []
 
     def reset(self, lo=0, hi=None):
         """Zero the accumulator planes [lo, hi) (default: all) before a volume."""
         self.acc[0, lo:hi].zero_()
 
-    def _replay(self, c, tiles):
-        c.graph.replay()
+    def _fill(self, c, imgs, origins_dev):
+        for j, im in enumerate(imgs):
+            c.static_in[j:j + 1].copy_(im, non_blocking=True)
+        c.origin_dev.copy_(origins_dev.reshape(len(imgs), 3), non_blocking=True)
+
+    def _count(self, c, tiles):
         self.tiles_replayed += tiles
         self.launches_replayed += c.launches
 
     def blend_tile(self, img, origin_dev_row):
         """``img`` [1,1,td,th,tw] on the device; ``origin_dev_row`` a device int32[3] = (d0, h0, w0) of the tile."""
-        c = self._graphs[1]
-        c.static_in.copy_(img, non_blocking=True)
-        c.origin_dev.copy_(origin_dev_row.reshape(1, 3), non_blocking=True)
-        self._replay(c, 1)
+        c = self._graphs[0][1]
+        self._fill(c, [img], origin_dev_row)
+        c.graph_f.replay()
+        c.graph_b.replay()
+        self._count(c, 1)
 
     def blend_tiles(self, imgs, origins_dev):
-        """``imgs``: a list of T device views [1,1,td,th,tw]; ``origins_dev`` device int32[T,3].  Full batches go through
-        the ``tile_batch`` graph, whatever is left through the single-tile graph, in list order."""
-        T, i = len(imgs), 0
+        """``imgs``: a list of T device views [1,1,td,th,tw]; ``origins_dev`` device int32[T,3].  Full batches, then the
+        remainder, in list order; the batches alternate between the lanes."""
+        T, i, k = len(imgs), 0, 0
+        cur = torch.cuda.current_stream()
+        if self.lanes > 1:
+            for s in self._streams:            # the tiles, the origins and the zeroed accumulator come from ``cur``
+                s.wait_stream(cur)
+        prev_done = None
         while i < T:
             tb = min(self.tile_batch, T - i)
-            if tb not in self._graphs:           # a run length this object was not built for: single tiles
-                tb = 1
-            c = self._graphs[tb]
-            for j in range(tb):
-                c.static_in[j:j + 1].copy_(imgs[i + j], non_blocking=True)
-            c.origin_dev.copy_(origins_dev[i:i + tb].reshape(tb, 3), non_blocking=True)
-            self._replay(c, tb)
+            lane = k % self.lanes
+            if tb not in self._graphs[lane]:       # a run length this object was not built for: single tiles
+                tb, lane = 1, 0
+            c = self._graphs[lane][tb]
+            if self.lanes > 1:
+                s = self._streams[lane]
+                with torch.cuda.stream(s):
+                    self._fill(c, imgs[i:i + tb], origins_dev[i:i + tb])
+                    c.graph_f.replay()
+                    if prev_done is not None:
+                        s.wait_event(prev_done)    # accumulate after the previous batch (reference tile order)
+                    c.graph_b.replay()
+                    c.done.record(s)
+                prev_done = c.done
+            else:
+                self._fill(c, imgs[i:i + tb], origins_dev[i:i + tb])
+                c.graph_f.replay()
+                c.graph_b.replay()
+            self._count(c, tb)
             i += tb
+            k += 1
+        for s in self._streams:
+            cur.wait_stream(s)
 
 
 def extant_file(x):

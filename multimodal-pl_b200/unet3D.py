@@ -284,6 +284,19 @@ class unet3D_baseline(nn.Module):
         ``sink`` (an ``ops.BlendSink``) by the classifier kernel itself (predict_sliding, evaluate_amos.py:244-276)."""
         self.precls_conv(self._features(input), blend=sink)
 
+    @torch.no_grad()
+    def blend_features(self, input):
+        """First half of ``blend_tile``: the classifier's input a = relu(gn(features)) of a batch of tiles."""
+        gn = self.precls_conv[0]
+        return ops.gn_relu(self._features(input), gn.weight, gn.bias, gn.num_groups, gn.eps)
+
+    @torch.no_grad()
+    def blend_accumulate(self, a, sink):
+        """Second half of ``blend_tile``: classifier + Gaussian-weighted accumulation of ``a`` into ``sink`` (so that the
+        network of the next tile batch can run on another stream while this one is accumulated, in tile order)."""
+        conv = self.precls_conv[2]
+        ops.classifier_blend(a, conv.weight, conv.bias, sink)
+
 
 class EAM(nn.Module):
     """Class-token cross attention (reference unet3D.py:142-212): same constructor, parameters (``kv``, ``q``, ``proj``,

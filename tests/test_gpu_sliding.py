@@ -165,12 +165,12 @@ def test_fused_classifier_blend_path_equals_generic_path():
     assert fused[3].shape == generic[3].shape and fused[3].dtype == torch.uint8
     assert torch.equal(fused[3], generic[3])
     assert [float(a) for a in fused[0]] == [float(a) for a in generic[0]]
-    # tile batches: 36 tiles as single replays, as 7 x 5 + 1, as 5 x 7 + one remainder replay of 1, and (default) as
-    # 4 x 8 + one remainder replay of 4 -- every tile is still accumulated by its own launch in the reference's order, so
-    # nothing may change
-    for tb in (1, 5, 7, None):
-        eng = GraphedSlidingWindow(model, (40, 72, 88), tile, 16, tile_batch=tb)
-        assert eng.tile_batch == (tb or 8) and eng.run == 36
+    # tile batches: 36 tiles as single replays, as 7 x 5 + 1, as 4 x 8 + one remainder replay of 4 on one stream, and
+    # (default) as 6 x 6 alternating between two streams -- every tile is still accumulated by its own launch in the
+    # reference's order (the accumulation of a batch waits for the previous batch's), so nothing may change
+    for tb, lanes in ((1, 2), (5, 2), (8, 1), (None, None)):
+        eng = GraphedSlidingWindow(model, (40, 72, 88), tile, 16, tile_batch=tb, lanes=lanes)
+        assert eng.tile_batch == (tb or 6) and eng.lanes == (lanes or 2) and eng.run == 36
         for _ in range(2):          # second volume: the accumulator is reset between volumes
             r0 = eng.tiles_replayed
             graphed = predict_sliding_dice(None, [eng], vol, tile, 16, None, label=lab.to(torch.uint8),
