@@ -776,7 +776,8 @@ def infer_record(model, dev, rank, world, steps, warmup, eager=False):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "all conv kernels of the forward pass (whole-volume average)",
                      "achieved": value * FWD_TFLOP_PER_TILE / world, "peak": peak_tf, "unit": "TFLOP/s per GPU",
-                     "frac": value * FWD_TFLOP_PER_TILE / peak_tf / world, "traffic": None, "peak_source": peak_src},
+                     "frac": value * FWD_TFLOP_PER_TILE / peak_tf / world, "traffic": None, "peak_source": peak_src,
+                     "frac_of_burst_peak": value * FWD_TFLOP_PER_TILE / (peaks.get("bf16_tflops") or 1670.0) / world},
     }
     if sw_par is not None:
         rec["sw_parity"] = sw_par
