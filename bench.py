@@ -500,18 +500,21 @@ def run_train(args):
     # enough to stall that loop (measured on B200: the identical loop 11.8-11.9 ms/step alone, 12.0-16.6 ms/step with the
     # sampler running; region 1 is immune because all its replays are queued within the first millisecond)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the pinned landing buffer of the losses exists before the clock starts: cudaHostAlloc is a millisecond-scale,
+    # device-synchronising call (it used to sit inside the region and cost ~12 ms once, i.e. 1.2 ms/step at 10 steps)
+    loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    torch.cuda.synchronize()
     f0.record()
     last = 0.0
     if use_graph:
         # the loss of every step is copied to pinned host memory right behind its step and READ one step later, like a
         # training loop that logs asynchronously: the host stays one step ahead, every step's result reaches the host inside
         # the timed region (the last one before the closing event)
-        loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
-        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
         step.stage(image_h, label_h)
         for i in range(args.steps):
             out = step.run_staged()
-            loss_pin[i % 2:i % 2 + 1].copy_(out.reshape(1), non_blocking=True)
+            loss_pin[i % 2:i % 2 + 1].copy_(out.detach().reshape(1), non_blocking=True)
             loss_ev[i % 2].record()
             if i + 1 < args.steps:
                 step.stage(image_h, label_h)           # next batch's PCIe transfer runs under this step's kernels
