@@ -130,6 +130,7 @@ cls_blend_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restric
   const int d0 = __ldg(q.origin), h0 = __ldg(q.origin + 1), w0 = __ldg(q.origin + 2);
   const int S = q.td * q.th * q.tw;
   const int64_t plane = static_cast<int64_t>(q.H) * q.W;
+  __shared__ float tile[8][16][36];     // per warp: [class][voxel of the chunk], pitch 36 keeps the fragment stores conflict-free
   const int nchunks = (S + 31) / 32;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warps) {
@@ -161,30 +162,39 @@ cls_blend_mma_kernel(const __nv_bfloat16* __restrict__ a, const float* __restric
           mma_bf16(acc[mt][nt], af[ks][0], af[ks][1], af[ks][2], af[ks][3], bl[ks][nt][0], bl[ks][nt][1]);
         }
     }
+    // Epilogue: transpose the 32 x 16 logits of the chunk through shared memory so that lane L owns voxel s0 + L and
+    // every read-modify-write instruction of the warp covers 32 consecutive voxels of ONE class plane (full 128-byte
+    // lines; the accumulator-fragment layout would touch four class planes with 32 bytes each).
+    float(*tw_)[36] = tile[threadIdx.x >> 5];
+    __syncwarp();
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int r = s0 + mt * 16 + g + half * 8;
-        if (r >= S) continue;
-        const int x = r % q.tw, yz = r / q.tw, y = yz % q.th, z = yz / q.th;
-        const int vd = d0 + z, vh = h0 + y, vw = w0 + x;
-        if (vd >= q.D || vh >= q.H || vw >= q.W || vd < 0 || vh < 0 || vw < 0) continue;    // memory safety only
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          tw_[nt * 8 + 2 * t + (i & 1)][mt * 16 + g + (i >> 1) * 8] = acc[mt][nt][i];
+    __syncwarp();
+    const int r = s0 + lane;
+    if (r < S) {
+      const int x = r % q.tw, yz = r / q.tw, y = yz % q.th, z = yz / q.th;
+      const int vd = d0 + z, vh = h0 + y, vw = w0 + x;
+      if (!(vd >= q.D || vh >= q.H || vw >= q.W || vd < 0 || vh < 0 || vw < 0)) {      // memory safety only
         const float gv = __ldg(q.gauss + r);
         const int64_t o = static_cast<int64_t>(vh) * q.W + vw;
-        if (q.wsum != nullptr && t == 0) q.wsum[vd * plane + o] += gv;
+        if (q.wsum != nullptr) q.wsum[vd * plane + o] += gv;
+        float* dst = q.acc + (q.d_outer ? static_cast<int64_t>(vd) * classes * plane + o : vd * plane + o);
+        const int64_t cstride = q.d_outer ? plane : static_cast<int64_t>(q.D) * plane;
+        // all loads of the voxel's class column first, then the stores: 16 independent 128-byte lines in flight per warp
+        float v[16];
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+        for (int c = 0; c < 16; ++c)
+          if (c < classes) v[c] = dst[c * cstride];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int c = nt * 8 + 2 * t + j;
-            if (c < classes) {
-              float* dst = q.acc + (q.d_outer ? (static_cast<int64_t>(vd) * classes + c) * plane + o
-                                              : (static_cast<int64_t>(c) * q.D + vd) * plane + o);
-              *dst += gv * acc[mt][nt][half * 2 + j];
-            }
-          }
+        for (int c = 0; c < 16; ++c)
+          if (c < classes) dst[c * cstride] = v[c] + gv * tw_[c][lane];
       }
+    }
   }
 }
 

@@ -199,6 +199,16 @@ def _zero_stats(numel: int, device) -> torch.Tensor:
     return torch.zeros(numel, dtype=torch.float64, device=device)
 
 
+class _StatsBox:
+    """The GroupNorm raw sums a producer's epilogue accumulated, handed out of an autograd Function as a NON-tensor output.
+    As a tensor output (even marked non-differentiable) autograd materialises a zero gradient for it in every backward:
+    one 64-element fill launch per convolution per step, 32 nodes on the critical path of the captured step."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+
 def to_cl(x: torch.Tensor, dtype=None) -> torch.Tensor:
     """Logical NCDHW tensor -> compute dtype with physically dense NDHWC storage (no copy if already so)."""
     dtype = dtype or _cfg["dtype"]
@@ -523,10 +533,7 @@ class WSConv3dFn(torch.autograd.Function):
         ctx.flops = flops
         ctx.key = ctx_key
         if want_stats:
-            if stats is None:
-                return y, torch.empty(0, dtype=torch.float64, device=dev)
-            ctx.mark_non_differentiable(stats)
-            return y, stats
+            return y, _StatsBox(stats)
         return y
 
     @staticmethod
@@ -637,9 +644,9 @@ def ws_conv3d(x, weight, stride=1, standardise=True, residual=None, want_stats=F
     epilogue) and attaches them to the returned tensor, where ``gn_relu`` picks them up."""
     if not want_stats:
         return WSConv3dFn.apply(x, weight, residual, int(stride), bool(standardise), False)
-    y, stats = WSConv3dFn.apply(x, weight, residual, int(stride), bool(standardise), True)
-    if stats.numel():
-        y._mmpl_gn_stats = (stats, 16)
+    y, box = WSConv3dFn.apply(x, weight, residual, int(stride), bool(standardise), True)
+    if box.t is not None:
+        y._mmpl_gn_stats = (box.t, 16)
     return y
 
 
@@ -705,10 +712,7 @@ class StemConvFn(torch.autograd.Function):
         ctx.ws_entry, ctx.ws_stamp = ws, ws.stamp
         ctx.meta = (n, d, h, w, cout, int(standardise), weight.dtype, use_tc, tc_fwd, kch, fused)
         ctx.weight = weight
-        if not tc_fwd or stats is None:
-            stats = torch.empty(0, dtype=torch.float64, device=dev)
-        ctx.mark_non_differentiable(stats)
-        return y, stats
+        return y, _StatsBox(stats if tc_fwd else None)
 
     @staticmethod
     def backward(ctx, dy, _dstats=None):
@@ -751,9 +755,9 @@ class StemConvFn(torch.autograd.Function):
 
 
 def stem_conv(image, weight, standardise=True):
-    y, stats = StemConvFn.apply(image, weight, bool(standardise))
-    if stats.numel():
-        y._mmpl_gn_stats = (stats, 16)
+    y, box = StemConvFn.apply(image, weight, bool(standardise))
+    if box.t is not None:
+        y._mmpl_gn_stats = (box.t, 16)
     return y
 
 
@@ -934,10 +938,7 @@ class Upsample2xAddFn(torch.autograd.Function):
         _lib.check(L.mmpl_upsample2x_add_fwd(_p(x_lo), _p(skip), _p(y), n, d, h, w, c, _lib.dtype_code(dt), _p(stats),
                                              _lib.stream_ptr()), "upsample2x_add_fwd")
         ctx.meta = (n, c, d, h, w, dt)
-        if stats is None:
-            stats = torch.empty(0, dtype=torch.float64, device=x_lo.device)
-        ctx.mark_non_differentiable(stats)
-        return y, stats
+        return y, _StatsBox(stats)
 
     @staticmethod
     def backward(ctx, dy, _dstats=None):
@@ -953,9 +954,9 @@ class Upsample2xAddFn(torch.autograd.Function):
 
 
 def upsample2x_add(x_lo, skip):
-    y, stats = Upsample2xAddFn.apply(x_lo, skip)
-    if stats.numel():
-        y._mmpl_gn_stats = (stats, 16)
+    y, box = Upsample2xAddFn.apply(x_lo, skip)
+    if box.t is not None:
+        y._mmpl_gn_stats = (box.t, 16)
     return y
 
 
