@@ -428,6 +428,20 @@ class GraphedInference:
         return self.static_out
 
 
+def plan_tile_batches(run: int, lanes: int = 2, tile_batch: Optional[int] = None, cap: int = 8):
+    """(tiles per forward, streams) for a rank that owns ``run`` tiles of a volume.  ``tile_batch`` given: clamped to the
+    run.  Otherwise: as few batches of at most ``cap`` tiles as cover the run, their number rounded up to a multiple of
+    ``lanes`` so that every stream gets the same number of batches, all of (nearly) the same size -- 96 tiles: 12 x 8; a
+    rank's 12 tiles of an 8-GPU job: 2 x 6, one batch per stream; 36 tiles: 6 x 6.  Never more streams than batches."""
+    run, lanes = max(int(run), 1), max(int(lanes), 1)
+    if tile_batch is None:
+        nb = (run + cap - 1) // cap
+        nb = min((nb + lanes - 1) // lanes * lanes, run)
+        tile_batch = (run + nb - 1) // nb
+    tile_batch = max(min(int(tile_batch), run), 1)
+    return tile_batch, max(min(lanes, (run + tile_batch - 1) // tile_batch), 1)
+
+
 class GraphedSlidingWindow:
     """One sliding-window step -- eval-mode forward of a batch of ``tile_batch`` tiles of the volume, classifier, Gaussian
     weighting and accumulation into the volume accumulator -- captured ONCE into CUDA graphs and replayed per tile batch;
@@ -469,14 +483,7 @@ class GraphedSlidingWindow:
             lanes = int(os.environ.get("MMPL_SW_LANES", "0")) or 2
         if tile_batch is None:
             tile_batch = int(os.environ.get("MMPL_SW_TILE_BATCH", "0")) or None
-        if tile_batch is None:
-            # as few batches of at most 8 tiles as cover the run, their number a multiple of the lanes, equal sizes
-            # (96 tiles: 12 x 8; a rank's 12 tiles of an 8-GPU job: 2 x 6, one batch per lane)
-            nb = (self.run + 7) // 8
-            nb = min((nb + lanes - 1) // lanes * lanes, self.run)
-            tile_batch = (self.run + nb - 1) // nb
-        self.tile_batch = max(min(int(tile_batch), self.run), 1)
-        self.lanes = max(min(int(lanes), (self.run + self.tile_batch - 1) // self.tile_batch), 1)
+        self.tile_batch, self.lanes = plan_tile_batches(self.run, lanes, tile_batch)
         self.acc = torch.zeros((1, self.dpad, classes, H, W), dtype=torch.float32, device=dev)
         self._dev, self._warmup = dev, max(int(warmup), 1)
         was_training = model.training

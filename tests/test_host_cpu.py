@@ -284,3 +284,29 @@ def test_sliding_window_plane_exchange_plan_sums_every_contribution_once(volume,
         np.testing.assert_allclose(out[r, r * slab:(r + 1) * slab], total[r * slab:(r + 1) * slab], rtol=1e-12)
     if world >= 4 and len(tiles) >= 4 * world:
         assert moved < 0.5 * (world - 1) * dpad, (moved, (world - 1) * dpad)
+
+
+def test_sliding_window_tile_batch_plan():
+    """engine.plan_tile_batches: tiles per forward and streams for a rank's run of tiles.  Every tile is covered exactly
+    once by full batches plus one remainder batch, a batch never exceeds 8 tiles unless asked for, the automatic choice
+    gives every stream the same number of batches, and there are never more streams than batches."""
+    from multimodal_pl_b200 import evaluate as E
+    from multimodal_pl_b200.engine import plan_tile_batches
+
+    assert plan_tile_batches(96) == (8, 2)            # one GPU, 300x512x512 / 64x192x192
+    assert plan_tile_batches(48) == (8, 2)            # 2 GPUs
+    assert plan_tile_batches(24) == (6, 2)            # 4 GPUs: 4 x 6 instead of 3 x 8 (two batches per stream)
+    assert plan_tile_batches(12) == (6, 2)            # 8 GPUs: one batch per stream instead of 8 + 4
+    assert plan_tile_batches(36) == (6, 2)
+    assert plan_tile_batches(1) == (1, 1)
+    assert plan_tile_batches(5, lanes=2) == (3, 2)    # 3 + 2
+    assert plan_tile_batches(36, lanes=1, tile_batch=8) == (8, 1)
+    assert plan_tile_batches(3, lanes=2, tile_batch=8) == (3, 1)     # clamped to the run: one batch, one stream
+    assert plan_tile_batches(96, lanes=3) == (8, 3)
+    for world in (1, 2, 3, 4, 8):
+        run = (len(E.tile_origins((1, 1, 300, 512, 512), (64, 192, 192))) + world - 1) // world
+        for lanes in (1, 2, 3):
+            tb, ln = plan_tile_batches(run, lanes)
+            nb = (run + tb - 1) // tb
+            assert 1 <= tb <= 8 and 1 <= ln <= min(lanes, nb)
+            assert (run // tb) * tb + run % tb == run and run % tb < tb
